@@ -1,0 +1,186 @@
+/*
+ * slpr.h — C ABI of the B200-native scanline path renderer (libslpr.so).
+ *
+ * This is the drop-in boundary for the compute path of galaxysailing/VkScanlinePR. Each entry
+ * point names the reference interface it replaces (file:line relative to the reference root).
+ * Plain pointers and sizes only: no C++ or torch types cross this boundary, no exceptions.
+ * Every function returns an int status (SLPR_OK = 0) unless noted; the message for the last
+ * failure on the calling thread is slpr_last_error().
+ *
+ * Threading: a context is one GPU + one stream and is not thread-safe; independent contexts are.
+ * There is no CPU fallback: if no CUDA device is usable, slpr_create() fails loudly.
+ */
+#ifndef SLPR_H_
+#define SLPR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define SLPR_API __declspec(dllexport)
+#else
+#define SLPR_API __attribute__((visibility("default")))
+#endif
+
+typedef struct slpr_ctx slpr_ctx;
+
+enum {
+    SLPR_OK = 0,
+    SLPR_ERR_INVALID = 1,     /* bad argument */
+    SLPR_ERR_CUDA = 2,        /* CUDA runtime error (message has the CUDA string) */
+    SLPR_ERR_STATE = 3,       /* call order violated (e.g. render before load_scene) */
+    SLPR_ERR_UNSUPPORTED = 4, /* feature not built (e.g. SLPR_FLAG_CONTRACT_FMA) */
+    SLPR_ERR_IO = 5           /* file / parse error (host scene helpers) */
+};
+
+enum {
+    /* Keep every reference-format intermediate buffer (fragment_data planes etc.) so that
+     * slpr_debug_copy() can return them for parity checks. Costs extra HBM traffic. */
+    SLPR_FLAG_TAPS = 1u << 0,
+    /* Evaluate LERP/dot with FMA contraction, as a Vulkan driver may. Not built. */
+    SLPR_FLAG_CONTRACT_FMA = 1u << 1,
+    /* Launch kernels directly instead of replaying the captured CUDA graph of the frame. */
+    SLPR_FLAG_NO_GRAPH = 1u << 2
+};
+
+/* Buffers that slpr_debug_copy() can return. Layouts are the reference's:
+ * int32 unless noted; sizes in elements. */
+enum {
+    SLPR_TAP_TRANSFORMED_POS = 0, /* float[2*n_points]        transform_pos.comp:85            */
+    SLPR_TAP_PATH_VISIBLE = 1,    /* int[n_paths]             transform_pos.comp:71-82         */
+    SLPR_TAP_CUT_CACHE = 2,       /* float[5*n_curves]        make_intersection_0.comp:368-372 */
+    SLPR_TAP_CURVE_COUNT = 3,     /* int[n_curves]            make_intersection_0.comp:410     */
+    SLPR_TAP_CURVE_OFFSET = 4,    /* int[n_curves+1]          scan #1, SR.cpp:338-358          */
+    SLPR_TAP_INTERSECTION = 5,    /* int[2*nf] (curve,tbits)  make_intersection_1.comp:361-375 */
+    SLPR_TAP_KEY = 6,             /* plane 0 before sort      gen_fragment.comp:221            */
+    SLPR_TAP_PATH = 7,            /* plane 2                  gen_fragment.comp:223            */
+    SLPR_TAP_WINDING = 8,         /* plane 4 (unsorted delta) gen_fragment.comp:224            */
+    SLPR_TAP_SORTED_KEY = 9,      /* plane 0 after sort       naive_seg_sort_pairs.comp        */
+    SLPR_TAP_SORTED_INDEX = 10,   /* plane 1 after sort                                        */
+    SLPR_TAP_WINDING_SCAN = 11,   /* int[nf+1] plane 3 after shuffle + scan #2, SR.cpp:479-506 */
+    SLPR_TAP_FLAGS = 12,          /* int[2*nf] [frag|span]    mark_merged_fragment_and_span.comp:92-93 */
+    SLPR_TAP_FLAG_SCAN = 13,      /* int[2*nf+1] plane 6      scan #3, SR.cpp:545-573          */
+    SLPR_TAP_RECORDS = 14,        /* int[4*(n_out_frag+n_span)] output_buf, gen_merged_fragment_and_span.comp:77,102 */
+    SLPR_TAP_SEGMENTS = 15        /* int[n_paths+1] sort segment table, gen_fragment.comp:226-244 */
+};
+
+/* Stage slots reported by slpr_stage_ms(). */
+enum {
+    SLPR_STAGE_TRANSFORM = 0, SLPR_STAGE_MONOTONIZE = 1, SLPR_STAGE_SCAN1 = 2,
+    SLPR_STAGE_INTERSECT = 3, SLPR_STAGE_FRAGMENT = 4, SLPR_STAGE_SORT = 5,
+    SLPR_STAGE_SPANS = 6, SLPR_STAGE_FILL = 7, SLPR_STAGE_COUNT = 8
+};
+
+SLPR_API const char *slpr_last_error(void);
+SLPR_API const char *slpr_version(void);
+
+/* Replaces ScanlineVGRasterizer::initialize(window,w,h) (scanline_rasterizer.cpp:42-55) and the
+ * Vulkan bring-up behind it (vulkan/vk_vg_rasterizer.cpp:16-94). Headless: there is no window.
+ * Returns NULL on failure (no CUDA device, bad size, unsupported flag). */
+SLPR_API slpr_ctx *slpr_create(int device, uint32_t width, uint32_t height, uint32_t flags);
+SLPR_API void slpr_destroy(slpr_ctx *ctx);
+
+/* Run all work of this context on a caller-owned cudaStream_t (e.g. torch's current stream)
+ * instead of the context's own stream. Pass NULL to go back to the internal stream. */
+SLPR_API int slpr_set_stream(slpr_ctx *ctx, void *cuda_stream);
+
+/* Replaces the 7 staging uploads at the end of ScanlineVGRasterizer::loadVG
+ * (scanline_rasterizer.cpp:120-146); the arguments are exactly loadVG's flat arrays
+ * (scanline/vk_vg_data.h:14-35). Host pointers; copied before return. */
+SLPR_API int slpr_load_scene(slpr_ctx *ctx,
+                             const float *pos_xy, const uint32_t *pos_path, uint32_t n_points,
+                             const uint32_t *curve_pos_map, const uint32_t *curve_type,
+                             const uint32_t *curve_path, uint32_t n_curves,
+                             const uint32_t *fill_rule, const uint32_t *fill_rgba8, uint32_t n_paths);
+
+/* Replaces ScanlineVGRasterizer::setMVP (scanline_rasterizer.cpp:191-197): rows m0..m3 of
+ * TransPosIn (scanline/compute_ubo.h:9-13), i.e. x' = dot((x,y,0,1), m0) / dot((x,y,0,1), m3). */
+SLPR_API int slpr_set_mvp(slpr_ctx *ctx, const float rows[16]);
+
+/* New (multi-GPU row bands): render only scanline rows [y_begin, y_end), both even.
+ * (0, height) restores the full frame. Rows are the reference's scanline rows (y up). */
+SLPR_API int slpr_set_band(slpr_ctx *ctx, uint32_t y_begin, uint32_t y_end);
+
+/* Render into a caller-owned device buffer (RGBA8, top-left origin, `stride_bytes` per image
+ * row) instead of the context's framebuffer — used to write bands straight into a peer-mapped
+ * frame on GPU0. NULL restores the internal framebuffer. */
+SLPR_API int slpr_set_target(slpr_ctx *ctx, void *dev_rgba, size_t stride_bytes);
+
+/* Replaces ScanlineVGRasterizer::render()/drawFrame() (scanline_rasterizer.cpp:57-65,282-696):
+ * the whole frame is enqueued asynchronously on the context's stream, with no host round trip. */
+SLPR_API int slpr_render(slpr_ctx *ctx);
+
+/* Headless replacement for acquire/present (vulkan/vk_vg_rasterizer.cpp:424-447): waits for the
+ * frame and copies the RGBA8 image (top-left origin, bytes R,G,B,A) to host memory. */
+SLPR_API int slpr_readback(slpr_ctx *ctx, uint8_t *rgba, size_t stride_bytes);
+
+/* set_mvp + render + readback in one call: the end-to-end path bench.py times as `e2e`. */
+SLPR_API int slpr_render_to_host(slpr_ctx *ctx, const float rows[16], uint8_t *rgba, size_t stride_bytes);
+
+/* Device pointer of the last rendered frame (RGBA8) and its row stride. Does not synchronise. */
+SLPR_API int slpr_framebuffer(slpr_ctx *ctx, void **dev_rgba, size_t *stride_bytes);
+
+/* Waits for the frame; the three host read-backs of drawFrame (scanline_rasterizer.cpp:356,578-580). */
+SLPR_API int slpr_get_counts(slpr_ctx *ctx, uint32_t *n_fragments, uint32_t *n_out_fragments, uint32_t *n_spans);
+
+/* Waits for the frame and copies one intermediate buffer (SLPR_TAP_*) to host memory. Needs
+ * SLPR_FLAG_TAPS for the planes the fast path does not materialise. `bytes` must not exceed
+ * the buffer's size for the last frame. Replaces drawDebug() (scanline_rasterizer.cpp:698-802). */
+SLPR_API int slpr_debug_copy(slpr_ctx *ctx, int which, void *dst, size_t bytes);
+
+/* Per-stage GPU milliseconds of the last frame rendered with direct launches (SLPR_FLAG_NO_GRAPH);
+ * fills min(n, SLPR_STAGE_COUNT) slots. New: the reference has no timers. */
+SLPR_API int slpr_stage_ms(slpr_ctx *ctx, float *ms, int n);
+
+/* Sort-pass geometry of the last frame: key bits, number of 8-bit passes, bytes of one key. */
+SLPR_API int slpr_sort_info(slpr_ctx *ctx, uint32_t *key_bits, uint32_t *passes, uint32_t *key_bytes);
+
+/* Stand-alone device primitives over caller-owned DEVICE buffers (the two roofline-graded
+ * kernels, exposed for micro-benchmarks and property tests).
+ * slpr_scan_i32: out[i] = sum_{j<i} in[j] for i in [0,n] (naive_scan.comp:27-73 semantics).
+ * slpr_sort_pairs: stable LSD radix sort of (u64 key, u32 value) on key bits [0,key_bits)
+ * (replaces naive_seg_sort_pairs.comp:26-97). Both run on the context's stream, asynchronously. */
+SLPR_API int slpr_scan_i32(slpr_ctx *ctx, const int32_t *dev_in, int32_t *dev_out, uint64_t n);
+SLPR_API int slpr_sort_pairs(slpr_ctx *ctx, uint64_t *dev_keys, uint32_t *dev_vals,
+                             uint64_t *dev_keys_tmp, uint32_t *dev_vals_tmp, uint64_t n,
+                             uint32_t key_bits, int *result_in_tmp);
+SLPR_API int slpr_synchronize(slpr_ctx *ctx);
+/* Number of kernels this library has launched on this context so far (graph nodes count). */
+SLPR_API uint64_t slpr_launch_count(slpr_ctx *ctx);
+
+/* ---------------------------------------------------------------------------------------------
+ * Host scene front end: RVG text -> VGContainer -> the 7 flat arrays.
+ * Replaces RVG::load (core/vg/rvg.cpp:9-255) and the flattening half of loadVG
+ * (scanline_rasterizer.cpp:67-118). Behaviour follows the reference parser, quirks included.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct slpr_vg slpr_vg;
+
+typedef struct slpr_scene_view { /* pointers owned by the slpr_vg; valid until slpr_vg_free */
+    const float *pos_xy; const uint32_t *pos_path; uint32_t n_points;
+    const uint32_t *curve_pos_map, *curve_type, *curve_path; uint32_t n_curves;
+    const uint32_t *fill_rule, *fill_rgba8; uint32_t n_paths;
+    float viewport[4], window[4];
+} slpr_scene_view;
+
+SLPR_API slpr_vg *slpr_vg_load_rvg(const char *path);
+/* Build a container from VGContainer-shaped arrays (vg_container.h:21-87). */
+SLPR_API slpr_vg *slpr_vg_from_arrays(const float *pos_xy, uint32_t n_points,
+                                      const uint32_t *curve_pos, const uint32_t *curve_type, uint32_t n_curves,
+                                      const uint32_t *path_curve, const uint32_t *fill_rule,
+                                      const float *fill_color_rgba, const float *fill_opacity, uint32_t n_paths);
+SLPR_API int slpr_vg_flatten(slpr_vg *vg, slpr_scene_view *out);
+/* Raw container arrays, for comparing the parser with the reference's (tests). */
+SLPR_API int slpr_vg_container(slpr_vg *vg, const float **pos_xy, uint32_t *n_points,
+                               const uint32_t **curve_pos, const uint32_t **curve_type, uint32_t *n_curves,
+                               const uint32_t **path_curve, const uint32_t **fill_rule,
+                               const float **fill_color, const float **fill_opacity, uint32_t *n_paths);
+SLPR_API void slpr_vg_free(slpr_vg *vg);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLPR_H_ */

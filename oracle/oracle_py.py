@@ -1,0 +1,146 @@
+"""ctypes binding of oracle/liboracle.so — the CPU restatement of the reference shaders.
+
+TEST INFRASTRUCTURE ONLY ("parity unpinned" for the shader stages, see oracle/oracle.h).
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+import this module. The product (vkscanlinepr_b200) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "liboracle.so")
+    src = os.path.join(_HERE, "oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def build_ref():
+    """Compile the reference's own RVG parser (oracle/_ref/rvg_dump) when /root/reference exists."""
+    subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
+    p = os.path.join(_HERE, "_ref", "rvg_dump")
+    return p if os.path.exists(p) else None
+
+
+class _Frame(C.Structure):
+    _fields_ = [
+        ("n_fragments", C.c_int32), ("n_out_frag", C.c_int32), ("n_span", C.c_int32),
+        ("n_points", C.c_uint32), ("n_curves", C.c_uint32), ("n_paths", C.c_uint32),
+        ("width", C.c_int), ("height", C.c_int),
+        ("tpos", C.POINTER(C.c_float)), ("path_visible", C.POINTER(C.c_int32)),
+        ("cut_cache", C.POINTER(C.c_float)), ("curve_count", C.POINTER(C.c_int32)),
+        ("curve_offset", C.POINTER(C.c_int32)), ("inter", C.POINTER(C.c_int32)),
+        ("key", C.POINTER(C.c_int32)), ("idx", C.POINTER(C.c_int32)),
+        ("path", C.POINTER(C.c_int32)), ("wind", C.POINTER(C.c_int32)),
+        ("seg", C.POINTER(C.c_int32)),
+        ("skey", C.POINTER(C.c_int32)), ("sidx", C.POINTER(C.c_int32)),
+        ("swind", C.POINTER(C.c_int32)), ("wn", C.POINTER(C.c_int32)),
+        ("flags", C.POINTER(C.c_int32)), ("scan3", C.POINTER(C.c_int32)),
+        ("records", C.POINTER(C.c_int32)), ("rgba", C.POINTER(C.c_uint8)),
+        ("ms", C.c_double * 8),
+    ]
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(build())
+        L.orc_render.restype = C.POINTER(_Frame)
+        L.orc_frame_free.argtypes = [C.POINTER(_Frame)]
+        L.orc_quantise_colour.restype = C.c_uint32
+        L.orc_num_threads.restype = C.c_int
+        _LIB = L
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _arr(ptr, n, dtype):
+    if n <= 0:
+        return np.zeros(0, dtype=dtype)
+    return np.ctypeslib.as_array(ptr, shape=(n,)).astype(dtype, copy=True)
+
+
+STAGE_NAMES = ("transform", "monotonize", "scan1", "intersect", "gen_fragment", "sort", "spans", "fill")
+
+
+def render(scene, rows, width, height, do_fill=True, threads=None):
+    """Run the whole oracle frame. `scene` has the 7 flat loadVG arrays (see scene.Scene).
+    Returns a dict of every intermediate buffer (numpy copies)."""
+    L = lib()
+    if threads:
+        L.orc_set_num_threads(int(threads))
+    rows = np.ascontiguousarray(rows, dtype=np.float32).reshape(16)
+    s = scene
+    fp = L.orc_render(C.c_uint32(s.n_points), _p(s.pos), _p(s.pos_path),
+                      C.c_uint32(s.n_curves), _p(s.curve_pos_map), _p(s.curve_type), _p(s.curve_path),
+                      C.c_uint32(s.n_paths), _p(s.fill_rule), _p(s.fill_info),
+                      _p(rows), C.c_int(width), C.c_int(height), C.c_int(1 if do_fill else 0))
+    f = fp.contents
+    nf = f.n_fragments
+    no = f.n_out_frag + f.n_span
+    out = dict(
+        n_fragments=nf, n_out_frag=f.n_out_frag, n_span=f.n_span,
+        tpos=_arr(f.tpos, 2 * s.n_points, np.float32).reshape(-1, 2),
+        path_visible=_arr(f.path_visible, s.n_paths, np.int32),
+        cut_cache=_arr(f.cut_cache, 5 * s.n_curves, np.float32).reshape(-1, 5),
+        curve_count=_arr(f.curve_count, s.n_curves, np.int32),
+        curve_offset=_arr(f.curve_offset, s.n_curves + 1, np.int32),
+        inter=_arr(f.inter, 2 * nf, np.int32).reshape(-1, 2),
+        key=_arr(f.key, nf, np.int32), idx=_arr(f.idx, nf, np.int32),
+        path=_arr(f.path, nf, np.int32), wind=_arr(f.wind, nf, np.int32),
+        seg=_arr(f.seg, s.n_paths + 1, np.int32),
+        skey=_arr(f.skey, nf, np.int32), sidx=_arr(f.sidx, nf, np.int32),
+        swind=_arr(f.swind, nf, np.int32), wn=_arr(f.wn, nf + 1, np.int32),
+        flags=_arr(f.flags, 2 * nf, np.int32), scan3=_arr(f.scan3, 2 * nf + 1, np.int32),
+        records=_arr(f.records, 4 * no, np.int32).reshape(-1, 4),
+        ms=dict(zip(STAGE_NAMES, list(f.ms))),
+    )
+    if do_fill:
+        out["rgba"] = _arr(f.rgba, 4 * width * height, np.uint8).reshape(height, width, 4)
+    L.orc_frame_free(fp)
+    return out
+
+
+def fill(records, width, height):
+    L = lib()
+    rec = np.ascontiguousarray(records, dtype=np.int32).reshape(-1, 4)
+    rgba = np.empty((height, width, 4), dtype=np.uint8)
+    L.orc_fill(C.c_int64(rec.shape[0]), _p(rec), C.c_int(width), C.c_int(height), _p(rgba))
+    return rgba
+
+
+def seg_sort(seg, key, idx, literal=False):
+    L = lib()
+    seg = np.ascontiguousarray(seg, dtype=np.int32)
+    key = np.array(key, dtype=np.int32, copy=True)
+    idx = np.array(idx, dtype=np.int32, copy=True)
+    fn = L.orc_seg_sort_literal if literal else L.orc_seg_sort
+    fn(C.c_uint32(len(seg) - 1), _p(seg), _p(key), _p(idx))
+    return key, idx
+
+
+def exclusive_scan(a):
+    L = lib()
+    a = np.ascontiguousarray(a, dtype=np.int32)
+    out = np.empty(a.shape[0] + 1, dtype=np.int32)
+    L.orc_exclusive_scan(C.c_int64(a.shape[0]), _p(a), _p(out))
+    return out
+
+
+def quantise_colour(rgba, opacity):
+    v = np.ascontiguousarray(rgba, dtype=np.float32)
+    return int(lib().orc_quantise_colour(_p(v), C.c_float(opacity)))
+
+
+def num_threads():
+    return int(lib().orc_num_threads())

@@ -1,0 +1,75 @@
+"""Shared helpers for the tests: golden scenes, matrices, oracle access (tests may use oracle/)."""
+import os
+
+import numpy as np
+
+from vkscanlinepr_b200 import scene as S
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+SHIPPED = ["test", "tiger", "reschart", "drops", "embrace"]
+EMPTY = ["car", "chord", "chord-black"]
+REF_RVG_DIR = "/root/reference/workdir/input/rvg"
+
+
+def golden_container(name):
+    return S.Container.from_npz(os.path.join(GOLDEN, name + ".npz"))
+
+
+def golden_scene(name):
+    c = golden_container(name)
+    return S.flatten_reference(c, name), c.vp
+
+
+def tiny_scene():
+    """Two overlapping closed paths (a square of lines, a blob of cubics) + one off-screen path."""
+    pos, pos_path, cpm, ctype, cpath = [], [], [], [], []
+
+    def add(curve_pts, path):
+        cpm.append(len(pos)); ctype.append(S.LINE if len(curve_pts) == 2 else S.CUBIC); cpath.append(path)
+        for p in curve_pts:
+            pos.append(p); pos_path.append(path)
+
+    sq = [(10.5, 8.25), (50.0, 8.25), (50.0, 40.0), (10.5, 40.0)]
+    for i in range(4):
+        add([sq[i], sq[(i + 1) % 4]], 0)
+    blob = [(30, 20), (45, 5), (75, 15), (70, 35), (65, 60), (40, 62), (25, 45), (20, 30), (22, 22), (30, 20)]
+    add(blob[0:4], 1); add(blob[3:7], 1); add(blob[6:10], 1)
+    off = [(-50, -50), (-40, -50), (-40, -40)]
+    for i in range(3):
+        add([off[i], off[(i + 1) % 3]], 2)
+    return S.Scene(np.array(pos, np.float32), np.array(pos_path, np.uint32), np.array(cpm, np.uint32),
+                   np.array(ctype, np.uint32), np.array(cpath, np.uint32), np.array([0, 1, 0], np.uint32),
+                   np.array([0xFF0000FF, 0xFF00FF00, 0xFFFF0000], np.uint32), "tiny")
+
+
+def psnr(a, b):
+    d = a.astype(np.float64) - b.astype(np.float64)
+    mse = float(np.mean(d * d))
+    return float("inf") if mse == 0 else 10 * np.log10(255.0 ** 2 / mse)
+
+
+def check_record_invariants(rec, width=None):
+    """Invariants of the reference's output_buf (gen_merged_fragment_and_span.comp:62-102) that hold
+    for test_data.csv / test_data3.csv and must hold for every record list we produce."""
+    rec = np.asarray(rec).reshape(-1, 4)
+    yx, w, fi = rec[:, 0], rec[:, 1], rec[:, 3]
+    x, y = yx & 0xFFFF, yx >> 16
+    is_frag = fi != 0
+    assert np.all(w[is_frag] == 2), "fragment records have width 2"
+    assert np.all((x % 2 == 0) & (y % 2 == 0)), "records sit on the even 2x2 grid"
+    assert np.all(w % 2 == 0) and np.all(w > 0)
+    assert np.array_equal(fi[is_frag], np.arange(1, is_frag.sum() + 1)), "frag_index counts 1..N in order"
+    # Emit order (GEN:64-66,83): fragment i at slot oi, then its span (from the previous fragment's
+    # x+2 up to fragment i's x) at oi+frag_flag. So a span record that directly follows a fragment
+    # record on its row either ENDS at that fragment (its own fragment), or STARTS right after it
+    # (its own fragment lies beyond the right edge and got no record).
+    sp = np.nonzero(~is_frag)[0]
+    sp = sp[sp > 0]
+    prev = sp - 1
+    m = is_frag[prev] & (y[sp] == y[prev])
+    own = x[sp[m]] + w[sp[m]] == x[prev[m]]
+    after = x[sp[m]] == x[prev[m]] + 2
+    assert np.all(own | after)
+    if width is not None:
+        assert np.all((x[sp[m]] + w[sp[m]])[~own] >= width)
+    return int(is_frag.sum()), int((~is_frag).sum())

@@ -1,0 +1,280 @@
+"""vkscanlinepr_b200 — B200-native scanline path renderer behind the reference's renderer interface.
+
+The product is libslpr.so (hand-written sm_100a CUDA kernels + a C ABI, include/slpr.h). This
+package is only the Python plumbing over that ABI, used by the tests and bench.py:
+`ScanlineRasterizer` mirrors Galaxysailing::VGRasterizer (VkScanlinePR/src/core/rasterizer.h:9-20:
+initialize / loadVG / setMVP / render) plus the headless readback. The C++ mirror of the same
+interface is include/slpr_rasterizer.hpp.
+
+There is no CPU fallback: if libslpr.so is missing or no CUDA device is usable, calls raise.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from . import scene as scene  # noqa: F401
+from .scene import Scene, Container
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libslpr.so")
+_LIB = None
+
+FLAG_TAPS, FLAG_CONTRACT_FMA, FLAG_NO_GRAPH = 1, 2, 4
+TAPS = dict(transformed_pos=0, path_visible=1, cut_cache=2, curve_count=3, curve_offset=4, intersection=5,
+            key=6, path=7, winding=8, sorted_key=9, sorted_index=10, winding_scan=11, flags=12,
+            flag_scan=13, records=14, segments=15)
+STAGES = ("transform", "monotonize", "scan1", "intersect", "gen_fragment", "sort", "spans", "fill")
+
+
+class SlprError(RuntimeError):
+    pass
+
+
+def build(force=False, verbose=False):
+    """Compile libslpr.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+    src_dir = os.path.join(_HERE, "csrc")
+    srcs = [os.path.join(src_dir, f) for f in os.listdir(src_dir) if f.endswith((".cu", ".cuh", ".cpp"))]
+    srcs.append(os.path.join(_HERE, "..", "include", "slpr.h"))
+    stale = (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
+    if force or stale:
+        r = subprocess.run(["make", "-C", src_dir, "../libslpr.so"], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise SlprError("building libslpr.so failed:\n" + r.stdout + r.stderr)
+        if verbose:
+            print(r.stdout)
+    return LIB_PATH
+
+
+def lib():
+    """Load libslpr.so (never builds implicitly on a GPU box: the .so travels with the repo)."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise SlprError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`; "
+                            "there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        L.slpr_last_error.restype = C.c_char_p
+        L.slpr_version.restype = C.c_char_p
+        L.slpr_create.restype = C.c_void_p
+        L.slpr_create.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.c_uint32]
+        L.slpr_destroy.argtypes = [C.c_void_p]
+        L.slpr_launch_count.restype = C.c_uint64
+        L.slpr_launch_count.argtypes = [C.c_void_p]
+        L.slpr_vg_load_rvg.restype = C.c_void_p
+        L.slpr_vg_load_rvg.argtypes = [C.c_char_p]
+        L.slpr_vg_from_arrays.restype = C.c_void_p
+        L.slpr_vg_free.argtypes = [C.c_void_p]
+        _LIB = L
+    return _LIB
+
+
+def _check(rc):
+    if rc != 0:
+        raise SlprError(f"slpr error {rc}: {lib().slpr_last_error().decode()}")
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class _SceneView(C.Structure):
+    _fields_ = [("pos_xy", C.POINTER(C.c_float)), ("pos_path", C.POINTER(C.c_uint32)), ("n_points", C.c_uint32),
+                ("curve_pos_map", C.POINTER(C.c_uint32)), ("curve_type", C.POINTER(C.c_uint32)),
+                ("curve_path", C.POINTER(C.c_uint32)), ("n_curves", C.c_uint32),
+                ("fill_rule", C.POINTER(C.c_uint32)), ("fill_rgba8", C.POINTER(C.c_uint32)), ("n_paths", C.c_uint32),
+                ("viewport", C.c_float * 4), ("window", C.c_float * 4)]
+
+
+def _np_from(ptr, n, dtype):
+    if n == 0:
+        return np.zeros(0, dtype=dtype)
+    return np.ctypeslib.as_array(ptr, shape=(n,)).astype(dtype, copy=True)
+
+
+def _flatten_handle(h, name):
+    L = lib()
+    v = _SceneView()
+    _check(L.slpr_vg_flatten(C.c_void_p(h), C.byref(v)))
+    sc = Scene(_np_from(v.pos_xy, 2 * v.n_points, np.float32), _np_from(v.pos_path, v.n_points, np.uint32),
+               _np_from(v.curve_pos_map, v.n_curves, np.uint32), _np_from(v.curve_type, v.n_curves, np.uint32),
+               _np_from(v.curve_path, v.n_curves, np.uint32), _np_from(v.fill_rule, v.n_paths, np.uint32),
+               _np_from(v.fill_rgba8, v.n_paths, np.uint32), name)
+    return sc, np.array(list(v.viewport), dtype=np.float32)
+
+
+def container_from_handle(h):
+    L = lib()
+    pos = C.POINTER(C.c_float)(); cpos = C.POINTER(C.c_uint32)(); ctype = C.POINTER(C.c_uint32)()
+    pcur = C.POINTER(C.c_uint32)(); frule = C.POINTER(C.c_uint32)(); fcol = C.POINTER(C.c_float)()
+    fop = C.POINTER(C.c_float)()
+    n_pts = C.c_uint32(); n_cur = C.c_uint32(); n_path = C.c_uint32()
+    _check(L.slpr_vg_container(C.c_void_p(h), C.byref(pos), C.byref(n_pts), C.byref(cpos), C.byref(ctype), C.byref(n_cur),
+                               C.byref(pcur), C.byref(frule), C.byref(fcol), C.byref(fop), C.byref(n_path)))
+    return Container(np.zeros(4, np.float32), np.zeros(4, np.float32),
+                     _np_from(pos, 2 * n_pts.value, np.float32).reshape(-1, 2),
+                     _np_from(cpos, n_cur.value, np.uint32), _np_from(ctype, n_cur.value, np.uint32),
+                     _np_from(pcur, n_path.value, np.uint32), _np_from(frule, n_path.value, np.uint32),
+                     _np_from(fcol, 4 * n_path.value, np.float32).reshape(-1, 4),
+                     _np_from(fop, n_path.value, np.float32))
+
+
+def load_rvg(path, name=None):
+    """RVG file -> (Scene, viewport, Container) through the library's parser (rvg.cpp:9-255 behaviour)."""
+    L = lib()
+    h = L.slpr_vg_load_rvg(os.fsencode(path))
+    if not h:
+        raise SlprError(L.slpr_last_error().decode())
+    try:
+        sc, vp = _flatten_handle(h, name or os.path.splitext(os.path.basename(path))[0])
+        cont = container_from_handle(h)
+        cont.vp = vp
+    finally:
+        L.slpr_vg_free(C.c_void_p(h))
+    return sc, vp, cont
+
+
+def flatten(cont: Container, name="scene"):
+    """Container -> Scene through the library's loadVG flattening (scanline_rasterizer.cpp:67-118)."""
+    L = lib()
+    pos = np.ascontiguousarray(cont.pos, np.float32)
+    cp = np.ascontiguousarray(cont.curve_pos, np.uint32); ct = np.ascontiguousarray(cont.curve_type, np.uint32)
+    pc = np.ascontiguousarray(cont.path_curve, np.uint32); fr = np.ascontiguousarray(cont.fill_rule, np.uint32)
+    fc = np.ascontiguousarray(cont.fill_color, np.float32); fo = np.ascontiguousarray(cont.fill_opacity, np.float32)
+    h = L.slpr_vg_from_arrays(_p(pos), C.c_uint32(pos.shape[0]), _p(cp), _p(ct), C.c_uint32(len(cp)),
+                              _p(pc), _p(fr), _p(fc), _p(fo), C.c_uint32(len(pc)))
+    if not h:
+        raise SlprError(L.slpr_last_error().decode())
+    try:
+        sc, _ = _flatten_handle(h, name)
+    finally:
+        L.slpr_vg_free(C.c_void_p(h))
+    return sc
+
+
+class ScanlineRasterizer:
+    """Mirror of Galaxysailing::ScanlineVGRasterizer's public interface over the C ABI.
+
+    initialize(window, w, h) / loadVG(scene) / setMVP(rows) / render() as in
+    VkScanlinePR/src/core/rasterizer.h:9-20 and app/vg_app.cpp:146-165, plus readback().
+    """
+
+    def __init__(self, device=0, flags=0):
+        self._h = None
+        self._device = device
+        self._flags = flags
+        self.width = self.height = 0
+
+    # -- VGRasterizer ------------------------------------------------------------------------
+    def initialize(self, window, w, h):
+        assert window is None, "headless: pass window=None"
+        self.close()
+        h_ = lib().slpr_create(self._device, w, h, self._flags)
+        if not h_:
+            raise SlprError(lib().slpr_last_error().decode())
+        self._h = C.c_void_p(h_)
+        self.width, self.height = int(w), int(h)
+        return self
+
+    def loadVG(self, sc):
+        if isinstance(sc, Container):
+            sc = flatten(sc)
+        self._scene = sc  # keep the arrays alive during the call
+        _check(lib().slpr_load_scene(self._h, _p(sc.pos), _p(sc.pos_path), C.c_uint32(sc.n_points),
+                                     _p(sc.curve_pos_map), _p(sc.curve_type), _p(sc.curve_path), C.c_uint32(sc.n_curves),
+                                     _p(sc.fill_rule), _p(sc.fill_info), C.c_uint32(sc.n_paths)))
+
+    def setMVP(self, rows):
+        r = np.ascontiguousarray(rows, dtype=np.float32).reshape(16)
+        _check(lib().slpr_set_mvp(self._h, _p(r)))
+
+    def render(self):
+        _check(lib().slpr_render(self._h))
+
+    # -- headless additions ------------------------------------------------------------------
+    def readback(self, out=None):
+        if out is None:
+            out = np.empty((self.height, self.width, 4), dtype=np.uint8)
+        _check(lib().slpr_readback(self._h, _p(out), C.c_size_t(out.strides[0])))
+        return out
+
+    def render_to_host(self, rows, out):
+        r = np.ascontiguousarray(rows, dtype=np.float32).reshape(16)
+        _check(lib().slpr_render_to_host(self._h, _p(r), _p(out), C.c_size_t(out.strides[0])))
+        return out
+
+    def set_band(self, y0, y1):
+        _check(lib().slpr_set_band(self._h, C.c_uint32(y0), C.c_uint32(y1)))
+
+    def set_stream(self, cuda_stream_ptr):
+        _check(lib().slpr_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def set_target(self, dev_ptr, stride_bytes):
+        _check(lib().slpr_set_target(self._h, C.c_void_p(dev_ptr), C.c_size_t(stride_bytes)))
+
+    def framebuffer(self):
+        p = C.c_void_p(); s = C.c_size_t()
+        _check(lib().slpr_framebuffer(self._h, C.byref(p), C.byref(s)))
+        return p.value, s.value
+
+    def synchronize(self):
+        _check(lib().slpr_synchronize(self._h))
+
+    def counts(self):
+        a, b, c = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        _check(lib().slpr_get_counts(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(n_fragments=a.value, n_out_frag=b.value, n_span=c.value)
+
+    def sort_info(self):
+        a, b, c = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        _check(lib().slpr_sort_info(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(key_bits=a.value, passes=b.value, key_bytes=c.value)
+
+    def stage_ms(self):
+        ms = (C.c_float * len(STAGES))()
+        _check(lib().slpr_stage_ms(self._h, ms, len(STAGES)))
+        return dict(zip(STAGES, [float(x) for x in ms]))
+
+    def launch_count(self):
+        return int(lib().slpr_launch_count(self._h))
+
+    def tap(self, name):
+        """Copy one reference-format intermediate buffer of the last frame (needs FLAG_TAPS for planes)."""
+        cnt = self.counts()
+        nf, no = cnt["n_fragments"], cnt["n_out_frag"] + cnt["n_span"]
+        sc = self._scene
+        shape, dt = {
+            "transformed_pos": ((sc.n_points, 2), np.float32), "path_visible": ((sc.n_paths,), np.int32),
+            "cut_cache": ((sc.n_curves, 5), np.float32), "curve_count": ((sc.n_curves,), np.int32),
+            "curve_offset": ((sc.n_curves + 1,), np.int32), "intersection": ((nf, 2), np.int32),
+            "key": ((nf + 1,), np.int32), "path": ((nf,), np.int32), "winding": ((nf,), np.int32),
+            "sorted_key": ((nf,), np.int32), "sorted_index": ((nf,), np.int32),
+            "winding_scan": ((nf + 1,), np.int32), "flags": ((2 * nf,), np.int32),
+            "flag_scan": ((2 * nf + 1,), np.int32), "records": ((no, 4), np.int32),
+            "segments": ((sc.n_paths + 1,), np.int32),
+        }[name]
+        out = np.empty(shape, dtype=dt)
+        _check(lib().slpr_debug_copy(self._h, TAPS[name], _p(out), C.c_size_t(out.nbytes)))
+        return out
+
+    # stand-alone primitives on raw device pointers (torch tensors' data_ptr())
+    def scan_i32(self, in_ptr, out_ptr, n):
+        _check(lib().slpr_scan_i32(self._h, C.c_void_p(in_ptr), C.c_void_p(out_ptr), C.c_uint64(n)))
+
+    def sort_pairs(self, keys_ptr, vals_ptr, keys_tmp_ptr, vals_tmp_ptr, n, key_bits):
+        r = C.c_int()
+        _check(lib().slpr_sort_pairs(self._h, C.c_void_p(keys_ptr), C.c_void_p(vals_ptr), C.c_void_p(keys_tmp_ptr),
+                                     C.c_void_p(vals_tmp_ptr), C.c_uint64(n), C.c_uint32(key_bits), C.byref(r)))
+        return r.value
+
+    def close(self):
+        if self._h:
+            lib().slpr_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,99 @@
+// common.cuh — shared device helpers and frame-wide structures for libslpr (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace slpr {
+
+constexpr int FRAG_SIZE = 2;
+constexpr uint32_t T_LINE = 0x02u, T_QUADRIC = 0x03u, T_CUBIC = 0x04u, T_ARC = 0x13u;
+constexpr int CUBIC_ITERATION_NUMBER = 24;  // make_intersection_1.comp:7
+constexpr int NUM_SMS_B200 = 148;
+
+// Everything a frame's kernels need that changes between frames or is only known on the device.
+// Lives in device memory so that a captured CUDA graph can be replayed with new matrices/counts.
+struct FrameParams {
+    float rows[16];  // m0..m3 of TransPosIn (compute_ubo.h:9-13)
+    int width, height;
+    int band_y0, band_y1;  // scanline rows [y0,y1) this context renders
+    int cull;              // 1 when the band is a strict subset of the frame
+    int pad[3];
+};
+
+// Device-resident counters (zeroed at the start of every frame).
+struct FrameCounters {
+    int n_fragments;   // total of scan #1 (SR.cpp:356)
+    int n_out_frag;    // SR.cpp:578
+    int n_span;        // SR.cpp:579-580
+    int overflow;      // set when n_fragments exceeded the allocated capacity
+    int n_records;     // n_out_frag + n_span
+    int wn_total;      // last element of the winding scan (residue diagnostic)
+    int pad[2];
+};
+
+// Key geometry for the compact 64-bit sort key (path | row rank | cell x), see DESIGN.md.
+struct KeyLayout {
+    int bits_x, bits_y, bits_path;
+    int ny;  // number of cell rows = (H+1)/2
+};
+
+__device__ __forceinline__ uint32_t f2u(float f) { return __float_as_uint(f); }
+__device__ __forceinline__ float u2f(uint32_t u) { return __uint_as_float(u); }
+// GLSL int(x): truncation; cvt.rzi saturates and maps NaN to 0 (the oracle pins the same).
+__device__ __forceinline__ int f2i(float x) { return __float2int_rz(x); }
+
+// LERP(a,b,t) = a + t*(b-a) with three separately rounded operations (no FMA contraction);
+// make_intersection_0.comp:10, make_intersection_1.comp:12, gen_fragment.comp:10.
+__device__ __forceinline__ float lerpf(float a, float b, float t) {
+    return __fadd_rn(a, __fmul_rn(t, __fsub_rn(b, a)));
+}
+
+// make_intersection_1.comp:76-79, gen_fragment.comp:54-57
+__device__ __forceinline__ int float2int_rd(float x) { return x >= 0.0f ? f2i(x) : f2i(__fsub_rn(x, 1.0f)); }
+
+// make_intersection_0.comp:14-20
+__device__ __forceinline__ bool path_invisible(int mask) {
+    uint32_t m = (uint32_t)mask;
+    return ((m & 0x11111000u) == 0) || ((m & 0x01101011u) == 0) || ((m & 0x00011111u) == 0) ||
+           ((m & 0x11010110u) == 0);
+}
+
+__device__ __forceinline__ float cubic_eval(float p0, float p1, float p2, float p3, float t) {
+    float q0 = lerpf(p0, p1, t), q1 = lerpf(p1, p2, t), q2 = lerpf(p2, p3, t);
+    float l0 = lerpf(q0, q1, t), l1 = lerpf(q1, q2, t);
+    return lerpf(l0, l1, t);
+}
+
+// interpolateGeneralCurve: make_intersection_0.comp:131-165 (dflt 1.0f), make_intersection_1.comp:81-148 (dflt 0.0f)
+__device__ __forceinline__ float interp_general(uint32_t type, float t, float p0, float p1, float p2, float p3,
+                                                float dflt) {
+    if (type == T_LINE) return lerpf(p0, p1, t);
+    if (type == T_CUBIC) return cubic_eval(p0, p1, p2, p3, t);
+    return dflt;
+}
+
+// streaming 128-bit accesses (bypass L1 allocation for data touched once; not .nc so that
+// in-place use is well defined)
+__device__ __forceinline__ int4 ld_stream(const int4 *p) {
+    int4 r;
+    asm volatile("ld.global.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream(int4 *p, const int4 &v) {
+    asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+                 "r"(v.w) : "memory");
+}
+
+__device__ __forceinline__ uint32_t lane_id() {
+    uint32_t l;
+    asm("mov.u32 %0, %%laneid;" : "=r"(l));
+    return l;
+}
+__device__ __forceinline__ uint32_t lanemask_lt() {
+    uint32_t m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+}  // namespace slpr

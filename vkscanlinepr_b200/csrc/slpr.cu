@@ -1,0 +1,662 @@
+// slpr.cu — context, device arena, frame orchestration and the C ABI of libslpr.so (include/slpr.h).
+//
+// Host side of the hot path, i.e. what ScanlineVGRasterizer::drawFrame does
+// (VkScanlinePR/src/core/scanline/scanline_rasterizer.cpp:282-696), re-designed for CUDA:
+//   * one stream, no host round trip inside a frame: the data-dependent sizes (n_fragments,
+//     n_records) stay in device memory (FrameCounters) and every downstream kernel is a
+//     grid-stride / ticketed persistent kernel that reads them there;
+//   * buffers are sized once from a counting pre-pass and grown only if a later frame overflows
+//     (detected on the device, handled at the next synchronisation point by re-rendering);
+//   * the whole frame is captured once into a CUDA graph and replayed; only the 96-byte
+//     FrameParams block (matrix rows, band) is refreshed per frame.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/slpr.h"
+#include "geom.cuh"
+#include "radix.cuh"
+#include "raster.cuh"
+#include "scan.cuh"
+#include "spans.cuh"
+
+using namespace slpr;
+
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) return fail(SLPR_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                                           __FILE__, __LINE__);                                          \
+    } while (0)
+
+extern "C" const char *slpr_last_error(void) { return g_err.c_str(); }
+extern "C" void slpr_internal_set_error(const char *msg) { g_err = msg ? msg : ""; }
+extern "C" const char *slpr_version(void) { return "slpr 0.1 (sm_100a)"; }
+
+static int ceil_log2(uint64_t v) {  // bits needed to represent values in [0, v-1]
+    int b = 0;
+    while ((1ull << b) < v) ++b;
+    return b;
+}
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+__global__ void k_set_params(FrameParams *dst, FrameParams src) { *dst = src; }
+
+// ------------------------------------------------------------------------------------------------
+struct slpr_ctx {
+    int device = 0;
+    uint32_t W = 0, H = 0, flags = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    int num_sms = NUM_SMS_B200;
+
+    // scene (slpr_load_scene)
+    bool scene_loaded = false;
+    uint32_t np = 0, nc = 0, P = 0;
+    float2 *d_pos = nullptr;
+    uint32_t *d_pos_path = nullptr, *d_cpm = nullptr, *d_ctype = nullptr, *d_cpath = nullptr, *d_frule = nullptr,
+             *d_finfo = nullptr;
+    float2 *d_tpos = nullptr;
+    int *d_pvis = nullptr;
+    float *d_cut = nullptr;
+    int *d_count = nullptr, *d_offset = nullptr, *d_seg_tap = nullptr;
+
+    // frame state
+    FrameParams hp{};
+    FrameParams *d_params = nullptr;
+    FrameCounters *h_ctr = nullptr;  // pinned
+    bool have_mvp = false;
+
+    // capacity-dependent buffers
+    int cap = 0;
+    int2 *d_inter = nullptr;
+    uint64_t *d_key[2] = {nullptr, nullptr};
+    uint32_t *d_val[2] = {nullptr, nullptr};
+    int *d_wn = nullptr;
+    int4 *d_rec = nullptr;
+    // taps
+    int *t_key32 = nullptr, *t_path = nullptr, *t_wind = nullptr, *t_skey32 = nullptr, *t_sidx = nullptr,
+        *t_flags = nullptr, *t_scan3 = nullptr;
+
+    // zero-per-frame temp block: [FrameCounters][tickets][hist][scan status x3][sort lookback]
+    unsigned char *d_temp = nullptr;
+    size_t temp_bytes = 0, temp_small_bytes = 0;
+    FrameCounters *d_ctr = nullptr;
+    int *d_tickets = nullptr;  // 3 scan tickets + RS_MAX_PASSES sort tickets
+    uint32_t *d_hist = nullptr;
+    unsigned long long *d_status[3] = {nullptr, nullptr, nullptr};
+    uint32_t *d_lookback = nullptr;
+    int sort_tiles_cap = 0;
+
+    KeyLayout L{};
+    int key_bits = 0, passes = 0, sorted_buf = 0;
+
+    uint32_t *d_cells = nullptr;
+    int cw = 0, ch = 0;
+    uint8_t *d_fb = nullptr;
+    size_t fb_stride = 0;
+    uint8_t *target = nullptr;
+    size_t target_stride = 0;
+
+    cudaGraphExec_t gexec = nullptr;
+    bool graph_valid = false;
+    cudaEvent_t ev[SLPR_STAGE_COUNT + 1] = {};
+    bool stage_times_valid = false;
+    uint64_t launches = 0;
+    int launches_per_frame = 0;
+    bool frame_pending = false, frame_done = false;
+
+    // stand-alone primitive temps
+    unsigned char *d_prim_temp = nullptr;
+    size_t prim_temp_bytes = 0;
+};
+
+static void free_capacity(slpr_ctx *c) {
+    cudaFree(c->d_inter); c->d_inter = nullptr;
+    for (int i = 0; i < 2; ++i) { cudaFree(c->d_key[i]); cudaFree(c->d_val[i]); c->d_key[i] = nullptr; c->d_val[i] = nullptr; }
+    cudaFree(c->d_wn); c->d_wn = nullptr;
+    cudaFree(c->d_rec); c->d_rec = nullptr;
+    cudaFree(c->t_key32); cudaFree(c->t_path); cudaFree(c->t_wind); cudaFree(c->t_skey32); cudaFree(c->t_sidx);
+    cudaFree(c->t_flags); cudaFree(c->t_scan3);
+    c->t_key32 = c->t_path = c->t_wind = c->t_skey32 = c->t_sidx = c->t_flags = c->t_scan3 = nullptr;
+    cudaFree(c->d_temp); c->d_temp = nullptr;
+    if (c->gexec) { cudaGraphExecDestroy(c->gexec); c->gexec = nullptr; }
+    c->graph_valid = false;
+    c->cap = 0;
+}
+
+static void free_scene(slpr_ctx *c) {
+    cudaFree(c->d_pos); cudaFree(c->d_pos_path); cudaFree(c->d_cpm); cudaFree(c->d_ctype); cudaFree(c->d_cpath);
+    cudaFree(c->d_frule); cudaFree(c->d_finfo); cudaFree(c->d_tpos); cudaFree(c->d_pvis); cudaFree(c->d_cut);
+    cudaFree(c->d_count); cudaFree(c->d_offset); cudaFree(c->d_seg_tap);
+    c->d_pos = nullptr; c->d_pos_path = c->d_cpm = c->d_ctype = c->d_cpath = c->d_frule = c->d_finfo = nullptr;
+    c->d_tpos = nullptr; c->d_pvis = nullptr; c->d_cut = nullptr; c->d_count = c->d_offset = c->d_seg_tap = nullptr;
+    c->scene_loaded = false;
+}
+
+static int alloc_capacity(slpr_ctx *c, int cap) {
+    free_capacity(c);
+    cap = (int)align_up((size_t)std::max(cap, 1 << 14), 4096);
+    const size_t n = (size_t)cap;
+    CU(cudaMalloc(&c->d_inter, (n + 1) * sizeof(int2)));
+    for (int i = 0; i < 2; ++i) {
+        CU(cudaMalloc(&c->d_key[i], n * 8));
+        CU(cudaMalloc(&c->d_val[i], n * 4));
+    }
+    CU(cudaMalloc(&c->d_wn, (n + 4) * 4));
+    CU(cudaMalloc(&c->d_rec, (2 * n + 1) * sizeof(int4)));
+    if (c->flags & SLPR_FLAG_TAPS) {
+        CU(cudaMalloc(&c->t_key32, (n + 1) * 4));
+        CU(cudaMalloc(&c->t_path, n * 4));
+        CU(cudaMalloc(&c->t_wind, n * 4));
+        CU(cudaMalloc(&c->t_skey32, n * 4));
+        CU(cudaMalloc(&c->t_sidx, n * 4));
+        CU(cudaMalloc(&c->t_flags, 2 * n * 4));
+        CU(cudaMalloc(&c->t_scan3, (2 * n + 1) * 4));
+    }
+    // per-frame zeroed temp block
+    const size_t scan_tiles[3] = {(size_t)c->nc / SCAN_TILE + 2, n / SCAN_TILE + 2, n / SCAN_TILE + 2};
+    c->sort_tiles_cap = (int)(n / RS_TILE + 2);
+    size_t off = 0;
+    const size_t o_ctr = off; off += align_up(sizeof(FrameCounters), 256);
+    const size_t o_tick = off; off += align_up((3 + RS_MAX_PASSES) * sizeof(int), 256);
+    const size_t o_hist = off; off += align_up((size_t)RS_MAX_PASSES * RS_BINS * 4, 256);
+    size_t o_status[3];
+    for (int i = 0; i < 3; ++i) { o_status[i] = off; off += align_up(scan_tiles[i] * 8, 256); }
+    c->temp_small_bytes = off;
+    const size_t o_lb = off; off += align_up((size_t)c->passes * c->sort_tiles_cap * RS_BINS * 4, 256);
+    c->temp_bytes = off;
+    CU(cudaMalloc(&c->d_temp, c->temp_bytes));
+    c->d_ctr = reinterpret_cast<FrameCounters *>(c->d_temp + o_ctr);
+    c->d_tickets = reinterpret_cast<int *>(c->d_temp + o_tick);
+    c->d_hist = reinterpret_cast<uint32_t *>(c->d_temp + o_hist);
+    for (int i = 0; i < 3; ++i) c->d_status[i] = reinterpret_cast<unsigned long long *>(c->d_temp + o_status[i]);
+    c->d_lookback = reinterpret_cast<uint32_t *>(c->d_temp + o_lb);
+    c->cap = cap;
+    return SLPR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" slpr_ctx *slpr_create(int device, uint32_t width, uint32_t height, uint32_t flags) {
+    if (width == 0 || height == 0 || width > 32766 || height > 32766) {
+        fail(SLPR_ERR_INVALID, "slpr_create: width/height must be in [1, 32766] (16-bit key fields, SURVEY D.6)");
+        return nullptr;
+    }
+    if (flags & SLPR_FLAG_CONTRACT_FMA) {
+        fail(SLPR_ERR_UNSUPPORTED, "slpr_create: SLPR_FLAG_CONTRACT_FMA is not built; the arithmetic policy is IEEE fp32 without contraction");
+        return nullptr;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        fail(SLPR_ERR_CUDA, "slpr_create: no usable CUDA device (%s); this library has no CPU fallback",
+             e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        return nullptr;
+    }
+    if (device < 0 || device >= ndev) { fail(SLPR_ERR_INVALID, "slpr_create: device %d out of range [0,%d)", device, ndev); return nullptr; }
+    if (cudaSetDevice(device) != cudaSuccess) { fail(SLPR_ERR_CUDA, "cudaSetDevice(%d) failed", device); return nullptr; }
+    slpr_ctx *c = new slpr_ctx();
+    c->device = device; c->W = width; c->H = height; c->flags = flags;
+    cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device);
+    bool ok = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) == cudaSuccess;
+    c->stream = c->own_stream;
+    ok = ok && cudaMalloc(&c->d_params, sizeof(FrameParams)) == cudaSuccess;
+    ok = ok && cudaMallocHost(&c->h_ctr, sizeof(FrameCounters)) == cudaSuccess;
+    c->cw = (int)(width + 1) / 2; c->ch = (int)(height + 1) / 2;
+    ok = ok && cudaMalloc(&c->d_cells, (size_t)c->cw * c->ch * 4) == cudaSuccess;
+    ok = ok && cudaMemset(c->d_cells, 0, (size_t)c->cw * c->ch * 4) == cudaSuccess;
+    c->fb_stride = (size_t)width * 4;
+    ok = ok && cudaMalloc(&c->d_fb, c->fb_stride * height) == cudaSuccess;
+    for (auto &ev : c->ev) ok = ok && cudaEventCreate(&ev) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_onesweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM_BYTES) == cudaSuccess;
+    if (!ok) {
+        fail(SLPR_ERR_CUDA, "slpr_create: device setup failed: %s", cudaGetErrorString(cudaGetLastError()));
+        slpr_destroy(c);
+        return nullptr;
+    }
+    memset(&c->hp, 0, sizeof c->hp);
+    const float ident[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    memcpy(c->hp.rows, ident, sizeof ident);
+    c->hp.width = (int)width; c->hp.height = (int)height;
+    c->hp.band_y0 = 0; c->hp.band_y1 = (int)height; c->hp.cull = 0;
+    return c;
+}
+
+extern "C" void slpr_destroy(slpr_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    free_capacity(c);
+    free_scene(c);
+    cudaFree(c->d_params); cudaFreeHost(c->h_ctr); cudaFree(c->d_cells); cudaFree(c->d_fb); cudaFree(c->d_prim_temp);
+    for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+extern "C" int slpr_set_stream(slpr_ctx *c, void *s) {
+    if (!c) return fail(SLPR_ERR_INVALID, "null context");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    c->stream = s ? reinterpret_cast<cudaStream_t>(s) : c->own_stream;
+    return SLPR_OK;
+}
+
+template <class T>
+static int upload(T **dst, const void *src, size_t count) {
+    CU(cudaMalloc(dst, std::max<size_t>(count, 1) * sizeof(T)));
+    if (count) CU(cudaMemcpy(*dst, src, count * sizeof(T), cudaMemcpyHostToDevice));
+    return SLPR_OK;
+}
+
+extern "C" int slpr_load_scene(slpr_ctx *c, const float *pos_xy, const uint32_t *pos_path, uint32_t n_points,
+                               const uint32_t *curve_pos_map, const uint32_t *curve_type, const uint32_t *curve_path,
+                               uint32_t n_curves, const uint32_t *fill_rule, const uint32_t *fill_rgba8, uint32_t n_paths) {
+    if (!c) return fail(SLPR_ERR_INVALID, "null context");
+    if ((n_points && (!pos_xy || !pos_path)) || (n_curves && (!curve_pos_map || !curve_type || !curve_path)) ||
+        (n_paths && (!fill_rule || !fill_rgba8)))
+        return fail(SLPR_ERR_INVALID, "slpr_load_scene: null array with non-zero count");
+    if (n_points >= (1u << 30) || n_curves >= (1u << 30) || n_paths >= (1u << 30))
+        return fail(SLPR_ERR_INVALID, "slpr_load_scene: counts must be < 2^30");
+    // validate indices on the host once: the kernels trust them
+    for (uint32_t i = 0; i < n_curves; ++i) {
+        const uint32_t npts = curve_type[i] & 7u;
+        if (curve_path[i] >= n_paths) return fail(SLPR_ERR_INVALID, "slpr_load_scene: curve %u has path %u >= n_paths", i, curve_path[i]);
+        if ((uint64_t)curve_pos_map[i] + std::max(npts, 1u) > (uint64_t)n_points && npts)
+            return fail(SLPR_ERR_INVALID, "slpr_load_scene: curve %u points [%u,+%u) exceed n_points", i, curve_pos_map[i], npts);
+        if (i && curve_path[i] < curve_path[i - 1]) return fail(SLPR_ERR_INVALID, "slpr_load_scene: curve_path must be non-decreasing");
+    }
+    for (uint32_t i = 0; i < n_points; ++i)
+        if (pos_path[i] >= n_paths) return fail(SLPR_ERR_INVALID, "slpr_load_scene: point %u has path %u >= n_paths", i, pos_path[i]);
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    free_capacity(c);
+    free_scene(c);
+    c->np = n_points; c->nc = n_curves; c->P = n_paths;
+    int rc;
+    if ((rc = upload(&c->d_pos, pos_xy, n_points))) return rc;
+    if ((rc = upload(&c->d_pos_path, pos_path, n_points))) return rc;
+    if ((rc = upload(&c->d_cpm, curve_pos_map, n_curves))) return rc;
+    if ((rc = upload(&c->d_ctype, curve_type, n_curves))) return rc;
+    if ((rc = upload(&c->d_cpath, curve_path, n_curves))) return rc;
+    if ((rc = upload(&c->d_frule, fill_rule, n_paths))) return rc;
+    if ((rc = upload(&c->d_finfo, fill_rgba8, n_paths))) return rc;
+    CU(cudaMalloc(&c->d_tpos, std::max<size_t>(n_points, 1) * sizeof(float2)));
+    CU(cudaMalloc(&c->d_pvis, std::max<size_t>(n_paths, 1) * 4));
+    CU(cudaMalloc(&c->d_cut, std::max<size_t>(n_curves, 1) * 5 * 4));
+    CU(cudaMalloc(&c->d_count, ((size_t)n_curves + 4) * 4));
+    CU(cudaMalloc(&c->d_offset, ((size_t)n_curves + 4) * 4));
+    if (c->flags & SLPR_FLAG_TAPS) CU(cudaMalloc(&c->d_seg_tap, ((size_t)n_paths + 1) * 4));
+    // compact key geometry: x cell in [0,(W'+4)/2], row rank in [0,ny], path in [0,P)
+    const int Wp = (int)(c->W & ~1u);
+    c->L.ny = (int)(c->H + 1) / 2;
+    c->L.bits_x = std::max(1, ceil_log2((uint64_t)(Wp + 4) / 2 + 1));
+    c->L.bits_y = std::max(1, ceil_log2((uint64_t)c->L.ny + 1));
+    c->L.bits_path = ceil_log2(std::max<uint64_t>(n_paths, 1));
+    c->key_bits = c->L.bits_x + c->L.bits_y + c->L.bits_path;
+    c->passes = std::max(1, (c->key_bits + 7) / 8);
+    c->scene_loaded = true;
+    c->frame_done = c->frame_pending = false;
+    return SLPR_OK;
+}
+
+extern "C" int slpr_set_mvp(slpr_ctx *c, const float rows[16]) {
+    if (!c || !rows) return fail(SLPR_ERR_INVALID, "slpr_set_mvp: null argument");
+    memcpy(c->hp.rows, rows, 16 * sizeof(float));
+    c->have_mvp = true;
+    return SLPR_OK;
+}
+
+extern "C" int slpr_set_band(slpr_ctx *c, uint32_t y0, uint32_t y1) {
+    if (!c) return fail(SLPR_ERR_INVALID, "null context");
+    if (y0 >= y1 || y1 > c->H || (y0 & 1) || ((y1 & 1) && y1 != c->H))
+        return fail(SLPR_ERR_INVALID, "slpr_set_band: need even 0 <= y_begin < y_end <= height (got %u,%u)", y0, y1);
+    c->hp.band_y0 = (int)y0; c->hp.band_y1 = (int)y1;
+    c->hp.cull = (y0 != 0 || y1 != c->H) ? 1 : 0;
+    return SLPR_OK;
+}
+
+extern "C" int slpr_set_target(slpr_ctx *c, void *dev_rgba, size_t stride_bytes) {
+    if (!c) return fail(SLPR_ERR_INVALID, "null context");
+    if (dev_rgba && stride_bytes < (size_t)c->W * 4) return fail(SLPR_ERR_INVALID, "slpr_set_target: stride smaller than a row");
+    if (c->target != dev_rgba || c->target_stride != stride_bytes) c->graph_valid = false;
+    c->target = reinterpret_cast<uint8_t *>(dev_rgba);
+    c->target_stride = stride_bytes;
+    return SLPR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+static int grid_for(const slpr_ctx *c, long long work_items, int threads, int per_sm) {
+    long long blocks = (work_items + threads - 1) / threads;
+    const long long cap = (long long)c->num_sms * per_sm;
+    return (int)std::max(1ll, std::min(blocks, cap));
+}
+
+// Counting prefix of the frame: transform, monotonize+count, scan #1. `timed` records stage events.
+static int enqueue_count_phase(slpr_ctx *c, cudaStream_t s, bool timed, int &launches) {
+    CU(cudaMemsetAsync(c->d_temp, 0, c->temp_bytes, s));
+    CU(cudaMemsetAsync(c->d_pvis, 0, std::max<size_t>(c->P, 1) * 4, s));
+    if (timed) CU(cudaEventRecord(c->ev[0], s));
+    k_transform<<<grid_for(c, c->np, 256, 8), 256, 0, s>>>(c->d_params, c->np, c->d_pos, c->d_pos_path, c->d_tpos, c->d_pvis);
+    ++launches;
+    if (timed) CU(cudaEventRecord(c->ev[1], s));
+    k_monotonize_count<<<grid_for(c, c->nc, 256, 8), 256, 0, s>>>(c->d_params, c->nc, c->d_ctype, c->d_cpm, c->d_cpath,
+                                                                   c->d_tpos, c->d_pvis, c->d_cut, c->d_count);
+    ++launches;
+    if (timed) CU(cudaEventRecord(c->ev[2], s));
+    ScanI32Op op1{c->d_count, c->d_offset, (long long)c->nc, &c->d_ctr->n_fragments, c->cap, &c->d_ctr->overflow};
+    k_lookback_scan<ScanI32Op><<<grid_for(c, (long long)c->nc / 16 + 1, SCAN_THREADS, 8), SCAN_THREADS, 0, s>>>(
+        op1, ScanTemp{c->d_status[0], c->d_tickets + 0});
+    ++launches;
+    if (timed) CU(cudaEventRecord(c->ev[3], s));
+    return SLPR_OK;
+}
+
+static int enqueue_frame(slpr_ctx *c, cudaStream_t s, bool timed, int &launches) {
+    int rc = enqueue_count_phase(c, s, timed, launches);
+    if (rc) return rc;
+    const bool taps = (c->flags & SLPR_FLAG_TAPS) != 0;
+    const int wide = c->num_sms * 8;
+    k_intersect<<<grid_for(c, c->nc, 128, 16), 128, 0, s>>>(c->d_params, c->nc, c->d_ctype, c->d_cpm, c->d_tpos, c->d_cut,
+                                                             c->d_offset, c->d_ctr, c->cap, c->d_inter);
+    ++launches;
+    if (timed) CU(cudaEventRecord(c->ev[4], s));
+    FragTaps ft{c->t_key32, c->t_path, c->t_wind};
+    k_gen_fragment<<<wide, 256, 0, s>>>(c->d_params, c->d_ctr, c->cap, c->L, c->d_inter, c->d_cpath, c->d_cpm, c->d_ctype,
+                                        c->d_tpos, c->d_key[0], c->d_val[0], ft);
+    ++launches;
+    if (taps) {
+        k_segments_tap<<<grid_for(c, (long long)c->nc + 1, 256, 8), 256, 0, s>>>(c->nc, c->P, c->d_cpath, c->d_offset, c->d_seg_tap);
+        ++launches;
+    }
+    if (timed) CU(cudaEventRecord(c->ev[5], s));
+    // ---- sort
+    SortCount cnt{&c->d_ctr->n_fragments, 0, c->cap};
+    SortTemp st{c->d_hist, c->d_lookback, c->d_tickets + 3, c->sort_tiles_cap};
+    k_radix_hist<<<c->num_sms * 4, RH_THREADS, 0, s>>>(c->d_key[0], cnt, c->passes, c->d_hist);
+    k_radix_hist_scan<<<c->passes, RS_BINS, 0, s>>>(c->d_hist);
+    launches += 2;
+    int cur = 0;
+    for (int p = 0; p < c->passes; ++p) {
+        k_onesweep<<<c->num_sms * 2, RS_THREADS, RS_SMEM_BYTES, s>>>(c->d_key[cur], c->d_val[cur], c->d_key[cur ^ 1],
+                                                                     c->d_val[cur ^ 1], cnt, p, 8 * p, st);
+        ++launches;
+        cur ^= 1;
+    }
+    c->sorted_buf = cur;
+    if (timed) CU(cudaEventRecord(c->ev[6], s));
+    // ---- winding scan, then mark + scan + emit
+    WindScanOp opA{c->d_val[cur], c->d_wn, c->t_sidx, c->d_ctr, c->cap};
+    k_lookback_scan<WindScanOp><<<wide, SCAN_THREADS, 0, s>>>(opA, ScanTemp{c->d_status[1], c->d_tickets + 1});
+    SpanEmitOp opB{c->d_key[cur], c->d_wn, c->d_frule, c->d_finfo, c->d_rec, c->d_ctr, c->L, (int)c->W, (int)c->H, c->cap,
+                   SpanTaps{c->t_skey32, c->t_flags, c->t_scan3}};
+    k_lookback_scan<SpanEmitOp><<<wide, SCAN_THREADS, 0, s>>>(opB, ScanTemp{c->d_status[2], c->d_tickets + 2});
+    launches += 2;
+    if (taps) {
+        k_scan3_fixup<<<wide, 256, 0, s>>>(c->d_ctr, c->cap, c->t_scan3);
+        ++launches;
+    }
+    if (timed) CU(cudaEventRecord(c->ev[7], s));
+    // ---- pixels
+    uint8_t *fb = c->target ? c->target : c->d_fb;
+    const size_t stride = c->target ? c->target_stride : c->fb_stride;
+    k_fill_cells<<<wide, 256, 0, s>>>(c->d_params, c->d_ctr, c->cap, c->d_rec, c->d_cells, c->cw);
+    k_resolve<<<wide, 256, 0, s>>>(c->d_params, c->d_rec, c->d_cells, c->cw, fb, stride);
+    launches += 2;
+    if (timed) CU(cudaEventRecord(c->ev[8], s));
+    CU(cudaMemcpyAsync(c->h_ctr, c->d_ctr, sizeof(FrameCounters), cudaMemcpyDeviceToHost, s));
+    CU(cudaGetLastError());
+    return SLPR_OK;
+}
+
+static int size_buffers_from_count(slpr_ctx *c) {
+    // first frame of a scene (or after an overflow): run the counting prefix synchronously to size
+    // the fragment buffers, with 25 % head-room for later frames.
+    if (!c->d_temp) {
+        int rc = alloc_capacity(c, 1 << 14);  // provisional, gives the count phase its temp block
+        if (rc) return rc;
+    }
+    k_set_params<<<1, 1, 0, c->stream>>>(c->d_params, c->hp);
+    int l = 1;
+    int rc = enqueue_count_phase(c, c->stream, false, l);
+    if (rc) return rc;
+    c->launches += l;
+    CU(cudaMemcpyAsync(c->h_ctr, c->d_ctr, sizeof(FrameCounters), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    const long long nf = c->h_ctr->n_fragments;
+    if (nf < 0 || nf >= (1ll << 30) - (1ll << 27)) return fail(SLPR_ERR_INVALID, "frame has %lld fragments; limit is 2^30", nf);
+    if (nf + 16 > c->cap) {
+        const long long want = nf + nf / 4 + 65536;
+        rc = alloc_capacity(c, (int)std::min<long long>(want, (1ll << 30) - 1));
+        if (rc) return rc;
+    }
+    return SLPR_OK;
+}
+
+extern "C" int slpr_render(slpr_ctx *c) {
+    if (!c) return fail(SLPR_ERR_INVALID, "null context");
+    if (!c->scene_loaded) return fail(SLPR_ERR_STATE, "slpr_render: no scene loaded (call slpr_load_scene first)");
+    CU(cudaSetDevice(c->device));
+    if (c->cap == 0) {
+        int rc = size_buffers_from_count(c);
+        if (rc) return rc;
+    }
+    k_set_params<<<1, 1, 0, c->stream>>>(c->d_params, c->hp);
+    ++c->launches;
+    if (c->flags & SLPR_FLAG_NO_GRAPH) {
+        int l = 0;
+        int rc = enqueue_frame(c, c->stream, true, l);
+        if (rc) return rc;
+        c->launches += l;
+        c->launches_per_frame = l;
+        c->stage_times_valid = true;
+    } else {
+        if (!c->graph_valid) {
+            if (c->gexec) { cudaGraphExecDestroy(c->gexec); c->gexec = nullptr; }
+            cudaGraph_t g = nullptr;
+            CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+            int l = 0;
+            int rc = enqueue_frame(c, c->stream, false, l);
+            cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+            if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+            if (e != cudaSuccess) return fail(SLPR_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+            e = cudaGraphInstantiate(&c->gexec, g, 0);
+            cudaGraphDestroy(g);
+            if (e != cudaSuccess) return fail(SLPR_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+            c->launches_per_frame = l;
+            c->graph_valid = true;
+        }
+        CU(cudaGraphLaunch(c->gexec, c->stream));
+        c->launches += c->launches_per_frame;
+        c->stage_times_valid = false;
+    }
+    c->frame_pending = true;
+    c->frame_done = false;
+    return SLPR_OK;
+}
+
+// Wait for the frame; if it overflowed the fragment capacity, grow and render it again.
+static int finish_frame(slpr_ctx *c) {
+    if (!c->frame_pending && !c->frame_done) return fail(SLPR_ERR_STATE, "no frame has been rendered");
+    CU(cudaSetDevice(c->device));
+    for (int attempt = 0; attempt < 4; ++attempt) {
+        CU(cudaStreamSynchronize(c->stream));
+        c->frame_pending = false;
+        if (!c->h_ctr->overflow) { c->frame_done = true; return SLPR_OK; }
+        const long long nf = c->h_ctr->n_fragments;
+        int rc = alloc_capacity(c, (int)std::min<long long>(nf + nf / 4 + 65536, (1ll << 30) - 1));
+        if (rc) return rc;
+        rc = slpr_render(c);
+        if (rc) return rc;
+    }
+    return fail(SLPR_ERR_STATE, "frame kept overflowing its fragment buffers");
+}
+
+extern "C" int slpr_synchronize(slpr_ctx *c) {
+    if (!c) return fail(SLPR_ERR_INVALID, "null context");
+    if (c->frame_pending) return finish_frame(c);
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    return SLPR_OK;
+}
+
+extern "C" int slpr_readback(slpr_ctx *c, uint8_t *rgba, size_t stride_bytes) {
+    if (!c || !rgba) return fail(SLPR_ERR_INVALID, "slpr_readback: null argument");
+    if (stride_bytes < (size_t)c->W * 4) return fail(SLPR_ERR_INVALID, "slpr_readback: stride smaller than a row");
+    int rc = finish_frame(c);
+    if (rc) return rc;
+    const uint8_t *fb = c->target ? c->target : c->d_fb;
+    const size_t stride = c->target ? c->target_stride : c->fb_stride;
+    CU(cudaMemcpy2DAsync(rgba, stride_bytes, fb, stride, (size_t)c->W * 4, c->H, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return SLPR_OK;
+}
+
+extern "C" int slpr_render_to_host(slpr_ctx *c, const float rows[16], uint8_t *rgba, size_t stride_bytes) {
+    int rc = slpr_set_mvp(c, rows);
+    if (rc) return rc;
+    if ((rc = slpr_render(c))) return rc;
+    return slpr_readback(c, rgba, stride_bytes);
+}
+
+extern "C" int slpr_framebuffer(slpr_ctx *c, void **dev_rgba, size_t *stride_bytes) {
+    if (!c || !dev_rgba || !stride_bytes) return fail(SLPR_ERR_INVALID, "slpr_framebuffer: null argument");
+    *dev_rgba = c->target ? c->target : c->d_fb;
+    *stride_bytes = c->target ? c->target_stride : c->fb_stride;
+    return SLPR_OK;
+}
+
+extern "C" int slpr_get_counts(slpr_ctx *c, uint32_t *nf, uint32_t *nof, uint32_t *nspan) {
+    if (!c) return fail(SLPR_ERR_INVALID, "null context");
+    int rc = finish_frame(c);
+    if (rc) return rc;
+    if (nf) *nf = (uint32_t)c->h_ctr->n_fragments;
+    if (nof) *nof = (uint32_t)c->h_ctr->n_out_frag;
+    if (nspan) *nspan = (uint32_t)c->h_ctr->n_span;
+    return SLPR_OK;
+}
+
+extern "C" int slpr_debug_copy(slpr_ctx *c, int which, void *dst, size_t bytes) {
+    if (!c || !dst) return fail(SLPR_ERR_INVALID, "slpr_debug_copy: null argument");
+    int rc = finish_frame(c);
+    if (rc) return rc;
+    const size_t nf = (size_t)c->h_ctr->n_fragments, no = (size_t)c->h_ctr->n_records;
+    const void *src = nullptr;
+    size_t avail = 0;
+    bool tap = false;
+    switch (which) {
+        case SLPR_TAP_TRANSFORMED_POS: src = c->d_tpos; avail = (size_t)c->np * 8; break;
+        case SLPR_TAP_PATH_VISIBLE: src = c->d_pvis; avail = (size_t)c->P * 4; break;
+        case SLPR_TAP_CUT_CACHE: src = c->d_cut; avail = (size_t)c->nc * 20; break;
+        case SLPR_TAP_CURVE_COUNT: src = c->d_count; avail = (size_t)c->nc * 4; break;
+        case SLPR_TAP_CURVE_OFFSET: src = c->d_offset; avail = ((size_t)c->nc + 1) * 4; break;
+        case SLPR_TAP_INTERSECTION: src = c->d_inter; avail = nf * 8; break;
+        case SLPR_TAP_KEY: src = c->t_key32; avail = (nf + 1) * 4; tap = true; break;
+        case SLPR_TAP_PATH: src = c->t_path; avail = nf * 4; tap = true; break;
+        case SLPR_TAP_WINDING: src = c->t_wind; avail = nf * 4; tap = true; break;
+        case SLPR_TAP_SORTED_KEY: src = c->t_skey32; avail = nf * 4; tap = true; break;
+        case SLPR_TAP_SORTED_INDEX: src = c->t_sidx; avail = nf * 4; tap = true; break;
+        case SLPR_TAP_WINDING_SCAN: src = c->d_wn; avail = (nf + 1) * 4; break;
+        case SLPR_TAP_FLAGS: src = c->t_flags; avail = 2 * nf * 4; tap = true; break;
+        case SLPR_TAP_FLAG_SCAN: src = c->t_scan3; avail = (2 * nf + 1) * 4; tap = true; break;
+        case SLPR_TAP_RECORDS: src = c->d_rec; avail = no * 16; break;
+        case SLPR_TAP_SEGMENTS: src = c->d_seg_tap; avail = ((size_t)c->P + 1) * 4; tap = true; break;
+        default: return fail(SLPR_ERR_INVALID, "slpr_debug_copy: unknown buffer %d", which);
+    }
+    if (tap && !(c->flags & SLPR_FLAG_TAPS)) return fail(SLPR_ERR_STATE, "slpr_debug_copy: buffer %d needs SLPR_FLAG_TAPS", which);
+    if (bytes > avail) return fail(SLPR_ERR_INVALID, "slpr_debug_copy: asked %zu bytes of buffer %d, it has %zu", bytes, which, avail);
+    if (bytes) CU(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    return SLPR_OK;
+}
+
+extern "C" int slpr_stage_ms(slpr_ctx *c, float *ms, int n) {
+    if (!c || !ms) return fail(SLPR_ERR_INVALID, "slpr_stage_ms: null argument");
+    if (!c->stage_times_valid) return fail(SLPR_ERR_STATE, "slpr_stage_ms: needs a frame rendered with SLPR_FLAG_NO_GRAPH");
+    int rc = finish_frame(c);
+    if (rc) return rc;
+    for (int i = 0; i < n && i < SLPR_STAGE_COUNT; ++i) CU(cudaEventElapsedTime(&ms[i], c->ev[i], c->ev[i + 1]));
+    return SLPR_OK;
+}
+
+extern "C" int slpr_sort_info(slpr_ctx *c, uint32_t *key_bits, uint32_t *passes, uint32_t *key_bytes) {
+    if (!c || !c->scene_loaded) return fail(SLPR_ERR_STATE, "slpr_sort_info: no scene loaded");
+    if (key_bits) *key_bits = (uint32_t)c->key_bits;
+    if (passes) *passes = (uint32_t)c->passes;
+    if (key_bytes) *key_bytes = 8;
+    return SLPR_OK;
+}
+
+extern "C" uint64_t slpr_launch_count(slpr_ctx *c) { return c ? c->launches : 0; }
+
+// ------------------------------------------------------------------------------------------------
+// stand-alone primitives
+static int prim_temp(slpr_ctx *c, size_t bytes) {
+    if (bytes > c->prim_temp_bytes) {
+        CU(cudaStreamSynchronize(c->stream));
+        cudaFree(c->d_prim_temp);
+        c->d_prim_temp = nullptr;
+        CU(cudaMalloc(&c->d_prim_temp, bytes));
+        c->prim_temp_bytes = bytes;
+    }
+    CU(cudaMemsetAsync(c->d_prim_temp, 0, bytes, c->stream));
+    return SLPR_OK;
+}
+
+extern "C" int slpr_scan_i32(slpr_ctx *c, const int32_t *in, int32_t *out, uint64_t n) {
+    if (!c || !in || !out) return fail(SLPR_ERR_INVALID, "slpr_scan_i32: null argument");
+    if (n >= (1ull << 40)) return fail(SLPR_ERR_INVALID, "slpr_scan_i32: n too large");
+    CU(cudaSetDevice(c->device));
+    const size_t tiles = n / SCAN_TILE + 2;
+    int rc = prim_temp(c, 256 + tiles * 8);
+    if (rc) return rc;
+    ScanI32Op op{in, out, (long long)n, nullptr, 0, nullptr};
+    ScanTemp t{reinterpret_cast<unsigned long long *>(c->d_prim_temp + 256), reinterpret_cast<int *>(c->d_prim_temp)};
+    k_lookback_scan<ScanI32Op><<<grid_for(c, (long long)tiles, 1, 8), SCAN_THREADS, 0, c->stream>>>(op, t);
+    ++c->launches;
+    CU(cudaGetLastError());
+    return SLPR_OK;
+}
+
+extern "C" int slpr_sort_pairs(slpr_ctx *c, uint64_t *keys, uint32_t *vals, uint64_t *keys_tmp, uint32_t *vals_tmp,
+                               uint64_t n, uint32_t key_bits, int *result_in_tmp) {
+    if (!c || !keys || !vals || !keys_tmp || !vals_tmp) return fail(SLPR_ERR_INVALID, "slpr_sort_pairs: null argument");
+    if (n >= (1ull << 30)) return fail(SLPR_ERR_INVALID, "slpr_sort_pairs: n must be < 2^30");
+    if (key_bits == 0 || key_bits > 64) return fail(SLPR_ERR_INVALID, "slpr_sort_pairs: key_bits must be in [1,64]");
+    CU(cudaSetDevice(c->device));
+    const int passes = (int)(key_bits + 7) / 8;
+    const int tiles_cap = (int)(n / RS_TILE + 2);
+    const size_t o_hist = 256, o_lb = o_hist + (size_t)RS_MAX_PASSES * RS_BINS * 4;
+    int rc = prim_temp(c, o_lb + (size_t)passes * tiles_cap * RS_BINS * 4);
+    if (rc) return rc;
+    SortCount cnt{nullptr, (long long)n, 0};
+    SortTemp st{reinterpret_cast<uint32_t *>(c->d_prim_temp + o_hist), reinterpret_cast<uint32_t *>(c->d_prim_temp + o_lb),
+                reinterpret_cast<int *>(c->d_prim_temp), tiles_cap};
+    k_radix_hist<<<c->num_sms * 4, RH_THREADS, 0, c->stream>>>(keys, cnt, passes, st.hist);
+    k_radix_hist_scan<<<passes, RS_BINS, 0, c->stream>>>(st.hist);
+    uint64_t *kb[2] = {keys, keys_tmp};
+    uint32_t *vb[2] = {vals, vals_tmp};
+    int cur = 0;
+    for (int p = 0; p < passes; ++p) {
+        k_onesweep<<<c->num_sms * 2, RS_THREADS, RS_SMEM_BYTES, c->stream>>>(kb[cur], vb[cur], kb[cur ^ 1], vb[cur ^ 1], cnt, p, 8 * p, st);
+        cur ^= 1;
+    }
+    c->launches += 2 + passes;
+    if (result_in_tmp) *result_in_tmp = cur;
+    CU(cudaGetLastError());
+    return SLPR_OK;
+}
