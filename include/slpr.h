@@ -70,9 +70,18 @@ enum {
 
 /* Stage slots reported by slpr_stage_ms(). */
 enum {
-    SLPR_STAGE_TRANSFORM = 0, SLPR_STAGE_MONOTONIZE = 1, SLPR_STAGE_SCAN1 = 2,
-    SLPR_STAGE_INTERSECT = 3, SLPR_STAGE_FRAGMENT = 4, SLPR_STAGE_SORT = 5,
-    SLPR_STAGE_SPANS = 6, SLPR_STAGE_FILL = 7, SLPR_STAGE_COUNT = 8
+    SLPR_STAGE_TRANSFORM = 0,   /* k_transform                                  */
+    SLPR_STAGE_MONOTONIZE = 1,  /* k_monotonize_count                           */
+    SLPR_STAGE_SCAN1 = 2,       /* look-back scan of the curve counts           */
+    SLPR_STAGE_INTERSECT = 3,   /* k_intersect                                  */
+    SLPR_STAGE_FRAGMENT = 4,    /* k_gen_fragment                               */
+    SLPR_STAGE_SORT_HIST = 5,   /* k_radix_hist + k_radix_hist_scan             */
+    SLPR_STAGE_SORT_PASSES = 6, /* all k_onesweep launches (slpr_sort_info: passes) */
+    SLPR_STAGE_WIND_SCAN = 7,   /* look-back scan of the winding deltas         */
+    SLPR_STAGE_SPAN_EMIT = 8,   /* mark + flag scan + record emit               */
+    SLPR_STAGE_FILL_CELLS = 9,  /* k_fill_cells                                 */
+    SLPR_STAGE_RESOLVE = 10,    /* k_resolve                                    */
+    SLPR_STAGE_COUNT = 11
 };
 
 SLPR_API const char *slpr_last_error(void);
@@ -84,8 +93,9 @@ SLPR_API const char *slpr_version(void);
 SLPR_API slpr_ctx *slpr_create(int device, uint32_t width, uint32_t height, uint32_t flags);
 SLPR_API void slpr_destroy(slpr_ctx *ctx);
 
-/* Run all work of this context on a caller-owned cudaStream_t (e.g. torch's current stream)
- * instead of the context's own stream. Pass NULL to go back to the internal stream. */
+/* Run all work of this context on a caller-owned cudaStream_t (e.g. a torch.cuda.Stream) instead of
+ * the context's own stream. NULL goes back to the internal stream (so the legacy default stream,
+ * whose handle is NULL, cannot be borrowed: create a real stream). */
 SLPR_API int slpr_set_stream(slpr_ctx *ctx, void *cuda_stream);
 
 /* Replaces the 7 staging uploads at the end of ScanlineVGRasterizer::loadVG

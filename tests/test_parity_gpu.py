@@ -1,0 +1,172 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle, stage by stage.
+
+Bar: bit-exact for every integer / index / bit-pattern buffer (intersection counts, t parameters,
+sorted fragment order, winding numbers, draw records) and identical RGBA8 (tolerance 0 LSB; the
+north star allows 1 LSB, PSNR is reported as inf).
+"""
+import numpy as np
+import pytest
+
+import util
+import vkscanlinepr_b200 as V
+from oracle import oracle_py as O
+from vkscanlinepr_b200 import scene as S
+
+pytestmark = pytest.mark.gpu
+
+INT_TAPS = ["path_visible", "curve_count", "curve_offset", "intersection", "path", "winding", "segments",
+            "sorted_key", "sorted_index", "winding_scan", "flags", "flag_scan", "records"]
+ORACLE_NAME = dict(path_visible="path_visible", curve_count="curve_count", curve_offset="curve_offset",
+                   intersection="inter", path="path", winding="wind", segments="seg", sorted_key="skey",
+                   sorted_index="sidx", winding_scan="wn", flags="flags", flag_scan="scan3", records="records")
+
+
+def render_gpu(sc, rows, W, H, flags):
+    r = V.ScanlineRasterizer(0, flags).initialize(None, W, H)
+    r.loadVG(sc)
+    r.setMVP(rows)
+    r.render()
+    return r
+
+
+def assert_frame_parity(sc, rows, W, H):
+    ref = O.render(sc, rows, W, H)
+    r = render_gpu(sc, rows, W, H, V.FLAG_TAPS | V.FLAG_NO_GRAPH)
+    cnt = r.counts()
+    assert cnt == {k: ref[k] for k in ("n_fragments", "n_out_frag", "n_span")}
+    assert np.array_equal(r.tap("transformed_pos").view(np.uint32), ref["tpos"].view(np.uint32)), "transformed_pos"
+    assert np.array_equal(r.tap("cut_cache").view(np.uint32), ref["cut_cache"].view(np.uint32)), "cut_cache"
+    key = r.tap("key")
+    assert np.array_equal(key[:-1], ref["key"]) and (ref["n_fragments"] == 0 or key[-1] == -1), "key plane"
+    for t in INT_TAPS:
+        got, exp = r.tap(t), ref[ORACLE_NAME[t]]
+        assert got.shape == exp.shape and np.array_equal(got, exp), f"tap {t} differs"
+    img = r.readback()
+    assert np.array_equal(img, ref["rgba"]), f"RGBA differs, PSNR {util.psnr(img, ref['rgba']):.2f} dB"
+    r.close()
+    # fast path: no taps, CUDA graph replay, twice (the second frame reuses the captured graph)
+    f = render_gpu(sc, rows, W, H, 0)
+    assert np.array_equal(f.readback(), ref["rgba"])
+    f.render()
+    assert np.array_equal(f.readback(), ref["rgba"])
+    assert f.counts() == cnt
+    assert np.array_equal(f.tap("records"), ref["records"])
+    f.close()
+    return ref
+
+
+@pytest.mark.parametrize("name", util.SHIPPED)
+@pytest.mark.parametrize("size", [(1024, 1024), (1920, 1080)])
+def test_shipped_scene_parity(name, size):
+    sc, vp = util.golden_scene(name)
+    W, H = size
+    assert_frame_parity(sc, S.fit_rows(vp, W, H), W, H)
+
+
+def test_paper_config_all_nonzero():
+    """BASELINE cfg1: test.rvg stands in for the missing paper-1.rvg, 1024x1024, uniform fit without
+    centring, once with the file's fill rules and once forced to nonzero."""
+    sc, vp = util.golden_scene("test")
+    rows = S.fit_rows(vp, 1024, 1024, centred=False)
+    assert_frame_parity(sc, rows, 1024, 1024)
+    assert_frame_parity(sc.with_fill_rule(S.NON_ZERO), rows, 1024, 1024)
+
+
+@pytest.mark.parametrize("name", util.EMPTY)
+def test_empty_scenes_render_white(name):
+    sc, vp = util.golden_scene(name)
+    ref = assert_frame_parity(sc, S.identity_rows(), 320, 200)
+    assert np.all(ref["rgba"] == 255)
+
+
+def test_tiny_scene_and_odd_sizes():
+    sc = util.tiny_scene()
+    for W, H in [(96, 80), (97, 81), (33, 17), (2, 2), (1, 1)]:
+        assert_frame_parity(sc, S.identity_rows(), W, H)
+
+
+def test_zoomed_and_offscreen_views():
+    sc, vp = util.golden_scene("tiger")
+    W, H = 800, 600
+    zoom = S.fit_rows(vp, W, H)
+    zoom[0, 0] *= 9; zoom[1, 1] *= 9; zoom[0, 3] = -2400; zoom[1, 3] = -1800   # deep zoom: long curves, clipping
+    assert_frame_parity(sc, zoom, W, H)
+    away = S.fit_rows(vp, W, H); away[0, 3] += 5000                              # everything off-screen
+    ref = assert_frame_parity(sc, away, W, H)
+    assert ref["n_fragments"] == 0
+    rot = S.anim_rows(37, W, H)                                                   # rotation + scale (cfg5 matrix)
+    assert_frame_parity(sc, (rot.astype(np.float64) @ S.fit_rows(vp, W, H).astype(np.float64)).astype(np.float32), W, H)
+
+
+def test_reference_hardcoded_matrix():
+    """The zoom matrix the reference hard-codes for frame 0 (scanline_rasterizer.cpp:1162-1165)."""
+    sc, _ = util.golden_scene("test")
+    rows = np.eye(4, dtype=np.float32)
+    rows[0, 0] = rows[1, 1] = np.float32(13.190648); rows[0, 3] = np.float32(-1142.983887); rows[1, 3] = np.float32(-6987.709961)
+    assert_frame_parity(sc, rows, 1200, 1024)
+
+
+def test_synthetic_scene_parity():
+    sc = S.synth_scene(4096, 1024, 768, 6.0, 30.0, seed=0x5CA71E01)
+    assert_frame_parity(sc, S.identity_rows(), 1024, 768)
+
+
+def test_mvp_changes_between_frames_and_capacity_growth():
+    """One context, several matrices: the graph is replayed with new FrameParams; a zoom that makes
+    far more fragments than the first frame forces the capacity to grow and the frame to be redone."""
+    sc, vp = util.golden_scene("tiger")
+    W, H = 640, 480
+    r = V.ScanlineRasterizer(0, 0).initialize(None, W, H)
+    r.loadVG(sc)
+    small = S.fit_rows(vp, W, H); small[0, 0] *= 0.05; small[1, 1] *= 0.05
+    for rows in (small, S.fit_rows(vp, W, H), S.anim_rows(11, W, H) @ S.fit_rows(vp, W, H), small):
+        rows = np.asarray(rows, np.float32)
+        r.setMVP(rows)
+        r.render()
+        ref = O.render(sc, rows, W, H)
+        assert np.array_equal(r.readback(), ref["rgba"])
+        assert r.counts()["n_fragments"] == ref["n_fragments"]
+    r.close()
+
+
+def test_row_bands_equal_full_frame():
+    """rendering even-aligned row bands independently and stacking them equals the full
+    frame (exact for scenes whose per-(path,row) winding sums are zero: closed paths)."""
+    W = H = 512
+    rows = S.identity_rows()
+    for seed in range(3, 40):  # first seed without a 4-cut cubic (MI0:340 slip leaves a winding residue)
+        sc = S.synth_scene(1024, 512, 512, 6.0, 40.0, seed=seed)
+        ref = O.render(sc, rows, W, H)
+        res = np.zeros(sc.n_paths, np.int64)
+        np.add.at(res, ref["path"], ref["wind"])
+        if not res.any():
+            break
+    assert ref["wn"][-1] == 0 and not res.any()
+    full = np.zeros((H, W, 4), np.uint8)
+    for G in (2, 4):
+        for g in range(G):
+            y0, y1 = g * H // G, (g + 1) * H // G
+            r = V.ScanlineRasterizer(0, 0).initialize(None, W, H)
+            r.loadVG(sc); r.setMVP(rows); r.set_band(y0, y1); r.render()
+            img = r.readback()
+            full[H - y1:H - y0] = img[H - y1:H - y0]   # image row = H-1-scanline row
+            assert r.counts()["n_fragments"] <= ref["n_fragments"]
+            r.close()
+        assert np.array_equal(full, ref["rgba"]), f"G={G}"
+
+
+def test_error_paths():
+    r = V.ScanlineRasterizer(0, 0).initialize(None, 64, 64)
+    with pytest.raises(V.SlprError):
+        r.render()                      # no scene
+    with pytest.raises(V.SlprError):
+        r.set_band(1, 64)               # odd band start
+    sc = util.tiny_scene()
+    bad = S.Scene(sc.pos, sc.pos_path, sc.curve_pos_map, sc.curve_type, sc.curve_path + 7, sc.fill_rule, sc.fill_info)
+    with pytest.raises(V.SlprError):
+        r.loadVG(bad)                   # path index out of range
+    r.close()
+    with pytest.raises(V.SlprError):
+        V.ScanlineRasterizer(0, V.FLAG_CONTRACT_FMA).initialize(None, 64, 64)
+    with pytest.raises(V.SlprError):
+        V.ScanlineRasterizer(0, 0).initialize(None, 40000, 64)

@@ -25,7 +25,8 @@ FLAG_TAPS, FLAG_CONTRACT_FMA, FLAG_NO_GRAPH = 1, 2, 4
 TAPS = dict(transformed_pos=0, path_visible=1, cut_cache=2, curve_count=3, curve_offset=4, intersection=5,
             key=6, path=7, winding=8, sorted_key=9, sorted_index=10, winding_scan=11, flags=12,
             flag_scan=13, records=14, segments=15)
-STAGES = ("transform", "monotonize", "scan1", "intersect", "gen_fragment", "sort", "spans", "fill")
+STAGES = ("transform", "monotonize", "scan1", "intersect", "gen_fragment", "sort_hist", "sort_passes",
+          "wind_scan", "span_emit", "fill_cells", "resolve")
 
 
 class SlprError(RuntimeError):

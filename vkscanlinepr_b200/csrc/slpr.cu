@@ -391,6 +391,7 @@ static int enqueue_frame(slpr_ctx *c, cudaStream_t s, bool timed, int &launches)
     k_radix_hist<<<c->num_sms * 4, RH_THREADS, 0, s>>>(c->d_key[0], cnt, c->passes, c->d_hist);
     k_radix_hist_scan<<<c->passes, RS_BINS, 0, s>>>(c->d_hist);
     launches += 2;
+    if (timed) CU(cudaEventRecord(c->ev[6], s));
     int cur = 0;
     for (int p = 0; p < c->passes; ++p) {
         k_onesweep<<<c->num_sms * 2, RS_THREADS, RS_SMEM_BYTES, s>>>(c->d_key[cur], c->d_val[cur], c->d_key[cur ^ 1],
@@ -399,10 +400,11 @@ static int enqueue_frame(slpr_ctx *c, cudaStream_t s, bool timed, int &launches)
         cur ^= 1;
     }
     c->sorted_buf = cur;
-    if (timed) CU(cudaEventRecord(c->ev[6], s));
+    if (timed) CU(cudaEventRecord(c->ev[7], s));
     // ---- winding scan, then mark + scan + emit
     WindScanOp opA{c->d_val[cur], c->d_wn, c->t_sidx, c->d_ctr, c->cap};
     k_lookback_scan<WindScanOp><<<wide, SCAN_THREADS, 0, s>>>(opA, ScanTemp{c->d_status[1], c->d_tickets + 1});
+    if (timed) CU(cudaEventRecord(c->ev[8], s));
     SpanEmitOp opB{c->d_key[cur], c->d_wn, c->d_frule, c->d_finfo, c->d_rec, c->d_ctr, c->L, (int)c->W, (int)c->H, c->cap,
                    SpanTaps{c->t_skey32, c->t_flags, c->t_scan3}};
     k_lookback_scan<SpanEmitOp><<<wide, SCAN_THREADS, 0, s>>>(opB, ScanTemp{c->d_status[2], c->d_tickets + 2});
@@ -411,14 +413,15 @@ static int enqueue_frame(slpr_ctx *c, cudaStream_t s, bool timed, int &launches)
         k_scan3_fixup<<<wide, 256, 0, s>>>(c->d_ctr, c->cap, c->t_scan3);
         ++launches;
     }
-    if (timed) CU(cudaEventRecord(c->ev[7], s));
+    if (timed) CU(cudaEventRecord(c->ev[9], s));
     // ---- pixels
     uint8_t *fb = c->target ? c->target : c->d_fb;
     const size_t stride = c->target ? c->target_stride : c->fb_stride;
     k_fill_cells<<<wide, 256, 0, s>>>(c->d_params, c->d_ctr, c->cap, c->d_rec, c->d_cells, c->cw);
+    if (timed) CU(cudaEventRecord(c->ev[10], s));
     k_resolve<<<wide, 256, 0, s>>>(c->d_params, c->d_rec, c->d_cells, c->cw, fb, stride);
     launches += 2;
-    if (timed) CU(cudaEventRecord(c->ev[8], s));
+    if (timed) CU(cudaEventRecord(c->ev[11], s));
     CU(cudaMemcpyAsync(c->h_ctr, c->d_ctr, sizeof(FrameCounters), cudaMemcpyDeviceToHost, s));
     CU(cudaGetLastError());
     return SLPR_OK;
