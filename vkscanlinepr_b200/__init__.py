@@ -18,7 +18,7 @@ from . import scene as scene  # noqa: F401
 from .scene import Scene, Container
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libslpr.so")
+LIB_PATH = os.environ.get("SLPR_LIB") or os.path.join(_HERE, "libslpr.so")  # SLPR_LIB: tuning variants
 _LIB = None
 
 FLAG_TAPS, FLAG_CONTRACT_FMA, FLAG_NO_GRAPH = 1, 2, 4

@@ -124,7 +124,10 @@ __global__ void __launch_bounds__(256) k_monotonize_count(const FrameParams *__r
                                                           float *__restrict__ cut_cache, int *__restrict__ count) {
     const int width = P->width, height = P->height;
     const bool cull = P->cull != 0;
-    const float band_lo = (float)(P->band_y0 - 1), band_hi = (float)(P->band_y1 + 1);
+    // Only interior band edges cull: beyond the frame edges the reference still emits (invalid-key)
+    // fragments whose winding deltas pair up across curves of a path (sampling rows -1 and H'+3).
+    const float band_lo = (P->band_y0 > 0) ? (float)(P->band_y0 - 1) : -3.0e38f;
+    const float band_hi = (P->band_y1 < P->height) ? (float)(P->band_y1 + 1) : 3.0e38f;
     for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n_curves; c += gridDim.x * blockDim.x) {
         const uint32_t type = curve_type[c];
         CurvePts cp;
@@ -204,77 +207,142 @@ __global__ void __launch_bounds__(256) k_monotonize_count(const FrameParams *__r
 }
 
 // ------------------------------------------------------------------------------------------------
-// K4: make_intersection_1.comp:217-447. One thread walks one curve: per monotone piece it merges
-// the x- and y-grid crossings in parameter order; lines in closed form, cubics by the reference's
-// 24-step bisection whose bracket starts at the previously emitted crossing (so the walk along a
-// piece is inherently sequential if the emitted t must be bit-identical).
+// K4: make_intersection_1.comp:217-447. The reference walks one curve per thread: per monotone piece
+// it merges the x- and y-grid crossings in parameter order; lines in closed form, cubics by a
+// 24-step bisection whose bracket starts at the previously emitted crossing on the same axis — so
+// the walk along a piece is inherently sequential if the emitted t must be bit-identical.
+//
+// B200 formulation (the arithmetic per step is the reference's, operation for operation):
+//   * the nested loops (pieces x crossings) are flattened into a per-lane state machine;
+//   * curves are handed out dynamically: each warp owns a chunk of curve indices (one global
+//     atomicAdd per WALK_CHUNK curves) and a lane that finishes its curve takes the next index by
+//     ballot, so no lane idles while work remains;
+//   * each outer iteration first advances every lane to its next crossing solve (emission, side
+//     selection, piece set-up and curve fetch are the cheap, divergent part) and then runs the
+//     24-step bisection — 70 % of all instructions — once, with the whole warp converged.
 // Writes (curve, tbits) records at the curve's scanned offset.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_intersect(const FrameParams *__restrict__ P, uint32_t n_curves,
-                                                   const uint32_t *__restrict__ curve_type,
-                                                   const uint32_t *__restrict__ curve_pos_map,
-                                                   const float2 *__restrict__ tpos,
-                                                   const float *__restrict__ cut_cache,
-                                                   const int *__restrict__ offsets,
-                                                   const FrameCounters *__restrict__ ctr, int capacity,
-                                                   int2 *__restrict__ inter) {
+constexpr int WALK_THREADS = 128;
+constexpr int WALK_CHUNK = 32;
+
+__global__ void __launch_bounds__(WALK_THREADS) k_intersect(const FrameParams *__restrict__ P, uint32_t n_curves,
+                                                            const uint32_t *__restrict__ curve_type,
+                                                            const uint32_t *__restrict__ curve_pos_map,
+                                                            const float2 *__restrict__ tpos,
+                                                            const float *__restrict__ cut_cache,
+                                                            const int *__restrict__ offsets,
+                                                            const FrameCounters *__restrict__ ctr, int capacity,
+                                                            int2 *__restrict__ inter, int *__restrict__ work_counter) {
     if (ctr->n_fragments > capacity) return;  // overflow: the host re-renders with larger buffers
     const int width = P->width, height = P->height;
-    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n_curves; c += gridDim.x * blockDim.x) {
-        int pcnt = offsets[c];
-        if (offsets[c + 1] == pcnt) continue;  // invisible or band-culled: nothing to emit
-        const uint32_t type = curve_type[c];
-        CurvePts cp;
-        load_points(type, curve_pos_map[c], tpos, cp);
-        float tq[5];
-        tq[0] = cut_cache[5 * c + 0]; tq[1] = cut_cache[5 * c + 1];
-        tq[2] = cut_cache[5 * c + 2]; tq[3] = cut_cache[5 * c + 3]; tq[4] = 0.f;
-        uint32_t n_cuts = f2u(cut_cache[5 * c + 4]);  // MI1:255
-        // count > 0 implies the path is visible (MI0:374-377), so MI1:257-260 always appends t = 1
-        if (n_cuts == 0) tq[0] = 1.f; else if (n_cuts == 1) tq[1] = 1.f; else if (n_cuts == 2) tq[2] = 1.f;
-        else if (n_cuts == 3) tq[3] = 1.f; else tq[4] = 1.f;
-        ++n_cuts;
+    const uint32_t lane = lane_id(), lt = lanemask_lt();
+    enum { NEED_CURVE = 0, NEED_PIECE = 1, WALK = 2, DONE = 3 };
+    int state = NEED_CURVE;
+    uint32_t wl_next = 0, wl_end = 0;  // this warp's chunk of curve indices (warp-uniform)
+    bool exhausted = false;
 
-        float t0_ms = 0.f;
-        float p0x = cp.x[0], p0y = cp.y[0];
-        for (uint32_t i = 0; i < n_cuts; ++i) {
-            float t1_ms = (i == 0) ? tq[0] : (i == 1) ? tq[1] : (i == 2) ? tq[2] : (i == 3) ? tq[3] : tq[4];
-            const float p1x = interp_general(type, t1_ms, cp.x[0], cp.x[1], cp.x[2], cp.x[3], 0.0f);
-            const float p1y = interp_general(type, t1_ms, cp.y[0], cp.y[1], cp.y[2], cp.y[3], 0.0f);
-            // MI1:271-276: tag t1 in its two mantissa LSBs
-            if (floorf(p1x) == p1x) t1_ms = u2f((f2u(t1_ms) & 0xFFFFFFFCu) | 2u);
-            else t1_ms = u2f(f2u(t1_ms) | 3u);
+    // per-curve state
+    uint32_t c = 0, type = 0, n_cuts = 0, piece = 0;
+    CurvePts cp;
+    float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+    float t0_ms = 0.f, p0x = 0.f, p0y = 0.f;
+    int pcnt = 0;
+    // per-piece state
+    float t1_ms = 0.f, p1x = 0.f, p1y = 0.f, x = 0.f, y = 0.f, dx = 0.f, dy = 0.f, tx = 0.f, ty = 0.f;
+    int n_x = 0, n_y = 0, n_loop = 0, it = 0, i_inte_last = 0;
+    // pending solve
+    bool pending = false;
+    int side = 0;
+    float cst = 0.f, t_min = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { cp.x[i] = 0.f; cp.y[i] = 0.f; }
 
-            // get_xy_begin_end_delta, MI1:150-170 (float2int_rd)
-            const bool xfwd = p0x <= p1x, yfwd = p0y <= p1y;
-            int xb = float2int_rd(__fdiv_rn(xfwd ? p0x : p1x, 2.0f)) * FRAG_SIZE + FRAG_SIZE;
-            int xe = float2int_rd(__fdiv_rn(xfwd ? p1x : p0x, 2.0f)) * FRAG_SIZE;
-            int yb = float2int_rd(__fdiv_rn(yfwd ? p0y : p1y, 2.0f)) * FRAG_SIZE + FRAG_SIZE;
-            int ye = float2int_rd(__fdiv_rn(yfwd ? p1y : p0y, 2.0f)) * FRAG_SIZE;
-            const float dx = xfwd ? 2.0f : -2.0f, dy = yfwd ? 2.0f : -2.0f;
-            int n_x = cut_range(width, xb, xe);
-            int n_y = cut_range(height, yb, ye);
-            const int n_loop = n_x + n_y + 1;
-            float x = (float)(dx < 0 ? xe : xb);  // MI1:301-302
-            float y = (float)(dy < 0 ? ye : yb);
-            float tx = t0_ms, ty = t0_ms;  // point_coords slots 8, 9
-            int i_inte_last = (int)f2u(-1.0f);
+    // MI1:440-443: store the tagged parameter on its side; the piece ends after n_loop+1 steps
+#define WALK_FINISH_STEP(T_SOLVE)                                                              \
+    do {                                                                                       \
+        const float tagged_ = u2f((f2u(T_SOLVE) & 0xFFFFFFFCu) | (uint32_t)side);              \
+        if (side) ty = tagged_; else tx = tagged_;                                             \
+        ++it;                                                                                  \
+        if (it == n_loop) {                                                                    \
+            t0_ms = t1_ms; p0x = p1x; p0y = p1y;                                               \
+            ++piece;                                                                           \
+            state = (piece < n_cuts) ? NEED_PIECE : NEED_CURVE;                                \
+        }                                                                                      \
+    } while (0)
 
-            for (int it = -1; it < n_loop; ++it) {  // MI1:310-441
-                float t_solve = 0.0f, cst = 0.0f, t_min;
-                int side = 0;
-                if (it == -1) {
-                    t_min = tx;
-                    if (n_x == 0) { side = 0; t_solve = 2.f; }
-                    else if (n_y == 0) { side = 1; t_solve = 2.f; }
-                    else { side = 0; --n_x; cst = x; x = __fadd_rn(x, dx); }
-                } else if (tx <= ty) {
-                    t_min = tx; side = 0;
-                    if (n_x > 0) { --n_x; cst = x; x = __fadd_rn(x, dx); } else t_solve = 2.f;
-                } else {
-                    t_min = ty; side = 1;
-                    if (n_y > 0) { --n_y; cst = y; y = __fadd_rn(y, dy); } else t_solve = 2.f;
+    while (true) {
+        // =========== advance every lane to its next solve ===========
+        while (true) {
+            const uint32_t busy = __ballot_sync(0xFFFFFFFFu, !pending && state != DONE);
+            if (!busy) break;
+            // ---- hand out curves to the lanes that need one
+            while (true) {
+                const uint32_t need = __ballot_sync(0xFFFFFFFFu, state == NEED_CURVE);
+                if (!need) break;
+                if (wl_next >= wl_end) {
+                    if (exhausted) {
+                        if (state == NEED_CURVE) state = DONE;
+                        break;
+                    }
+                    uint32_t base = 0;
+                    if (lane == 0) base = (uint32_t)atomicAdd(work_counter, WALK_CHUNK);
+                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                    if (base >= n_curves) { exhausted = true; continue; }
+                    wl_next = base;
+                    wl_end = min(base + (uint32_t)WALK_CHUNK, n_curves);
                 }
+                const uint32_t avail = wl_end - wl_next;
+                const uint32_t rank = __popc(need & lt);
+                if (state == NEED_CURVE && rank < avail) {
+                    c = wl_next + rank;
+                    pcnt = offsets[c];
+                    if (offsets[c + 1] != pcnt) {  // count 0 = invisible or band-culled curve: take another one
+                        type = curve_type[c];
+                        load_points(type, curve_pos_map[c], tpos, cp);
+                        q0 = cut_cache[5 * c + 0]; q1 = cut_cache[5 * c + 1];
+                        q2 = cut_cache[5 * c + 2]; q3 = cut_cache[5 * c + 3];
+                        // count > 0 implies the path is visible (MI0:374-377), so MI1:257-260 appends t = 1
+                        n_cuts = f2u(cut_cache[5 * c + 4]) + 1u;  // MI1:255
+                        piece = 0;
+                        t0_ms = 0.f; p0x = cp.x[0]; p0y = cp.y[0];
+                        state = NEED_PIECE;
+                    }
+                }
+                wl_next += min((uint32_t)__popc(need), avail);
+            }
+            // ---- set up the next monotone piece (MI1:266-308)
+            if (state == NEED_PIECE) {
+                const bool last = piece + 1 == n_cuts;  // the appended t = 1
+                t1_ms = last ? 1.f : (piece == 0) ? q0 : (piece == 1) ? q1 : (piece == 2) ? q2 : q3;
+                p1x = interp_general(type, t1_ms, cp.x[0], cp.x[1], cp.x[2], cp.x[3], 0.0f);
+                p1y = interp_general(type, t1_ms, cp.y[0], cp.y[1], cp.y[2], cp.y[3], 0.0f);
+                // MI1:271-276: tag t1 in its two mantissa LSBs
+                if (floorf(p1x) == p1x) t1_ms = u2f((f2u(t1_ms) & 0xFFFFFFFCu) | 2u);
+                else t1_ms = u2f(f2u(t1_ms) | 3u);
+                // get_xy_begin_end_delta, MI1:150-170 (float2int_rd)
+                const bool xfwd = p0x <= p1x, yfwd = p0y <= p1y;
+                int xb = float2int_rd(__fdiv_rn(xfwd ? p0x : p1x, 2.0f)) * FRAG_SIZE + FRAG_SIZE;
+                int xe = float2int_rd(__fdiv_rn(xfwd ? p1x : p0x, 2.0f)) * FRAG_SIZE;
+                int yb = float2int_rd(__fdiv_rn(yfwd ? p0y : p1y, 2.0f)) * FRAG_SIZE + FRAG_SIZE;
+                int ye = float2int_rd(__fdiv_rn(yfwd ? p1y : p0y, 2.0f)) * FRAG_SIZE;
+                dx = xfwd ? 2.0f : -2.0f; dy = yfwd ? 2.0f : -2.0f;
+                n_x = cut_range(width, xb, xe);
+                n_y = cut_range(height, yb, ye);
+                n_loop = n_x + n_y + 1;
+                x = (float)(dx < 0 ? xe : xb);  // MI1:301-302
+                y = (float)(dy < 0 ? ye : yb);
+                tx = t0_ms; ty = t0_ms;  // point_coords slots 8, 9
+                i_inte_last = (int)f2u(-1.0f);
+                it = -1;
+                state = WALK;
+            }
+            // ---- first half of one walk step (MI1:310-375): pick the side, emit the record
+            if (state == WALK && !pending) {
+                const bool first = it == -1;
+                // MI1:321-359 written without branches: side, whether that side is exhausted, t_min
+                side = first ? ((n_x != 0 && n_y == 0) ? 1 : 0) : ((tx <= ty) ? 0 : 1);
+                const bool park = first ? (n_x == 0 || n_y == 0) : ((side ? n_y : n_x) <= 0);
+                t_min = first ? tx : (side ? ty : tx);
                 if (it >= 0) {  // MI1:361-375
                     int i_out = (int)f2u(t_min);
                     if ((f2u(t_min) & 0xFFFFFFFCu) == ((uint32_t)i_inte_last & 0xFFFFFFFCu)) {
@@ -285,42 +353,75 @@ __global__ void __launch_bounds__(128) k_intersect(const FrameParams *__restrict
                     i_inte_last = i_out;
                     ++pcnt;
                 }
-                if (t_solve < 2.f) {
-                    const float c0 = side ? cp.y[0] : cp.x[0], c1 = side ? cp.y[1] : cp.x[1];
-                    if (type == T_LINE) {  // MI1:379-385
-                        float a = __fsub_rn(c1, c0);
-                        a = (a != 0.0f) ? __fdiv_rn(1.0f, a) : 0.0f;
-                        float v = __fmul_rn(__fsub_rn(cst, c0), a);
-                        v = (v < t_min) ? t_min : v;          // GLSL max(x,y) = x<y ? y : x
-                        t_solve = (t1_ms < v) ? t1_ms : v;    // GLSL min(x,y) = y<x ? y : x
-                    } else if (type == T_QUADRIC || type == T_ARC) {
-                        // TODO arms in the reference: t_solve stays 0
-                    } else {  // MI1:392-436
-                        const float c2 = side ? cp.y[2] : cp.x[2], c3 = side ? cp.y[3] : cp.x[3];
-                        float t0 = t_min, t1 = t1_ms;
-                        float vt0 = interp_general(type, t0, c0, c1, c2, c3, 0.0f);
-                        t_solve = t0;
-                        if (vt0 != cst) {
-                            const float raw_t0 = t0;
-                            float last_vtm = 0.f;
-#pragma unroll 4
-                            for (int j = 0; j < CUBIC_ITERATION_NUMBER; ++j) {
-                                const float tm = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
-                                const float vtm = interp_general(type, tm, c0, c1, c2, c3, 0.0f);
-                                t_solve = tm; last_vtm = vtm;
-                                if ((int)(f2u(__fsub_rn(vtm, cst)) ^ f2u(__fsub_rn(vt0, cst))) >= 0) { t0 = tm; vt0 = vtm; }
-                                else t1 = tm;
-                            }
-                            if (fabsf(__fsub_rn(last_vtm, cst)) > 1.f) t_solve = raw_t0;  // MI1:430-433
-                        }
-                    }
+                if (park) {
+                    WALK_FINISH_STEP(2.0f);  // t_solve = 2: the side is exhausted
+                } else {
+                    if (side) { --n_y; cst = y; y = __fadd_rn(y, dy); }
+                    else { --n_x; cst = x; x = __fadd_rn(x, dx); }
+                    pending = true;
                 }
-                const float tagged = u2f((f2u(t_solve) & 0xFFFFFFFCu) | (uint32_t)side);  // MI1:440
-                if (side) ty = tagged; else tx = tagged;
             }
-            t0_ms = t1_ms; p0x = p1x; p0y = p1y;  // MI1:442-443
+        }
+        if (__all_sync(0xFFFFFFFFu, state == DONE)) break;
+
+        // =========== solve the pending crossing, whole warp converged (MI1:377-437) ===========
+        if (pending) {
+            float t_solve = 0.0f;
+            const float c0 = side ? cp.y[0] : cp.x[0], c1 = side ? cp.y[1] : cp.x[1];
+            if (type == T_CUBIC) {  // MI1:392-436
+                const float c2 = side ? cp.y[2] : cp.x[2], c3 = side ? cp.y[3] : cp.x[3];
+                // LERP(a,b,t) = a + t*(b-a): the first-level differences do not depend on t
+                const float d01 = __fsub_rn(c1, c0), d12 = __fsub_rn(c2, c1), d23 = __fsub_rn(c3, c2);
+                float t0 = t_min, t1 = t1_ms;
+                float vt0;
+                {
+                    const float a0 = __fadd_rn(c0, __fmul_rn(t0, d01)), a1 = __fadd_rn(c1, __fmul_rn(t0, d12)),
+                                a2 = __fadd_rn(c2, __fmul_rn(t0, d23));
+                    const float b0 = lerpf(a0, a1, t0), b1 = lerpf(a1, a2, t0);
+                    vt0 = lerpf(b0, b1, t0);
+                }
+                t_solve = t0;
+                if (vt0 != cst) {
+                    const float raw_t0 = t0;
+                    uint32_t s0 = f2u(__fsub_rn(vt0, cst)), s_last = 0;
+#pragma unroll 4
+                    for (int j = 0; j < CUBIC_ITERATION_NUMBER; ++j) {
+                        const float tm = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
+                        const float a0 = __fadd_rn(c0, __fmul_rn(tm, d01)), a1 = __fadd_rn(c1, __fmul_rn(tm, d12)),
+                                    a2 = __fadd_rn(c2, __fmul_rn(tm, d23));
+                        const float b0 = lerpf(a0, a1, tm), b1 = lerpf(a1, a2, tm);
+                        const float vtm = lerpf(b0, b1, tm);
+                        t_solve = tm;
+                        s_last = f2u(__fsub_rn(vtm, cst));
+                        if ((int)(s_last ^ s0) >= 0) { t0 = tm; s0 = s_last; }  // vt0 = vtm
+                        else t1 = tm;
+                    }
+                    if (fabsf(u2f(s_last)) > 1.f) t_solve = raw_t0;  // MI1:430-433
+                }
+            } else if (type == T_LINE) {  // MI1:379-385
+                float a = __fsub_rn(c1, c0);
+                a = (a != 0.0f) ? __fdiv_rn(1.0f, a) : 0.0f;
+                float v = __fmul_rn(__fsub_rn(cst, c0), a);
+                v = (v < t_min) ? t_min : v;        // GLSL max(x,y) = x<y ? y : x
+                t_solve = (t1_ms < v) ? t1_ms : v;  // GLSL min(x,y) = y<x ? y : x
+            } else if (type == T_QUADRIC || type == T_ARC) {
+                // TODO arms in the reference: t_solve stays 0
+            } else {  // any other type value: interpolateGeneralCurve returns 0 (MI1:81-83,144)
+                t_solve = t_min;
+                if (0.0f != cst) {
+                    float t0 = t_min;
+                    for (int j = 0; j < CUBIC_ITERATION_NUMBER; ++j) {  // vtm - c == vt0 - c: t0 always moves
+                        const float tm = __fmul_rn(__fadd_rn(t0, t1_ms), 0.5f);
+                        t_solve = tm; t0 = tm;
+                    }
+                    if (fabsf(__fsub_rn(0.0f, cst)) > 1.f) t_solve = t_min;
+                }
+            }
+            WALK_FINISH_STEP(t_solve);
+            pending = false;
         }
     }
+#undef WALK_FINISH_STEP
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -16,9 +16,22 @@
 
 namespace slpr {
 
-constexpr int RS_THREADS = 384;
+#ifndef SLPR_RS_THREADS
+#define SLPR_RS_THREADS 384
+#endif
+#ifndef SLPR_RS_ITEMS
+#define SLPR_RS_ITEMS 16
+#endif
+#ifndef SLPR_RS_BLOCKS
+#define SLPR_RS_BLOCKS 2
+#endif
+#ifndef SLPR_RS_LATE_VALUES
+#define SLPR_RS_LATE_VALUES 1
+#endif
+constexpr int RS_THREADS = SLPR_RS_THREADS;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_ITEMS = 16;
+constexpr int RS_ITEMS = SLPR_RS_ITEMS;
+constexpr int RS_BLOCKS_PER_SM = SLPR_RS_BLOCKS;
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 6144 pairs per tile
 constexpr int RS_BINS = 256;
 constexpr int RS_MAX_PASSES = 8;
@@ -120,7 +133,7 @@ __global__ void __launch_bounds__(RS_BINS) k_radix_hist_scan(uint32_t *__restric
 // ------------------------------------------------------------------------------------------------
 // One onesweep pass over digit bits [shift, shift+8).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(RS_THREADS, 2) k_onesweep(const uint64_t *__restrict__ keys_in,
+__global__ void __launch_bounds__(RS_THREADS, RS_BLOCKS_PER_SM) k_onesweep(const uint64_t *__restrict__ keys_in,
                                                             const uint32_t *__restrict__ vals_in,
                                                             uint64_t *__restrict__ keys_out,
                                                             uint32_t *__restrict__ vals_out, SortCount cnt, int pass,
@@ -172,6 +185,7 @@ __global__ void __launch_bounds__(RS_THREADS, 2) k_onesweep(const uint64_t *__re
             rank[i] = (uint16_t)(before + __popc(peers & lt));
             __syncwarp();
         }
+#if !SLPR_RS_LATE_VALUES
         // values are loaded now so that their latency overlaps the histogram scan and the look-back
         uint32_t val[RS_ITEMS];
 #pragma unroll
@@ -179,6 +193,7 @@ __global__ void __launch_bounds__(RS_THREADS, 2) k_onesweep(const uint64_t *__re
             const int o = wbase + i * 32 + lane;
             val[i] = (o < valid) ? vals_in[base + o] : 0u;
         }
+#endif
         __syncthreads();
 
         // ---- per digit: exclusive scan over warps (in place), tile count, look-back
@@ -228,6 +243,14 @@ __global__ void __launch_bounds__(RS_THREADS, 2) k_onesweep(const uint64_t *__re
         __syncthreads();
 
         // ---- scatter into shared memory in digit order
+#if SLPR_RS_LATE_VALUES
+        uint32_t val[RS_ITEMS];
+#pragma unroll
+        for (int i = 0; i < RS_ITEMS; ++i) {
+            const int o = wbase + i * 32 + lane;
+            val[i] = (o < valid) ? vals_in[base + o] : 0u;
+        }
+#endif
 #pragma unroll
         for (int i = 0; i < RS_ITEMS; ++i) {
             const uint32_t d = (uint32_t)(key[i] >> shift) & 0xFFu;

@@ -16,8 +16,9 @@
 namespace slpr {
 
 constexpr int SCAN_THREADS = 256;
-constexpr int SCAN_VECS = 4;
-constexpr int SCAN_TILE = SCAN_THREADS * SCAN_VECS * 4;
+constexpr int SCAN_VECS_MAX = 4;                              // int4 vectors per thread (Op::VECS <= this)
+constexpr int SCAN_TILE_MIN = SCAN_THREADS * 4;               // smallest tile any op may use (VECS = 1)
+template <class Op> constexpr int scan_tile() { return SCAN_THREADS * Op::VECS * 4; }
 
 #define ST_MASK ((1ull << 62) - 1)
 #define ST_AGG (1ull << 62)
@@ -43,8 +44,11 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
 }
 
 template <class Op>
-__global__ void __launch_bounds__(SCAN_THREADS) k_lookback_scan(Op op, ScanTemp tmp) {
-    __shared__ unsigned long long s_part[SCAN_VECS * (SCAN_THREADS / 32)];  // 32 partials
+__global__ void __launch_bounds__(SCAN_THREADS, Op::MIN_BLOCKS) k_lookback_scan(Op op, ScanTemp tmp) {
+    constexpr int SCAN_VECS = Op::VECS;
+    constexpr int SCAN_TILE = SCAN_THREADS * SCAN_VECS * 4;
+    static_assert(SCAN_VECS >= 1 && SCAN_VECS <= SCAN_VECS_MAX, "partials must fit one warp");
+    __shared__ unsigned long long s_part[32];  // (vector, warp) partials, scanned by warp 0
     __shared__ unsigned long long s_prefix;
     __shared__ long long s_tile;
 
@@ -76,7 +80,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_lookback_scan(Op op, ScanTemp 
         }
         __syncthreads();
         if (warp == 0) {
-            const unsigned long long p = s_part[lane];
+            const unsigned long long p = (lane < SCAN_VECS * (SCAN_THREADS / 32)) ? s_part[lane] : 0ull;
             const unsigned long long pi = warp_incl_scan_u64(p);
             s_part[lane] = pi - p;  // exclusive offset of (vector, warp) inside the tile
             const unsigned long long tile_total = __shfl_sync(0xFFFFFFFFu, pi, 31);
@@ -127,6 +131,7 @@ struct NoAux {};
 // ------------------------------------------------------------------------------------------------
 struct ScanI32Op {
     using Aux = NoAux;
+    static constexpr int VECS = 4, MIN_BLOCKS = 4;
     const int *in;
     int *out;
     long long n_static;

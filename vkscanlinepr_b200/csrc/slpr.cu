@@ -97,7 +97,7 @@ struct slpr_ctx {
     unsigned char *d_temp = nullptr;
     size_t temp_bytes = 0, temp_small_bytes = 0;
     FrameCounters *d_ctr = nullptr;
-    int *d_tickets = nullptr;  // 3 scan tickets + RS_MAX_PASSES sort tickets
+    int *d_tickets = nullptr;  // 3 scan tickets + RS_MAX_PASSES sort tickets + 1 curve-walk work counter
     uint32_t *d_hist = nullptr;
     unsigned long long *d_status[3] = {nullptr, nullptr, nullptr};
     uint32_t *d_lookback = nullptr;
@@ -170,11 +170,11 @@ static int alloc_capacity(slpr_ctx *c, int cap) {
         CU(cudaMalloc(&c->t_scan3, (2 * n + 1) * 4));
     }
     // per-frame zeroed temp block
-    const size_t scan_tiles[3] = {(size_t)c->nc / SCAN_TILE + 2, n / SCAN_TILE + 2, n / SCAN_TILE + 2};
+    const size_t scan_tiles[3] = {(size_t)c->nc / SCAN_TILE_MIN + 2, n / SCAN_TILE_MIN + 2, n / SCAN_TILE_MIN + 2};
     c->sort_tiles_cap = (int)(n / RS_TILE + 2);
     size_t off = 0;
     const size_t o_ctr = off; off += align_up(sizeof(FrameCounters), 256);
-    const size_t o_tick = off; off += align_up((3 + RS_MAX_PASSES) * sizeof(int), 256);
+    const size_t o_tick = off; off += align_up((3 + RS_MAX_PASSES + 1) * sizeof(int), 256);
     const size_t o_hist = off; off += align_up((size_t)RS_MAX_PASSES * RS_BINS * 4, 256);
     size_t o_status[3];
     for (int i = 0; i < 3; ++i) { o_status[i] = off; off += align_up(scan_tiles[i] * 8, 256); }
@@ -372,8 +372,9 @@ static int enqueue_frame(slpr_ctx *c, cudaStream_t s, bool timed, int &launches)
     if (rc) return rc;
     const bool taps = (c->flags & SLPR_FLAG_TAPS) != 0;
     const int wide = c->num_sms * 8;
-    k_intersect<<<grid_for(c, c->nc, 128, 16), 128, 0, s>>>(c->d_params, c->nc, c->d_ctype, c->d_cpm, c->d_tpos, c->d_cut,
-                                                             c->d_offset, c->d_ctr, c->cap, c->d_inter);
+    k_intersect<<<grid_for(c, ((long long)c->nc + 3) / 4, WALK_THREADS, 8), WALK_THREADS, 0, s>>>(
+        c->d_params, c->nc, c->d_ctype, c->d_cpm, c->d_tpos, c->d_cut, c->d_offset, c->d_ctr, c->cap, c->d_inter,
+        c->d_tickets + 3 + RS_MAX_PASSES);
     ++launches;
     if (timed) CU(cudaEventRecord(c->ev[4], s));
     FragTaps ft{c->t_key32, c->t_path, c->t_wind};
@@ -394,7 +395,7 @@ static int enqueue_frame(slpr_ctx *c, cudaStream_t s, bool timed, int &launches)
     if (timed) CU(cudaEventRecord(c->ev[6], s));
     int cur = 0;
     for (int p = 0; p < c->passes; ++p) {
-        k_onesweep<<<c->num_sms * 2, RS_THREADS, RS_SMEM_BYTES, s>>>(c->d_key[cur], c->d_val[cur], c->d_key[cur ^ 1],
+        k_onesweep<<<c->num_sms * RS_BLOCKS_PER_SM, RS_THREADS, RS_SMEM_BYTES, s>>>(c->d_key[cur], c->d_val[cur], c->d_key[cur ^ 1],
                                                                      c->d_val[cur ^ 1], cnt, p, 8 * p, st);
         ++launches;
         cur ^= 1;
@@ -624,7 +625,7 @@ extern "C" int slpr_scan_i32(slpr_ctx *c, const int32_t *in, int32_t *out, uint6
     if (!c || !in || !out) return fail(SLPR_ERR_INVALID, "slpr_scan_i32: null argument");
     if (n >= (1ull << 40)) return fail(SLPR_ERR_INVALID, "slpr_scan_i32: n too large");
     CU(cudaSetDevice(c->device));
-    const size_t tiles = n / SCAN_TILE + 2;
+    const size_t tiles = n / SCAN_TILE_MIN + 2;
     int rc = prim_temp(c, 256 + tiles * 8);
     if (rc) return rc;
     ScanI32Op op{in, out, (long long)n, nullptr, 0, nullptr};
@@ -655,7 +656,7 @@ extern "C" int slpr_sort_pairs(slpr_ctx *c, uint64_t *keys, uint32_t *vals, uint
     uint32_t *vb[2] = {vals, vals_tmp};
     int cur = 0;
     for (int p = 0; p < passes; ++p) {
-        k_onesweep<<<c->num_sms * 2, RS_THREADS, RS_SMEM_BYTES, c->stream>>>(kb[cur], vb[cur], kb[cur ^ 1], vb[cur ^ 1], cnt, p, 8 * p, st);
+        k_onesweep<<<c->num_sms * RS_BLOCKS_PER_SM, RS_THREADS, RS_SMEM_BYTES, c->stream>>>(kb[cur], vb[cur], kb[cur ^ 1], vb[cur ^ 1], cnt, p, 8 * p, st);
         cur ^= 1;
     }
     c->launches += 2 + passes;

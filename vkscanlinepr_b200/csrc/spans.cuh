@@ -14,6 +14,7 @@ namespace slpr {
 
 struct WindScanOp {
     using Aux = NoAux;
+    static constexpr int VECS = 4, MIN_BLOCKS = 4;
     const uint32_t *sval;  // sorted values: index | (delta+1) << 30
     int *wn;               // [nf+1] exclusive winding scan (plane 3 after scan #2)
     int *sidx_tap;         // optional: plane 1 after sort
@@ -70,6 +71,7 @@ struct SpanAux {
 
 struct SpanEmitOp {
     using Aux = SpanAux;
+    static constexpr int VECS = 2, MIN_BLOCKS = 2;  // fat per-element state: smaller tile, 2 blocks/SM
     const uint64_t *skey;  // sorted compact keys
     const int *wn;         // exclusive winding scan
     const uint32_t *fill_rule, *fill_info;
