@@ -25,8 +25,14 @@ namespace slpr {
 #ifndef SLPR_RS_BLOCKS
 #define SLPR_RS_BLOCKS 2
 #endif
-#ifndef SLPR_RS_LATE_VALUES
-#define SLPR_RS_LATE_VALUES 1
+#ifndef SLPR_RS_MATCH_INSTR
+#define SLPR_RS_MATCH_INSTR 1   /* 1: match.any instruction, 0: eight ballots (measured: about equal) */
+#endif
+#ifndef SLPR_RS_VAL_POS
+#define SLPR_RS_VAL_POS 2       /* where the values are loaded: 0 after ranking, 1 before look-back, 2 at the scatter */
+#endif
+#ifndef SLPR_RS_LB_WINDOW
+#define SLPR_RS_LB_WINDOW 4     /* predecessors polled per look-back round trip */
 #endif
 constexpr int RS_THREADS = SLPR_RS_THREADS;
 constexpr int RS_WARPS = RS_THREADS / 32;
@@ -130,6 +136,23 @@ __global__ void __launch_bounds__(RS_BINS) k_radix_hist_scan(uint32_t *__restric
     h[t] = base + s - v;
 }
 
+// Lanes of the warp whose 8-bit digit equals mine: 8 ballots + 8 LOP3 (the match.any instruction is
+// microcoded and slower for 8-bit labels).
+__device__ __forceinline__ uint32_t match_digit(uint32_t d) {
+#if SLPR_RS_MATCH_INSTR
+    return __match_any_sync(0xFFFFFFFFu, d);
+#else
+    uint32_t peers = 0xFFFFFFFFu;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+        const bool bit = (d >> b) & 1u;
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, bit);
+        peers &= bit ? m : ~m;
+    }
+    return peers;
+#endif
+}
+
 // ------------------------------------------------------------------------------------------------
 // One onesweep pass over digit bits [shift, shift+8).
 // ------------------------------------------------------------------------------------------------
@@ -177,7 +200,7 @@ __global__ void __launch_bounds__(RS_THREADS, RS_BLOCKS_PER_SM) k_onesweep(const
 #pragma unroll
         for (int i = 0; i < RS_ITEMS; ++i) {
             const uint32_t d = (uint32_t)(key[i] >> shift) & 0xFFu;
-            const uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
+            const uint32_t peers = match_digit(d);
             const int leader = __ffs(peers) - 1;
             uint32_t before = 0;
             if (lane == leader) { before = wh[d]; wh[d] = before + __popc(peers); }
@@ -185,7 +208,7 @@ __global__ void __launch_bounds__(RS_THREADS, RS_BLOCKS_PER_SM) k_onesweep(const
             rank[i] = (uint16_t)(before + __popc(peers & lt));
             __syncwarp();
         }
-#if !SLPR_RS_LATE_VALUES
+#if SLPR_RS_VAL_POS == 0
         // values are loaded now so that their latency overlaps the histogram scan and the look-back
         uint32_t val[RS_ITEMS];
 #pragma unroll
@@ -220,20 +243,38 @@ __global__ void __launch_bounds__(RS_THREADS, RS_BLOCKS_PER_SM) k_onesweep(const
             s_start[tid] = s - mine;  // warp-local exclusive; fixed below
         }
         __syncthreads();
+#if SLPR_RS_VAL_POS == 1
+        // values are fetched here: after the ranking (whose registers are dead now) and before the
+        // look-back, whose L2 round trips hide the load latency
+        uint32_t val[RS_ITEMS];
+#pragma unroll
+        for (int i = 0; i < RS_ITEMS; ++i) {
+            const int o = wbase + i * 32 + lane;
+            val[i] = (o < valid) ? vals_in[base + o] : 0u;
+        }
+#endif
         if (tid < RS_BINS) {
             uint32_t wb = 0;
             for (int w = 0; w < warp; ++w) wb += s_misc[w];
             const uint32_t start = s_start[tid] + wb;
-            // chained look-back for this digit
+            // chained look-back for this digit; SLPR_RS_LB_WINDOW predecessors are polled per round trip
             uint32_t excl = 0;
             if (tile > 0) {
                 long long t = tile - 1;
-                while (true) {
-                    uint32_t w;
-                    do { w = lookback[(size_t)t * RS_BINS + tid]; } while ((w >> 30) == 0);
-                    excl += w & LB_MASK;
-                    if ((w >> 30) == 2 || t == 0) break;
-                    --t;
+                bool done = false;
+                while (!done) {
+                    uint32_t w[SLPR_RS_LB_WINDOW];
+#pragma unroll
+                    for (int k = 0; k < SLPR_RS_LB_WINDOW; ++k)
+                        w[k] = (t - k >= 0) ? lookback[(size_t)(t - k) * RS_BINS + tid] : LB_PREFIX;
+#pragma unroll
+                    for (int k = 0; k < SLPR_RS_LB_WINDOW; ++k) {
+                        if (done) break;
+                        if ((w[k] >> 30) == 0) break;  // not published yet: poll again from here
+                        excl += w[k] & LB_MASK;
+                        --t;
+                        if ((w[k] >> 30) == 2) done = true;
+                    }
                 }
                 lookback[(size_t)tile * RS_BINS + tid] = LB_PREFIX | ((excl + count) & LB_MASK);
             }
@@ -243,7 +284,7 @@ __global__ void __launch_bounds__(RS_THREADS, RS_BLOCKS_PER_SM) k_onesweep(const
         __syncthreads();
 
         // ---- scatter into shared memory in digit order
-#if SLPR_RS_LATE_VALUES
+#if SLPR_RS_VAL_POS == 2
         uint32_t val[RS_ITEMS];
 #pragma unroll
         for (int i = 0; i < RS_ITEMS; ++i) {
