@@ -73,12 +73,12 @@ enum {
     SLPR_STAGE_TRANSFORM = 0,   /* k_transform                                  */
     SLPR_STAGE_MONOTONIZE = 1,  /* k_monotonize_count                           */
     SLPR_STAGE_SCAN1 = 2,       /* look-back scan of the curve counts           */
-    SLPR_STAGE_INTERSECT = 3,   /* k_intersect                                  */
-    SLPR_STAGE_FRAGMENT = 4,    /* k_gen_fragment                               */
+    SLPR_STAGE_INTERSECT = 3,   /* k_intersect: intersection walk + fragment generation */
+    SLPR_STAGE_FRAGMENT = 4,    /* (folded into INTERSECT; only the segment-table tap) */
     SLPR_STAGE_SORT_HIST = 5,   /* k_radix_hist + k_radix_hist_scan             */
     SLPR_STAGE_SORT_PASSES = 6, /* all k_onesweep launches (slpr_sort_info: passes) */
-    SLPR_STAGE_WIND_SCAN = 7,   /* look-back scan of the winding deltas         */
-    SLPR_STAGE_SPAN_EMIT = 8,   /* mark + flag scan + record emit               */
+    SLPR_STAGE_WIND_SCAN = 7,   /* (folded into SPAN_EMIT: always ~0)           */
+    SLPR_STAGE_SPAN_EMIT = 8,   /* k_spans: winding scan + mark + flag scan + record emit */
     SLPR_STAGE_FILL_CELLS = 9,  /* k_fill_cells                                 */
     SLPR_STAGE_RESOLVE = 10,    /* k_resolve                                    */
     SLPR_STAGE_COUNT = 11

@@ -24,6 +24,7 @@
 #include "raster.cuh"
 #include "scan.cuh"
 #include "spans.cuh"
+#include "walk.cuh"
 
 using namespace slpr;
 
@@ -64,6 +65,7 @@ struct slpr_ctx {
     uint32_t W = 0, H = 0, flags = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     int num_sms = NUM_SMS_B200;
+    int walk_blocks_per_sm = 7, span_blocks_per_sm = 4;  // resident blocks of the persistent kernels (occupancy API)
 
     // scene (slpr_load_scene)
     bool scene_loaded = false;
@@ -75,6 +77,9 @@ struct slpr_ctx {
     int *d_pvis = nullptr;
     float *d_cut = nullptr;
     int *d_count = nullptr, *d_offset = nullptr, *d_seg_tap = nullptr;
+    uint32_t *d_slots = nullptr;       // [5*nc] (length bucket << 26 | rank) of every monotone piece
+    PieceRec *d_pieces = nullptr;      // [5*nc] piece records in length-sorted order
+    float2 *d_boundary = nullptr;      // [5*nc] first / last emitted parameter of every piece
 
     // frame state
     FrameParams hp{};
@@ -99,6 +104,7 @@ struct slpr_ctx {
     FrameCounters *d_ctr = nullptr;
     int *d_tickets = nullptr;  // 3 scan tickets + RS_MAX_PASSES sort tickets + 1 curve-walk work counter
     uint32_t *d_hist = nullptr;
+    uint32_t *d_bucket_hist = nullptr;  // [WALK_BUCKETS] pieces per length bucket
     unsigned long long *d_status[3] = {nullptr, nullptr, nullptr};
     uint32_t *d_lookback = nullptr;
     int sort_tiles_cap = 0;
@@ -144,6 +150,8 @@ static void free_scene(slpr_ctx *c) {
     cudaFree(c->d_pos); cudaFree(c->d_pos_path); cudaFree(c->d_cpm); cudaFree(c->d_ctype); cudaFree(c->d_cpath);
     cudaFree(c->d_frule); cudaFree(c->d_finfo); cudaFree(c->d_tpos); cudaFree(c->d_pvis); cudaFree(c->d_cut);
     cudaFree(c->d_count); cudaFree(c->d_offset); cudaFree(c->d_seg_tap);
+    cudaFree(c->d_slots); cudaFree(c->d_pieces); cudaFree(c->d_boundary);
+    c->d_slots = nullptr; c->d_pieces = nullptr; c->d_boundary = nullptr;
     c->d_pos = nullptr; c->d_pos_path = c->d_cpm = c->d_ctype = c->d_cpath = c->d_frule = c->d_finfo = nullptr;
     c->d_tpos = nullptr; c->d_pvis = nullptr; c->d_cut = nullptr; c->d_count = c->d_offset = c->d_seg_tap = nullptr;
     c->scene_loaded = false;
@@ -153,14 +161,14 @@ static int alloc_capacity(slpr_ctx *c, int cap) {
     free_capacity(c);
     cap = (int)align_up((size_t)std::max(cap, 1 << 14), 4096);
     const size_t n = (size_t)cap;
-    CU(cudaMalloc(&c->d_inter, (n + 1) * sizeof(int2)));
     for (int i = 0; i < 2; ++i) {
         CU(cudaMalloc(&c->d_key[i], n * 8));
         CU(cudaMalloc(&c->d_val[i], n * 4));
     }
-    CU(cudaMalloc(&c->d_wn, (n + 4) * 4));
     CU(cudaMalloc(&c->d_rec, (2 * n + 1) * sizeof(int4)));
     if (c->flags & SLPR_FLAG_TAPS) {
+        CU(cudaMalloc(&c->d_wn, (n + 4) * 4));
+        CU(cudaMalloc(&c->d_inter, (n + 1) * sizeof(int2)));
         CU(cudaMalloc(&c->t_key32, (n + 1) * 4));
         CU(cudaMalloc(&c->t_path, n * 4));
         CU(cudaMalloc(&c->t_wind, n * 4));
@@ -175,6 +183,7 @@ static int alloc_capacity(slpr_ctx *c, int cap) {
     size_t off = 0;
     const size_t o_ctr = off; off += align_up(sizeof(FrameCounters), 256);
     const size_t o_tick = off; off += align_up((3 + RS_MAX_PASSES + 1) * sizeof(int), 256);
+    const size_t o_bhist = off; off += align_up(WALK_BUCKETS * sizeof(uint32_t), 256);
     const size_t o_hist = off; off += align_up((size_t)RS_MAX_PASSES * RS_BINS * 4, 256);
     size_t o_status[3];
     for (int i = 0; i < 3; ++i) { o_status[i] = off; off += align_up(scan_tiles[i] * 8, 256); }
@@ -185,6 +194,7 @@ static int alloc_capacity(slpr_ctx *c, int cap) {
     c->d_ctr = reinterpret_cast<FrameCounters *>(c->d_temp + o_ctr);
     c->d_tickets = reinterpret_cast<int *>(c->d_temp + o_tick);
     c->d_hist = reinterpret_cast<uint32_t *>(c->d_temp + o_hist);
+    c->d_bucket_hist = reinterpret_cast<uint32_t *>(c->d_temp + o_bhist);
     for (int i = 0; i < 3; ++i) c->d_status[i] = reinterpret_cast<unsigned long long *>(c->d_temp + o_status[i]);
     c->d_lookback = reinterpret_cast<uint32_t *>(c->d_temp + o_lb);
     c->cap = cap;
@@ -224,6 +234,8 @@ extern "C" slpr_ctx *slpr_create(int device, uint32_t width, uint32_t height, ui
     ok = ok && cudaMalloc(&c->d_fb, c->fb_stride * height) == cudaSuccess;
     for (auto &ev : c->ev) ok = ok && cudaEventCreate(&ev) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_onesweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM_BYTES) == cudaSuccess;
+    ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->walk_blocks_per_sm, k_walk, WALK_THREADS, 0) == cudaSuccess;
+    ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->span_blocks_per_sm, k_spans, SP_THREADS, 0) == cudaSuccess;
     if (!ok) {
         fail(SLPR_ERR_CUDA, "slpr_create: device setup failed: %s", cudaGetErrorString(cudaGetLastError()));
         slpr_destroy(c);
@@ -301,6 +313,9 @@ extern "C" int slpr_load_scene(slpr_ctx *c, const float *pos_xy, const uint32_t 
     CU(cudaMalloc(&c->d_cut, std::max<size_t>(n_curves, 1) * 5 * 4));
     CU(cudaMalloc(&c->d_count, ((size_t)n_curves + 4) * 4));
     CU(cudaMalloc(&c->d_offset, ((size_t)n_curves + 4) * 4));
+    CU(cudaMalloc(&c->d_slots, std::max<size_t>(n_curves, 1) * 5 * 4));
+    CU(cudaMalloc(&c->d_pieces, std::max<size_t>(n_curves, 1) * 5 * sizeof(PieceRec)));
+    CU(cudaMalloc(&c->d_boundary, std::max<size_t>(n_curves, 1) * 5 * sizeof(float2)));
     if (c->flags & SLPR_FLAG_TAPS) CU(cudaMalloc(&c->d_seg_tap, ((size_t)n_paths + 1) * 4));
     // compact key geometry: x cell in [0,(W'+4)/2], row rank in [0,ny], path in [0,P)
     const int Wp = (int)(c->W & ~1u);
@@ -356,7 +371,8 @@ static int enqueue_count_phase(slpr_ctx *c, cudaStream_t s, bool timed, int &lau
     ++launches;
     if (timed) CU(cudaEventRecord(c->ev[1], s));
     k_monotonize_count<<<grid_for(c, c->nc, 256, 8), 256, 0, s>>>(c->d_params, c->nc, c->d_ctype, c->d_cpm, c->d_cpath,
-                                                                   c->d_tpos, c->d_pvis, c->d_cut, c->d_count);
+                                                                   c->d_tpos, c->d_pvis, c->d_cut, c->d_count, c->d_slots,
+                                                                   c->d_bucket_hist);
     ++launches;
     if (timed) CU(cudaEventRecord(c->ev[2], s));
     ScanI32Op op1{c->d_count, c->d_offset, (long long)c->nc, &c->d_ctr->n_fragments, c->cap, &c->d_ctr->overflow};
@@ -372,15 +388,19 @@ static int enqueue_frame(slpr_ctx *c, cudaStream_t s, bool timed, int &launches)
     if (rc) return rc;
     const bool taps = (c->flags & SLPR_FLAG_TAPS) != 0;
     const int wide = c->num_sms * 8;
-    k_intersect<<<grid_for(c, ((long long)c->nc + 3) / 4, WALK_THREADS, 8), WALK_THREADS, 0, s>>>(
-        c->d_params, c->nc, c->d_ctype, c->d_cpm, c->d_tpos, c->d_cut, c->d_offset, c->d_ctr, c->cap, c->d_inter,
-        c->d_tickets + 3 + RS_MAX_PASSES);
-    ++launches;
-    if (timed) CU(cudaEventRecord(c->ev[4], s));
     FragTaps ft{c->t_key32, c->t_path, c->t_wind};
-    k_gen_fragment<<<wide, 256, 0, s>>>(c->d_params, c->d_ctr, c->cap, c->L, c->d_inter, c->d_cpath, c->d_cpm, c->d_ctype,
-                                        c->d_tpos, c->d_key[0], c->d_val[0], ft);
-    ++launches;
+    k_piece_emit<<<grid_for(c, c->nc, 256, 8), 256, 0, s>>>(c->d_params, c->nc, c->d_ctype, c->d_cpm, c->d_tpos, c->d_cut,
+                                                             c->d_offset, c->d_slots, c->d_ctr, c->cap, c->d_bucket_hist,
+                                                             c->d_pieces);
+    k_walk<<<c->num_sms * std::max(1, c->walk_blocks_per_sm), WALK_THREADS, 0, s>>>(
+        c->d_params, c->d_pieces, c->d_cpath, c->d_ctr, c->cap, WalkTemp{c->d_bucket_hist, c->d_tickets + 3 + RS_MAX_PASSES},
+        c->L, c->d_key[0], c->d_val[0], ft, c->d_inter, c->d_boundary);
+    k_piece_close<<<grid_for(c, c->nc, 256, 8), 256, 0, s>>>(c->d_params, c->nc, c->d_ctype, c->d_cpm, c->d_cpath, c->d_tpos,
+                                                              c->d_cut, c->d_offset, c->d_slots, c->d_ctr, c->cap,
+                                                              c->d_bucket_hist, c->d_pieces, c->d_boundary, c->L, c->d_key[0],
+                                                              c->d_val[0], ft);
+    launches += 3;
+    if (timed) CU(cudaEventRecord(c->ev[4], s));
     if (taps) {
         k_segments_tap<<<grid_for(c, (long long)c->nc + 1, 256, 8), 256, 0, s>>>(c->nc, c->P, c->d_cpath, c->d_offset, c->d_seg_tap);
         ++launches;
@@ -402,14 +422,13 @@ static int enqueue_frame(slpr_ctx *c, cudaStream_t s, bool timed, int &launches)
     }
     c->sorted_buf = cur;
     if (timed) CU(cudaEventRecord(c->ev[7], s));
-    // ---- winding scan, then mark + scan + emit
-    WindScanOp opA{c->d_val[cur], c->d_wn, c->t_sidx, c->d_ctr, c->cap};
-    k_lookback_scan<WindScanOp><<<wide, SCAN_THREADS, 0, s>>>(opA, ScanTemp{c->d_status[1], c->d_tickets + 1});
+    // ---- winding scan + mark + flag scan + emit: one kernel, two chained look-backs
+    SpanTaps stp{c->d_wn, c->t_sidx, c->t_skey32, c->t_flags, c->t_scan3};
+    SpanTemp stmp{c->d_status[1], c->d_status[2], c->d_tickets + 1};
     if (timed) CU(cudaEventRecord(c->ev[8], s));
-    SpanEmitOp opB{c->d_key[cur], c->d_wn, c->d_frule, c->d_finfo, c->d_rec, c->d_ctr, c->L, (int)c->W, (int)c->H, c->cap,
-                   SpanTaps{c->t_skey32, c->t_flags, c->t_scan3}};
-    k_lookback_scan<SpanEmitOp><<<wide, SCAN_THREADS, 0, s>>>(opB, ScanTemp{c->d_status[2], c->d_tickets + 2});
-    launches += 2;
+    k_spans<<<c->num_sms * std::max(1, c->span_blocks_per_sm), SP_THREADS, 0, s>>>(c->d_key[cur], c->d_val[cur], c->d_frule, c->d_finfo, c->d_rec, c->d_ctr,
+                                                  c->L, (int)c->W, (int)c->H, c->cap, stp, stmp);
+    ++launches;
     if (taps) {
         k_scan3_fixup<<<wide, 256, 0, s>>>(c->d_ctr, c->cap, c->t_scan3);
         ++launches;
@@ -569,13 +588,13 @@ extern "C" int slpr_debug_copy(slpr_ctx *c, int which, void *dst, size_t bytes) 
         case SLPR_TAP_CUT_CACHE: src = c->d_cut; avail = (size_t)c->nc * 20; break;
         case SLPR_TAP_CURVE_COUNT: src = c->d_count; avail = (size_t)c->nc * 4; break;
         case SLPR_TAP_CURVE_OFFSET: src = c->d_offset; avail = ((size_t)c->nc + 1) * 4; break;
-        case SLPR_TAP_INTERSECTION: src = c->d_inter; avail = nf * 8; break;
+        case SLPR_TAP_INTERSECTION: src = c->d_inter; avail = nf * 8; tap = true; break;
         case SLPR_TAP_KEY: src = c->t_key32; avail = (nf + 1) * 4; tap = true; break;
         case SLPR_TAP_PATH: src = c->t_path; avail = nf * 4; tap = true; break;
         case SLPR_TAP_WINDING: src = c->t_wind; avail = nf * 4; tap = true; break;
         case SLPR_TAP_SORTED_KEY: src = c->t_skey32; avail = nf * 4; tap = true; break;
         case SLPR_TAP_SORTED_INDEX: src = c->t_sidx; avail = nf * 4; tap = true; break;
-        case SLPR_TAP_WINDING_SCAN: src = c->d_wn; avail = (nf + 1) * 4; break;
+        case SLPR_TAP_WINDING_SCAN: src = c->d_wn; avail = (nf + 1) * 4; tap = true; break;
         case SLPR_TAP_FLAGS: src = c->t_flags; avail = 2 * nf * 4; tap = true; break;
         case SLPR_TAP_FLAG_SCAN: src = c->t_scan3; avail = (2 * nf + 1) * 4; tap = true; break;
         case SLPR_TAP_RECORDS: src = c->d_rec; avail = no * 16; break;

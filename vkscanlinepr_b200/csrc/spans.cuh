@@ -1,184 +1,298 @@
-// spans.cuh — everything after the sort, as two streaming look-back passes:
-//   pass A  shuffle_fragment.comp:17-27 + scan #2 (SR.cpp:479-506): the winding delta travels in the
-//           two top bits of the sorted value, so the gather disappears; the scan is global and
-//           unsegmented exactly like the reference's.
-//   pass B  mark_merged_fragment_and_span.comp:22-94 + scan #3 (SR.cpp:545-573) +
-//           gen_merged_fragment_and_span.comp:33-103: flags are computed on the fly from the sorted
-//           keys and the winding scan, both flag counts are scanned in one 2x31-bit packed value,
-//           and the draw records are written straight from the scan's store step.
+// spans.cuh — everything after the sort in ONE streaming kernel with two chained decoupled
+// look-backs per tile:
+//   chain W  shuffle_fragment.comp:17-27 + scan #2 (SR.cpp:479-506): the winding delta travels in the
+//            two top bits of the sorted value, so the gather disappears; the prefix sum is global and
+//            unsegmented exactly like the reference's;
+//   chain F  mark_merged_fragment_and_span.comp:22-94 + scan #3 (SR.cpp:545-573) +
+//            gen_merged_fragment_and_span.comp:33-103: the flags need the global winding prefix, so
+//            their tile aggregate is published after chain W resolves; both flag counts travel in one
+//            2x31-bit word and the draw records are written straight from the tile.
+// A tile is 512 threads x 8 consecutive fragments (128-bit loads of 2 keys / 4 values); tiles are
+// ticketed for forward progress. Nothing but the draw records (16 B each) is written in the fast
+// path; the reference planes (winding scan, flags, flag scan, sorted key/index) only with taps.
 #pragma once
 #include "geom.cuh"
 #include "scan.cuh"
 
 namespace slpr {
 
-struct WindScanOp {
-    using Aux = NoAux;
-    static constexpr int VECS = 4, MIN_BLOCKS = 4;
-    const uint32_t *sval;  // sorted values: index | (delta+1) << 30
-    int *wn;               // [nf+1] exclusive winding scan (plane 3 after scan #2)
-    int *sidx_tap;         // optional: plane 1 after sort
-    FrameCounters *ctr;
-    int capacity;
-    __device__ long long count() const {
-        const int nf = ctr->n_fragments;
-        return nf > capacity ? -1 : nf;
-    }
-    __device__ void load(long long i, long long n, unsigned long long x[4], Aux &) const {
-        uint32_t v[4];
-        if (i + 3 < n) {
-            const int4 q = ld_stream(reinterpret_cast<const int4 *>(sval + i));
-            v[0] = (uint32_t)q.x; v[1] = (uint32_t)q.y; v[2] = (uint32_t)q.z; v[3] = (uint32_t)q.w;
-        } else {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) v[k] = (i + k < n) ? sval[i + k] : (1u << 30);
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) x[k] = (uint32_t)((int)(v[k] >> 30) - 1);  // zero-extended int32 delta
-        if (sidx_tap) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (i + k < n) sidx_tap[i + k] = (int)(v[k] & 0x3FFFFFFFu);
-        }
-    }
-    __device__ void store(long long i, long long n, const unsigned long long e[4], const unsigned long long *,
-                          const Aux &) const {
-        if (i + 3 < n) {
-            st_stream(reinterpret_cast<int4 *>(wn + i), make_int4((int)e[0], (int)e[1], (int)e[2], (int)e[3]));
-        } else {
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (i + k < n) wn[i + k] = (int)e[k];
-        }
-    }
-    __device__ void finish(long long n, unsigned long long total) const {
-        wn[n] = (int)total;
-        ctr->wn_total = (int)total;
-    }
-};
+constexpr int SP_THREADS = 512;
+constexpr int SP_ITEMS = 8;
+constexpr int SP_BLOCKS = 2;
+constexpr int SP_LOOK = 4;  // tile states polled per lane per look-back round trip (window = 32 * SP_LOOK tiles)
+constexpr int SP_TILE = SP_THREADS * SP_ITEMS;
 
 struct SpanTaps {
+    int *wn;      // [nf+1] plane 3 after shuffle + scan #2
+    int *sidx;    // plane 1 after sort
     int *skey32;  // plane 0 after sort
     int *flags;   // [2*nf] = [frag | span]                     (MARK:92-93)
     int *scan3;   // [2*nf+1]; second half needs + n_out_frag   (k_scan3_fixup)
 };
 
-struct SpanAux {
-    uint32_t xy[4];     // per element: cell x (low 16) | row (high 16), only meaningful when flagged
-    uint32_t xprev[4];  // per element: previous fragment's cell x + 2, clamped at 0 (span start)
-    uint32_t path[4];
+struct SpanTemp {
+    unsigned long long *status_w;  // chain W tile states (zeroed per frame)
+    unsigned long long *status_f;  // chain F tile states
+    int *ticket;
 };
 
-struct SpanEmitOp {
-    using Aux = SpanAux;
-    static constexpr int VECS = 2, MIN_BLOCKS = 2;  // fat per-element state: smaller tile, 2 blocks/SM
-    const uint64_t *skey;  // sorted compact keys
-    const int *wn;         // exclusive winding scan
-    const uint32_t *fill_rule, *fill_info;
-    int4 *records;         // output_buf (GEN:77,102)
-    FrameCounters *ctr;
-    KeyLayout L;
-    int width, height;
-    int capacity;
-    SpanTaps taps;
-
-    __device__ long long count() const {
-        const int nf = ctr->n_fragments;
-        return nf > capacity ? -1 : nf;
+// One decoupled look-back by a full warp: publishes this tile's aggregate, returns the exclusive
+// prefix of all earlier tiles (in every lane) and publishes the inclusive prefix. The chain of
+// tiles ripples at (window tiles) per L2 round trip, so the window is 32 * SP_LOOK = 128 tiles:
+// lane l polls tiles look-4l .. look-4l-3 with four independent loads per round trip.
+__device__ __forceinline__ unsigned long long warp_lookback(volatile unsigned long long *status, long long tile,
+                                                           unsigned long long tile_total, int lane) {
+    if (lane == 0) status[tile] = ((tile == 0) ? ST_PREFIX : ST_AGG) | (tile_total & ST_MASK);
+    unsigned long long excl = 0;
+    if (tile > 0) {
+        long long look = tile - 1;
+        while (true) {
+            const long long first_idx = look - (long long)lane * SP_LOOK;
+            unsigned long long w[SP_LOOK];
+            bool empty;
+            do {
+                empty = false;
+#pragma unroll
+                for (int q = 0; q < SP_LOOK; ++q) {
+                    const long long idx = first_idx - q;
+                    w[q] = (idx >= 0) ? status[idx] : ST_PREFIX;
+                    empty |= (w[q] >> 62) == 0;
+                }
+            } while (__any_sync(0xFFFFFFFFu, empty));
+            // this lane's partial: nearest -> farthest, up to and including its first inclusive prefix
+            unsigned long long part = 0;
+            bool has_prefix = false;
+#pragma unroll
+            for (int q = 0; q < SP_LOOK; ++q) {
+                if (!has_prefix) {
+                    part += w[q] & ST_MASK;
+                    has_prefix = (w[q] >> 62) == 2;
+                }
+            }
+            const uint32_t pm = __ballot_sync(0xFFFFFFFFu, has_prefix);
+            const int first = pm ? (__ffs(pm) - 1) : 32;
+            excl += warp_sum_u64((lane <= first) ? part : 0ull);
+            if (pm) break;
+            look -= 32 * SP_LOOK;
+        }
+        if (lane == 0) status[tile] = ST_PREFIX | ((excl + tile_total) & ST_MASK);
     }
+    return excl;
+}
 
-    __device__ __forceinline__ void decode(uint64_t k, uint32_t &path, int &x, int &y, uint32_t &yk) const {
-        const uint32_t xk = (uint32_t)(k & ((1ull << L.bits_x) - 1));
-        yk = (uint32_t)((k >> L.bits_x) & ((1ull << L.bits_y) - 1));
-        path = (uint32_t)(k >> (L.bits_x + L.bits_y));
-        if (yk == (uint32_t)(L.ny - 1)) { x = 0x7FFF; y = 0x7FFF; }  // invalid key decodes to (32767, 32767), MARK:41-42
-        else { x = (int)xk * 2 - FRAG_SIZE; y = (yk == (uint32_t)L.ny) ? 0 : (int)(yk + 1) * 2; }
-    }
+struct KeyFields {
+    uint32_t path;
+    int x, y;
+};
 
-    __device__ void load(long long i, long long n, unsigned long long x[4], Aux &a) const {
-        uint64_t k[5];  // k[0] = key[i-1]
-        k[0] = (i > 0 && i - 1 < n) ? skey[i - 1] : 0ull;
-        int w[4];
-        if (i + 3 < n) {
-            const int4 q0 = ld_stream(reinterpret_cast<const int4 *>(skey + i));
-            const int4 q1 = ld_stream(reinterpret_cast<const int4 *>(skey + i + 2));
-            k[1] = ((uint64_t)(uint32_t)q0.y << 32) | (uint32_t)q0.x;
-            k[2] = ((uint64_t)(uint32_t)q0.w << 32) | (uint32_t)q0.z;
-            k[3] = ((uint64_t)(uint32_t)q1.y << 32) | (uint32_t)q1.x;
-            k[4] = ((uint64_t)(uint32_t)q1.w << 32) | (uint32_t)q1.z;
-            const int4 qw = ld_stream(reinterpret_cast<const int4 *>(wn + i));
-            w[0] = qw.x; w[1] = qw.y; w[2] = qw.z; w[3] = qw.w;
+__device__ __forceinline__ KeyFields decode_key(const KeyLayout &L, uint64_t k) {
+    KeyFields f;
+    const uint32_t xk = (uint32_t)(k & ((1ull << L.bits_x) - 1));
+    const uint32_t yk = (uint32_t)((k >> L.bits_x) & ((1ull << L.bits_y) - 1));
+    f.path = (uint32_t)(k >> (L.bits_x + L.bits_y));
+    if (yk == (uint32_t)(L.ny - 1)) { f.x = 0x7FFF; f.y = 0x7FFF; }  // the invalid key decodes to (32767, 32767), MARK:41-42
+    else { f.x = (int)xk * 2 - FRAG_SIZE; f.y = (yk == (uint32_t)L.ny) ? 0 : (int)(yk + 1) * 2; }
+    return f;
+}
+
+__global__ void __launch_bounds__(SP_THREADS, SP_BLOCKS) k_spans(const uint64_t *__restrict__ skey,
+                                                         const uint32_t *__restrict__ sval,
+                                                         const uint32_t *__restrict__ fill_rule,
+                                                         const uint32_t *__restrict__ fill_info,
+                                                         int4 *__restrict__ records, FrameCounters *__restrict__ ctr,
+                                                         KeyLayout L, int width, int height, int capacity, SpanTaps taps,
+                                                         SpanTemp tmp) {
+    __shared__ uint32_t s_warp[SP_THREADS / 32];
+    __shared__ unsigned long long s_prefix;
+    __shared__ long long s_tile;
+    const int nf = ctr->n_fragments;
+    if (nf > capacity) return;
+    const long long n = nf;
+    const long long ntiles = (n == 0) ? 1 : (n + SP_TILE - 1) / SP_TILE;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    while (true) {
+        if (tid == 0) s_tile = (long long)atomicAdd(tmp.ticket, 1);
+        __syncthreads();
+        const long long tile = s_tile;
+        if (tile >= ntiles) break;
+        const long long i0 = tile * SP_TILE + (long long)tid * SP_ITEMS;
+
+        // ---- load 8 consecutive sorted keys and values
+        uint64_t k[SP_ITEMS + 1];  // k[0] = key of element i0-1
+        uint32_t dpack = 0;        // 8 x 2-bit (delta + 1)
+        if (i0 + SP_ITEMS <= n) {
+#pragma unroll
+            for (int j = 0; j < SP_ITEMS; j += 2) {
+                const int4 q = *reinterpret_cast<const int4 *>(skey + i0 + j);
+                k[j + 1] = ((uint64_t)(uint32_t)q.y << 32) | (uint32_t)q.x;
+                k[j + 2] = ((uint64_t)(uint32_t)q.w << 32) | (uint32_t)q.z;
+            }
+#pragma unroll
+            for (int j = 0; j < SP_ITEMS; j += 4) {
+                const int4 q = *reinterpret_cast<const int4 *>(sval + i0 + j);
+                const uint32_t v[4] = {(uint32_t)q.x, (uint32_t)q.y, (uint32_t)q.z, (uint32_t)q.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    dpack |= (v[e] >> 30) << (2 * (j + e));
+                    if (taps.sidx) taps.sidx[i0 + j + e] = (int)(v[e] & 0x3FFFFFFFu);
+                }
+            }
         } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                k[j + 1] = (i + j < n) ? skey[i + j] : 0ull;
-                w[j] = (i + j < n) ? wn[i + j] : 0;
+            for (int j = 0; j < SP_ITEMS; ++j) {
+                const bool in = i0 + j < n;
+                k[j + 1] = in ? skey[i0 + j] : 0ull;
+                const uint32_t v = in ? sval[i0 + j] : (1u << 30);
+                dpack |= (v >> 30) << (2 * j);
+                if (in && taps.sidx) taps.sidx[i0 + j] = (int)(v & 0x3FFFFFFFu);
             }
         }
-        uint32_t p0; int x0, y0; uint32_t yk0;
-        decode(k[0], p0, x0, y0, yk0);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            uint32_t p1; int x1, y1; uint32_t yk1;
-            decode(k[j + 1], p1, x1, y1, yk1);
-            uint32_t frag = 0, span = 0;
-            if (i + j < n) {
-                const bool oob = (x1 < 0 || y1 < 0 || x1 >= width || y1 >= height);  // MARK:45,69
-                if (i + j == 0) {
-                    frag = oob ? 0u : 1u;  // MARK:44-51
-                } else {
-                    frag = (!oob && (p0 != p1 || k[j] != k[j + 1])) ? 1u : 0u;  // MARK:69-77
-                    const uint32_t rule = fill_rule[p1];
-                    const bool wn_flag = ((rule == 0) && (w[j] != 0)) || ((rule == 1) && ((w[j] & 1) != 0));  // MARK:82
-                    span = (y0 == y1 && (x0 + FRAG_SIZE) < x1 && p0 == p1 && wn_flag) ? 1u : 0u;             // MARK:84
-                }
-                if (taps.flags) {
-                    taps.flags[i + j] = (int)frag;
-                    taps.flags[n + i + j] = (int)span;
-                    uint32_t pp;
-                    taps.skey32[i + j] = unpack_key32(L, k[j + 1], pp);
-                }
-            }
-            x[j] = (unsigned long long)frag | ((unsigned long long)span << 31);
-            a.xy[j] = ((uint32_t)y1 << 16) | ((uint32_t)x1 & 0xFFFFu);
-            a.xprev[j] = (uint32_t)max(0, x0 + FRAG_SIZE);  // GEN:88-92
-            a.path[j] = p1;
-            p0 = p1; x0 = x1; y0 = y1;
+        {   // key of the element before this thread's run: neighbour lane, or global for lane 0
+            const uint32_t lo = __shfl_up_sync(0xFFFFFFFFu, (uint32_t)k[SP_ITEMS], 1);
+            const uint32_t hi = __shfl_up_sync(0xFFFFFFFFu, (uint32_t)(k[SP_ITEMS] >> 32), 1);
+            k[0] = ((uint64_t)hi << 32) | lo;
+            if (lane == 0) k[0] = (i0 > 0 && i0 - 1 < n) ? skey[i0 - 1] : 0ull;
         }
-    }
 
-    __device__ void store(long long i, long long n, const unsigned long long e[4], const unsigned long long *x,
-                          const Aux &a) const {
+        // ---- chain W: exclusive prefix of the winding deltas (int32, wraps like the shader's adds)
+        int dsum = 0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (i + j >= n) break;
-            const int frag_before = (int)(e[j] & 0x7FFFFFFFu), span_before = (int)((e[j] >> 31) & 0x7FFFFFFFu);
-            const int frag = (int)(x[j] & 1u), span = (int)((x[j] >> 31) & 1u);
-            if (taps.scan3) {
-                taps.scan3[i + j] = frag_before;
-                taps.scan3[n + i + j] = span_before;  // + n_out_frag, added by k_scan3_fixup
+        for (int j = 0; j < SP_ITEMS; ++j) dsum += (int)((dpack >> (2 * j)) & 3u) - 1;
+        int wincl = dsum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(0xFFFFFFFFu, wincl, d);
+            if (lane >= d) wincl += o;
+        }
+        if (lane == 31) s_warp[warp] = (uint32_t)wincl;
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t p = (lane < SP_THREADS / 32) ? s_warp[lane] : 0u;
+            uint32_t pi = p;
+#pragma unroll
+            for (int d = 1; d < SP_THREADS / 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, pi, d);
+                if (lane >= d) pi += o;
             }
-            if (frag | span) {
-                const int fill = (int)fill_info[a.path[j]];
-                const int oi = frag_before + span_before;  // GEN:64-66
-                if (frag) records[oi] = make_int4((int)a.xy[j], 2, fill, frag_before + 1);  // GEN:77 (frag_index is inclusive)
-                if (span) {
-                    const int xs = (int)a.xprev[j];
-                    const int xe = (int)(a.xy[j] & 0xFFFFu);  // span flag implies a valid key, so x1 >= 0
-                    records[oi + frag] = make_int4((int)((a.xy[j] & 0xFFFF0000u) | (uint32_t)xs), xe - xs, fill, 0);  // GEN:102
+            const uint32_t total = __shfl_sync(0xFFFFFFFFu, pi, SP_THREADS / 32 - 1);
+            const unsigned long long excl = warp_lookback(tmp.status_w, tile, (unsigned long long)total, lane);
+            if (lane < SP_THREADS / 32) s_warp[lane] = pi - p;  // exclusive offset of each warp
+            if (lane == 0) {
+                s_prefix = excl;
+                if (tile == ntiles - 1) {
+                    const int wtotal = (int)(uint32_t)(excl + total);
+                    ctr->wn_total = wtotal;
+                    if (taps.wn) taps.wn[n] = wtotal;
                 }
             }
         }
-    }
+        __syncthreads();
+        int wn = (int)(uint32_t)s_prefix + (int)s_warp[warp] + (wincl - dsum);  // winding left of element i0
+        __syncthreads();  // s_warp is reused by chain F
 
-    __device__ void finish(long long n, unsigned long long total) const {
-        const int nfrag = (int)(total & 0x7FFFFFFFu), nspan = (int)((total >> 31) & 0x7FFFFFFFu);
-        ctr->n_out_frag = nfrag;
-        ctr->n_span = nspan;
-        ctr->n_records = nfrag + nspan;
-        if (taps.scan3) { taps.scan3[n] = 0; taps.scan3[2 * n] = nspan; }  // fixed up with + n_out_frag
+        // ---- flags (MARK:38-93) from the keys and the winding prefix
+        uint32_t fmask = 0, smask = 0;
+        {
+            KeyFields a = decode_key(L, k[0]);
+#pragma unroll
+            for (int j = 0; j < SP_ITEMS; ++j) {
+                const KeyFields b = decode_key(L, k[j + 1]);
+                if (i0 + j < n) {
+                    if (taps.wn) taps.wn[i0 + j] = wn;
+                    const bool oob = (b.x < 0 || b.y < 0 || b.x >= width || b.y >= height);  // MARK:45,69
+                    uint32_t frag, span = 0;
+                    if (i0 + j == 0) {
+                        frag = oob ? 0u : 1u;  // MARK:44-51
+                    } else {
+                        frag = (!oob && k[j] != k[j + 1]) ? 1u : 0u;  // MARK:69-77 (the compact key holds the path)
+                        const uint32_t rule = fill_rule[b.path];
+                        const bool wn_flag = ((rule == 0) && (wn != 0)) || ((rule == 1) && ((wn & 1) != 0));  // MARK:82
+                        span = (a.y == b.y && (a.x + FRAG_SIZE) < b.x && a.path == b.path && wn_flag) ? 1u : 0u;  // MARK:84
+                    }
+                    fmask |= frag << j;
+                    smask |= span << j;
+                    if (taps.flags) {
+                        taps.flags[i0 + j] = (int)frag;
+                        taps.flags[n + i0 + j] = (int)span;
+                        uint32_t pp;
+                        taps.skey32[i0 + j] = unpack_key32(L, k[j + 1], pp);
+                    }
+                }
+                wn += (int)((dpack >> (2 * j)) & 3u) - 1;
+                a = b;
+            }
+        }
+
+        // ---- chain F: exclusive prefix of (frag count | span count << 16) inside the tile, 2x31 bits across tiles
+        const uint32_t cnt = (uint32_t)__popc(fmask) | ((uint32_t)__popc(smask) << 16);
+        uint32_t cincl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, cincl, d);
+            if (lane >= d) cincl += o;
+        }
+        if (lane == 31) s_warp[warp] = cincl;
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t p = (lane < SP_THREADS / 32) ? s_warp[lane] : 0u;
+            uint32_t pi = p;
+#pragma unroll
+            for (int d = 1; d < SP_THREADS / 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, pi, d);
+                if (lane >= d) pi += o;
+            }
+            const uint32_t total = __shfl_sync(0xFFFFFFFFu, pi, SP_THREADS / 32 - 1);
+            const unsigned long long total64 = (unsigned long long)(total & 0xFFFFu) | ((unsigned long long)(total >> 16) << 31);
+            const unsigned long long excl = warp_lookback(tmp.status_f, tile, total64, lane);
+            if (lane < SP_THREADS / 32) s_warp[lane] = pi - p;
+            if (lane == 0) {
+                s_prefix = excl;
+                if (tile == ntiles - 1) {  // SR.cpp:578-580
+                    const unsigned long long tot = excl + total64;
+                    const int nfrag = (int)(tot & 0x7FFFFFFFu), nspan = (int)((tot >> 31) & 0x7FFFFFFFu);
+                    ctr->n_out_frag = nfrag;
+                    ctr->n_span = nspan;
+                    ctr->n_records = nfrag + nspan;
+                    if (taps.scan3) { taps.scan3[n] = 0; taps.scan3[2 * n] = nspan; }  // + n_out_frag in k_scan3_fixup
+                }
+            }
+        }
+        __syncthreads();
+        const unsigned long long tp = s_prefix;
+        const uint32_t local = s_warp[warp] + (cincl - cnt);
+        int frag_before = (int)(tp & 0x7FFFFFFFu) + (int)(local & 0xFFFFu);
+        int span_before = (int)((tp >> 31) & 0x7FFFFFFFu) + (int)(local >> 16);
+
+        // ---- emit the draw records (GEN:42-102)
+        if ((fmask | smask) || taps.scan3) {
+            KeyFields a = decode_key(L, k[0]);
+#pragma unroll
+            for (int j = 0; j < SP_ITEMS; ++j) {
+                const KeyFields b = decode_key(L, k[j + 1]);
+                const uint32_t frag = (fmask >> j) & 1u, span = (smask >> j) & 1u;
+                if (taps.scan3 && i0 + j < n) {
+                    taps.scan3[i0 + j] = frag_before;
+                    taps.scan3[n + i0 + j] = span_before;
+                }
+                if (frag | span) {
+                    const int fill = (int)fill_info[b.path];
+                    const int oi = frag_before + span_before;  // GEN:64-66
+                    if (frag)  // GEN:77: (y<<16 | x, 2, rgba, inclusive fragment index)
+                        records[oi] = make_int4((int)(((uint32_t)b.y << 16) | (uint32_t)b.x), 2, fill, frag_before + 1);
+                    if (span) {  // GEN:85-102: from the previous fragment's right edge to this fragment
+                        const int xs = max(0, a.x + FRAG_SIZE);
+                        records[oi + (int)frag] = make_int4((int)(((uint32_t)a.y << 16) | (uint32_t)xs), b.x - xs, fill, 0);
+                    }
+                }
+                frag_before += (int)frag;
+                span_before += (int)span;
+                a = b;
+            }
+        }
+        // the __syncthreads after the next ticket fetch orders the reuse of s_warp / s_prefix
     }
-};
+}
 
 // scan3[nf + i] += n_out_frag for i in [0, nf] (tap only): turns the two separate counts into the
 // reference's single scan over the concatenated [frag | span] flag array (SR.cpp:545-573).

@@ -1,0 +1,307 @@
+// walk.cuh — make_intersection_1.comp:217-447 + gen_fragment.comp:90-246, re-formulated per
+// monotone PIECE instead of per curve.
+//
+// The reference walks one curve per thread: per monotone piece it merges the x- and y-grid
+// crossings in parameter order; lines in closed form, cubics by a 24-step bisection whose bracket
+// starts at the previously emitted crossing on the same axis, so the walk along a piece is
+// inherently sequential if the emitted t is to be bit-identical. Pieces, however, are independent:
+// a piece starts from (t0, p0) = the previous piece's tagged end parameter and end point, both
+// functions of the cut parameters alone. So:
+//   k_piece_emit   one thread per curve: set up every piece (MI1:266-308) and store it as a 64-byte
+//                  record at its slot in LENGTH-SORTED order (bucket, rank) from k_monotonize_count;
+//   k_walk         one lane per piece, 32 consecutive records per warp = 32 pieces of (nearly) equal
+//                  length, so the whole warp runs the same number of merge steps and the 24-step
+//                  bisection — 70 % of all instructions — executes converged; every emitted record
+//                  also closes the fragment that began at the previous record (gen_fragment fused,
+//                  the (curve, tbits) intersection records are only a debug tap now);
+//   k_piece_close  one thread per curve: the fragment that spans a piece boundary (last record of a
+//                  piece -> first record of the next piece, or t = 1 at the curve end, GF:99,113-115).
+// The arithmetic of every step is the reference's, operation for operation.
+#pragma once
+#include "geom.cuh"
+
+namespace slpr {
+
+struct __align__(16) PieceRec {
+    float4 px, py;  // control points of the curve (x[0..3], y[0..3])
+    float4 tt;      // t0_ms (tagged start), t1_ms (tagged end), first x grid line, first y grid line
+    uint4 m;        // n_x | n_y << 15 | dx<0 << 30 | dy<0 << 31;  curve;  first record index;  type | piece << 8
+};
+
+struct WalkTemp {
+    const uint32_t *bucket_hist;  // [WALK_BUCKETS] pieces per length bucket (from k_monotonize_count)
+    int *group_counter;           // zeroed per frame
+};
+
+// position of (bucket, rank) in the length-sorted piece array: longest bucket first
+__device__ __forceinline__ uint32_t piece_position(const uint32_t *s_dbase, uint32_t slot) {
+    return s_dbase[slot >> 26] + (slot & 0x03FFFFFFu);
+}
+
+__device__ __forceinline__ void bucket_bases(const uint32_t *__restrict__ hist, uint32_t *s_dbase, uint32_t *s_total) {
+    // descending exclusive scan of the 64 bucket counts, by one warp
+    if (threadIdx.x < 32) {
+        const uint32_t l = threadIdx.x;
+        const uint32_t hi = hist[WALK_BUCKETS - 1 - l], lo = hist[WALK_BUCKETS - 1 - (l + 32)];  // reversed order
+        uint32_t a = hi, b = lo;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t oa = __shfl_up_sync(0xFFFFFFFFu, a, d), ob = __shfl_up_sync(0xFFFFFFFFu, b, d);
+            if ((int)l >= d) { a += oa; b += ob; }
+        }
+        const uint32_t first_half = __shfl_sync(0xFFFFFFFFu, a, 31);
+        s_dbase[WALK_BUCKETS - 1 - l] = a - hi;
+        s_dbase[WALK_BUCKETS - 1 - (l + 32)] = first_half + b - lo;
+        if (l == 31) *s_total = first_half + b;
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_piece_emit(const FrameParams *__restrict__ P, uint32_t n_curves,
+                                                    const uint32_t *__restrict__ curve_type,
+                                                    const uint32_t *__restrict__ curve_pos_map,
+                                                    const float2 *__restrict__ tpos, const float *__restrict__ cut_cache,
+                                                    const int *__restrict__ offsets, const uint32_t *__restrict__ slots,
+                                                    const FrameCounters *__restrict__ ctr, int capacity,
+                                                    const uint32_t *__restrict__ bucket_hist, PieceRec *__restrict__ pieces) {
+    __shared__ uint32_t s_dbase[WALK_BUCKETS];
+    __shared__ uint32_t s_total;
+    if (ctr->n_fragments > capacity) return;
+    bucket_bases(bucket_hist, s_dbase, &s_total);
+    const int width = P->width, height = P->height;
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n_curves; c += gridDim.x * blockDim.x) {
+        int pcnt = offsets[c];
+        if (offsets[c + 1] == pcnt) continue;  // invisible or band-culled
+        const uint32_t type = curve_type[c];
+        CurvePts cp;
+        load_points(type, curve_pos_map[c], tpos, cp);
+        const float q0 = cut_cache[5 * c + 0], q1 = cut_cache[5 * c + 1], q2 = cut_cache[5 * c + 2], q3 = cut_cache[5 * c + 3];
+        // count > 0 implies the path is visible (MI0:374-377), so MI1:257-260 appends t = 1
+        const uint32_t n_cuts = f2u(cut_cache[5 * c + 4]) + 1u;  // MI1:255
+        float t0_ms = 0.f, p0x = cp.x[0], p0y = cp.y[0];
+        for (uint32_t piece = 0; piece < n_cuts; ++piece) {  // MI1:266-308
+            float t1_ms = (piece + 1 == n_cuts) ? 1.f : (piece == 0) ? q0 : (piece == 1) ? q1 : (piece == 2) ? q2 : q3;
+            const float p1x = interp_general(type, t1_ms, cp.x[0], cp.x[1], cp.x[2], cp.x[3], 0.0f);
+            const float p1y = interp_general(type, t1_ms, cp.y[0], cp.y[1], cp.y[2], cp.y[3], 0.0f);
+            // MI1:271-276: tag t1 in its two mantissa LSBs
+            if (floorf(p1x) == p1x) t1_ms = u2f((f2u(t1_ms) & 0xFFFFFFFCu) | 2u);
+            else t1_ms = u2f(f2u(t1_ms) | 3u);
+            // get_xy_begin_end_delta, MI1:150-170 (float2int_rd)
+            const bool xfwd = p0x <= p1x, yfwd = p0y <= p1y;
+            int xb = float2int_rd(__fmul_rn(xfwd ? p0x : p1x, 0.5f)) * FRAG_SIZE + FRAG_SIZE;
+            int xe = float2int_rd(__fmul_rn(xfwd ? p1x : p0x, 0.5f)) * FRAG_SIZE;
+            int yb = float2int_rd(__fmul_rn(yfwd ? p0y : p1y, 0.5f)) * FRAG_SIZE + FRAG_SIZE;
+            int ye = float2int_rd(__fmul_rn(yfwd ? p1y : p0y, 0.5f)) * FRAG_SIZE;
+            const int n_x = cut_range(width, xb, xe);
+            const int n_y = cut_range(height, yb, ye);
+            PieceRec r;
+            r.px = make_float4(cp.x[0], cp.x[1], cp.x[2], cp.x[3]);
+            r.py = make_float4(cp.y[0], cp.y[1], cp.y[2], cp.y[3]);
+            r.tt = make_float4(t0_ms, t1_ms, (float)(xfwd ? xb : xe), (float)(yfwd ? yb : ye));  // MI1:301-302
+            r.m = make_uint4((uint32_t)n_x | ((uint32_t)n_y << 15) | (xfwd ? 0u : 1u << 30) | (yfwd ? 0u : 1u << 31), c,
+                             (uint32_t)pcnt, (type & 0xFFu) | (piece << 8) | ((type > 0xFFu) ? 0x80u : 0u));
+            pieces[piece_position(s_dbase, slots[5 * c + piece])] = r;
+            pcnt += n_x + n_y + 1;
+            t0_ms = t1_ms; p0x = p1x; p0y = p1y;  // MI1:442-443
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+constexpr int WALK_THREADS = 128;
+
+__global__ void __launch_bounds__(WALK_THREADS) k_walk(const FrameParams *__restrict__ P,
+                                                       const PieceRec *__restrict__ pieces,
+                                                       const uint32_t *__restrict__ curve_path,
+                                                       const FrameCounters *__restrict__ ctr, int capacity, WalkTemp tmp,
+                                                       KeyLayout L, uint64_t *__restrict__ key64,
+                                                       uint32_t *__restrict__ val, FragTaps taps,
+                                                       int2 *__restrict__ inter, float2 *__restrict__ boundary) {
+    const int nf_total = ctr->n_fragments;
+    if (nf_total > capacity) return;
+    if (taps.key32 && blockIdx.x == 0 && threadIdx.x == 0 && nf_total > 0) taps.key32[nf_total] = -1;  // GF:240
+    const uint32_t lane = lane_id();
+    uint32_t n_pieces = 0;
+    {
+        const uint32_t h = tmp.bucket_hist[lane] + tmp.bucket_hist[lane + 32];
+        n_pieces = __reduce_add_sync(0xFFFFFFFFu, h);
+    }
+    while (true) {
+        uint32_t g = 0;
+        if (lane == 0) g = (uint32_t)atomicAdd(tmp.group_counter, 1);
+        g = __shfl_sync(0xFFFFFFFFu, g, 0);
+        if ((unsigned long long)g * 32ull >= n_pieces) break;
+        const uint32_t idx = g * 32u + lane;
+        const bool active = idx < n_pieces;
+
+        // ---- load the piece (64 contiguous bytes per lane: fully coalesced across the warp)
+        CurvePts cp;
+        float t0_ms = 0.f, t1_ms = 0.f, x = 0.f, y = 0.f, dx = 2.f, dy = 2.f;
+        int n_x = 0, n_y = 0, n_loop = -2, pcnt = 0;
+        uint32_t c = 0, type = T_LINE, piece = 0, pidx = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { cp.x[i] = 0.f; cp.y[i] = 0.f; }
+        if (active) {
+            const PieceRec *r = pieces + idx;
+            const float4 a = r->px, b = r->py, t = r->tt;
+            const uint4 m = r->m;
+            cp.x[0] = a.x; cp.x[1] = a.y; cp.x[2] = a.z; cp.x[3] = a.w;
+            cp.y[0] = b.x; cp.y[1] = b.y; cp.y[2] = b.z; cp.y[3] = b.w;
+            t0_ms = t.x; t1_ms = t.y; x = t.z; y = t.w;
+            n_x = (int)(m.x & 0x7FFFu); n_y = (int)((m.x >> 15) & 0x7FFFu);
+            dx = (m.x & (1u << 30)) ? -2.f : 2.f; dy = (m.x & (1u << 31)) ? -2.f : 2.f;
+            c = m.y; pcnt = (int)m.z;
+            type = (m.w & 0x80u) ? 0xFFFFu : (m.w & 0x7Fu);  // types above 0xFF only need to be "other"
+            piece = m.w >> 8;
+            n_loop = n_x + n_y + 1;
+            pidx = curve_path[c];
+        }
+        float tx = t0_ms, ty = t0_ms;  // point_coords slots 8, 9 (MI1:304-305)
+        int i_inte_last = (int)f2u(-1.0f);
+        bool have_prev = false;
+        float prev_t = 0.f, prev_x = 0.f, prev_y = 0.f;
+        uint32_t first_bits = 0, last_bits = 0;
+
+        for (int it = -1;; ++it) {  // MI1:310-441, the whole warp in lock step
+            const bool live = active && it < n_loop;
+            if (!__any_sync(0xFFFFFFFFu, live)) break;
+            // MI1:321-359 without branches: side, whether that side is exhausted, t_min
+            const bool first = it == -1;
+            const int side = first ? ((n_x != 0 && n_y == 0) ? 1 : 0) : ((tx <= ty) ? 0 : 1);
+            const bool park = first ? (n_x == 0 || n_y == 0) : ((side ? n_y : n_x) <= 0);
+            const float t_min = first ? tx : (side ? ty : tx);
+            float cst = 0.f;
+            if (live && !park) {
+                if (side) { --n_y; cst = y; y = __fadd_rn(y, dy); }
+                else { --n_x; cst = x; x = __fadd_rn(x, dx); }
+            }
+            if (live && it >= 0) {  // MI1:361-375 + gen_fragment for the fragment that ends here
+                if (inter) {
+                    int i_out = (int)f2u(t_min);
+                    if ((f2u(t_min) & 0xFFFFFFFCu) == ((uint32_t)i_inte_last & 0xFFFFFFFCu)) {
+                        i_out |= i_inte_last;
+                        inter[pcnt - 1] = make_int2((int)c, i_out);
+                    }
+                    inter[pcnt] = make_int2((int)c, i_out);
+                    i_inte_last = i_out;
+                }
+                if (it == 0) first_bits = f2u(t_min);
+                last_bits = f2u(t_min);
+                // GF:101-104: the record's parameter without its tag bits, clamped at 0
+                float tc = u2f(f2u(t_min) & 0xFFFFFFFCu);
+                tc = (tc < 0.0f) ? 0.0f : tc;
+                float ex, ey;
+                eval_point(type, cp, tc, ex, ey);
+                if (have_prev) emit_fragment(P, L, pcnt - 1, pidx, prev_t, tc, prev_x, prev_y, ex, ey, key64, val, taps);
+                prev_t = tc; prev_x = ex; prev_y = ey; have_prev = true;
+                ++pcnt;
+            }
+            // ---- solve the next crossing on `side` (MI1:377-437); converged: every lane is at the same step
+            float t_solve = park ? 2.0f : 0.0f;
+            const bool solve = live && !park;
+            if (__any_sync(0xFFFFFFFFu, solve)) {
+                if (solve) {
+                    const float c0 = side ? cp.y[0] : cp.x[0], c1 = side ? cp.y[1] : cp.x[1];
+                    if (type == T_CUBIC) {  // MI1:392-436
+                        const float c2 = side ? cp.y[2] : cp.x[2], c3 = side ? cp.y[3] : cp.x[3];
+                        // LERP(a,b,t) = a + t*(b-a): the first-level differences do not depend on t
+                        const float d01 = __fsub_rn(c1, c0), d12 = __fsub_rn(c2, c1), d23 = __fsub_rn(c3, c2);
+                        float t0 = t_min, t1 = t1_ms;
+                        float vt0;
+                        {
+                            const float a0 = __fadd_rn(c0, __fmul_rn(t0, d01)), a1 = __fadd_rn(c1, __fmul_rn(t0, d12)),
+                                        a2 = __fadd_rn(c2, __fmul_rn(t0, d23));
+                            const float b0 = lerpf(a0, a1, t0), b1 = lerpf(a1, a2, t0);
+                            vt0 = lerpf(b0, b1, t0);
+                        }
+                        t_solve = t0;
+                        if (vt0 != cst) {
+                            const float raw_t0 = t0;
+                            uint32_t s0 = f2u(__fsub_rn(vt0, cst)), s_last = 0;
+#pragma unroll 4
+                            for (int j = 0; j < CUBIC_ITERATION_NUMBER; ++j) {
+                                const float tm = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
+                                const float a0 = __fadd_rn(c0, __fmul_rn(tm, d01)), a1 = __fadd_rn(c1, __fmul_rn(tm, d12)),
+                                            a2 = __fadd_rn(c2, __fmul_rn(tm, d23));
+                                const float b0 = lerpf(a0, a1, tm), b1 = lerpf(a1, a2, tm);
+                                const float vtm = lerpf(b0, b1, tm);
+                                t_solve = tm;
+                                s_last = f2u(__fsub_rn(vtm, cst));
+                                if ((int)(s_last ^ s0) >= 0) { t0 = tm; s0 = s_last; }  // vt0 = vtm
+                                else t1 = tm;
+                            }
+                            if (fabsf(u2f(s_last)) > 1.f) t_solve = raw_t0;  // MI1:430-433
+                        }
+                    } else if (type == T_LINE) {  // MI1:379-385
+                        float a = __fsub_rn(c1, c0);
+                        a = (a != 0.0f) ? __fdiv_rn(1.0f, a) : 0.0f;
+                        float v = __fmul_rn(__fsub_rn(cst, c0), a);
+                        v = (v < t_min) ? t_min : v;        // GLSL max(x,y) = x<y ? y : x
+                        t_solve = (t1_ms < v) ? t1_ms : v;  // GLSL min(x,y) = y<x ? y : x
+                    } else if (type == T_QUADRIC || type == T_ARC) {
+                        t_solve = 0.0f;  // TODO arms in the reference: t_solve stays 0
+                    } else {  // any other type value: interpolateGeneralCurve returns 0 (MI1:81-83,144)
+                        t_solve = t_min;
+                        if (0.0f != cst) {
+                            float t0 = t_min;
+                            for (int j = 0; j < CUBIC_ITERATION_NUMBER; ++j) {  // vtm - c == vt0 - c: t0 always moves
+                                const float tm = __fmul_rn(__fadd_rn(t0, t1_ms), 0.5f);
+                                t_solve = tm; t0 = tm;
+                            }
+                            if (fabsf(__fsub_rn(0.0f, cst)) > 1.f) t_solve = t_min;
+                        }
+                    }
+                }
+            }
+            if (live) {  // MI1:440
+                const float tagged = u2f((f2u(t_solve) & 0xFFFFFFFCu) | (uint32_t)side);
+                if (side) ty = tagged; else tx = tagged;
+            }
+        }
+        // first / last emitted parameter of the piece, for the fragment across the piece boundary
+        if (active) boundary[5 * c + piece] = make_float2(u2f(first_bits), u2f(last_bits));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_piece_close(const FrameParams *__restrict__ P, uint32_t n_curves,
+                                                     const uint32_t *__restrict__ curve_type,
+                                                     const uint32_t *__restrict__ curve_pos_map,
+                                                     const uint32_t *__restrict__ curve_path,
+                                                     const float2 *__restrict__ tpos, const float *__restrict__ cut_cache,
+                                                     const int *__restrict__ offsets, const uint32_t *__restrict__ slots,
+                                                     const FrameCounters *__restrict__ ctr, int capacity,
+                                                     const uint32_t *__restrict__ bucket_hist,
+                                                     const PieceRec *__restrict__ pieces, const float2 *__restrict__ boundary,
+                                                     KeyLayout L, uint64_t *__restrict__ key64, uint32_t *__restrict__ val,
+                                                     FragTaps taps) {
+    __shared__ uint32_t s_dbase[WALK_BUCKETS];
+    __shared__ uint32_t s_total;
+    if (ctr->n_fragments > capacity) return;
+    bucket_bases(bucket_hist, s_dbase, &s_total);
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n_curves; c += gridDim.x * blockDim.x) {
+        if (offsets[c + 1] == offsets[c]) continue;
+        const uint32_t type = curve_type[c];
+        const uint32_t pidx = curve_path[c];
+        CurvePts cp;
+        load_points(type, curve_pos_map[c], tpos, cp);
+        const uint32_t n_cuts = f2u(cut_cache[5 * c + 4]) + 1u;
+        for (uint32_t piece = 0; piece < n_cuts; ++piece) {
+            const uint4 m = pieces[piece_position(s_dbase, slots[5 * c + piece])].m;
+            const int n_loop = (int)(m.x & 0x7FFFu) + (int)((m.x >> 15) & 0x7FFFu) + 1;
+            const int f = (int)m.z + n_loop - 1;  // last record of the piece
+            // GF:99-104,113-115: t0 from this record, t1 from the next record of the curve or 1.0 at its end
+            float t0 = u2f(f2u(boundary[5 * c + piece].y) & 0xFFFFFFFCu);
+            float t1 = (piece + 1 < n_cuts) ? u2f(f2u(boundary[5 * c + piece + 1].x) & 0xFFFFFFFCu) : 1.0f;
+            t0 = (t0 < 0.0f) ? 0.0f : t0;
+            t1 = (t1 < 0.0f) ? 0.0f : t1;
+            float ax, ay, bx, by;
+            eval_point(type, cp, t0, ax, ay);
+            eval_point(type, cp, t1, bx, by);
+            emit_fragment(P, L, f, pidx, t0, t1, ax, ay, bx, by, key64, val, taps);
+        }
+    }
+}
+
+}  // namespace slpr
