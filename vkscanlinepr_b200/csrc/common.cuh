@@ -85,6 +85,25 @@ __device__ __forceinline__ void st_stream(int4 *p, const int4 &v) {
                  "r"(v.w) : "memory");
 }
 
+// Tile-status words of the decoupled look-backs: GPU-scope relaxed accesses (a `volatile` access
+// compiles to .STRONG.SYS, i.e. system scope, which is needlessly expensive on a two-die part).
+__device__ __forceinline__ unsigned long long ld_status64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_status64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_status32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_status32(uint32_t *p, uint32_t v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 __device__ __forceinline__ uint32_t lane_id() {
     uint32_t l;
     asm("mov.u32 %0, %%laneid;" : "=r"(l));

@@ -269,8 +269,11 @@ __device__ __forceinline__ int unpack_key32(const KeyLayout &L, uint64_t k, uint
 
 // gen_fragment.comp:117-224 for one fragment: the curve piece between two consecutive intersection
 // records (parameters t0 < t1, end points pf / pl already evaluated) lies in one 2x2 cell. Emits the
-// sort input: compact key (path | row rank | cell x) and value (fragment index | (delta+1) << 30).
+// sort input: compact key (path | row rank | cell x) and value
+// (fragment index | fill rule of the path << 29 | (delta+1) << 30): the span kernel then needs no gather.
+constexpr uint32_t VAL_INDEX_MASK = 0x1FFFFFFFu;
 __device__ __forceinline__ void emit_fragment(const FrameParams *__restrict__ P, const KeyLayout &L, int f, uint32_t pidx,
+                                              uint32_t rule_bit,
                                               float t0, float t1, float pfx, float pfy, float plx, float ply,
                                               uint64_t *__restrict__ key64, uint32_t *__restrict__ val,
                                               const FragTaps &taps) {
@@ -290,7 +293,7 @@ __device__ __forceinline__ void emit_fragment(const FrameParams *__restrict__ P,
         if (P->cull && valid && (pos_y < P->band_y0 || pos_y >= P->band_y1)) { valid = false; wn = 0; }  // band mode (new)
     }
     key64[f] = pack_key(L, pidx, valid, pos_x, pos_y);
-    val[f] = (uint32_t)f | ((uint32_t)(wn + 1) << 30);
+    val[f] = (uint32_t)f | (rule_bit << 29) | ((uint32_t)(wn + 1) << 30);
     if (taps.key32) {
         taps.key32[f] = valid ? (int)(((uint32_t)(pos_y + 0x7FFF) << 16) | ((uint32_t)(pos_x + 0x7FFF) & 0xFFFFu))
                               : (int)0xFFFEFFFEu;

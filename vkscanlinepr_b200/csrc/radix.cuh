@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(RS_THREADS, RS_BLOCKS_PER_SM) k_onesweep(const
     const long long ntiles = (n + RS_TILE - 1) / RS_TILE;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t *ghist = tmp.hist + pass * RS_BINS;
-    volatile uint32_t *lookback = tmp.lookback + (size_t)pass * tmp.tiles_cap * RS_BINS;
+    uint32_t *lookback = tmp.lookback + (size_t)pass * tmp.tiles_cap * RS_BINS;
     const uint32_t lt = lanemask_lt();
 
     while (true) {
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(RS_THREADS, RS_BLOCKS_PER_SM) k_onesweep(const
             }
             if (tid == RS_BINS - 1) count -= (uint32_t)(RS_TILE - valid);  // padding keys all land in bin 255
             // publish the aggregate early so that successors can make progress
-            lookback[(size_t)tile * RS_BINS + tid] = ((tile == 0) ? LB_PREFIX : LB_AGG) | count;
+            st_status32(lookback + (size_t)tile * RS_BINS + tid, ((tile == 0) ? LB_PREFIX : LB_AGG) | count);
             // exclusive scan of the 256 tile counts -> start of each digit inside the staged tile
             uint32_t s = (tid == RS_BINS - 1) ? count + (uint32_t)(RS_TILE - valid) : count;
             const uint32_t mine = s;
@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(RS_THREADS, RS_BLOCKS_PER_SM) k_onesweep(const
                     uint32_t w[SLPR_RS_LB_WINDOW];
 #pragma unroll
                     for (int k = 0; k < SLPR_RS_LB_WINDOW; ++k)
-                        w[k] = (t - k >= 0) ? lookback[(size_t)(t - k) * RS_BINS + tid] : LB_PREFIX;
+                        w[k] = (t - k >= 0) ? ld_status32(lookback + (size_t)(t - k) * RS_BINS + tid) : LB_PREFIX;
 #pragma unroll
                     for (int k = 0; k < SLPR_RS_LB_WINDOW; ++k) {
                         if (done) break;
@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(RS_THREADS, RS_BLOCKS_PER_SM) k_onesweep(const
                         if ((w[k] >> 30) == 2) done = true;
                     }
                 }
-                lookback[(size_t)tile * RS_BINS + tid] = LB_PREFIX | ((excl + count) & LB_MASK);
+                st_status32(lookback + (size_t)tile * RS_BINS + tid, LB_PREFIX | ((excl + count) & LB_MASK));
             }
             s_gbase[tid] = ghist[tid] + excl - start;
             s_start[tid] = start;

@@ -84,16 +84,16 @@ __global__ void __launch_bounds__(SCAN_THREADS, Op::MIN_BLOCKS) k_lookback_scan(
             const unsigned long long pi = warp_incl_scan_u64(p);
             s_part[lane] = pi - p;  // exclusive offset of (vector, warp) inside the tile
             const unsigned long long tile_total = __shfl_sync(0xFFFFFFFFu, pi, 31);
-            volatile unsigned long long *status = tmp.status;
-            if (lane == 0) status[tile] = ((tile == 0) ? ST_PREFIX : ST_AGG) | (tile_total & ST_MASK);
+            unsigned long long *status = tmp.status;
+            if (lane == 0) st_status64(status + tile, ((tile == 0) ? ST_PREFIX : ST_AGG) | (tile_total & ST_MASK));
             unsigned long long excl = 0;
             if (tile > 0) {
                 long long look = tile - 1;
                 while (true) {
                     const long long idx = look - lane;
-                    unsigned long long w = (idx >= 0) ? status[idx] : ST_PREFIX;
+                    unsigned long long w = (idx >= 0) ? ld_status64(status + idx) : ST_PREFIX;
                     while (__any_sync(0xFFFFFFFFu, (w >> 62) == 0)) {
-                        if ((w >> 62) == 0) w = status[idx];
+                        if ((w >> 62) == 0) w = ld_status64(status + idx);
                     }
                     const uint32_t pm = __ballot_sync(0xFFFFFFFFu, (w >> 62) == 2);
                     const int first = pm ? (__ffs(pm) - 1) : 32;
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, Op::MIN_BLOCKS) k_lookback_scan(
                     if (pm) break;
                     look -= 32;
                 }
-                if (lane == 0) status[tile] = ST_PREFIX | ((excl + tile_total) & ST_MASK);
+                if (lane == 0) st_status64(status + tile, ST_PREFIX | ((excl + tile_total) & ST_MASK));
             }
             if (lane == 0) {
                 s_prefix = excl;

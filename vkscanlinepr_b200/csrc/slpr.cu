@@ -293,6 +293,8 @@ extern "C" int slpr_load_scene(slpr_ctx *c, const float *pos_xy, const uint32_t 
             return fail(SLPR_ERR_INVALID, "slpr_load_scene: curve %u points [%u,+%u) exceed n_points", i, curve_pos_map[i], npts);
         if (i && curve_path[i] < curve_path[i - 1]) return fail(SLPR_ERR_INVALID, "slpr_load_scene: curve_path must be non-decreasing");
     }
+    for (uint32_t i = 0; i < n_paths; ++i)
+        if (fill_rule[i] > 1u) return fail(SLPR_ERR_INVALID, "slpr_load_scene: path %u has fill rule %u (0 = nonzero, 1 = even-odd)", i, fill_rule[i]);
     for (uint32_t i = 0; i < n_points; ++i)
         if (pos_path[i] >= n_paths) return fail(SLPR_ERR_INVALID, "slpr_load_scene: point %u has path %u >= n_paths", i, pos_path[i]);
     CU(cudaSetDevice(c->device));
@@ -393,9 +395,9 @@ static int enqueue_frame(slpr_ctx *c, cudaStream_t s, bool timed, int &launches)
                                                              c->d_offset, c->d_slots, c->d_ctr, c->cap, c->d_bucket_hist,
                                                              c->d_pieces);
     k_walk<<<c->num_sms * std::max(1, c->walk_blocks_per_sm), WALK_THREADS, 0, s>>>(
-        c->d_params, c->d_pieces, c->d_cpath, c->d_ctr, c->cap, WalkTemp{c->d_bucket_hist, c->d_tickets + 3 + RS_MAX_PASSES},
+        c->d_params, c->d_pieces, c->d_cpath, c->d_frule, c->d_ctr, c->cap, WalkTemp{c->d_bucket_hist, c->d_tickets + 3 + RS_MAX_PASSES},
         c->L, c->d_key[0], c->d_val[0], ft, c->d_inter, c->d_boundary);
-    k_piece_close<<<grid_for(c, c->nc, 256, 8), 256, 0, s>>>(c->d_params, c->nc, c->d_ctype, c->d_cpm, c->d_cpath, c->d_tpos,
+    k_piece_close<<<grid_for(c, c->nc, 256, 8), 256, 0, s>>>(c->d_params, c->nc, c->d_ctype, c->d_cpm, c->d_cpath, c->d_frule, c->d_tpos,
                                                               c->d_cut, c->d_offset, c->d_slots, c->d_ctr, c->cap,
                                                               c->d_bucket_hist, c->d_pieces, c->d_boundary, c->L, c->d_key[0],
                                                               c->d_val[0], ft);
@@ -426,7 +428,7 @@ static int enqueue_frame(slpr_ctx *c, cudaStream_t s, bool timed, int &launches)
     SpanTaps stp{c->d_wn, c->t_sidx, c->t_skey32, c->t_flags, c->t_scan3};
     SpanTemp stmp{c->d_status[1], c->d_status[2], c->d_tickets + 1};
     if (timed) CU(cudaEventRecord(c->ev[8], s));
-    k_spans<<<c->num_sms * std::max(1, c->span_blocks_per_sm), SP_THREADS, 0, s>>>(c->d_key[cur], c->d_val[cur], c->d_frule, c->d_finfo, c->d_rec, c->d_ctr,
+    k_spans<<<c->num_sms * std::max(1, c->span_blocks_per_sm), SP_THREADS, 0, s>>>(c->d_key[cur], c->d_val[cur], c->d_finfo, c->d_rec, c->d_ctr,
                                                   c->L, (int)c->W, (int)c->H, c->cap, stp, stmp);
     ++launches;
     if (taps) {
@@ -462,10 +464,10 @@ static int size_buffers_from_count(slpr_ctx *c) {
     CU(cudaMemcpyAsync(c->h_ctr, c->d_ctr, sizeof(FrameCounters), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     const long long nf = c->h_ctr->n_fragments;
-    if (nf < 0 || nf >= (1ll << 30) - (1ll << 27)) return fail(SLPR_ERR_INVALID, "frame has %lld fragments; limit is 2^30", nf);
+    if (nf < 0 || nf >= (1ll << 29) - (1ll << 26)) return fail(SLPR_ERR_INVALID, "frame has %lld fragments; limit is 2^29", nf);
     if (nf + 16 > c->cap) {
         const long long want = nf + nf / 4 + 65536;
-        rc = alloc_capacity(c, (int)std::min<long long>(want, (1ll << 30) - 1));
+        rc = alloc_capacity(c, (int)std::min<long long>(want, (1ll << 29) - 1));
         if (rc) return rc;
     }
     return SLPR_OK;
@@ -522,7 +524,7 @@ static int finish_frame(slpr_ctx *c) {
         c->frame_pending = false;
         if (!c->h_ctr->overflow) { c->frame_done = true; return SLPR_OK; }
         const long long nf = c->h_ctr->n_fragments;
-        int rc = alloc_capacity(c, (int)std::min<long long>(nf + nf / 4 + 65536, (1ll << 30) - 1));
+        int rc = alloc_capacity(c, (int)std::min<long long>(nf + nf / 4 + 65536, (1ll << 29) - 1));
         if (rc) return rc;
         rc = slpr_render(c);
         if (rc) return rc;

@@ -16,10 +16,28 @@
 
 namespace slpr {
 
-constexpr int SP_THREADS = 512;
+#ifndef SLPR_SP_THREADS
+#define SLPR_SP_THREADS 512
+#endif
+#ifndef SLPR_SP_BLOCKS
+#define SLPR_SP_BLOCKS 2
+#endif
+#ifndef SLPR_SP_LOOK
+#define SLPR_SP_LOOK 1
+#endif
+#ifndef SLPR_SP_SLEEP
+#define SLPR_SP_SLEEP 0
+#endif
+#ifndef SLPR_SP_FAKE
+#define SLPR_SP_FAKE 0   /* timing experiments only: skip the look-back (wrong results) */
+#endif
+#ifndef SLPR_SP_NOSTORE
+#define SLPR_SP_NOSTORE 0 /* timing experiments only: skip the record stores */
+#endif
+constexpr int SP_THREADS = SLPR_SP_THREADS;
 constexpr int SP_ITEMS = 8;
-constexpr int SP_BLOCKS = 2;
-constexpr int SP_LOOK = 4;  // tile states polled per lane per look-back round trip (window = 32 * SP_LOOK tiles)
+constexpr int SP_BLOCKS = SLPR_SP_BLOCKS;
+constexpr int SP_LOOK = SLPR_SP_LOOK;  // tile states polled per lane per look-back round trip (window = 32 * SP_LOOK tiles)
 constexpr int SP_TILE = SP_THREADS * SP_ITEMS;
 
 struct SpanTaps {
@@ -38,13 +56,13 @@ struct SpanTemp {
 
 // One decoupled look-back by a full warp: publishes this tile's aggregate, returns the exclusive
 // prefix of all earlier tiles (in every lane) and publishes the inclusive prefix. The chain of
-// tiles ripples at (window tiles) per L2 round trip, so the window is 32 * SP_LOOK = 128 tiles:
-// lane l polls tiles look-4l .. look-4l-3 with four independent loads per round trip.
-__device__ __forceinline__ unsigned long long warp_lookback(volatile unsigned long long *status, long long tile,
+// tiles ripples at (window tiles) per L2 round trip; the window is 32 * SP_LOOK tiles (measured: 32 is best):
+// lane l polls tiles look-SP_LOOK*l .. with SP_LOOK independent loads per round trip.
+__device__ __forceinline__ unsigned long long warp_lookback(unsigned long long *status, long long tile,
                                                            unsigned long long tile_total, int lane) {
-    if (lane == 0) status[tile] = ((tile == 0) ? ST_PREFIX : ST_AGG) | (tile_total & ST_MASK);
+    if (lane == 0) st_status64(status + tile, ((tile == 0) ? ST_PREFIX : ST_AGG) | (tile_total & ST_MASK));
     unsigned long long excl = 0;
-    if (tile > 0) {
+    if (tile > 0 && !SLPR_SP_FAKE) {
         long long look = tile - 1;
         while (true) {
             const long long first_idx = look - (long long)lane * SP_LOOK;
@@ -55,9 +73,10 @@ __device__ __forceinline__ unsigned long long warp_lookback(volatile unsigned lo
 #pragma unroll
                 for (int q = 0; q < SP_LOOK; ++q) {
                     const long long idx = first_idx - q;
-                    w[q] = (idx >= 0) ? status[idx] : ST_PREFIX;
+                    w[q] = (idx >= 0) ? ld_status64(status + idx) : ST_PREFIX;
                     empty |= (w[q] >> 62) == 0;
                 }
+                if (SLPR_SP_SLEEP && empty) __nanosleep(SLPR_SP_SLEEP);
             } while (__any_sync(0xFFFFFFFFu, empty));
             // this lane's partial: nearest -> farthest, up to and including its first inclusive prefix
             unsigned long long part = 0;
@@ -75,7 +94,7 @@ __device__ __forceinline__ unsigned long long warp_lookback(volatile unsigned lo
             if (pm) break;
             look -= 32 * SP_LOOK;
         }
-        if (lane == 0) status[tile] = ST_PREFIX | ((excl + tile_total) & ST_MASK);
+        if (lane == 0) st_status64(status + tile, ST_PREFIX | ((excl + tile_total) & ST_MASK));
     }
     return excl;
 }
@@ -97,7 +116,6 @@ __device__ __forceinline__ KeyFields decode_key(const KeyLayout &L, uint64_t k) 
 
 __global__ void __launch_bounds__(SP_THREADS, SP_BLOCKS) k_spans(const uint64_t *__restrict__ skey,
                                                          const uint32_t *__restrict__ sval,
-                                                         const uint32_t *__restrict__ fill_rule,
                                                          const uint32_t *__restrict__ fill_info,
                                                          int4 *__restrict__ records, FrameCounters *__restrict__ ctr,
                                                          KeyLayout L, int width, int height, int capacity, SpanTaps taps,
@@ -121,6 +139,7 @@ __global__ void __launch_bounds__(SP_THREADS, SP_BLOCKS) k_spans(const uint64_t 
         // ---- load 8 consecutive sorted keys and values
         uint64_t k[SP_ITEMS + 1];  // k[0] = key of element i0-1
         uint32_t dpack = 0;        // 8 x 2-bit (delta + 1)
+        uint32_t rpack = 0;        // 8 x 1-bit fill rule of the fragment's path (carried in bit 29 of the value)
         if (i0 + SP_ITEMS <= n) {
 #pragma unroll
             for (int j = 0; j < SP_ITEMS; j += 2) {
@@ -135,7 +154,8 @@ __global__ void __launch_bounds__(SP_THREADS, SP_BLOCKS) k_spans(const uint64_t 
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     dpack |= (v[e] >> 30) << (2 * (j + e));
-                    if (taps.sidx) taps.sidx[i0 + j + e] = (int)(v[e] & 0x3FFFFFFFu);
+                    rpack |= ((v[e] >> 29) & 1u) << (j + e);
+                    if (taps.sidx) taps.sidx[i0 + j + e] = (int)(v[e] & VAL_INDEX_MASK);
                 }
             }
         } else {
@@ -145,7 +165,8 @@ __global__ void __launch_bounds__(SP_THREADS, SP_BLOCKS) k_spans(const uint64_t 
                 k[j + 1] = in ? skey[i0 + j] : 0ull;
                 const uint32_t v = in ? sval[i0 + j] : (1u << 30);
                 dpack |= (v >> 30) << (2 * j);
-                if (in && taps.sidx) taps.sidx[i0 + j] = (int)(v & 0x3FFFFFFFu);
+                rpack |= ((v >> 29) & 1u) << j;
+                if (in && taps.sidx) taps.sidx[i0 + j] = (int)(v & VAL_INDEX_MASK);
             }
         }
         {   // key of the element before this thread's run: neighbour lane, or global for lane 0
@@ -206,8 +227,9 @@ __global__ void __launch_bounds__(SP_THREADS, SP_BLOCKS) k_spans(const uint64_t 
                         frag = oob ? 0u : 1u;  // MARK:44-51
                     } else {
                         frag = (!oob && k[j] != k[j + 1]) ? 1u : 0u;  // MARK:69-77 (the compact key holds the path)
-                        const uint32_t rule = fill_rule[b.path];
-                        const bool wn_flag = ((rule == 0) && (wn != 0)) || ((rule == 1) && ((wn & 1) != 0));  // MARK:82
+                        const bool even_odd = (rpack >> j) & 1u;  // fill_rule[path] == 1
+                        // MARK:82 (rule values other than 0/1 never set the flag there; the loader only produces 0/1)
+                        const bool wn_flag = even_odd ? ((wn & 1) != 0) : (wn != 0);
                         span = (a.y == b.y && (a.x + FRAG_SIZE) < b.x && a.path == b.path && wn_flag) ? 1u : 0u;  // MARK:84
                     }
                     fmask |= frag << j;
@@ -265,7 +287,14 @@ __global__ void __launch_bounds__(SP_THREADS, SP_BLOCKS) k_spans(const uint64_t 
         int span_before = (int)((tp >> 31) & 0x7FFFFFFFu) + (int)(local >> 16);
 
         // ---- emit the draw records (GEN:42-102)
-        if ((fmask | smask) || taps.scan3) {
+        if (SLPR_SP_FAKE) { frag_before = (int)(tile * SP_TILE) + (int)(local & 0xFFFFu); span_before = (int)(local >> 16); }
+        if (((fmask | smask) || taps.scan3) && !(SLPR_SP_NOSTORE && frag_before >= 0)) {
+            int fillc[SP_ITEMS];  // colours first: eight independent gathers instead of eight dependent ones
+#pragma unroll
+            for (int j = 0; j < SP_ITEMS; ++j) {
+                const uint32_t path = (uint32_t)(k[j + 1] >> (L.bits_x + L.bits_y));
+                fillc[j] = (((fmask | smask) >> j) & 1u) ? (int)fill_info[path] : 0;
+            }
             KeyFields a = decode_key(L, k[0]);
 #pragma unroll
             for (int j = 0; j < SP_ITEMS; ++j) {
@@ -276,7 +305,7 @@ __global__ void __launch_bounds__(SP_THREADS, SP_BLOCKS) k_spans(const uint64_t 
                     taps.scan3[n + i0 + j] = span_before;
                 }
                 if (frag | span) {
-                    const int fill = (int)fill_info[b.path];
+                    const int fill = fillc[j];
                     const int oi = frag_before + span_before;  // GEN:64-66
                     if (frag)  // GEN:77: (y<<16 | x, 2, rgba, inclusive fragment index)
                         records[oi] = make_int4((int)(((uint32_t)b.y << 16) | (uint32_t)b.x), 2, fill, frag_before + 1);

@@ -114,6 +114,7 @@ constexpr int WALK_THREADS = 128;
 __global__ void __launch_bounds__(WALK_THREADS) k_walk(const FrameParams *__restrict__ P,
                                                        const PieceRec *__restrict__ pieces,
                                                        const uint32_t *__restrict__ curve_path,
+                                                       const uint32_t *__restrict__ fill_rule,
                                                        const FrameCounters *__restrict__ ctr, int capacity, WalkTemp tmp,
                                                        KeyLayout L, uint64_t *__restrict__ key64,
                                                        uint32_t *__restrict__ val, FragTaps taps,
@@ -139,7 +140,7 @@ __global__ void __launch_bounds__(WALK_THREADS) k_walk(const FrameParams *__rest
         CurvePts cp;
         float t0_ms = 0.f, t1_ms = 0.f, x = 0.f, y = 0.f, dx = 2.f, dy = 2.f;
         int n_x = 0, n_y = 0, n_loop = -2, pcnt = 0;
-        uint32_t c = 0, type = T_LINE, piece = 0, pidx = 0;
+        uint32_t c = 0, type = T_LINE, piece = 0, pidx = 0, rule_bit = 0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) { cp.x[i] = 0.f; cp.y[i] = 0.f; }
         if (active) {
@@ -156,6 +157,7 @@ __global__ void __launch_bounds__(WALK_THREADS) k_walk(const FrameParams *__rest
             piece = m.w >> 8;
             n_loop = n_x + n_y + 1;
             pidx = curve_path[c];
+            rule_bit = fill_rule[pidx] == 1u ? 1u : 0u;  // MARK:82 only distinguishes rule 1 (even-odd) from 0
         }
         float tx = t0_ms, ty = t0_ms;  // point_coords slots 8, 9 (MI1:304-305)
         int i_inte_last = (int)f2u(-1.0f);
@@ -193,7 +195,7 @@ __global__ void __launch_bounds__(WALK_THREADS) k_walk(const FrameParams *__rest
                 tc = (tc < 0.0f) ? 0.0f : tc;
                 float ex, ey;
                 eval_point(type, cp, tc, ex, ey);
-                if (have_prev) emit_fragment(P, L, pcnt - 1, pidx, prev_t, tc, prev_x, prev_y, ex, ey, key64, val, taps);
+                if (have_prev) emit_fragment(P, L, pcnt - 1, pidx, rule_bit, prev_t, tc, prev_x, prev_y, ex, ey, key64, val, taps);
                 prev_t = tc; prev_x = ex; prev_y = ey; have_prev = true;
                 ++pcnt;
             }
@@ -218,7 +220,9 @@ __global__ void __launch_bounds__(WALK_THREADS) k_walk(const FrameParams *__rest
                         t_solve = t0;
                         if (vt0 != cst) {
                             const float raw_t0 = t0;
-                            uint32_t s0 = f2u(__fsub_rn(vt0, cst)), s_last = 0;
+                            // the sign of (vt0 - c) never changes: t0 only moves to points of the same sign
+                            const uint32_t s0 = f2u(__fsub_rn(vt0, cst));
+                            uint32_t s_last = 0;
 #pragma unroll 4
                             for (int j = 0; j < CUBIC_ITERATION_NUMBER; ++j) {
                                 const float tm = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
@@ -228,7 +232,7 @@ __global__ void __launch_bounds__(WALK_THREADS) k_walk(const FrameParams *__rest
                                 const float vtm = lerpf(b0, b1, tm);
                                 t_solve = tm;
                                 s_last = f2u(__fsub_rn(vtm, cst));
-                                if ((int)(s_last ^ s0) >= 0) { t0 = tm; s0 = s_last; }  // vt0 = vtm
+                                if ((int)(s_last ^ s0) >= 0) t0 = tm;  // vt0 = vtm (MI1:421-424)
                                 else t1 = tm;
                             }
                             if (fabsf(u2f(s_last)) > 1.f) t_solve = raw_t0;  // MI1:430-433
@@ -269,6 +273,7 @@ __global__ void __launch_bounds__(256) k_piece_close(const FrameParams *__restri
                                                      const uint32_t *__restrict__ curve_type,
                                                      const uint32_t *__restrict__ curve_pos_map,
                                                      const uint32_t *__restrict__ curve_path,
+                                                     const uint32_t *__restrict__ fill_rule,
                                                      const float2 *__restrict__ tpos, const float *__restrict__ cut_cache,
                                                      const int *__restrict__ offsets, const uint32_t *__restrict__ slots,
                                                      const FrameCounters *__restrict__ ctr, int capacity,
@@ -284,6 +289,7 @@ __global__ void __launch_bounds__(256) k_piece_close(const FrameParams *__restri
         if (offsets[c + 1] == offsets[c]) continue;
         const uint32_t type = curve_type[c];
         const uint32_t pidx = curve_path[c];
+        const uint32_t rule_bit = fill_rule[pidx] == 1u ? 1u : 0u;
         CurvePts cp;
         load_points(type, curve_pos_map[c], tpos, cp);
         const uint32_t n_cuts = f2u(cut_cache[5 * c + 4]) + 1u;
@@ -299,7 +305,7 @@ __global__ void __launch_bounds__(256) k_piece_close(const FrameParams *__restri
             float ax, ay, bx, by;
             eval_point(type, cp, t0, ax, ay);
             eval_point(type, cp, t1, bx, by);
-            emit_fragment(P, L, f, pidx, t0, t1, ax, ay, bx, by, key64, val, taps);
+            emit_fragment(P, L, f, pidx, rule_bit, t0, t1, ax, ay, bx, by, key64, val, taps);
         }
     }
 }
