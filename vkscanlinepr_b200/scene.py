@@ -116,12 +116,14 @@ def identity_rows():
 def fit_rows(vp, width, height, centred=True):
     """Uniform fit of the scene's `viewport` box to the frame. Rows m0..m3
     as TransPosIn expects them (compute_ubo.h:9-13): x' = dot((x,y,0,1), m0)."""
-    x0, y0, x1, y1 = [float(v) for v in vp]
-    s = np.float32(min(width / (x1 - x0), height / (y1 - y0)))
-    tx = ty = np.float32(0)
+    # every step in fp32, in the order tools/slpr_render.cpp uses, so that Python and C++ drivers agree bit for bit
+    f = np.float32
+    x0, y0, x1, y1 = [f(v) for v in vp]
+    s = min(f(width) / (x1 - x0), f(height) / (y1 - y0))
+    tx = ty = f(0)
     if centred:
-        tx = np.float32((width - float(s) * (x1 - x0)) * 0.5 - float(s) * x0)
-        ty = np.float32((height - float(s) * (y1 - y0)) * 0.5 - float(s) * y0)
+        tx = (f(width) - s * (x1 - x0)) * f(0.5) - s * x0
+        ty = (f(height) - s * (y1 - y0)) * f(0.5) - s * y0
     m = np.eye(4, dtype=np.float32)
     m[0, 0] = s; m[0, 3] = tx
     m[1, 1] = s; m[1, 3] = ty
