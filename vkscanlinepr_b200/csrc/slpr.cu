@@ -80,6 +80,7 @@ struct slpr_ctx {
     uint32_t *d_slots = nullptr;       // [5*nc] (length bucket << 26 | rank) of every monotone piece
     PieceRec *d_pieces = nullptr;      // [5*nc] piece records in length-sorted order
     float2 *d_boundary = nullptr;      // [5*nc] first / last emitted parameter of every piece
+    uint8_t *d_fixflag = nullptr;      // [5*nc] piece whose predecessor's boundary fragment must be redone
 
     // frame state
     FrameParams hp{};
@@ -94,6 +95,7 @@ struct slpr_ctx {
     uint32_t *d_val[2] = {nullptr, nullptr};
     int *d_wn = nullptr;
     int4 *d_rec = nullptr;
+    int *d_wsum = nullptr;  // per span tile: delta sum, then exclusive winding prefix
     // taps
     int *t_key32 = nullptr, *t_path = nullptr, *t_wind = nullptr, *t_skey32 = nullptr, *t_sidx = nullptr,
         *t_flags = nullptr, *t_scan3 = nullptr;
@@ -137,6 +139,7 @@ static void free_capacity(slpr_ctx *c) {
     for (int i = 0; i < 2; ++i) { cudaFree(c->d_key[i]); cudaFree(c->d_val[i]); c->d_key[i] = nullptr; c->d_val[i] = nullptr; }
     cudaFree(c->d_wn); c->d_wn = nullptr;
     cudaFree(c->d_rec); c->d_rec = nullptr;
+    cudaFree(c->d_wsum); c->d_wsum = nullptr;
     cudaFree(c->t_key32); cudaFree(c->t_path); cudaFree(c->t_wind); cudaFree(c->t_skey32); cudaFree(c->t_sidx);
     cudaFree(c->t_flags); cudaFree(c->t_scan3);
     c->t_key32 = c->t_path = c->t_wind = c->t_skey32 = c->t_sidx = c->t_flags = c->t_scan3 = nullptr;
@@ -150,8 +153,8 @@ static void free_scene(slpr_ctx *c) {
     cudaFree(c->d_pos); cudaFree(c->d_pos_path); cudaFree(c->d_cpm); cudaFree(c->d_ctype); cudaFree(c->d_cpath);
     cudaFree(c->d_frule); cudaFree(c->d_finfo); cudaFree(c->d_tpos); cudaFree(c->d_pvis); cudaFree(c->d_cut);
     cudaFree(c->d_count); cudaFree(c->d_offset); cudaFree(c->d_seg_tap);
-    cudaFree(c->d_slots); cudaFree(c->d_pieces); cudaFree(c->d_boundary);
-    c->d_slots = nullptr; c->d_pieces = nullptr; c->d_boundary = nullptr;
+    cudaFree(c->d_slots); cudaFree(c->d_pieces); cudaFree(c->d_boundary); cudaFree(c->d_fixflag);
+    c->d_slots = nullptr; c->d_pieces = nullptr; c->d_boundary = nullptr; c->d_fixflag = nullptr;
     c->d_pos = nullptr; c->d_pos_path = c->d_cpm = c->d_ctype = c->d_cpath = c->d_frule = c->d_finfo = nullptr;
     c->d_tpos = nullptr; c->d_pvis = nullptr; c->d_cut = nullptr; c->d_count = c->d_offset = c->d_seg_tap = nullptr;
     c->scene_loaded = false;
@@ -166,6 +169,7 @@ static int alloc_capacity(slpr_ctx *c, int cap) {
         CU(cudaMalloc(&c->d_val[i], n * 4));
     }
     CU(cudaMalloc(&c->d_rec, (2 * n + 1) * sizeof(int4)));
+    CU(cudaMalloc(&c->d_wsum, (n / SP_TILE + 4) * sizeof(int)));
     if (c->flags & SLPR_FLAG_TAPS) {
         CU(cudaMalloc(&c->d_wn, (n + 4) * 4));
         CU(cudaMalloc(&c->d_inter, (n + 1) * sizeof(int2)));
@@ -318,6 +322,7 @@ extern "C" int slpr_load_scene(slpr_ctx *c, const float *pos_xy, const uint32_t 
     CU(cudaMalloc(&c->d_slots, std::max<size_t>(n_curves, 1) * 5 * 4));
     CU(cudaMalloc(&c->d_pieces, std::max<size_t>(n_curves, 1) * 5 * sizeof(PieceRec)));
     CU(cudaMalloc(&c->d_boundary, std::max<size_t>(n_curves, 1) * 5 * sizeof(float2)));
+    CU(cudaMalloc(&c->d_fixflag, std::max<size_t>(n_curves, 1) * 5));
     if (c->flags & SLPR_FLAG_TAPS) CU(cudaMalloc(&c->d_seg_tap, ((size_t)n_paths + 1) * 4));
     // compact key geometry: x cell in [0,(W'+4)/2], row rank in [0,ny], path in [0,P)
     const int Wp = (int)(c->W & ~1u);
@@ -396,10 +401,10 @@ static int enqueue_frame(slpr_ctx *c, cudaStream_t s, bool timed, int &launches)
                                                              c->d_pieces);
     k_walk<<<c->num_sms * std::max(1, c->walk_blocks_per_sm), WALK_THREADS, 0, s>>>(
         c->d_params, c->d_pieces, c->d_cpath, c->d_frule, c->d_ctr, c->cap, WalkTemp{c->d_bucket_hist, c->d_tickets + 3 + RS_MAX_PASSES},
-        c->L, c->d_key[0], c->d_val[0], ft, c->d_inter, c->d_boundary);
-    k_piece_close<<<grid_for(c, c->nc, 256, 8), 256, 0, s>>>(c->d_params, c->nc, c->d_ctype, c->d_cpm, c->d_cpath, c->d_frule, c->d_tpos,
+        c->L, c->d_key[0], c->d_val[0], ft, c->d_inter, c->d_boundary, c->d_fixflag);
+    k_piece_fix<<<grid_for(c, c->nc, 256, 8), 256, 0, s>>>(c->d_params, c->nc, c->d_ctype, c->d_cpm, c->d_cpath, c->d_frule, c->d_tpos,
                                                               c->d_cut, c->d_offset, c->d_slots, c->d_ctr, c->cap,
-                                                              c->d_bucket_hist, c->d_pieces, c->d_boundary, c->L, c->d_key[0],
+                                                              c->d_bucket_hist, c->d_pieces, c->d_boundary, c->d_fixflag, c->L, c->d_key[0],
                                                               c->d_val[0], ft);
     launches += 3;
     if (timed) CU(cudaEventRecord(c->ev[4], s));
@@ -426,7 +431,12 @@ static int enqueue_frame(slpr_ctx *c, cudaStream_t s, bool timed, int &launches)
     if (timed) CU(cudaEventRecord(c->ev[7], s));
     // ---- winding scan + mark + flag scan + emit: one kernel, two chained look-backs
     SpanTaps stp{c->d_wn, c->t_sidx, c->t_skey32, c->t_flags, c->t_scan3};
-    SpanTemp stmp{c->d_status[1], c->d_status[2], c->d_tickets + 1};
+    SpanTemp stmp{c->d_wsum, c->d_status[1], c->d_status[2], c->d_tickets + 1};
+#if SLPR_SP_WPRE
+    k_wsum<<<c->num_sms * 4, SP_THREADS, 0, s>>>(c->d_val[cur], c->d_ctr, c->cap, c->d_wsum);
+    k_wscan<<<1, 1024, 0, s>>>(c->d_ctr, c->cap, c->d_wsum, c->d_wn);
+    launches += 2;
+#endif
     if (timed) CU(cudaEventRecord(c->ev[8], s));
     k_spans<<<c->num_sms * std::max(1, c->span_blocks_per_sm), SP_THREADS, 0, s>>>(c->d_key[cur], c->d_val[cur], c->d_finfo, c->d_rec, c->d_ctr,
                                                   c->L, (int)c->W, (int)c->H, c->cap, stp, stmp);

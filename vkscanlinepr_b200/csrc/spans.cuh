@@ -28,6 +28,9 @@ namespace slpr {
 #ifndef SLPR_SP_SLEEP
 #define SLPR_SP_SLEEP 0
 #endif
+#ifndef SLPR_SP_WPRE
+#define SLPR_SP_WPRE 1   /* 1: winding prefix per tile from k_wsum + k_wscan (no chain W); 0: chained look-back */
+#endif
 #ifndef SLPR_SP_FAKE
 #define SLPR_SP_FAKE 0   /* timing experiments only: skip the look-back (wrong results) */
 #endif
@@ -35,7 +38,10 @@ namespace slpr {
 #define SLPR_SP_NOSTORE 0 /* timing experiments only: skip the record stores */
 #endif
 constexpr int SP_THREADS = SLPR_SP_THREADS;
-constexpr int SP_ITEMS = 8;
+#ifndef SLPR_SP_ITEMS
+#define SLPR_SP_ITEMS 8
+#endif
+constexpr int SP_ITEMS = SLPR_SP_ITEMS;  // consecutive fragments per thread (4 or 8)
 constexpr int SP_BLOCKS = SLPR_SP_BLOCKS;
 constexpr int SP_LOOK = SLPR_SP_LOOK;  // tile states polled per lane per look-back round trip (window = 32 * SP_LOOK tiles)
 constexpr int SP_TILE = SP_THREADS * SP_ITEMS;
@@ -49,7 +55,8 @@ struct SpanTaps {
 };
 
 struct SpanTemp {
-    unsigned long long *status_w;  // chain W tile states (zeroed per frame)
+    const int *wprefix;            // [tiles] exclusive winding prefix per tile (k_wsum + k_wscan), SLPR_SP_WPRE
+    unsigned long long *status_w;  // chain W tile states (zeroed per frame), !SLPR_SP_WPRE
     unsigned long long *status_f;  // chain F tile states
     int *ticket;
 };
@@ -197,11 +204,15 @@ __global__ void __launch_bounds__(SP_THREADS, SP_BLOCKS) k_spans(const uint64_t 
                 if (lane >= d) pi += o;
             }
             const uint32_t total = __shfl_sync(0xFFFFFFFFu, pi, SP_THREADS / 32 - 1);
+#if SLPR_SP_WPRE
+            const unsigned long long excl = (unsigned long long)(uint32_t)tmp.wprefix[tile];
+#else
             const unsigned long long excl = warp_lookback(tmp.status_w, tile, (unsigned long long)total, lane);
+#endif
             if (lane < SP_THREADS / 32) s_warp[lane] = pi - p;  // exclusive offset of each warp
             if (lane == 0) {
                 s_prefix = excl;
-                if (tile == ntiles - 1) {
+                if (!SLPR_SP_WPRE && tile == ntiles - 1) {
                     const int wtotal = (int)(uint32_t)(excl + total);
                     ctr->wn_total = wtotal;
                     if (taps.wn) taps.wn[n] = wtotal;
@@ -320,6 +331,91 @@ __global__ void __launch_bounds__(SP_THREADS, SP_BLOCKS) k_spans(const uint64_t 
             }
         }
         // the __syncthreads after the next ticket fetch orders the reuse of s_warp / s_prefix
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Winding prefix per span tile without a chain: tile sums of the deltas (k_wsum, reads the 4-byte
+// values once), then one block scans the few thousand tile sums (k_wscan). k_spans then starts
+// every tile with its global winding prefix known and needs a single look-back chain (the flag
+// counts), whose aggregate no longer waits for another chain to resolve.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SP_THREADS) k_wsum(const uint32_t *__restrict__ sval, const FrameCounters *__restrict__ ctr,
+                                                     int capacity, int *__restrict__ wsum) {
+    __shared__ int s_w[SP_THREADS / 32];
+    const int nf = ctr->n_fragments;
+    if (nf > capacity) return;
+    const long long n = nf;
+    const long long ntiles = (n == 0) ? 1 : (n + SP_TILE - 1) / SP_TILE;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long i0 = tile * SP_TILE + (long long)tid * SP_ITEMS;
+        int dsum = 0;
+        if (i0 + SP_ITEMS <= n) {
+#pragma unroll
+            for (int j = 0; j < SP_ITEMS; j += 4) {
+                const int4 q = ld_stream(reinterpret_cast<const int4 *>(sval + i0 + j));
+                dsum += (int)((uint32_t)q.x >> 30) + (int)((uint32_t)q.y >> 30) + (int)((uint32_t)q.z >> 30) + (int)((uint32_t)q.w >> 30) - 4;
+            }
+        } else {
+            for (int j = 0; j < SP_ITEMS; ++j)
+                if (i0 + j < n) dsum += (int)(sval[i0 + j] >> 30) - 1;
+        }
+        dsum = __reduce_add_sync(0xFFFFFFFFu, dsum);
+        if (lane == 0) s_w[warp] = dsum;
+        __syncthreads();
+        if (warp == 0) {
+            int v = (lane < SP_THREADS / 32) ? s_w[lane] : 0;
+            v = __reduce_add_sync(0xFFFFFFFFu, v);
+            if (lane == 0) wsum[tile] = v;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(1024) k_wscan(FrameCounters *__restrict__ ctr, int capacity, int *__restrict__ wsum,
+                                                int *__restrict__ wn_tap) {
+    __shared__ int s_w[32];
+    __shared__ int s_carry;
+    const int nf = ctr->n_fragments;
+    if (nf > capacity) return;
+    const long long n = nf;
+    const int ntiles = (int)((n == 0) ? 1 : (n + SP_TILE - 1) / SP_TILE);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < ntiles; base += 1024) {
+        const int i = base + tid;
+        const int v = (i < ntiles) ? wsum[i] : 0;
+        int incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        if (lane == 31) s_w[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int w = s_w[lane];
+            int wi = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o = __shfl_up_sync(0xFFFFFFFFu, wi, d);
+                if (lane >= d) wi += o;
+            }
+            s_w[lane] = wi - w;
+        }
+        __syncthreads();
+        const int carry = s_carry;
+        const int excl = carry + s_w[warp] + incl - v;
+        if (i < ntiles) wsum[i] = excl;  // exclusive winding prefix of tile i
+        __syncthreads();
+        if (tid == 1023) s_carry = excl + v;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        ctr->wn_total = s_carry;
+        if (wn_tap) wn_tap[n] = s_carry;
     }
 }
 

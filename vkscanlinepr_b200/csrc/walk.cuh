@@ -14,8 +14,8 @@
 //                  bisection — 70 % of all instructions — executes converged; every emitted record
 //                  also closes the fragment that began at the previous record (gen_fragment fused,
 //                  the (curve, tbits) intersection records are only a debug tap now);
-//   k_piece_close  one thread per curve: the fragment that spans a piece boundary (last record of a
-//                  piece -> first record of the next piece, or t = 1 at the curve end, GF:99,113-115).
+//   k_piece_fix    one thread per curve: re-emits the boundary fragment of the rare pieces whose successor
+//                  did not start exactly at its t0 (only possible after the MI0:340 cut-order slip).
 // The arithmetic of every step is the reference's, operation for operation.
 #pragma once
 #include "geom.cuh"
@@ -118,7 +118,8 @@ __global__ void __launch_bounds__(WALK_THREADS) k_walk(const FrameParams *__rest
                                                        const FrameCounters *__restrict__ ctr, int capacity, WalkTemp tmp,
                                                        KeyLayout L, uint64_t *__restrict__ key64,
                                                        uint32_t *__restrict__ val, FragTaps taps,
-                                                       int2 *__restrict__ inter, float2 *__restrict__ boundary) {
+                                                       int2 *__restrict__ inter, float2 *__restrict__ boundary,
+                                                       uint8_t *__restrict__ fixflag) {
     const int nf_total = ctr->n_fragments;
     if (nf_total > capacity) return;
     if (taps.key32 && blockIdx.x == 0 && threadIdx.x == 0 && nf_total > 0) taps.key32[nf_total] = -1;  // GF:240
@@ -263,13 +264,27 @@ __global__ void __launch_bounds__(WALK_THREADS) k_walk(const FrameParams *__rest
                 if (side) ty = tagged; else tx = tagged;
             }
         }
-        // first / last emitted parameter of the piece, for the fragment across the piece boundary
-        if (active) boundary[5 * c + piece] = make_float2(u2f(first_bits), u2f(last_bits));
+        // ---- the fragment across the piece boundary: last record of this piece -> first record of the
+        //      next piece of the curve, or t = 1 at the curve's end (GF:99,113-115). The next piece's first
+        //      record is its start parameter t0 = this piece's tagged t1 (MI1:304-305,442) in every case
+        //      but one: when the MI0:340 slip leaves the cuts out of order, a bisection can land below t0.
+        //      So the boundary fragment is emitted here with t1 = (t1_ms without tag bits), and a piece
+        //      whose first record does not match its t0 raises a flag for k_piece_fix to redo its
+        //      predecessor's boundary fragment from the recorded parameters.
+        if (active) {
+            float tcl = u2f(f2u(t1_ms) & 0xFFFFFFFCu);
+            tcl = (tcl < 0.0f) ? 0.0f : tcl;
+            float ex, ey;
+            eval_point(type, cp, tcl, ex, ey);
+            emit_fragment(P, L, pcnt - 1, pidx, rule_bit, prev_t, tcl, prev_x, prev_y, ex, ey, key64, val, taps);
+            boundary[5 * c + piece] = make_float2(u2f(first_bits), u2f(last_bits));
+            fixflag[5 * c + piece] = (piece > 0 && (first_bits & 0xFFFFFFFCu) != (f2u(t0_ms) & 0xFFFFFFFCu)) ? 1 : 0;
+        }
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_piece_close(const FrameParams *__restrict__ P, uint32_t n_curves,
+__global__ void __launch_bounds__(256) k_piece_fix(const FrameParams *__restrict__ P, uint32_t n_curves,
                                                      const uint32_t *__restrict__ curve_type,
                                                      const uint32_t *__restrict__ curve_pos_map,
                                                      const uint32_t *__restrict__ curve_path,
@@ -279,7 +294,7 @@ __global__ void __launch_bounds__(256) k_piece_close(const FrameParams *__restri
                                                      const FrameCounters *__restrict__ ctr, int capacity,
                                                      const uint32_t *__restrict__ bucket_hist,
                                                      const PieceRec *__restrict__ pieces, const float2 *__restrict__ boundary,
-                                                     KeyLayout L, uint64_t *__restrict__ key64, uint32_t *__restrict__ val,
+                                                     const uint8_t *__restrict__ fixflag, KeyLayout L, uint64_t *__restrict__ key64, uint32_t *__restrict__ val,
                                                      FragTaps taps) {
     __shared__ uint32_t s_dbase[WALK_BUCKETS];
     __shared__ uint32_t s_total;
@@ -287,19 +302,23 @@ __global__ void __launch_bounds__(256) k_piece_close(const FrameParams *__restri
     bucket_bases(bucket_hist, s_dbase, &s_total);
     for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n_curves; c += gridDim.x * blockDim.x) {
         if (offsets[c + 1] == offsets[c]) continue;
+        const uint32_t n_cuts = f2u(cut_cache[5 * c + 4]) + 1u;
+        bool any = false;
+        for (uint32_t piece = 1; piece < n_cuts; ++piece) any |= fixflag[5 * c + piece] != 0;
+        if (!any) continue;  // the common case: nothing to redo
         const uint32_t type = curve_type[c];
         const uint32_t pidx = curve_path[c];
         const uint32_t rule_bit = fill_rule[pidx] == 1u ? 1u : 0u;
         CurvePts cp;
         load_points(type, curve_pos_map[c], tpos, cp);
-        const uint32_t n_cuts = f2u(cut_cache[5 * c + 4]) + 1u;
-        for (uint32_t piece = 0; piece < n_cuts; ++piece) {
+        for (uint32_t piece = 0; piece + 1 < n_cuts; ++piece) {
+            if (!fixflag[5 * c + piece + 1]) continue;
             const uint4 m = pieces[piece_position(s_dbase, slots[5 * c + piece])].m;
             const int n_loop = (int)(m.x & 0x7FFFu) + (int)((m.x >> 15) & 0x7FFFu) + 1;
             const int f = (int)m.z + n_loop - 1;  // last record of the piece
-            // GF:99-104,113-115: t0 from this record, t1 from the next record of the curve or 1.0 at its end
+            // GF:99-104: t0 from this record, t1 from the next record of the curve
             float t0 = u2f(f2u(boundary[5 * c + piece].y) & 0xFFFFFFFCu);
-            float t1 = (piece + 1 < n_cuts) ? u2f(f2u(boundary[5 * c + piece + 1].x) & 0xFFFFFFFCu) : 1.0f;
+            float t1 = u2f(f2u(boundary[5 * c + piece + 1].x) & 0xFFFFFFFCu);
             t0 = (t0 < 0.0f) ? 0.0f : t0;
             t1 = (t1 < 0.0f) ? 0.0f : t1;
             float ax, ay, bx, by;
