@@ -31,6 +31,9 @@ namespace slpr {
 #ifndef SLPR_RS_VAL_POS
 #define SLPR_RS_VAL_POS 2       /* where the values are loaded: 0 after ranking, 1 before look-back, 2 at the scatter */
 #endif
+#ifndef SLPR_RS_CHAINS
+#define SLPR_RS_CHAINS 1        /* independent ranking chains per warp (each with its own shared histogram row) */
+#endif
 #ifndef SLPR_RS_LB_WINDOW
 #define SLPR_RS_LB_WINDOW 4     /* predecessors polled per look-back round trip */
 #endif
@@ -39,12 +42,15 @@ constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_ITEMS = SLPR_RS_ITEMS;
 constexpr int RS_BLOCKS_PER_SM = SLPR_RS_BLOCKS;
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 6144 pairs per tile
+constexpr int RS_CHAINS = SLPR_RS_CHAINS;
+constexpr int RS_ROWS = RS_WARPS * RS_CHAINS;   // histogram rows: (warp, chain) in tile order
+static_assert(RS_ITEMS % RS_CHAINS == 0, "items must split evenly into ranking chains");
 constexpr int RS_BINS = 256;
 constexpr int RS_MAX_PASSES = 8;
 #define LB_MASK ((1u << 30) - 1)
 #define LB_AGG (1u << 30)
 #define LB_PREFIX (2u << 30)
-constexpr size_t RS_SMEM_BYTES = (size_t)RS_TILE * 12 + (size_t)RS_WARPS * RS_BINS * 4 + 3 * RS_BINS * 4 + 64;
+constexpr size_t RS_SMEM_BYTES = (size_t)RS_TILE * 12 + (size_t)RS_ROWS * RS_BINS * 4 + 3 * RS_BINS * 4 + 64;
 
 struct SortCount {  // where the element count comes from (device counter for the frame, static for the API)
     const int *n_dev;
@@ -164,8 +170,8 @@ __global__ void __launch_bounds__(RS_THREADS, RS_BLOCKS_PER_SM) k_onesweep(const
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t *s_keys = reinterpret_cast<uint64_t *>(smem_raw);                              // [RS_TILE]
     uint32_t *s_vals = reinterpret_cast<uint32_t *>(smem_raw + (size_t)RS_TILE * 8);        // [RS_TILE]
-    uint32_t *s_whist = reinterpret_cast<uint32_t *>(smem_raw + (size_t)RS_TILE * 12);      // [RS_WARPS][256]
-    uint32_t *s_start = s_whist + RS_WARPS * RS_BINS;                                       // [256] tile digit start
+    uint32_t *s_whist = reinterpret_cast<uint32_t *>(smem_raw + (size_t)RS_TILE * 12);      // [RS_ROWS][256]
+    uint32_t *s_start = s_whist + RS_ROWS * RS_BINS;                                       // [256] tile digit start
     uint32_t *s_gbase = s_start + RS_BINS;                                                  // [256] global base - start
     uint32_t *s_misc = s_gbase + RS_BINS;                                                   // [256]: warp sums, ticket
     const long long n = cnt.get();
@@ -178,7 +184,7 @@ __global__ void __launch_bounds__(RS_THREADS, RS_BLOCKS_PER_SM) k_onesweep(const
 
     while (true) {
         if (tid == 0) s_misc[32] = (uint32_t)atomicAdd(&tmp.tickets[pass], 1);
-        for (int i = tid; i < RS_WARPS * RS_BINS; i += RS_THREADS) s_whist[i] = 0;
+        for (int i = tid; i < RS_ROWS * RS_BINS; i += RS_THREADS) s_whist[i] = 0;
         __syncthreads();
         const long long tile = (long long)s_misc[32];
         if (tile >= ntiles) break;
@@ -195,17 +201,24 @@ __global__ void __launch_bounds__(RS_THREADS, RS_BLOCKS_PER_SM) k_onesweep(const
         }
         // ---- rank inside the warp's chunk: match.any groups lanes with the same digit; the lowest lane
         //      of each group bumps the warp-private bin, everyone takes bin_before + rank in group.
+        //      The chunk is cut into RS_CHAINS consecutive sub-chunks with their own histogram rows, ranked
+        //      in an interleaved loop: the serial shared-memory read-modify-write chains overlap.
         uint16_t rank[RS_ITEMS];
-        uint32_t *wh = s_whist + warp * RS_BINS;
+        constexpr int PER = RS_ITEMS / RS_CHAINS;
 #pragma unroll
-        for (int i = 0; i < RS_ITEMS; ++i) {
-            const uint32_t d = (uint32_t)(key[i] >> shift) & 0xFFu;
-            const uint32_t peers = match_digit(d);
-            const int leader = __ffs(peers) - 1;
-            uint32_t before = 0;
-            if (lane == leader) { before = wh[d]; wh[d] = before + __popc(peers); }
-            before = __shfl_sync(0xFFFFFFFFu, before, leader);
-            rank[i] = (uint16_t)(before + __popc(peers & lt));
+        for (int i = 0; i < PER; ++i) {
+#pragma unroll
+            for (int g = 0; g < RS_CHAINS; ++g) {
+                const int it = g * PER + i;
+                uint32_t *wh = s_whist + (warp * RS_CHAINS + g) * RS_BINS;
+                const uint32_t d = (uint32_t)(key[it] >> shift) & 0xFFu;
+                const uint32_t peers = match_digit(d);
+                const int leader = __ffs(peers) - 1;
+                uint32_t before = 0;
+                if (lane == leader) { before = wh[d]; wh[d] = before + __popc(peers); }
+                before = __shfl_sync(0xFFFFFFFFu, before, leader);
+                rank[it] = (uint16_t)(before + __popc(peers & lt));
+            }
             __syncwarp();
         }
 #if SLPR_RS_VAL_POS == 0
@@ -223,7 +236,7 @@ __global__ void __launch_bounds__(RS_THREADS, RS_BLOCKS_PER_SM) k_onesweep(const
         uint32_t count = 0;
         if (tid < RS_BINS) {
 #pragma unroll
-            for (int w = 0; w < RS_WARPS; ++w) {
+            for (int w = 0; w < RS_ROWS; ++w) {
                 const uint32_t c = s_whist[w * RS_BINS + tid];
                 s_whist[w * RS_BINS + tid] = count;
                 count += c;
@@ -257,6 +270,9 @@ __global__ void __launch_bounds__(RS_THREADS, RS_BLOCKS_PER_SM) k_onesweep(const
             uint32_t wb = 0;
             for (int w = 0; w < warp; ++w) wb += s_misc[w];
             const uint32_t start = s_start[tid] + wb;
+            // fold the digit's start into every row offset: the scatter then needs one table read per key
+#pragma unroll
+            for (int w = 0; w < RS_ROWS; ++w) s_whist[w * RS_BINS + tid] += start;
             // chained look-back for this digit; SLPR_RS_LB_WINDOW predecessors are polled per round trip
             uint32_t excl = 0;
             if (tile > 0) {
@@ -295,7 +311,7 @@ __global__ void __launch_bounds__(RS_THREADS, RS_BLOCKS_PER_SM) k_onesweep(const
 #pragma unroll
         for (int i = 0; i < RS_ITEMS; ++i) {
             const uint32_t d = (uint32_t)(key[i] >> shift) & 0xFFu;
-            const uint32_t pos = s_start[d] + s_whist[warp * RS_BINS + d] + rank[i];
+            const uint32_t pos = s_whist[(warp * RS_CHAINS + i / (RS_ITEMS / RS_CHAINS)) * RS_BINS + d] + rank[i];
             s_keys[pos] = key[i];
             s_vals[pos] = val[i];
         }
