@@ -1,6 +1,6 @@
 /*
  * oracle.c — CPU restatement of the VkScanlinePR compute shaders.
- * TEST INFRASTRUCTURE ONLY; "parity unpinned" for the shader stages — see oracle.h.
+ * TEST INFRASTRUCTURE ONLY; parity pinned against the shipped SPIR-V by interpretation — see oracle.h.
  * Build: gcc -O2 -ffp-contract=off -fno-fast-math -fopenmp (oracle/Makefile).
  */
 #include "oracle.h"

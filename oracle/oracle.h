@@ -5,13 +5,20 @@
  * and bench.py's cpu_baseline / --impl reference legs may load it. The shipped renderer
  * (vkscanlinepr_b200/csrc, libslpr.so) never links or calls anything in oracle/.
  *
- * PARITY STATUS: "parity unpinned" for the shader stages. The reference implements this
- * path only as GLSL/SPIR-V (no CPU code, no tests, no golden outputs for the shipped
- * scenes) and no Vulkan ICD exists in the build container or on the GPU box, so the
- * restatement below cannot be checked against a live run of the reference. What IS
- * pinned: (1) scene flattening (loadVG + RVG parser) against the reference's own parser
- * compiled from its sources (oracle/_ref, see oracle/Makefile); (2) the output record
- * format / ordering invariants against workdir/test_data.csv and test_data3.csv.
+ * PARITY STATUS: pinned against the reference's own shipped binaries, by interpretation. The
+ * reference implements this path only as GLSL/SPIR-V (no CPU code, no tests, no golden outputs for
+ * its scenes) and no Vulkan loader/ICD exists in the build container or on the GPU box, so the
+ * shaders cannot run on a driver. Instead oracle/spirv_exec.py (a SPIR-V interpreter written for
+ * this purpose) executes the prebuilt workdir/shaders/**/spv/*.comp.spv along drawFrame's dispatch
+ * sequence (tools/make_spirv_golden.py); every buffer of those frames is committed under
+ * tests/golden/spirv_*.npz and this restatement reproduces all of them bit for bit
+ * (tests/test_spirv_golden.py: 5 scenes incl. a 4-cut cubic, QUADRIC-typed curves, clipping on
+ * all edges, a tiger subset with a winding residue). Caveats: the interpreter evaluates fp32
+ * without FMA contraction and sums OpDot left to right (a real driver may differ),
+ * and the fixed-function line raster of stage 5 is restated from the Vulkan rules, not executed.
+ * Also pinned: (1) scene flattening (loadVG + RVG parser) against the reference's own parser
+ * compiled from its sources (oracle/_ref, see oracle/Makefile); (2) the output record format /
+ * ordering invariants against workdir/test_data.csv and test_data3.csv.
  *
  * All citations are file:line relative to /root/reference/.
  *   TP   = workdir/shaders/scanline/compute/transform_pos.comp

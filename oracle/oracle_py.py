@@ -1,6 +1,6 @@
 """ctypes binding of oracle/liboracle.so — the CPU restatement of the reference shaders.
 
-TEST INFRASTRUCTURE ONLY ("parity unpinned" for the shader stages, see oracle/oracle.h).
+TEST INFRASTRUCTURE ONLY (parity status: see oracle/oracle.h).
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
 import this module. The product (vkscanlinepr_b200) never does.
 """

@@ -73,3 +73,43 @@ def check_record_invariants(rec, width=None):
     if width is not None:
         assert np.all((x[sp[m]] + w[sp[m]])[~own] >= width)
     return int(is_frag.sum()), int((~is_frag).sum())
+
+
+def edge_scene():
+    """Corner cases for a 64x48 frame: a cubic with four monotonic cuts (the MI0:340 slip leaves them out of
+    order), a curve typed QUADRIC (the shaders' TODO arms), edges on exact grid lines and exact negative
+    integers (float2int_rd vs floor), curves leaving the frame on all four sides, a path entirely outside."""
+    pos, pos_path, cpm, ctype, cpath = [], [], [], [], []
+
+    def add(pts, path, typ=None):
+        cpm.append(len(pos)); ctype.append(typ if typ is not None else (S.LINE if len(pts) == 2 else S.CUBIC)); cpath.append(path)
+        for p in pts:
+            pos.append(p); pos_path.append(path)
+
+    # path 0: closed shape whose first segment is an S-shaped cubic with 2 x-extrema and 2 y-extrema
+    add([(8, 8), (60, 4), (-6, 40), (50, 30)], 0)
+    add([(50, 30), (52, 44)], 0)
+    add([(52, 44), (6, 42)], 0)
+    add([(6, 42), (8, 8)], 0)
+    # path 1: axis-aligned rectangle on exact even grid lines, partly left of and below the frame (exact negative integers)
+    rect = [(-4.0, -2.0), (20.0, -2.0), (20.0, 10.0), (-4.0, 10.0)]
+    for i in range(4):
+        add([rect[i], rect[(i + 1) % 4]], 1)
+    # path 2: big triangle leaving the frame on the right and the top
+    tri = [(30.5, 20.25), (90.0, 25.0), (40.0, 70.0)]
+    for i in range(3):
+        add([tri[i], tri[(i + 1) % 3]], 2)
+    # path 3: contains a QUADRIC-typed curve (3 points; the reference's parser never emits one) between two lines
+    add([(12, 30), (20, 36)], 3)
+    add([(20, 36), (26, 28), (30, 34)], 3, typ=S.QUADRIC)
+    add([(30, 34), (12, 30)], 3)
+    # path 4: entirely outside (invisible)
+    out = [(100, 100), (120, 100), (110, 120)]
+    for i in range(3):
+        add([out[i], out[(i + 1) % 3]], 4)
+    # path 5: a closed blob of two cubics (1-2 cuts each), even-odd
+    add([(34, 6), (48, 2), (58, 14), (44, 18)], 5)
+    add([(44, 18), (30, 22), (24, 10), (34, 6)], 5)
+    return S.Scene(np.array(pos, np.float32), np.array(pos_path, np.uint32), np.array(cpm, np.uint32),
+                   np.array(ctype, np.uint32), np.array(cpath, np.uint32), np.array([0, 1, 0, 0, 0, 1], np.uint32),
+                   np.array([0xFF0000FF, 0xFF00FF00, 0xFFFF0000, 0xFF00FFFF, 0xFFFFFFFF, 0xFF808080], np.uint32), "edge")
