@@ -3,6 +3,7 @@
  * TEST INFRASTRUCTURE ONLY; parity pinned against the shipped SPIR-V by interpretation — see oracle.h.
  * Build: gcc -O2 -ffp-contract=off -fno-fast-math -fopenmp (oracle/Makefile).
  */
+#define _POSIX_C_SOURCE 200809L /* clock_gettime */
 #include "oracle.h"
 #include <math.h>
 #include <stdlib.h>
