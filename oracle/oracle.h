@@ -9,7 +9,7 @@
  * reference implements this path only as GLSL/SPIR-V (no CPU code, no tests, no golden outputs for
  * its scenes) and no Vulkan loader/ICD exists in the build container or on the GPU box, so the
  * shaders cannot run on a driver. Instead oracle/spirv_exec.py (a SPIR-V interpreter written for
- * this purpose) executes the prebuilt workdir/shaders/**/spv/*.comp.spv along drawFrame's dispatch
+ * this purpose) executes the prebuilt workdir/shaders/<dir>/spv/<name>.comp.spv along drawFrame's dispatch
  * sequence (tools/make_spirv_golden.py); every buffer of those frames is committed under
  * tests/golden/spirv_*.npz and this restatement reproduces all of them bit for bit
  * (tests/test_spirv_golden.py: 5 scenes incl. a 4-cut cubic, QUADRIC-typed curves, clipping on
