@@ -131,6 +131,13 @@ SLPR_API int slpr_readback(slpr_ctx *ctx, uint8_t *rgba, size_t stride_bytes);
 /* set_mvp + render + readback in one call: the end-to-end path bench.py times as `e2e`. */
 SLPR_API int slpr_render_to_host(slpr_ctx *ctx, const float rows[16], uint8_t *rgba, size_t stride_bytes);
 
+/* Pipelined variant of slpr_render_to_host for frame sequences: returns as soon as the frame and
+ * its device-to-host copy are enqueued (two framebuffers, a second stream for the copies), so the
+ * copy of frame i overlaps the rendering of frame i+1. `rgba` (pinned memory for a truly
+ * asynchronous copy) holds the frame after slpr_wait_host(); use two host buffers alternately. */
+SLPR_API int slpr_submit_to_host(slpr_ctx *ctx, const float rows[16], uint8_t *rgba, size_t stride_bytes);
+SLPR_API int slpr_wait_host(slpr_ctx *ctx);
+
 /* Device pointer of the last rendered frame (RGBA8) and its row stride. Does not synchronise. */
 SLPR_API int slpr_framebuffer(slpr_ctx *ctx, void **dev_rgba, size_t *stride_bytes);
 

@@ -170,3 +170,22 @@ def test_error_paths():
         V.ScanlineRasterizer(0, V.FLAG_CONTRACT_FMA).initialize(None, 64, 64)
     with pytest.raises(V.SlprError):
         V.ScanlineRasterizer(0, 0).initialize(None, 40000, 64)
+
+
+def test_pipelined_submit_to_host():
+    """slpr_submit_to_host / slpr_wait_host: two framebuffers, copies on a second stream; every frame of a
+    sequence with changing matrices must land in its host buffer intact."""
+    import torch
+    sc, vp = util.golden_scene("tiger")
+    W, H = 512, 384
+    mats = [np.asarray(S.anim_rows(f, W, H) @ S.fit_rows(vp, W, H), np.float32) for f in (0, 5, 9, 14, 20)]
+    refs = [O.render(sc, m, W, H)["rgba"] for m in mats]
+    r = V.ScanlineRasterizer(0, 0).initialize(None, W, H)
+    r.loadVG(sc)
+    bufs = [torch.empty((H, W, 4), dtype=torch.uint8, pin_memory=True).numpy() for _ in mats]
+    for m, b in zip(mats, bufs):
+        r.submit_to_host(m, b)
+    r.wait_host()
+    for i, (b, ref) in enumerate(zip(bufs, refs)):
+        assert np.array_equal(b, ref), f"frame {i}"
+    r.close()

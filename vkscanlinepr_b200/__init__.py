@@ -205,6 +205,14 @@ class ScanlineRasterizer:
         _check(lib().slpr_render_to_host(self._h, _p(r), _p(out), C.c_size_t(out.strides[0])))
         return out
 
+    def submit_to_host(self, rows, out):
+        """Pipelined render + readback: returns once enqueued; `out` is valid after wait_host()."""
+        r = np.ascontiguousarray(rows, dtype=np.float32).reshape(16)
+        _check(lib().slpr_submit_to_host(self._h, _p(r), _p(out), C.c_size_t(out.strides[0])))
+
+    def wait_host(self):
+        _check(lib().slpr_wait_host(self._h))
+
     def set_band(self, y0, y1):
         _check(lib().slpr_set_band(self._h, C.c_uint32(y0), C.c_uint32(y1)))
 

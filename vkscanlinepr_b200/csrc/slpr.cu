@@ -117,12 +117,19 @@ struct slpr_ctx {
     uint32_t *d_cells = nullptr;
     int cw = 0, ch = 0;
     uint8_t *d_fb = nullptr;
+    uint8_t *d_fb2 = nullptr;          // second framebuffer of the pipelined host path (lazy)
+    uint8_t *fb_cur = nullptr;         // framebuffer the next frame renders into (d_fb unless pipelining)
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_rendered[2] = {}, ev_copied[2] = {};
+    bool copy_pending[2] = {false, false};
+    unsigned pipe_frame = 0;
     size_t fb_stride = 0;
     uint8_t *target = nullptr;
     size_t target_stride = 0;
 
-    cudaGraphExec_t gexec = nullptr;
-    bool graph_valid = false;
+    cudaGraphExec_t gexec = nullptr;   // graph of the frame for `graph_fb`
+    cudaGraphExec_t gexec2 = nullptr;  // and for the second framebuffer
+    bool graph_valid = false, graph2_valid = false;
     cudaEvent_t ev[SLPR_STAGE_COUNT + 1] = {};
     bool stage_times_valid = false;
     uint64_t launches = 0;
@@ -145,7 +152,8 @@ static void free_capacity(slpr_ctx *c) {
     c->t_key32 = c->t_path = c->t_wind = c->t_skey32 = c->t_sidx = c->t_flags = c->t_scan3 = nullptr;
     cudaFree(c->d_temp); c->d_temp = nullptr;
     if (c->gexec) { cudaGraphExecDestroy(c->gexec); c->gexec = nullptr; }
-    c->graph_valid = false;
+    if (c->gexec2) { cudaGraphExecDestroy(c->gexec2); c->gexec2 = nullptr; }
+    c->graph_valid = c->graph2_valid = false;
     c->cap = 0;
 }
 
@@ -236,6 +244,7 @@ extern "C" slpr_ctx *slpr_create(int device, uint32_t width, uint32_t height, ui
     ok = ok && cudaMemset(c->d_cells, 0, (size_t)c->cw * c->ch * 4) == cudaSuccess;
     c->fb_stride = (size_t)width * 4;
     ok = ok && cudaMalloc(&c->d_fb, c->fb_stride * height) == cudaSuccess;
+    c->fb_cur = c->d_fb;
     for (auto &ev : c->ev) ok = ok && cudaEventCreate(&ev) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_onesweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->walk_blocks_per_sm, k_walk, WALK_THREADS, 0) == cudaSuccess;
@@ -259,7 +268,9 @@ extern "C" void slpr_destroy(slpr_ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     free_capacity(c);
     free_scene(c);
-    cudaFree(c->d_params); cudaFreeHost(c->h_ctr); cudaFree(c->d_cells); cudaFree(c->d_fb); cudaFree(c->d_prim_temp);
+    cudaFree(c->d_params); cudaFreeHost(c->h_ctr); cudaFree(c->d_cells); cudaFree(c->d_fb); cudaFree(c->d_fb2); cudaFree(c->d_prim_temp);
+    if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    for (int i = 0; i < 2; ++i) { if (c->ev_rendered[i]) cudaEventDestroy(c->ev_rendered[i]); if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]); }
     for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
@@ -356,7 +367,7 @@ extern "C" int slpr_set_band(slpr_ctx *c, uint32_t y0, uint32_t y1) {
 extern "C" int slpr_set_target(slpr_ctx *c, void *dev_rgba, size_t stride_bytes) {
     if (!c) return fail(SLPR_ERR_INVALID, "null context");
     if (dev_rgba && stride_bytes < (size_t)c->W * 4) return fail(SLPR_ERR_INVALID, "slpr_set_target: stride smaller than a row");
-    if (c->target != dev_rgba || c->target_stride != stride_bytes) c->graph_valid = false;
+    if (c->target != dev_rgba || c->target_stride != stride_bytes) c->graph_valid = c->graph2_valid = false;
     c->target = reinterpret_cast<uint8_t *>(dev_rgba);
     c->target_stride = stride_bytes;
     return SLPR_OK;
@@ -447,7 +458,7 @@ static int enqueue_frame(slpr_ctx *c, cudaStream_t s, bool timed, int &launches)
     }
     if (timed) CU(cudaEventRecord(c->ev[9], s));
     // ---- pixels
-    uint8_t *fb = c->target ? c->target : c->d_fb;
+    uint8_t *fb = c->target ? c->target : c->fb_cur;
     const size_t stride = c->target ? c->target_stride : c->fb_stride;
     k_fill_cells<<<wide, 256, 0, s>>>(c->d_params, c->d_ctr, c->cap, c->d_rec, c->d_cells, c->cw);
     if (timed) CU(cudaEventRecord(c->ev[10], s));
@@ -501,8 +512,11 @@ extern "C" int slpr_render(slpr_ctx *c) {
         c->launches_per_frame = l;
         c->stage_times_valid = true;
     } else {
-        if (!c->graph_valid) {
-            if (c->gexec) { cudaGraphExecDestroy(c->gexec); c->gexec = nullptr; }
+        const bool second = !c->target && c->fb_cur == c->d_fb2 && c->d_fb2;
+        cudaGraphExec_t &ge = second ? c->gexec2 : c->gexec;
+        bool &valid = second ? c->graph2_valid : c->graph_valid;
+        if (!valid) {
+            if (ge) { cudaGraphExecDestroy(ge); ge = nullptr; }
             cudaGraph_t g = nullptr;
             CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
             int l = 0;
@@ -510,13 +524,13 @@ extern "C" int slpr_render(slpr_ctx *c) {
             cudaError_t e = cudaStreamEndCapture(c->stream, &g);
             if (rc) { if (g) cudaGraphDestroy(g); return rc; }
             if (e != cudaSuccess) return fail(SLPR_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
-            e = cudaGraphInstantiate(&c->gexec, g, 0);
+            e = cudaGraphInstantiate(&ge, g, 0);
             cudaGraphDestroy(g);
             if (e != cudaSuccess) return fail(SLPR_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
             c->launches_per_frame = l;
-            c->graph_valid = true;
+            valid = true;
         }
-        CU(cudaGraphLaunch(c->gexec, c->stream));
+        CU(cudaGraphLaunch(ge, c->stream));
         c->launches += c->launches_per_frame;
         c->stage_times_valid = false;
     }
@@ -555,7 +569,7 @@ extern "C" int slpr_readback(slpr_ctx *c, uint8_t *rgba, size_t stride_bytes) {
     if (stride_bytes < (size_t)c->W * 4) return fail(SLPR_ERR_INVALID, "slpr_readback: stride smaller than a row");
     int rc = finish_frame(c);
     if (rc) return rc;
-    const uint8_t *fb = c->target ? c->target : c->d_fb;
+    const uint8_t *fb = c->target ? c->target : c->fb_cur;
     const size_t stride = c->target ? c->target_stride : c->fb_stride;
     CU(cudaMemcpy2DAsync(rgba, stride_bytes, fb, stride, (size_t)c->W * 4, c->H, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -569,9 +583,54 @@ extern "C" int slpr_render_to_host(slpr_ctx *c, const float rows[16], uint8_t *r
     return slpr_readback(c, rgba, stride_bytes);
 }
 
+// Pipelined end-to-end path: frame i renders into one of two framebuffers while frame i-1 is still
+// being copied to the host on a second stream. The pixels of a submitted frame are valid in `rgba`
+// after slpr_wait_host() (or after the second-next submit returns).
+extern "C" int slpr_submit_to_host(slpr_ctx *c, const float rows[16], uint8_t *rgba, size_t stride_bytes) {
+    if (!c || !rows || !rgba) return fail(SLPR_ERR_INVALID, "slpr_submit_to_host: null argument");
+    if (stride_bytes < (size_t)c->W * 4) return fail(SLPR_ERR_INVALID, "slpr_submit_to_host: stride smaller than a row");
+    if (c->target) return fail(SLPR_ERR_STATE, "slpr_submit_to_host: not available with an external target");
+    CU(cudaSetDevice(c->device));
+    if (!c->copy_stream) {
+        CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        CU(cudaMalloc(&c->d_fb2, c->fb_stride * c->H));
+        for (int i = 0; i < 2; ++i) {
+            CU(cudaEventCreateWithFlags(&c->ev_rendered[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
+        }
+    }
+    const int k = (int)(c->pipe_frame++ & 1u);
+    if (c->copy_pending[k]) {  // the copy that last read this framebuffer must be done before it is rendered into again
+        CU(cudaStreamWaitEvent(c->stream, c->ev_copied[k], 0));
+        c->copy_pending[k] = false;
+    }
+    c->fb_cur = k ? c->d_fb2 : c->d_fb;
+    int rc = slpr_set_mvp(c, rows);
+    if (!rc) rc = slpr_render(c);
+    if (rc) return rc;
+    if (c->h_ctr->overflow) {  // an earlier frame outgrew the fragment buffers: grow them and redo this frame now
+        if ((rc = finish_frame(c))) return rc;
+    }
+    CU(cudaEventRecord(c->ev_rendered[k], c->stream));
+    CU(cudaStreamWaitEvent(c->copy_stream, c->ev_rendered[k], 0));
+    CU(cudaMemcpy2DAsync(rgba, stride_bytes, c->fb_cur, c->fb_stride, (size_t)c->W * 4, c->H, cudaMemcpyDeviceToHost, c->copy_stream));
+    CU(cudaEventRecord(c->ev_copied[k], c->copy_stream));
+    c->copy_pending[k] = true;
+    return SLPR_OK;
+}
+
+extern "C" int slpr_wait_host(slpr_ctx *c) {
+    if (!c) return fail(SLPR_ERR_INVALID, "null context");
+    CU(cudaSetDevice(c->device));
+    int rc = c->frame_pending ? finish_frame(c) : SLPR_OK;
+    if (c->copy_stream) CU(cudaStreamSynchronize(c->copy_stream));
+    c->copy_pending[0] = c->copy_pending[1] = false;
+    return rc;
+}
+
 extern "C" int slpr_framebuffer(slpr_ctx *c, void **dev_rgba, size_t *stride_bytes) {
     if (!c || !dev_rgba || !stride_bytes) return fail(SLPR_ERR_INVALID, "slpr_framebuffer: null argument");
-    *dev_rgba = c->target ? c->target : c->d_fb;
+    *dev_rgba = c->target ? c->target : c->fb_cur;
     *stride_bytes = c->target ? c->target_stride : c->fb_stride;
     return SLPR_OK;
 }
