@@ -88,6 +88,18 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic(kernel, workload):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/*_traffic.json)."""
+    best = None
+    pdir = os.path.join(ROOT, "profiles")
+    for f in sorted(os.listdir(pdir)) if os.path.isdir(pdir) else []:
+        if f.endswith("_traffic.json"):
+            d = json.load(open(os.path.join(pdir, f)))
+            if d.get("workload") == workload and kernel in d.get("dram_bytes_per_launch", {}):
+                best = (d["dram_bytes_per_launch"][kernel], f)
+    return best
+
+
 def cpu_frame(sc, rows, W, H, threads=None):
     from oracle import oracle_py as O
     t = time.perf_counter()
@@ -297,7 +309,8 @@ def main():
         scan_bytes = 8 * (sc.n_curves + nf)                     # scan #1 + winding scan (8 B / element)
         scan_ms = stage_avg["scan1"] + stage_avg["wind_scan"]
         roof = {"bound": "hbm", "kernel": "k_onesweep", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": (ncu_traffic("k_onesweep", args.workload) or (None, None))[0],
+                "traffic_source": (ncu_traffic("k_onesweep", args.workload) or (None, None))[1], "peak_source": peak_src,
                 "launches_per_step": info["passes"], "ms_per_launch": pass_ms, "bytes_per_launch": pass_bytes,
                 "timing": "cudaEvent pairs around the k_onesweep launches, direct-launch mode, averaged over the same K steps",
                 "sort_total": {"bytes": sort_bytes, "ms": sort_ms, "gbs": sort_bytes / (sort_ms * 1e-3) / 1e9,
