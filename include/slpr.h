@@ -44,7 +44,10 @@ enum {
     /* Evaluate LERP/dot with FMA contraction, as a Vulkan driver may. Not built. */
     SLPR_FLAG_CONTRACT_FMA = 1u << 1,
     /* Launch kernels directly instead of replaying the captured CUDA graph of the frame. */
-    SLPR_FLAG_NO_GRAPH = 1u << 2
+    SLPR_FLAG_NO_GRAPH = 1u << 2,
+    /* Always sort with the onesweep LSD radix sort; by default scenes whose paths all have at most 4096
+     * fragments use the one-pass segmented sort (csrc/segsort.cuh), falling back to the radix sort otherwise. */
+    SLPR_FLAG_RADIX_SORT = 1u << 3
 };
 
 /* Buffers that slpr_debug_copy() can return. Layouts are the reference's:
@@ -75,8 +78,8 @@ enum {
     SLPR_STAGE_SCAN1 = 2,       /* look-back scan of the curve counts           */
     SLPR_STAGE_INTERSECT = 3,   /* k_intersect: intersection walk + fragment generation */
     SLPR_STAGE_FRAGMENT = 4,    /* (folded into INTERSECT; only the segment-table tap) */
-    SLPR_STAGE_SORT_HIST = 5,   /* k_radix_hist + k_radix_hist_scan             */
-    SLPR_STAGE_SORT_PASSES = 6, /* all k_onesweep launches (slpr_sort_info: passes) */
+    SLPR_STAGE_SORT_HIST = 5,   /* k_segments (+ k_radix_hist + k_radix_hist_scan in radix mode) */
+    SLPR_STAGE_SORT_PASSES = 6, /* radix mode: all k_onesweep launches; segmented mode: k_segsort_warp + k_segsort_block */
     SLPR_STAGE_WIND_SCAN = 7,   /* (folded into SPAN_EMIT: always ~0)           */
     SLPR_STAGE_SPAN_EMIT = 8,   /* k_spans: winding scan + mark + flag scan + record emit */
     SLPR_STAGE_FILL_CELLS = 9,  /* k_fill_cells                                 */
@@ -153,7 +156,9 @@ SLPR_API int slpr_debug_copy(slpr_ctx *ctx, int which, void *dst, size_t bytes);
  * fills min(n, SLPR_STAGE_COUNT) slots. New: the reference has no timers. */
 SLPR_API int slpr_stage_ms(slpr_ctx *ctx, float *ms, int n);
 
-/* Sort-pass geometry of the last frame: key bits, number of 8-bit passes, bytes of one key. */
+/* Sort-pass geometry of the last frame: key bits, number of 8-bit passes, bytes of one key.
+ * slpr_sort_mode: 0 = segmented one-pass sort in use, 1 = onesweep radix sort in use. */
+SLPR_API int slpr_sort_mode(slpr_ctx *ctx, int *mode);
 SLPR_API int slpr_sort_info(slpr_ctx *ctx, uint32_t *key_bits, uint32_t *passes, uint32_t *key_bytes);
 
 /* Stand-alone device primitives over caller-owned DEVICE buffers (the two roofline-graded

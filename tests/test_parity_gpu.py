@@ -52,6 +52,13 @@ def assert_frame_parity(sc, rows, W, H):
     assert f.counts() == cnt
     assert np.array_equal(f.tap("records"), ref["records"])
     f.close()
+    # the other sort: the default picks the segmented sort unless a path is too long for it
+    g = render_gpu(sc, rows, W, H, V.FLAG_RADIX_SORT | V.FLAG_TAPS)
+    assert g.counts() == cnt and g.sort_mode() == "radix"
+    for t in ("sorted_key", "sorted_index", "records"):
+        assert np.array_equal(g.tap(t), ref[ORACLE_NAME[t]]), f"radix sort: tap {t} differs"
+    assert np.array_equal(g.readback(), ref["rgba"])
+    g.close()
     return ref
 
 
@@ -109,6 +116,40 @@ def test_reference_hardcoded_matrix():
 def test_synthetic_scene_parity():
     sc = S.synth_scene(4096, 1024, 768, 6.0, 30.0, seed=0x5CA71E01)
     assert_frame_parity(sc, S.identity_rows(), 1024, 768)
+
+
+def test_sort_modes_by_path_size():
+    """Segmented sort: warp network (paths up to 256 fragments), block network (up to 4096), and the
+    switch to the radix sort when a path is longer than that. Sorted order must equal the oracle's
+    in every mode (naive_seg_sort_pairs.comp:26-97: signed (key, index) order inside each path)."""
+    W = H = 1024
+    small = S.synth_scene(3000, W, H, 10.0, 40.0, seed=0x5E650001)     # glyph-sized paths
+    medium = S.synth_scene(300, W, H, 150.0, 400.0, seed=0x5E650002)   # hundreds .. thousands per path
+    sc, vp = util.golden_scene("tiger")
+    for scn, rows, want in ((small, S.identity_rows(), "segmented"), (medium, S.identity_rows(), "segmented"),
+                            (sc, S.fit_rows(vp, W, H), None)):
+        ref = O.render(scn, rows, W, H)
+        seg = ref["seg"]
+        longest = int(np.max(np.diff(seg))) if len(seg) > 1 else 0
+        r = render_gpu(scn, rows, W, H, V.FLAG_TAPS)
+        assert r.counts()["n_fragments"] == ref["n_fragments"]  # completes the frame (and a possible fallback)
+        expect = want or ("segmented" if longest <= 4096 else "radix")
+        assert r.sort_mode() == expect, (longest, r.sort_mode())
+        assert np.array_equal(r.tap("sorted_key"), ref["skey"]) and np.array_equal(r.tap("sorted_index"), ref["sidx"])
+        assert np.array_equal(r.tap("records"), ref["records"])
+        assert np.array_equal(r.readback(), ref["rgba"])
+        r.close()
+    # a scene with one path longer than 4096 fragments: first frame falls back, later frames stay on radix
+    big = S.synth_scene(6, 4096, 4096, 1800.0, 2000.0, seed=0x5E650003)
+    ref = O.render(big, S.identity_rows(), 4096, 4096)
+    assert int(np.max(np.diff(ref["seg"]))) > 4096
+    r = render_gpu(big, S.identity_rows(), 4096, 4096, 0)
+    assert r.counts()["n_fragments"] == ref["n_fragments"]
+    assert r.sort_mode() == "radix"
+    assert np.array_equal(r.readback(), ref["rgba"]) and np.array_equal(r.tap("records"), ref["records"])
+    r.render()
+    assert np.array_equal(r.readback(), ref["rgba"])
+    r.close()
 
 
 def test_mvp_changes_between_frames_and_capacity_growth():

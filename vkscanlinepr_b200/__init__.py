@@ -21,7 +21,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SLPR_LIB") or os.path.join(_HERE, "libslpr.so")  # SLPR_LIB: tuning variants
 _LIB = None
 
-FLAG_TAPS, FLAG_CONTRACT_FMA, FLAG_NO_GRAPH = 1, 2, 4
+FLAG_TAPS, FLAG_CONTRACT_FMA, FLAG_NO_GRAPH, FLAG_RADIX_SORT = 1, 2, 4, 8
 TAPS = dict(transformed_pos=0, path_visible=1, cut_cache=2, curve_count=3, curve_offset=4, intersection=5,
             key=6, path=7, winding=8, sorted_key=9, sorted_index=10, winding_scan=11, flags=12,
             flag_scan=13, records=14, segments=15)
@@ -239,6 +239,11 @@ class ScanlineRasterizer:
         a, b, c = C.c_uint32(), C.c_uint32(), C.c_uint32()
         _check(lib().slpr_sort_info(self._h, C.byref(a), C.byref(b), C.byref(c)))
         return dict(key_bits=a.value, passes=b.value, key_bytes=c.value)
+
+    def sort_mode(self):
+        m = C.c_int()
+        _check(lib().slpr_sort_mode(self._h, C.byref(m)))
+        return "radix" if m.value else "segmented"
 
     def stage_ms(self):
         ms = (C.c_float * len(STAGES))()

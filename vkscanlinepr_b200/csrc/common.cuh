@@ -28,7 +28,8 @@ struct FrameCounters {
     int overflow;      // set when n_fragments exceeded the allocated capacity
     int n_records;     // n_out_frag + n_span
     int wn_total;      // last element of the winding scan (residue diagnostic)
-    int pad[2];
+    int sort_fallback; // segmented sort met a path with more than SEG_BLOCK_MAX fragments
+    int n_big_segments;  // paths queued for k_segsort_block
 };
 
 // Key geometry for the compact 64-bit sort key (path | row rank | cell x), see DESIGN.md.

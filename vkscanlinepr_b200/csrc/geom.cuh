@@ -272,15 +272,24 @@ __device__ __forceinline__ int unpack_key32(const KeyLayout &L, uint64_t k, uint
 // sort input: compact key (path | row rank | cell x) and value
 // (fragment index | fill rule of the path << 29 | (delta+1) << 30): the span kernel then needs no gather.
 constexpr uint32_t VAL_INDEX_MASK = 0x1FFFFFFFu;
-__device__ __forceinline__ void emit_fragment(const FrameParams *__restrict__ P, const KeyLayout &L, int f, uint32_t pidx,
+
+// the frame constants gen_fragment needs, read from FrameParams once per thread
+struct FragEnv {
+    int width, height, cull, band_y0, band_y1;
+};
+__device__ __forceinline__ FragEnv load_frag_env(const FrameParams *__restrict__ P) {
+    return FragEnv{P->width, P->height, P->cull, P->band_y0, P->band_y1};
+}
+
+// make_fragment computes the pair; emit_fragment also stores it.
+__device__ __forceinline__ void make_fragment(const FragEnv &P, const KeyLayout &L, int f, uint32_t pidx,
                                               uint32_t rule_bit,
                                               float t0, float t1, float pfx, float pfy, float plx, float ply,
-                                              uint64_t *__restrict__ key64, uint32_t *__restrict__ val,
-                                              const FragTaps &taps) {
+                                              uint64_t &key_out, uint32_t &val_out, const FragTaps &taps) {
     bool valid = false;
     int pos_x = 0, pos_y = 0, wn = 0;
     if (t0 < t1) {  // GF:119
-        const int width = P->width, height = P->height;
+        const int width = P.width, height = P.height;
         const int raw_x = float2int_rd(__fmul_rn(__fmul_rn(__fadd_rn(pfx, plx), 0.5f), 0.5f)) * FRAG_SIZE;  // GF:169-170
         const int raw_y = float2int_rd(__fmul_rn(__fmul_rn(__fadd_rn(pfy, ply), 0.5f), 0.5f)) * FRAG_SIZE;
         pos_x = min(max(raw_x, -FRAG_SIZE), (int)(((uint32_t)width & 0xFFFFFFFEu) + FRAG_SIZE));  // GF:177-178
@@ -290,16 +299,27 @@ __device__ __forceinline__ void emit_fragment(const FrameParams *__restrict__ P,
         if (pfy == ply) wn = 0;  // GF:190-199
         else if (pfy < wn_y && wn_y <= ply) wn = -1;
         else if (ply < wn_y && wn_y <= pfy) wn = 1;
-        if (P->cull && valid && (pos_y < P->band_y0 || pos_y >= P->band_y1)) { valid = false; wn = 0; }  // band mode (new)
+        if (P.cull && valid && (pos_y < P.band_y0 || pos_y >= P.band_y1)) { valid = false; wn = 0; }  // band mode (new)
     }
-    key64[f] = pack_key(L, pidx, valid, pos_x, pos_y);
-    val[f] = (uint32_t)f | (rule_bit << 29) | ((uint32_t)(wn + 1) << 30);
+    key_out = pack_key(L, pidx, valid, pos_x, pos_y);
+    val_out = (uint32_t)f | (rule_bit << 29) | ((uint32_t)(wn + 1) << 30);
     if (taps.key32) {
         taps.key32[f] = valid ? (int)(((uint32_t)(pos_y + 0x7FFF) << 16) | ((uint32_t)(pos_x + 0x7FFF) & 0xFFFFu))
                               : (int)0xFFFEFFFEu;
         taps.path[f] = (int)pidx;
         taps.wind[f] = wn;
     }
+}
+
+__device__ __forceinline__ void emit_fragment(const FragEnv &P, const KeyLayout &L, int f, uint32_t pidx,
+                                              uint32_t rule_bit,
+                                              float t0, float t1, float pfx, float pfy, float plx, float ply,
+                                              uint64_t *__restrict__ key64, uint32_t *__restrict__ val,
+                                              const FragTaps &taps) {
+    uint64_t k; uint32_t v;
+    make_fragment(P, L, f, pidx, rule_bit, t0, t1, pfx, pfy, plx, ply, k, v, taps);
+    key64[f] = k;
+    val[f] = v;
 }
 
 // curve_interpolate of gen_fragment.comp:59-87 (default result cv0; only LINE and CUBIC evaluate)

@@ -1,0 +1,202 @@
+// segsort.cuh — segmented sort fast path for scenes whose paths are all small.
+//
+// The reference sorts each path's fragments separately (naive_seg_sort_pairs.comp:26-97, one
+// workgroup per path, segments from gen_fragment.comp:226-244). Fragments are generated in path
+// order, so a path's fragments already sit in one contiguous range [seg[p], seg[p+1]); the general
+// path (radix.cuh) ignores that and runs a global LSD sort on (path | row | x) — 4-6 full passes
+// over the 12-byte pairs. When every path is small (a glyph, a blob: tens to hundreds of
+// fragments) it is much cheaper to sort each range on chip, reading and writing every pair ONCE:
+//   k_segsort_warp   one warp per path, up to 256 fragments: bitonic network on one 64-bit word per
+//                    fragment (row|x in the high half, fragment index and the 3 payload bits in the
+//                    low half, so a single unsigned compare gives the reference's (key, index)
+//                    order) held in registers, compare-exchange by warp shuffles;
+//   k_segsort_block  paths of 257..4096 fragments (queued by the warp kernel): bitonic network in
+//                    shared memory, one block per path.
+// A path with more than 4096 fragments raises FrameCounters::sort_fallback; the host then switches
+// the scene to the onesweep radix sort and renders the frame again. Output format is identical to
+// the radix path (compact 64-bit key, 32-bit value), so everything downstream is unchanged.
+#pragma once
+#include "geom.cuh"
+
+namespace slpr {
+
+constexpr int SEG_WARP_MAX = 256;    // largest path sorted by one warp (8 words per lane)
+constexpr int SEG_BLOCK_MAX = 4096;  // largest path sorted by one block
+constexpr int SEG_BLOCK_THREADS = 512;
+
+__device__ __forceinline__ uint64_t seg_pack(uint64_t key, uint32_t val, int yx_bits) {
+    const uint64_t yx = key & ((1ull << yx_bits) - 1);
+    return (yx << 32) | ((uint64_t)(val & VAL_INDEX_MASK) << 3) | (uint64_t)(val >> 29);
+}
+__device__ __forceinline__ void seg_unpack(uint64_t w, uint64_t path_bits, uint64_t &key, uint32_t &val) {
+    key = path_bits | (w >> 32);
+    val = (uint32_t)((w >> 3) & VAL_INDEX_MASK) | ((uint32_t)(w & 7u) << 29);
+}
+
+// Bitonic sort of 32*R words held as e[r] = element r*32 + lane, ascending.
+template <int R, typename W>
+__device__ __forceinline__ void warp_bitonic(W (&e)[R], int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32 * R; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= 32) {  // partner lives in another register of the same lane
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int rp = r ^ (j >> 5);
+                    if (rp > r) {
+                        const bool asc = (((r * 32 + lane) & k) == 0);
+                        const W a = e[r], b = e[rp];
+                        const W lo = a < b ? a : b, hi = a < b ? b : a;
+                        e[r] = asc ? lo : hi;
+                        e[rp] = asc ? hi : lo;
+                    }
+                }
+            } else {  // partner lives in lane ^ j
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const W o = __shfl_xor_sync(0xFFFFFFFFu, e[r], j);
+                    const bool asc = (((r * 32 + lane) & k) == 0);
+                    const bool lower = (lane & j) == 0;
+                    const W mn = e[r] < o ? e[r] : o, mx = e[r] < o ? o : e[r];
+                    e[r] = (asc == lower) ? mn : mx;
+                }
+            }
+        }
+    }
+}
+
+template <int R>
+__device__ __forceinline__ void warp_sort_segment(const uint64_t *__restrict__ key_in, const uint32_t *__restrict__ val_in,
+                                                  uint64_t *__restrict__ key_out, uint32_t *__restrict__ val_out, int b, int n,
+                                                  int yx_bits, int lane) {
+    uint64_t e[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int j = r * 32 + lane;
+        e[r] = (j < n) ? seg_pack(key_in[b + j], val_in[b + j], yx_bits) : ~0ull;
+    }
+    const uint64_t path_bits = key_in[b] & ~((1ull << yx_bits) - 1);  // same for the whole segment
+    warp_bitonic<R, uint64_t>(e, lane);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int j = r * 32 + lane;
+        if (j < n) {
+            uint64_t k; uint32_t v;
+            seg_unpack(e[r], path_bits, k, v);
+            key_out[b + j] = k;
+            val_out[b + j] = v;
+        }
+    }
+}
+
+// Same, on 32-bit words (row|x above the fragment's position inside the path): half the shuffle
+// traffic of the 64-bit network. Usable when yx_bits + log2(32 R) <= 32 — every frame up to 4K.
+// A fragment's index is its position, so (row|x, position) is the reference's (key, index) order;
+// the value word is fetched again (an L1 hit) from the position the sorted word names.
+template <int R>
+__device__ __forceinline__ void warp_sort_segment32(const uint64_t *__restrict__ key_in, const uint32_t *__restrict__ val_in,
+                                                    uint64_t *__restrict__ key_out, uint32_t *__restrict__ val_out, int b, int n,
+                                                    int yx_bits, int lane) {
+    constexpr int IB = (R == 1) ? 5 : (R == 2) ? 6 : (R == 4) ? 7 : 8;
+    static_assert(R == 1 || R == 2 || R == 4 || R == 8, "R must be 1, 2, 4 or 8");
+    const uint64_t mask = (1ull << yx_bits) - 1;
+    uint32_t e[R];
+    uint64_t path_bits = 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int j = r * 32 + lane;
+        if (j < n) {
+            const uint64_t k = key_in[b + j];
+            path_bits = k & ~mask;
+            e[r] = ((uint32_t)(k & mask) << IB) | (uint32_t)j;
+        } else
+            e[r] = 0xFFFFFFFFu;
+    }
+    path_bits = __shfl_sync(0xFFFFFFFFu, path_bits, 0);  // lane 0 always holds fragment 0
+    warp_bitonic<R, uint32_t>(e, lane);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int j = r * 32 + lane;
+        if (j < n) {
+            key_out[b + j] = path_bits | (uint64_t)(e[r] >> IB);
+            val_out[b + j] = val_in[b + (e[r] & ((1u << IB) - 1))];
+        }
+    }
+}
+
+template <int R>
+__device__ __forceinline__ void warp_sort_dispatch(const uint64_t *__restrict__ key_in, const uint32_t *__restrict__ val_in,
+                                                   uint64_t *__restrict__ key_out, uint32_t *__restrict__ val_out, int b, int n,
+                                                   int yx_bits, int lane) {
+    constexpr int IB = (R == 1) ? 5 : (R == 2) ? 6 : (R == 4) ? 7 : 8;
+    if (yx_bits + IB <= 32) warp_sort_segment32<R>(key_in, val_in, key_out, val_out, b, n, yx_bits, lane);
+    else warp_sort_segment<R>(key_in, val_in, key_out, val_out, b, n, yx_bits, lane);
+}
+
+__global__ void __launch_bounds__(256) k_segsort_warp(const int *__restrict__ seg, uint32_t n_paths,
+                                                      const uint64_t *__restrict__ key_in, const uint32_t *__restrict__ val_in,
+                                                      uint64_t *__restrict__ key_out, uint32_t *__restrict__ val_out,
+                                                      FrameCounters *__restrict__ ctr, int capacity, int yx_bits,
+                                                      int *__restrict__ big_list) {
+    if (ctr->n_fragments > capacity) return;
+    const int lane = threadIdx.x & 31;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; p < n_paths; p += warps) {
+        const int b = seg[p], n = seg[p + 1] - b;
+        if (n <= 0) continue;
+        if (n == 1) {
+            if (lane == 0) { key_out[b] = key_in[b]; val_out[b] = val_in[b]; }
+        } else if (n <= 32) warp_sort_dispatch<1>(key_in, val_in, key_out, val_out, b, n, yx_bits, lane);
+        else if (n <= 64) warp_sort_dispatch<2>(key_in, val_in, key_out, val_out, b, n, yx_bits, lane);
+        else if (n <= 128) warp_sort_dispatch<4>(key_in, val_in, key_out, val_out, b, n, yx_bits, lane);
+        else if (n <= SEG_WARP_MAX) warp_sort_dispatch<8>(key_in, val_in, key_out, val_out, b, n, yx_bits, lane);
+        else if (lane == 0) {
+            if (n > SEG_BLOCK_MAX) ctr->sort_fallback = 1;  // the host re-renders with the radix sort
+            else big_list[atomicAdd(&ctr->n_big_segments, 1)] = (int)p;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(SEG_BLOCK_THREADS) k_segsort_block(const int *__restrict__ seg,
+                                                                     const uint64_t *__restrict__ key_in,
+                                                                     const uint32_t *__restrict__ val_in,
+                                                                     uint64_t *__restrict__ key_out,
+                                                                     uint32_t *__restrict__ val_out,
+                                                                     const FrameCounters *__restrict__ ctr, int capacity,
+                                                                     int yx_bits, const int *__restrict__ big_list) {
+    __shared__ uint64_t s[SEG_BLOCK_MAX];
+    if (ctr->n_fragments > capacity || ctr->sort_fallback) return;
+    const int nbig = ctr->n_big_segments;
+    for (int q = blockIdx.x; q < nbig; q += gridDim.x) {
+        const int p = big_list[q];
+        const int b = seg[p], n = seg[p + 1] - b;
+        int m = 512;  // power of two >= n
+        while (m < n) m <<= 1;
+        for (int j = threadIdx.x; j < m; j += SEG_BLOCK_THREADS)
+            s[j] = (j < n) ? seg_pack(key_in[b + j], val_in[b + j], yx_bits) : ~0ull;
+        const uint64_t path_bits = key_in[b] & ~((1ull << yx_bits) - 1);
+        __syncthreads();
+        for (int k = 2; k <= m; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int t = threadIdx.x; t < m / 2; t += SEG_BLOCK_THREADS) {
+                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // lower index of the pair
+                    const int ip = i | j;
+                    const bool asc = (i & k) == 0;
+                    const uint64_t a = s[i], c = s[ip];
+                    if ((a > c) == asc) { s[i] = c; s[ip] = a; }
+                }
+                __syncthreads();
+            }
+        }
+        for (int j = threadIdx.x; j < n; j += SEG_BLOCK_THREADS) {
+            uint64_t k; uint32_t v;
+            seg_unpack(s[j], path_bits, k, v);
+            key_out[b + j] = k;
+            val_out[b + j] = v;
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace slpr

@@ -23,6 +23,7 @@
 #include "radix.cuh"
 #include "raster.cuh"
 #include "scan.cuh"
+#include "segsort.cuh"
 #include "spans.cuh"
 #include "walk.cuh"
 
@@ -76,7 +77,9 @@ struct slpr_ctx {
     float2 *d_tpos = nullptr;
     int *d_pvis = nullptr;
     float *d_cut = nullptr;
-    int *d_count = nullptr, *d_offset = nullptr, *d_seg_tap = nullptr;
+    int *d_count = nullptr, *d_offset = nullptr, *d_seg_tap = nullptr;  // d_seg_tap: [P+1] sort segment table (always built)
+    int *d_big = nullptr;              // [P] paths queued for the block-level segmented sort
+    bool radix_mode = false;           // false: one-pass segmented sort; true: onesweep radix sort
     uint32_t *d_slots = nullptr;       // [5*nc] (length bucket << 26 | rank) of every monotone piece
     PieceRec *d_pieces = nullptr;      // [5*nc] piece records in length-sorted order
     float2 *d_boundary = nullptr;      // [5*nc] first / last emitted parameter of every piece
@@ -161,6 +164,7 @@ static void free_scene(slpr_ctx *c) {
     cudaFree(c->d_pos); cudaFree(c->d_pos_path); cudaFree(c->d_cpm); cudaFree(c->d_ctype); cudaFree(c->d_cpath);
     cudaFree(c->d_frule); cudaFree(c->d_finfo); cudaFree(c->d_tpos); cudaFree(c->d_pvis); cudaFree(c->d_cut);
     cudaFree(c->d_count); cudaFree(c->d_offset); cudaFree(c->d_seg_tap);
+    cudaFree(c->d_big); c->d_big = nullptr;
     cudaFree(c->d_slots); cudaFree(c->d_pieces); cudaFree(c->d_boundary); cudaFree(c->d_fixflag);
     c->d_slots = nullptr; c->d_pieces = nullptr; c->d_boundary = nullptr; c->d_fixflag = nullptr;
     c->d_pos = nullptr; c->d_pos_path = c->d_cpm = c->d_ctype = c->d_cpath = c->d_frule = c->d_finfo = nullptr;
@@ -334,7 +338,9 @@ extern "C" int slpr_load_scene(slpr_ctx *c, const float *pos_xy, const uint32_t 
     CU(cudaMalloc(&c->d_pieces, std::max<size_t>(n_curves, 1) * 5 * sizeof(PieceRec)));
     CU(cudaMalloc(&c->d_boundary, std::max<size_t>(n_curves, 1) * 5 * sizeof(float2)));
     CU(cudaMalloc(&c->d_fixflag, std::max<size_t>(n_curves, 1) * 5));
-    if (c->flags & SLPR_FLAG_TAPS) CU(cudaMalloc(&c->d_seg_tap, ((size_t)n_paths + 1) * 4));
+    CU(cudaMalloc(&c->d_seg_tap, ((size_t)n_paths + 1) * 4));
+    CU(cudaMalloc(&c->d_big, std::max<size_t>(n_paths, 1) * 4));
+    c->radix_mode = (c->flags & SLPR_FLAG_RADIX_SORT) != 0;
     // compact key geometry: x cell in [0,(W'+4)/2], row rank in [0,ny], path in [0,P)
     const int Wp = (int)(c->W & ~1u);
     c->L.ny = (int)(c->H + 1) / 2;
@@ -407,11 +413,11 @@ static int enqueue_frame(slpr_ctx *c, cudaStream_t s, bool timed, int &launches)
     const bool taps = (c->flags & SLPR_FLAG_TAPS) != 0;
     const int wide = c->num_sms * 8;
     FragTaps ft{c->t_key32, c->t_path, c->t_wind};
-    k_piece_emit<<<grid_for(c, c->nc, 256, 8), 256, 0, s>>>(c->d_params, c->nc, c->d_ctype, c->d_cpm, c->d_tpos, c->d_cut,
+    k_piece_emit<<<grid_for(c, c->nc, 256, 8), 256, 0, s>>>(c->d_params, c->nc, c->d_ctype, c->d_cpm, c->d_cpath, c->d_frule, c->d_tpos, c->d_cut,
                                                              c->d_offset, c->d_slots, c->d_ctr, c->cap, c->d_bucket_hist,
                                                              c->d_pieces);
     k_walk<<<c->num_sms * std::max(1, c->walk_blocks_per_sm), WALK_THREADS, 0, s>>>(
-        c->d_params, c->d_pieces, c->d_cpath, c->d_frule, c->d_ctr, c->cap, WalkTemp{c->d_bucket_hist, c->d_tickets + 3 + RS_MAX_PASSES},
+        c->d_params, c->d_pieces, c->d_ctr, c->cap, WalkTemp{c->d_bucket_hist, c->d_tickets + 3 + RS_MAX_PASSES},
         c->L, c->d_key[0], c->d_val[0], ft, c->d_inter, c->d_boundary, c->d_fixflag);
     k_piece_fix<<<grid_for(c, c->nc, 256, 8), 256, 0, s>>>(c->d_params, c->nc, c->d_ctype, c->d_cpm, c->d_cpath, c->d_frule, c->d_tpos,
                                                               c->d_cut, c->d_offset, c->d_slots, c->d_ctr, c->cap,
@@ -419,24 +425,33 @@ static int enqueue_frame(slpr_ctx *c, cudaStream_t s, bool timed, int &launches)
                                                               c->d_val[0], ft);
     launches += 3;
     if (timed) CU(cudaEventRecord(c->ev[4], s));
-    if (taps) {
-        k_segments_tap<<<grid_for(c, (long long)c->nc + 1, 256, 8), 256, 0, s>>>(c->nc, c->P, c->d_cpath, c->d_offset, c->d_seg_tap);
-        ++launches;
-    }
     if (timed) CU(cudaEventRecord(c->ev[5], s));
+    k_segments_tap<<<grid_for(c, (long long)c->nc + 1, 256, 8), 256, 0, s>>>(c->nc, c->P, c->d_cpath, c->d_offset, c->d_seg_tap);
+    ++launches;
     // ---- sort
+    int cur = 0;
+    if (!c->radix_mode) {  // every path sorted on chip, one read + one write of the pairs (segsort.cuh)
+        if (timed) CU(cudaEventRecord(c->ev[6], s));
+        const int yx_bits = c->L.bits_x + c->L.bits_y;
+        k_segsort_warp<<<grid_for(c, (long long)c->P * 32, 256, 8), 256, 0, s>>>(c->d_seg_tap, c->P, c->d_key[0], c->d_val[0], c->d_key[1],
+                                                                                c->d_val[1], c->d_ctr, c->cap, yx_bits, c->d_big);
+        k_segsort_block<<<c->num_sms * 2, SEG_BLOCK_THREADS, 0, s>>>(c->d_seg_tap, c->d_key[0], c->d_val[0], c->d_key[1], c->d_val[1],
+                                                                     c->d_ctr, c->cap, yx_bits, c->d_big);
+        launches += 2;
+        cur = 1;
+    } else {
     SortCount cnt{&c->d_ctr->n_fragments, 0, c->cap};
     SortTemp st{c->d_hist, c->d_lookback, c->d_tickets + 3, c->sort_tiles_cap};
     k_radix_hist<<<c->num_sms * 4, RH_THREADS, 0, s>>>(c->d_key[0], cnt, c->passes, c->d_hist);
     k_radix_hist_scan<<<c->passes, RS_BINS, 0, s>>>(c->d_hist);
     launches += 2;
     if (timed) CU(cudaEventRecord(c->ev[6], s));
-    int cur = 0;
     for (int p = 0; p < c->passes; ++p) {
         k_onesweep<<<c->num_sms * RS_BLOCKS_PER_SM, RS_THREADS, RS_SMEM_BYTES, s>>>(c->d_key[cur], c->d_val[cur], c->d_key[cur ^ 1],
                                                                      c->d_val[cur ^ 1], cnt, p, 8 * p, st);
         ++launches;
         cur ^= 1;
+    }
     }
     c->sorted_buf = cur;
     if (timed) CU(cudaEventRecord(c->ev[7], s));
@@ -546,6 +561,14 @@ static int finish_frame(slpr_ctx *c) {
     for (int attempt = 0; attempt < 4; ++attempt) {
         CU(cudaStreamSynchronize(c->stream));
         c->frame_pending = false;
+        if (c->h_ctr->sort_fallback && !c->radix_mode && !c->h_ctr->overflow) {
+            // a path outgrew the segmented sort: this scene uses the radix sort from now on; redo the frame
+            c->radix_mode = true;
+            c->graph_valid = c->graph2_valid = false;
+            int rc2 = slpr_render(c);
+            if (rc2) return rc2;
+            continue;
+        }
         if (!c->h_ctr->overflow) { c->frame_done = true; return SLPR_OK; }
         const long long nf = c->h_ctr->n_fragments;
         int rc = alloc_capacity(c, (int)std::min<long long>(nf + nf / 4 + 65536, (1ll << 29) - 1));
@@ -669,7 +692,7 @@ extern "C" int slpr_debug_copy(slpr_ctx *c, int which, void *dst, size_t bytes) 
         case SLPR_TAP_FLAGS: src = c->t_flags; avail = 2 * nf * 4; tap = true; break;
         case SLPR_TAP_FLAG_SCAN: src = c->t_scan3; avail = (2 * nf + 1) * 4; tap = true; break;
         case SLPR_TAP_RECORDS: src = c->d_rec; avail = no * 16; break;
-        case SLPR_TAP_SEGMENTS: src = c->d_seg_tap; avail = ((size_t)c->P + 1) * 4; tap = true; break;
+        case SLPR_TAP_SEGMENTS: src = c->d_seg_tap; avail = ((size_t)c->P + 1) * 4; break;
         default: return fail(SLPR_ERR_INVALID, "slpr_debug_copy: unknown buffer %d", which);
     }
     if (tap && !(c->flags & SLPR_FLAG_TAPS)) return fail(SLPR_ERR_STATE, "slpr_debug_copy: buffer %d needs SLPR_FLAG_TAPS", which);
@@ -692,6 +715,12 @@ extern "C" int slpr_sort_info(slpr_ctx *c, uint32_t *key_bits, uint32_t *passes,
     if (key_bits) *key_bits = (uint32_t)c->key_bits;
     if (passes) *passes = (uint32_t)c->passes;
     if (key_bytes) *key_bytes = 8;
+    return SLPR_OK;
+}
+
+extern "C" int slpr_sort_mode(slpr_ctx *c, int *mode) {
+    if (!c || !mode) return fail(SLPR_ERR_INVALID, "slpr_sort_mode: null argument");
+    *mode = c->radix_mode ? 1 : 0;
     return SLPR_OK;
 }
 

@@ -11,7 +11,9 @@
 //                  record at its slot in LENGTH-SORTED order (bucket, rank) from k_monotonize_count;
 //   k_walk         one lane per piece, 32 consecutive records per warp = 32 pieces of (nearly) equal
 //                  length, so the whole warp runs the same number of merge steps and the 24-step
-//                  bisection — 70 % of all instructions — executes converged; every emitted record
+//                  bisection — 70 % of all instructions — executes converged; the next group's
+//                  ticket and its 2 KB of records are fetched (cp.async into shared memory) while
+//                  the current group is walked; every emitted record
 //                  also closes the fragment that began at the previous record (gen_fragment fused,
 //                  the (curve, tbits) intersection records are only a debug tap now);
 //   k_piece_fix    one thread per curve: re-emits the boundary fragment of the rare pieces whose successor
@@ -24,7 +26,8 @@ namespace slpr {
 
 struct __align__(16) PieceRec {
     float4 px, py;  // control points of the curve (x[0..3], y[0..3])
-    float4 tt;      // t0_ms (tagged start), t1_ms (tagged end), first x grid line, first y grid line
+    float4 tt;      // t0_ms (tagged start), t1_ms (tagged end), bits: first x grid line | first y grid line << 16,
+                    // bits: path | even-odd rule << 31
     uint4 m;        // n_x | n_y << 15 | dx<0 << 30 | dy<0 << 31;  curve;  first record index;  type | piece << 8
 };
 
@@ -61,6 +64,8 @@ __device__ __forceinline__ void bucket_bases(const uint32_t *__restrict__ hist, 
 __global__ void __launch_bounds__(256) k_piece_emit(const FrameParams *__restrict__ P, uint32_t n_curves,
                                                     const uint32_t *__restrict__ curve_type,
                                                     const uint32_t *__restrict__ curve_pos_map,
+                                                    const uint32_t *__restrict__ curve_path,
+                                                    const uint32_t *__restrict__ fill_rule,
                                                     const float2 *__restrict__ tpos, const float *__restrict__ cut_cache,
                                                     const int *__restrict__ offsets, const uint32_t *__restrict__ slots,
                                                     const FrameCounters *__restrict__ ctr, int capacity,
@@ -74,6 +79,9 @@ __global__ void __launch_bounds__(256) k_piece_emit(const FrameParams *__restric
         int pcnt = offsets[c];
         if (offsets[c + 1] == pcnt) continue;  // invisible or band-culled
         const uint32_t type = curve_type[c];
+        const uint32_t pidx = curve_path[c];
+        // MARK:82 only distinguishes rule 1 (even-odd) from the rest
+        const uint32_t path_rule = pidx | (fill_rule[pidx] == 1u ? 0x80000000u : 0u);
         CurvePts cp;
         load_points(type, curve_pos_map[c], tpos, cp);
         const float q0 = cut_cache[5 * c + 0], q1 = cut_cache[5 * c + 1], q2 = cut_cache[5 * c + 2], q3 = cut_cache[5 * c + 3];
@@ -98,7 +106,9 @@ __global__ void __launch_bounds__(256) k_piece_emit(const FrameParams *__restric
             PieceRec r;
             r.px = make_float4(cp.x[0], cp.x[1], cp.x[2], cp.x[3]);
             r.py = make_float4(cp.y[0], cp.y[1], cp.y[2], cp.y[3]);
-            r.tt = make_float4(t0_ms, t1_ms, (float)(xfwd ? xb : xe), (float)(yfwd ? yb : ye));  // MI1:301-302
+            // MI1:301-302; the grid lines are clamped to [0, dim + 2] whenever they are used (count > 0)
+            r.tt = make_float4(t0_ms, t1_ms, u2f(((uint32_t)(xfwd ? xb : xe) & 0xFFFFu) | ((uint32_t)(yfwd ? yb : ye) << 16)),
+                               u2f(path_rule));
             r.m = make_uint4((uint32_t)n_x | ((uint32_t)n_y << 15) | (xfwd ? 0u : 1u << 30) | (yfwd ? 0u : 1u << 31), c,
                              (uint32_t)pcnt, (type & 0xFFu) | (piece << 8) | ((type > 0xFFu) ? 0x80u : 0u));
             pieces[piece_position(s_dbase, slots[5 * c + piece])] = r;
@@ -109,12 +119,68 @@ __global__ void __launch_bounds__(256) k_piece_emit(const FrameParams *__restric
 }
 
 // ------------------------------------------------------------------------------------------------
-constexpr int WALK_THREADS = 128;
+// Plain PTX atomic: atomicAdd() by one lane is compiled into the warp-aggregated form whose result
+// is shuffled — and therefore waited for — right away; here the ticket is only read a group later.
+__device__ __forceinline__ uint32_t take_ticket(int *counter) {
+    uint32_t t;
+    asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(t) : "l"(counter) : "memory");
+    return t;
+}
 
-__global__ void __launch_bounds__(WALK_THREADS) k_walk(const FrameParams *__restrict__ P,
+// A piece's fragments have consecutive indices, so a lane holds keys back until it has an aligned
+// pair (one 16-byte store instead of two 8-byte ones) and values until it has an aligned quad: the
+// scattered stores of the walk are its second cost after the bisection.
+#ifndef SLPR_WALK_PAIR
+#define SLPR_WALK_PAIR 1
+#endif
+struct FragStore {
+    uint64_t pk;
+    uint32_t pv0, pv1, pv2;
+    int f_first;
+    __device__ __forceinline__ void put(int f, uint64_t k, uint32_t v, uint64_t *__restrict__ key64, uint32_t *__restrict__ val) {
+#if !SLPR_WALK_PAIR
+        key64[f] = k; val[f] = v;
+        return;
+#endif
+        if (f & 1) {
+            if (f > f_first) *reinterpret_cast<ulonglong2 *>(key64 + f - 1) = make_ulonglong2(pk, k);
+            else key64[f] = k;
+        } else
+            pk = k;
+        const int q = f & 3;
+        if (q == 3) {
+            if (f - 3 >= f_first) *reinterpret_cast<uint4 *>(val + f - 3) = make_uint4(pv0, pv1, pv2, v);
+            else {
+                if (f - 2 >= f_first) val[f - 2] = pv1;
+                if (f - 1 >= f_first) val[f - 1] = pv2;
+                val[f] = v;
+            }
+        } else if (q == 0) pv0 = v;
+        else if (q == 1) pv1 = v;
+        else pv2 = v;
+    }
+    // after the piece's last fragment
+    __device__ __forceinline__ void flush(int f_last, uint64_t *__restrict__ key64, uint32_t *__restrict__ val) {
+#if !SLPR_WALK_PAIR
+        return;
+#endif
+        if (!(f_last & 1)) key64[f_last] = pk;
+        const int q = f_last & 3, base = f_last - q;
+        if (q != 3) {
+            if (base >= f_first) val[base] = pv0;
+            if (q >= 1 && base + 1 >= f_first) val[base + 1] = pv1;
+            if (q >= 2) val[base + 2] = pv2;
+        }
+    }
+};
+
+constexpr int WALK_THREADS = 128;
+#ifndef SLPR_WALK_MIN_BLOCKS
+#define SLPR_WALK_MIN_BLOCKS 1
+#endif
+
+__global__ void __launch_bounds__(WALK_THREADS, SLPR_WALK_MIN_BLOCKS) k_walk(const FrameParams *__restrict__ P,
                                                        const PieceRec *__restrict__ pieces,
-                                                       const uint32_t *__restrict__ curve_path,
-                                                       const uint32_t *__restrict__ fill_rule,
                                                        const FrameCounters *__restrict__ ctr, int capacity, WalkTemp tmp,
                                                        KeyLayout L, uint64_t *__restrict__ key64,
                                                        uint32_t *__restrict__ val, FragTaps taps,
@@ -124,20 +190,49 @@ __global__ void __launch_bounds__(WALK_THREADS) k_walk(const FrameParams *__rest
     if (nf_total > capacity) return;
     if (taps.key32 && blockIdx.x == 0 && threadIdx.x == 0 && nf_total > 0) taps.key32[nf_total] = -1;  // GF:240
     const uint32_t lane = lane_id();
+    const uint32_t warp = threadIdx.x >> 5;
+    __shared__ uint4 s_stage[WALK_THREADS / 32][2][128];  // per warp: two groups of 32 records (2 KB each)
     uint32_t n_pieces = 0;
     {
         const uint32_t h = tmp.bucket_hist[lane] + tmp.bucket_hist[lane + 32];
         n_pieces = __reduce_add_sync(0xFFFFFFFFu, h);
     }
-    while (true) {
-        uint32_t g = 0;
-        if (lane == 0) g = (uint32_t)atomicAdd(tmp.group_counter, 1);
-        g = __shfl_sync(0xFFFFFFFFu, g, 0);
-        if ((unsigned long long)g * 32ull >= n_pieces) break;
-        const uint32_t idx = g * 32u + lane;
+    const FragEnv env = load_frag_env(P);
+    const uint32_t n_chunks = n_pieces * 4u;  // 16-byte chunks in the record array
+    // group g's records -> stage st, one commit group per call (empty past the end)
+    auto stage_group = [&](uint32_t g, int st) {
+        const unsigned long long first = (unsigned long long)g * 128ull;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t q = j * 32 + lane;
+            if (first + q < n_chunks) {
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&s_stage[warp][st][q]);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst),
+                             "l"(reinterpret_cast<const uint4 *>(pieces) + first + q));
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    // tickets are taken two groups ahead so that neither the atomic nor the record fetch is waited for
+    uint32_t g_cur = 0, g_next = 0;
+    if (lane == 0) {
+        g_cur = take_ticket(tmp.group_counter);
+        g_next = take_ticket(tmp.group_counter);
+    }
+    g_cur = __shfl_sync(0xFFFFFFFFu, g_cur, 0);
+    g_next = __shfl_sync(0xFFFFFFFFu, g_next, 0);
+    stage_group(g_cur, 0);
+    for (int st = 0;; st ^= 1) {
+        if ((unsigned long long)g_cur * 32ull >= n_pieces) break;  // tickets only grow: nothing left for this warp
+        uint32_t g_after = 0;
+        if (lane == 0) g_after = take_ticket(tmp.group_counter);
+        stage_group(g_next, st ^ 1);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncwarp();
+        const uint32_t idx = g_cur * 32u + lane;
         const bool active = idx < n_pieces;
 
-        // ---- load the piece (64 contiguous bytes per lane: fully coalesced across the warp)
+        // ---- the piece, from the staged copy
         CurvePts cp;
         float t0_ms = 0.f, t1_ms = 0.f, x = 0.f, y = 0.f, dx = 2.f, dy = 2.f;
         int n_x = 0, n_y = 0, n_loop = -2, pcnt = 0;
@@ -145,21 +240,25 @@ __global__ void __launch_bounds__(WALK_THREADS) k_walk(const FrameParams *__rest
 #pragma unroll
         for (int i = 0; i < 4; ++i) { cp.x[i] = 0.f; cp.y[i] = 0.f; }
         if (active) {
-            const PieceRec *r = pieces + idx;
-            const float4 a = r->px, b = r->py, t = r->tt;
-            const uint4 m = r->m;
-            cp.x[0] = a.x; cp.x[1] = a.y; cp.x[2] = a.z; cp.x[3] = a.w;
-            cp.y[0] = b.x; cp.y[1] = b.y; cp.y[2] = b.z; cp.y[3] = b.w;
-            t0_ms = t.x; t1_ms = t.y; x = t.z; y = t.w;
+            const uint4 *r = &s_stage[warp][st][4 * lane];
+            const uint4 a = r[0], b = r[1], t = r[2], m = r[3];
+            cp.x[0] = u2f(a.x); cp.x[1] = u2f(a.y); cp.x[2] = u2f(a.z); cp.x[3] = u2f(a.w);
+            cp.y[0] = u2f(b.x); cp.y[1] = u2f(b.y); cp.y[2] = u2f(b.z); cp.y[3] = u2f(b.w);
+            t0_ms = u2f(t.x); t1_ms = u2f(t.y);
+            x = (float)(t.z & 0xFFFFu); y = (float)(t.z >> 16);
+            pidx = t.w & 0x7FFFFFFFu; rule_bit = t.w >> 31;
             n_x = (int)(m.x & 0x7FFFu); n_y = (int)((m.x >> 15) & 0x7FFFu);
             dx = (m.x & (1u << 30)) ? -2.f : 2.f; dy = (m.x & (1u << 31)) ? -2.f : 2.f;
             c = m.y; pcnt = (int)m.z;
             type = (m.w & 0x80u) ? 0xFFFFu : (m.w & 0x7Fu);  // types above 0xFF only need to be "other"
             piece = m.w >> 8;
             n_loop = n_x + n_y + 1;
-            pidx = curve_path[c];
-            rule_bit = fill_rule[pidx] == 1u ? 1u : 0u;  // MARK:82 only distinguishes rule 1 (even-odd) from 0
         }
+        __syncwarp();  // every lane has read its record: the stage may be refilled two groups from now
+        g_cur = g_next;
+        g_next = __shfl_sync(0xFFFFFFFFu, g_after, 0);
+        FragStore fs;
+        fs.pk = 0; fs.pv0 = fs.pv1 = fs.pv2 = 0; fs.f_first = pcnt;
         float tx = t0_ms, ty = t0_ms;  // point_coords slots 8, 9 (MI1:304-305)
         int i_inte_last = (int)f2u(-1.0f);
         bool have_prev = false;
@@ -196,7 +295,11 @@ __global__ void __launch_bounds__(WALK_THREADS) k_walk(const FrameParams *__rest
                 tc = (tc < 0.0f) ? 0.0f : tc;
                 float ex, ey;
                 eval_point(type, cp, tc, ex, ey);
-                if (have_prev) emit_fragment(P, L, pcnt - 1, pidx, rule_bit, prev_t, tc, prev_x, prev_y, ex, ey, key64, val, taps);
+                if (have_prev) {
+                    uint64_t k; uint32_t v;
+                    make_fragment(env, L, pcnt - 1, pidx, rule_bit, prev_t, tc, prev_x, prev_y, ex, ey, k, v, taps);
+                    fs.put(pcnt - 1, k, v, key64, val);
+                }
                 prev_t = tc; prev_x = ex; prev_y = ey; have_prev = true;
                 ++pcnt;
             }
@@ -276,7 +379,10 @@ __global__ void __launch_bounds__(WALK_THREADS) k_walk(const FrameParams *__rest
             tcl = (tcl < 0.0f) ? 0.0f : tcl;
             float ex, ey;
             eval_point(type, cp, tcl, ex, ey);
-            emit_fragment(P, L, pcnt - 1, pidx, rule_bit, prev_t, tcl, prev_x, prev_y, ex, ey, key64, val, taps);
+            uint64_t k; uint32_t v;
+            make_fragment(env, L, pcnt - 1, pidx, rule_bit, prev_t, tcl, prev_x, prev_y, ex, ey, k, v, taps);
+            fs.put(pcnt - 1, k, v, key64, val);
+            fs.flush(pcnt - 1, key64, val);
             boundary[5 * c + piece] = make_float2(u2f(first_bits), u2f(last_bits));
             fixflag[5 * c + piece] = (piece > 0 && (first_bits & 0xFFFFFFFCu) != (f2u(t0_ms) & 0xFFFFFFFCu)) ? 1 : 0;
         }
@@ -300,6 +406,7 @@ __global__ void __launch_bounds__(256) k_piece_fix(const FrameParams *__restrict
     __shared__ uint32_t s_total;
     if (ctr->n_fragments > capacity) return;
     bucket_bases(bucket_hist, s_dbase, &s_total);
+    const FragEnv env = load_frag_env(P);
     for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n_curves; c += gridDim.x * blockDim.x) {
         if (offsets[c + 1] == offsets[c]) continue;
         const uint32_t n_cuts = f2u(cut_cache[5 * c + 4]) + 1u;
@@ -324,7 +431,7 @@ __global__ void __launch_bounds__(256) k_piece_fix(const FrameParams *__restrict
             float ax, ay, bx, by;
             eval_point(type, cp, t0, ax, ay);
             eval_point(type, cp, t1, bx, by);
-            emit_fragment(P, L, f, pidx, rule_bit, t0, t1, ax, ay, bx, by, key64, val, taps);
+            emit_fragment(env, L, f, pidx, rule_bit, t0, t1, ax, ay, bx, by, key64, val, taps);
         }
     }
 }
