@@ -147,6 +147,7 @@ def main():
     ap.add_argument("--workload", default="synth_1m_4k")
     ap.add_argument("--mode", default="frames", choices=["frames", "bands"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-radix-leg", action="store_true", help="skip timing the radix sort beside the segmented sort")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -284,39 +285,75 @@ def main():
     else:
         e2e = None
 
-    # ---- roofline of the dominant kernel (k_onesweep): per-launch time from CUDA events around the
-    #      sort passes in direct-launch mode, same K steps, on the launching stream.
+    # ---- roofline: per-kernel times from CUDA events around the stages in direct-launch mode, same K
+    #      steps, on the launching stream. The headline object is the kernel with the largest share
+    #      of the frame; the sort and the scans (the north star's HBM-bound stages) are listed too.
     roof = stage_avg = None
     if rank == 0 and not bands:
-        ri = make_ctx(V.FLAG_NO_GRAPH)
-        for _ in range(3):
-            ri.render()
-        ri.synchronize()
-        acc = {}
-        for _ in range(K):
-            ri.render()
-            for k, v in ri.stage_ms().items():
-                acc[k] = acc.get(k, 0.0) + v
-        stage_avg = {k: v / K for k, v in acc.items()}
-        ri.close()
+        def stage_times(flags):
+            ri = make_ctx(flags)
+            for _ in range(3):
+                ri.render()
+            ri.synchronize()
+            acc = {}
+            for _ in range(K):
+                ri.render()
+                for k, v in ri.stage_ms().items():
+                    acc[k] = acc.get(k, 0.0) + v
+            out = {k: v / K for k, v in acc.items()}, ri.sort_mode(), ri.n_pieces(), ri.sort_info()
+            ri.close()
+            return out
+
+        stage_avg, mode, n_pieces, _ = stage_times(V.FLAG_NO_GRAPH)
         nf = cnt["n_fragments"]
+        nrec = cnt["n_out_frag"] + cnt["n_span"]
         peak, peak_src = peaks()
-        pass_ms = stage_avg["sort_passes"] / info["passes"]
-        pass_bytes = nf * 2 * (info["key_bytes"] + 4)          # 2*(K+4) B per fragment per pass
-        achieved = pass_bytes / (pass_ms * 1e-3) / 1e9
-        sort_bytes = nf * (info["key_bytes"] + info["passes"] * 2 * (info["key_bytes"] + 4))
-        sort_ms = stage_avg["sort_hist"] + stage_avg["sort_passes"]
+
+        def entry(kernel, nbytes, ms, launches=1, note=None):
+            gbs = nbytes / (ms * 1e-3) / 1e9
+            tr = ncu_traffic(kernel, args.workload) or (None, None)
+            e = {"kernel": kernel, "bytes_per_launch": nbytes / launches, "ms_per_launch": ms / launches,
+                 "launches_per_step": launches, "achieved": gbs, "frac": gbs / peak, "traffic": tr[0], "traffic_source": tr[1]}
+            if note:
+                e["note"] = note
+            return e
+
+        kb = info["key_bytes"]
+        kernels = {
+            # 64-byte piece records in, (key, value) pairs and the boundary parameters out
+            "walk": entry("k_walk", n_pieces * 64 + nf * (kb + 4) + n_pieces * 9, stage_avg["walk"],
+                          note="issue-bound, not HBM-bound: 2/3 of its instructions are the reference's 24-step fp32 "
+                               "bisection, reproduced operation for operation (no FMA); see DESIGN.md"),
+            "spans": entry("k_spans", nf * (kb + 4) + nrec * 16, stage_avg["span_emit"]),
+            "fill": entry("k_fill_cells", nrec * 16, stage_avg["fill_cells"]),
+        }
+        if mode == "segmented":  # one read + one write of every pair
+            kernels["sort"] = entry("k_segsort_warp", nf * 2 * (kb + 4), stage_avg["sort_passes"])
+        else:                    # 2*(K+4) B per fragment per pass
+            kernels["sort"] = entry("k_onesweep", nf * 2 * (kb + 4) * info["passes"], stage_avg["sort_passes"], info["passes"])
+        dominant = max(kernels.values(), key=lambda e: e["ms_per_launch"] * e["launches_per_step"])
         scan_bytes = 8 * (sc.n_curves + nf)                     # scan #1 + winding scan (8 B / element)
         scan_ms = stage_avg["scan1"] + stage_avg["wind_scan"]
-        roof = {"bound": "hbm", "kernel": "k_onesweep", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": (ncu_traffic("k_onesweep", args.workload) or (None, None))[0],
-                "traffic_source": (ncu_traffic("k_onesweep", args.workload) or (None, None))[1], "peak_source": peak_src,
-                "launches_per_step": info["passes"], "ms_per_launch": pass_ms, "bytes_per_launch": pass_bytes,
-                "timing": "cudaEvent pairs around the k_onesweep launches, direct-launch mode, averaged over the same K steps",
-                "sort_total": {"bytes": sort_bytes, "ms": sort_ms, "gbs": sort_bytes / (sort_ms * 1e-3) / 1e9,
-                               "frac": sort_bytes / (sort_ms * 1e-3) / 1e9 / peak},
+        roof = {"bound": "hbm", "kernel": dominant["kernel"], "achieved": dominant["achieved"], "peak": peak, "unit": "GB/s",
+                "frac": dominant["frac"], "traffic": dominant["traffic"], "traffic_source": dominant["traffic_source"],
+                "peak_source": peak_src, "launches_per_step": dominant["launches_per_step"],
+                "ms_per_launch": dominant["ms_per_launch"], "bytes_per_launch": dominant["bytes_per_launch"],
+                "note": dominant.get("note"),
+                "timing": "cudaEvent pairs around each stage, direct-launch mode, averaged over the same K steps",
+                "sort_mode": mode, "kernels": kernels,
                 "scans": {"bytes": scan_bytes, "ms": scan_ms, "gbs": scan_bytes / (scan_ms * 1e-3) / 1e9,
                           "frac": scan_bytes / (scan_ms * 1e-3) / 1e9 / peak}}
+        if mode == "segmented" and not args.no_radix_leg:
+            # the general sort (paths of any length), timed on the same frame for comparison
+            st_r, _, _, info_r = stage_times(V.FLAG_NO_GRAPH | V.FLAG_RADIX_SORT)
+            pass_ms = st_r["sort_passes"] / info_r["passes"]
+            pass_bytes = nf * 2 * (info_r["key_bytes"] + 4)
+            tr = ncu_traffic("k_onesweep", args.workload) or (None, None)
+            roof["radix_sort"] = {"kernel": "k_onesweep", "launches_per_step": info_r["passes"], "ms_per_launch": pass_ms,
+                                  "bytes_per_launch": pass_bytes, "achieved": pass_bytes / (pass_ms * 1e-3) / 1e9,
+                                  "frac": pass_bytes / (pass_ms * 1e-3) / 1e9 / peak, "traffic": tr[0], "traffic_source": tr[1],
+                                  "sort_total_ms": st_r["sort_hist"] + st_r["sort_passes"],
+                                  "frame_ms_direct": sum(st_r.values())}
 
     # ---- CPU baseline beside it (rank 0, N=1 only): the oracle port on a bounded sample
     cpu = None
@@ -341,7 +378,8 @@ def main():
             "vs_baseline": None, "dtype": "f32+i32", "data": "synthetic",
             "config": {"workload": args.workload, "width": W, "height": H, "curves": sc.n_curves, "paths": sc.n_paths,
                        "points": sc.n_points, "fragments": cnt["n_fragments"], "records": cnt["n_out_frag"] + cnt["n_span"],
-                       "scene_sha256": sc.sha256()[:16], "sort_key_bits": info["key_bits"], "sort_passes": info["passes"],
+                       "scene_sha256": sc.sha256()[:16], "sort": r.sort_mode(), "sort_key_bits": info["key_bits"],
+                       "radix_passes_if_radix": info["passes"],
                        "parallelism": ("bands%d+nccl-gather" % world) if bands else ("frames-dp%d" % world),
                        "l2": "per-frame working set (fragments x 44 B + 33 MB frame) exceeds the 126 MB L2; no flush needed",
                        "frame_replay": "cuda-graph"},

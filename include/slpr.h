@@ -76,8 +76,8 @@ enum {
     SLPR_STAGE_TRANSFORM = 0,   /* k_transform                                  */
     SLPR_STAGE_MONOTONIZE = 1,  /* k_monotonize_count                           */
     SLPR_STAGE_SCAN1 = 2,       /* look-back scan of the curve counts           */
-    SLPR_STAGE_INTERSECT = 3,   /* k_intersect: intersection walk + fragment generation */
-    SLPR_STAGE_FRAGMENT = 4,    /* (folded into INTERSECT; only the segment-table tap) */
+    SLPR_STAGE_INTERSECT = 3,   /* k_piece_emit: set-up of the monotone pieces (MI1:266-308)      */
+    SLPR_STAGE_FRAGMENT = 4,    /* k_walk + k_piece_fix: intersection walk + fragment generation  */
     SLPR_STAGE_SORT_HIST = 5,   /* k_segments (+ k_radix_hist + k_radix_hist_scan in radix mode) */
     SLPR_STAGE_SORT_PASSES = 6, /* radix mode: all k_onesweep launches; segmented mode: k_segsort_warp + k_segsort_block */
     SLPR_STAGE_WIND_SCAN = 7,   /* (folded into SPAN_EMIT: always ~0)           */
@@ -156,10 +156,13 @@ SLPR_API int slpr_debug_copy(slpr_ctx *ctx, int which, void *dst, size_t bytes);
  * fills min(n, SLPR_STAGE_COUNT) slots. New: the reference has no timers. */
 SLPR_API int slpr_stage_ms(slpr_ctx *ctx, float *ms, int n);
 
-/* Sort-pass geometry of the last frame: key bits, number of 8-bit passes, bytes of one key.
- * slpr_sort_mode: 0 = segmented one-pass sort in use, 1 = onesweep radix sort in use. */
-SLPR_API int slpr_sort_mode(slpr_ctx *ctx, int *mode);
+/* Sort geometry of the last frame: key bits, number of 8-bit radix passes, bytes of one key. */
 SLPR_API int slpr_sort_info(slpr_ctx *ctx, uint32_t *key_bits, uint32_t *passes, uint32_t *key_bytes);
+/* Which sort the context uses: 0 = segmented one-pass sort (csrc/segsort.cuh), 1 = onesweep radix
+ * sort (SLPR_FLAG_RADIX_SORT, or a path had more than 4096 fragments). */
+SLPR_API int slpr_sort_mode(slpr_ctx *ctx, int *mode);
+/* Monotone pieces walked by the last frame (64-byte piece records read by k_walk). */
+SLPR_API int slpr_walk_info(slpr_ctx *ctx, uint32_t *n_pieces);
 
 /* Stand-alone device primitives over caller-owned DEVICE buffers (the two roofline-graded
  * kernels, exposed for micro-benchmarks and property tests).

@@ -25,7 +25,7 @@ FLAG_TAPS, FLAG_CONTRACT_FMA, FLAG_NO_GRAPH, FLAG_RADIX_SORT = 1, 2, 4, 8
 TAPS = dict(transformed_pos=0, path_visible=1, cut_cache=2, curve_count=3, curve_offset=4, intersection=5,
             key=6, path=7, winding=8, sorted_key=9, sorted_index=10, winding_scan=11, flags=12,
             flag_scan=13, records=14, segments=15)
-STAGES = ("transform", "monotonize", "scan1", "intersect", "gen_fragment", "sort_hist", "sort_passes",
+STAGES = ("transform", "monotonize", "scan1", "piece_setup", "walk", "sort_hist", "sort_passes",
           "wind_scan", "span_emit", "fill_cells", "resolve")
 
 
@@ -244,6 +244,11 @@ class ScanlineRasterizer:
         m = C.c_int()
         _check(lib().slpr_sort_mode(self._h, C.byref(m)))
         return "radix" if m.value else "segmented"
+
+    def n_pieces(self):
+        n = C.c_uint32()
+        _check(lib().slpr_walk_info(self._h, C.byref(n)))
+        return int(n.value)
 
     def stage_ms(self):
         ms = (C.c_float * len(STAGES))()

@@ -30,6 +30,8 @@ struct FrameCounters {
     int wn_total;      // last element of the winding scan (residue diagnostic)
     int sort_fallback; // segmented sort met a path with more than SEG_BLOCK_MAX fragments
     int n_big_segments;  // paths queued for k_segsort_block
+    int n_pieces;      // monotone pieces walked this frame (k_piece_emit)
+    int pad[3];
 };
 
 // Key geometry for the compact 64-bit sort key (path | row rank | cell x), see DESIGN.md.

@@ -416,6 +416,7 @@ static int enqueue_frame(slpr_ctx *c, cudaStream_t s, bool timed, int &launches)
     k_piece_emit<<<grid_for(c, c->nc, 256, 8), 256, 0, s>>>(c->d_params, c->nc, c->d_ctype, c->d_cpm, c->d_cpath, c->d_frule, c->d_tpos, c->d_cut,
                                                              c->d_offset, c->d_slots, c->d_ctr, c->cap, c->d_bucket_hist,
                                                              c->d_pieces);
+    if (timed) CU(cudaEventRecord(c->ev[4], s));
     k_walk<<<c->num_sms * std::max(1, c->walk_blocks_per_sm), WALK_THREADS, 0, s>>>(
         c->d_params, c->d_pieces, c->d_ctr, c->cap, WalkTemp{c->d_bucket_hist, c->d_tickets + 3 + RS_MAX_PASSES},
         c->L, c->d_key[0], c->d_val[0], ft, c->d_inter, c->d_boundary, c->d_fixflag);
@@ -424,7 +425,6 @@ static int enqueue_frame(slpr_ctx *c, cudaStream_t s, bool timed, int &launches)
                                                               c->d_bucket_hist, c->d_pieces, c->d_boundary, c->d_fixflag, c->L, c->d_key[0],
                                                               c->d_val[0], ft);
     launches += 3;
-    if (timed) CU(cudaEventRecord(c->ev[4], s));
     if (timed) CU(cudaEventRecord(c->ev[5], s));
     k_segments_tap<<<grid_for(c, (long long)c->nc + 1, 256, 8), 256, 0, s>>>(c->nc, c->P, c->d_cpath, c->d_offset, c->d_seg_tap);
     ++launches;
@@ -721,6 +721,14 @@ extern "C" int slpr_sort_info(slpr_ctx *c, uint32_t *key_bits, uint32_t *passes,
 extern "C" int slpr_sort_mode(slpr_ctx *c, int *mode) {
     if (!c || !mode) return fail(SLPR_ERR_INVALID, "slpr_sort_mode: null argument");
     *mode = c->radix_mode ? 1 : 0;
+    return SLPR_OK;
+}
+
+extern "C" int slpr_walk_info(slpr_ctx *c, uint32_t *n_pieces) {
+    if (!c || !n_pieces) return fail(SLPR_ERR_INVALID, "slpr_walk_info: null argument");
+    int rc = finish_frame(c);
+    if (rc) return rc;
+    *n_pieces = (uint32_t)c->h_ctr->n_pieces;
     return SLPR_OK;
 }
 

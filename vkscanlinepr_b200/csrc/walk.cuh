@@ -68,12 +68,13 @@ __global__ void __launch_bounds__(256) k_piece_emit(const FrameParams *__restric
                                                     const uint32_t *__restrict__ fill_rule,
                                                     const float2 *__restrict__ tpos, const float *__restrict__ cut_cache,
                                                     const int *__restrict__ offsets, const uint32_t *__restrict__ slots,
-                                                    const FrameCounters *__restrict__ ctr, int capacity,
+                                                    FrameCounters *__restrict__ ctr, int capacity,
                                                     const uint32_t *__restrict__ bucket_hist, PieceRec *__restrict__ pieces) {
     __shared__ uint32_t s_dbase[WALK_BUCKETS];
     __shared__ uint32_t s_total;
     if (ctr->n_fragments > capacity) return;
     bucket_bases(bucket_hist, s_dbase, &s_total);
+    if (blockIdx.x == 0 && threadIdx.x == 0) ctr->n_pieces = (int)s_total;
     const int width = P->width, height = P->height;
     for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n_curves; c += gridDim.x * blockDim.x) {
         int pcnt = offsets[c];
