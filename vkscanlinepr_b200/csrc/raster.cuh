@@ -13,6 +13,10 @@
 
 namespace slpr {
 
+#ifndef SLPR_FILL_NARROW
+#define SLPR_FILL_NARROW 8 /* records up to this many cells are filled by their own thread (measured: 4 -> 0.162, 8 -> 0.147, 16 -> 0.199 ms) */
+#endif
+
 __global__ void __launch_bounds__(256) k_fill_cells(const FrameParams *__restrict__ P,
                                                     const FrameCounters *__restrict__ ctr, int capacity,
                                                     const int4 *__restrict__ records, uint32_t *__restrict__ cells,
@@ -34,12 +38,12 @@ __global__ void __launch_bounds__(256) k_fill_cells(const FrameParams *__restric
             }
         }
         const uint32_t prio = (uint32_t)r + 1u;
-        if (ncell > 0 && ncell <= 4) {
+        if (ncell > 0 && ncell <= SLPR_FILL_NARROW) {
             uint32_t *row = cells + (size_t)cy * cw + cx0;
             for (int c = 0; c < ncell; ++c) atomicMax(row + c, prio);
         }
         // wide spans: the whole warp fills them, one after the other
-        uint32_t wide = __ballot_sync(0xFFFFFFFFu, ncell > 4);
+        uint32_t wide = __ballot_sync(0xFFFFFFFFu, ncell > SLPR_FILL_NARROW);
         while (wide) {
             const int src = __ffs(wide) - 1;
             wide &= wide - 1;

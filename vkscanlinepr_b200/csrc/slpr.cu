@@ -433,8 +433,8 @@ static int enqueue_frame(slpr_ctx *c, cudaStream_t s, bool timed, int &launches)
     if (!c->radix_mode) {  // every path sorted on chip, one read + one write of the pairs (segsort.cuh)
         if (timed) CU(cudaEventRecord(c->ev[6], s));
         const int yx_bits = c->L.bits_x + c->L.bits_y;
-        k_segsort_warp<<<grid_for(c, (long long)c->P * 32, 256, 8), 256, 0, s>>>(c->d_seg_tap, c->P, c->d_key[0], c->d_val[0], c->d_key[1],
-                                                                                c->d_val[1], c->d_ctr, c->cap, yx_bits, c->d_big);
+        k_segsort_warp<<<grid_for(c, ((long long)c->P + SEG_CHUNK - 1) / SEG_CHUNK * 32, 256, 8), 256, 0, s>>>(
+            c->d_seg_tap, c->P, c->d_key[0], c->d_val[0], c->d_key[1], c->d_val[1], c->d_ctr, c->cap, yx_bits, c->d_big);
         k_segsort_block<<<c->num_sms * 2, SEG_BLOCK_THREADS, 0, s>>>(c->d_seg_tap, c->d_key[0], c->d_val[0], c->d_key[1], c->d_val[1],
                                                                      c->d_ctr, c->cap, yx_bits, c->d_big);
         launches += 2;

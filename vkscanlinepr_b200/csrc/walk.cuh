@@ -176,6 +176,10 @@ struct FragStore {
 };
 
 constexpr int WALK_THREADS = 128;
+#ifndef SLPR_WALK_UNROLL
+#define SLPR_WALK_UNROLL 4
+#endif
+constexpr int WALK_UNROLL = SLPR_WALK_UNROLL;  // bisection steps per loop trip
 #ifndef SLPR_WALK_MIN_BLOCKS
 #define SLPR_WALK_MIN_BLOCKS 1
 #endif
@@ -326,9 +330,9 @@ __global__ void __launch_bounds__(WALK_THREADS, SLPR_WALK_MIN_BLOCKS) k_walk(con
                         if (vt0 != cst) {
                             const float raw_t0 = t0;
                             // the sign of (vt0 - c) never changes: t0 only moves to points of the same sign
-                            const uint32_t s0 = f2u(__fsub_rn(vt0, cst));
+                            const bool neg0 = (int)f2u(__fsub_rn(vt0, cst)) < 0;
                             uint32_t s_last = 0;
-#pragma unroll 4
+#pragma unroll WALK_UNROLL
                             for (int j = 0; j < CUBIC_ITERATION_NUMBER; ++j) {
                                 const float tm = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
                                 const float a0 = __fadd_rn(c0, __fmul_rn(tm, d01)), a1 = __fadd_rn(c1, __fmul_rn(tm, d12)),
@@ -337,8 +341,12 @@ __global__ void __launch_bounds__(WALK_THREADS, SLPR_WALK_MIN_BLOCKS) k_walk(con
                                 const float vtm = lerpf(b0, b1, tm);
                                 t_solve = tm;
                                 s_last = f2u(__fsub_rn(vtm, cst));
-                                if ((int)(s_last ^ s0) >= 0) t0 = tm;  // vt0 = vtm (MI1:421-424)
-                                else t1 = tm;
+                                // same sign as at t0: t0 = tm (vt0 = vtm, MI1:421-424), else t1 = tm. One
+                                // predicate instruction (sign test XOR the loop-invariant sign) + two selects.
+                                asm("{\n\t.reg .pred p, q;\n\tsetp.ne.s32 q, %3, 0;\n\tsetp.lt.xor.s32 p, %2, 0, q;\n\t"
+                                    "selp.f32 %0, %0, %4, p;\n\tselp.f32 %1, %4, %1, p;\n\t}"
+                                    : "+f"(t0), "+f"(t1)
+                                    : "r"(s_last), "r"((int)neg0), "f"(tm));
                             }
                             if (fabsf(u2f(s_last)) > 1.f) t_solve = raw_t0;  // MI1:430-433
                         }
