@@ -252,7 +252,8 @@ extern "C" slpr_ctx *slpr_create(int device, uint32_t width, uint32_t height, ui
     for (auto &ev : c->ev) ok = ok && cudaEventCreate(&ev) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_onesweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->walk_blocks_per_sm, k_walk, WALK_THREADS, 0) == cudaSuccess;
-    ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->span_blocks_per_sm, k_spans, SP_THREADS, 0) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_spans, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_STAGE_BYTES) == cudaSuccess;
+    ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->span_blocks_per_sm, k_spans, SP_THREADS, SP_STAGE_BYTES) == cudaSuccess;
     if (!ok) {
         fail(SLPR_ERR_CUDA, "slpr_create: device setup failed: %s", cudaGetErrorString(cudaGetLastError()));
         slpr_destroy(c);
@@ -464,7 +465,7 @@ static int enqueue_frame(slpr_ctx *c, cudaStream_t s, bool timed, int &launches)
     launches += 2;
 #endif
     if (timed) CU(cudaEventRecord(c->ev[8], s));
-    k_spans<<<c->num_sms * std::max(1, c->span_blocks_per_sm), SP_THREADS, 0, s>>>(c->d_key[cur], c->d_val[cur], c->d_finfo, c->d_rec, c->d_ctr,
+    k_spans<<<c->num_sms * std::max(1, c->span_blocks_per_sm), SP_THREADS, SP_STAGE_BYTES, s>>>(c->d_key[cur], c->d_val[cur], c->d_finfo, c->d_rec, c->d_ctr,
                                                   c->L, (int)c->W, (int)c->H, c->cap, stp, stmp);
     ++launches;
     if (taps) {
