@@ -45,9 +45,12 @@ enum {
     SLPR_FLAG_CONTRACT_FMA = 1u << 1,
     /* Launch kernels directly instead of replaying the captured CUDA graph of the frame. */
     SLPR_FLAG_NO_GRAPH = 1u << 2,
-    /* Always sort with the onesweep LSD radix sort; by default scenes whose paths all have at most 4096
-     * fragments use the one-pass segmented sort (csrc/segsort.cuh), falling back to the radix sort otherwise. */
-    SLPR_FLAG_RADIX_SORT = 1u << 3
+    /* Sort selection. Default: the context picks per scene and view from the path sizes of the last frame —
+     * the one-pass segmented sort (csrc/segsort.cuh) for many small paths, the onesweep LSD radix sort
+     * (csrc/radix.cuh) for small scenes with long paths; a path of more than 4096 fragments always means radix.
+     * RADIX_SORT: always radix. SEGMENTED_SORT: segmented whenever no path exceeds 4096 fragments. */
+    SLPR_FLAG_RADIX_SORT = 1u << 3,
+    SLPR_FLAG_SEGMENTED_SORT = 1u << 4
 };
 
 /* Buffers that slpr_debug_copy() can return. Layouts are the reference's:

@@ -119,31 +119,36 @@ def test_synthetic_scene_parity():
 
 
 def test_sort_modes_by_path_size():
-    """Segmented sort: warp network (paths up to 256 fragments), block network (up to 4096), and the
-    switch to the radix sort when a path is longer than that. Sorted order must equal the oracle's
-    in every mode (naive_seg_sort_pairs.comp:26-97: signed (key, index) order inside each path)."""
+    """Segmented sort: warp network (paths up to 512 fragments), block network (up to 4096), and the
+    switch to the radix sort when a path is longer than that or when the host's cost model prefers it.
+    Sorted order must equal the oracle's in every mode (naive_seg_sort_pairs.comp:26-97: signed
+    (key, index) order inside each path)."""
     W = H = 1024
     small = S.synth_scene(3000, W, H, 10.0, 40.0, seed=0x5E650001)     # glyph-sized paths
     medium = S.synth_scene(300, W, H, 150.0, 400.0, seed=0x5E650002)   # hundreds .. thousands per path
     sc, vp = util.golden_scene("tiger")
-    for scn, rows, want in ((small, S.identity_rows(), "segmented"), (medium, S.identity_rows(), "segmented"),
-                            (sc, S.fit_rows(vp, W, H), None)):
+    cases = ((small, S.identity_rows(), V.FLAG_SEGMENTED_SORT, "segmented"),
+             (medium, S.identity_rows(), V.FLAG_SEGMENTED_SORT, "segmented"),  # exercises k_segsort_block
+             (small, S.identity_rows(), 0, "segmented"),                        # many small paths: the model keeps it
+             (medium, S.identity_rows(), 0, "radix"),                           # few long paths: the model leaves it
+             (sc, S.fit_rows(vp, W, H), 0, "radix"))                            # a path of more than 4096 fragments
+    for scn, rows, flags, want in cases:
         ref = O.render(scn, rows, W, H)
-        seg = ref["seg"]
-        longest = int(np.max(np.diff(seg))) if len(seg) > 1 else 0
-        r = render_gpu(scn, rows, W, H, V.FLAG_TAPS)
-        assert r.counts()["n_fragments"] == ref["n_fragments"]  # completes the frame (and a possible fallback)
-        expect = want or ("segmented" if longest <= 4096 else "radix")
-        assert r.sort_mode() == expect, (longest, r.sort_mode())
-        assert np.array_equal(r.tap("sorted_key"), ref["skey"]) and np.array_equal(r.tap("sorted_index"), ref["sidx"])
-        assert np.array_equal(r.tap("records"), ref["records"])
-        assert np.array_equal(r.readback(), ref["rgba"])
+        r = render_gpu(scn, rows, W, H, V.FLAG_TAPS | flags)
+        for frame in range(2):  # the second frame runs in the mode chosen after the first
+            assert r.counts()["n_fragments"] == ref["n_fragments"]  # completes the frame (and a possible fallback)
+            assert np.array_equal(r.tap("sorted_key"), ref["skey"]) and np.array_equal(r.tap("sorted_index"), ref["sidx"])
+            assert np.array_equal(r.tap("records"), ref["records"])
+            assert np.array_equal(r.readback(), ref["rgba"])
+            r.render()
+        r.synchronize()
+        assert r.sort_mode() == want, (int(np.max(np.diff(ref["seg"]))), r.sort_mode(), want)
         r.close()
     # a scene with one path longer than 4096 fragments: first frame falls back, later frames stay on radix
     big = S.synth_scene(6, 4096, 4096, 1800.0, 2000.0, seed=0x5E650003)
     ref = O.render(big, S.identity_rows(), 4096, 4096)
     assert int(np.max(np.diff(ref["seg"]))) > 4096
-    r = render_gpu(big, S.identity_rows(), 4096, 4096, 0)
+    r = render_gpu(big, S.identity_rows(), 4096, 4096, V.FLAG_SEGMENTED_SORT)
     assert r.counts()["n_fragments"] == ref["n_fragments"]
     assert r.sort_mode() == "radix"
     assert np.array_equal(r.readback(), ref["rgba"]) and np.array_equal(r.tap("records"), ref["records"])

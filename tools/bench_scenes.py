@@ -12,17 +12,18 @@ from vkscanlinepr_b200 import scene as S
 from oracle import oracle_py as O
 
 scenes = ["test", "tiger", "reschart", "drops", "embrace"]
+FLAGS = int(os.environ.get("SLPR_SCENE_FLAGS", "0"))  # e.g. 8 = SLPR_FLAG_RADIX_SORT
 sizes = [(1024, 1024), (1920, 1080), (3840, 2160)]
 frames = 50
-print("| scene | size | curves | fragments | records | ms/frame | Mpixel/s | oracle ms (threads) | RGBA8 vs oracle |")
-print("|---|---|---:|---:|---:|---:|---:|---:|---|")
+print("| scene | size | curves | fragments | records | ms/frame | Mpixel/s | oracle ms (threads) | RGBA8 vs oracle | sort |")
+print("|---|---|---:|---:|---:|---:|---:|---:|---|---|")
 stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
 for name in scenes:
     c = S.Container.from_npz(os.path.join(ROOT, "tests", "golden", name + ".npz"))
     sc = V.flatten(c, name)
     for W, H in sizes:
         rows = S.fit_rows(c.vp, W, H, centred=not (name == "test" and W == 1024))
-        r = V.ScanlineRasterizer(0, 0).initialize(None, W, H)
+        r = V.ScanlineRasterizer(0, FLAGS).initialize(None, W, H)
         r.set_stream(stream.cuda_stream); r.loadVG(sc); r.setMVP(rows)
         for _ in range(5): r.render()
         r.synchronize()
@@ -36,5 +37,5 @@ for name in scenes:
         same = np.array_equal(img, ref["rgba"]) and cnt["n_fragments"] == ref["n_fragments"]
         diff = int(np.abs(img.astype(int) - ref["rgba"].astype(int)).max())
         print(f"| {name} | {W}x{H} | {sc.n_curves} | {cnt['n_fragments']} | {cnt['n_out_frag'] + cnt['n_span']} | {ms:.3f} | {W*H/ms/1e3:.0f} | "
-              f"{tor:.0f} ({O.num_threads()}) | {'identical' if same else 'max diff %d' % diff} |")
+              f"{tor:.0f} ({O.num_threads()}) | {'identical' if same else 'max diff %d' % diff} | {r.sort_mode()} |")
         r.close()

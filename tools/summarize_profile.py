@@ -39,34 +39,32 @@ with open(os.path.join(P, f"{tag}_launches.md"), "w") as f:
 os.replace(os.path.join(G, f"launches_{tag}.csv"), os.path.join(P, f"{tag}_launches.csv")) if False else None
 import shutil; shutil.copy(os.path.join(G, f"launches_{tag}.csv"), os.path.join(P, f"{tag}_launches.csv"))
 
-# ---- full capture
-rep = os.path.join(G, f"prof_{tag}.ncu-rep")
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-rr = list(csv.reader(io.StringIO(raw))); hh, uu = rr[0], rr[1]
-def col(r, name, default=""):
-    return r[hh.index(name)] if name in hh else default
+# ---- full captures: the default frame (segmented sort) and, when present, the radix sort kernels
 want = [("gpu__time_duration.sum", "time"), ("dram__bytes_read.sum", "DRAM rd"), ("dram__bytes_write.sum", "DRAM wr"),
         ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "DRAM %"), ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM %"),
         ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue %"), ("sm__warps_active.avg.pct_of_peak_sustained_active", "occupancy %"),
         ("launch__registers_per_thread", "regs"), ("smsp__thread_inst_executed_per_inst_executed.ratio", "thr/inst")]
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
-sr = list(csv.reader(io.StringIO(src)))
-starts = [i for i, r in enumerate(sr) if r and r[0] == "Address"]
-stalls = []
-for si, st in enumerate(starts):
-    hdr = sr[st]; end = starts[si + 1] - 1 if si + 1 < len(starts) else len(sr)
-    reasons = [(i, x) for i, x in enumerate(hdr) if x.startswith("stall_") and "Not Issued" not in x]
-    acc = {}
-    for r in sr[st + 1:end]:
-        for i, x in reasons:
-            if i < len(r) and r[i].isdigit(): acc[x[6:]] = acc.get(x[6:], 0) + int(r[i])
-    t = sum(acc.values()) or 1
-    nm = short(sr[st - 1][1]) if st > 0 and len(sr[st - 1]) > 1 else "?"
-    stalls.append((nm, ", ".join(f"{k} {100*v/t:.0f}%" for k, v in sorted(acc.items(), key=lambda kv: -kv[1])[:4])))
 traffic = {}
-with open(os.path.join(P, f"{tag}_kernels.md"), "w") as f:
-    f.write(f"# ncu --set full, one frame of synth_1m_4k ({tag})\n\n`ncu --set full --clock-control none --import-source on` on `tools/prof_frame.py synth_1m_4k 2` "
-            "(second frame, direct launches). Times under ncu are serialised and slower than in situ.\n\n| kernel | " + " | ".join(w[1] for w in want) + " | top stalls |\n|---|" + "---:|" * len(want) + "---|\n")
+
+def process(rep, f):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rr = list(csv.reader(io.StringIO(raw))); hh, uu = rr[0], rr[1]
+    def col(r, name, default=""):
+        return r[hh.index(name)] if name in hh else default
+    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    sr = list(csv.reader(io.StringIO(src)))
+    starts = [i for i, r in enumerate(sr) if r and r[0] == "Address"]
+    stalls = []
+    for si, st in enumerate(starts):
+        hdr = sr[st]; end = starts[si + 1] - 1 if si + 1 < len(starts) else len(sr)
+        reasons = [(i, x) for i, x in enumerate(hdr) if x.startswith("stall_") and "Not Issued" not in x]
+        acc = {}
+        for r in sr[st + 1:end]:
+            for i, x in reasons:
+                if i < len(r) and r[i].isdigit(): acc[x[6:]] = acc.get(x[6:], 0) + int(r[i])
+        t = sum(acc.values()) or 1
+        nm = short(sr[st - 1][1]) if st > 0 and len(sr[st - 1]) > 1 else "?"
+        stalls.append((nm, ", ".join(f"{k} {100*v/t:.0f}%" for k, v in sorted(acc.items(), key=lambda kv: -kv[1])[:4])))
     for n, r in enumerate(rr[2:]):
         name = short(col(r, "Kernel Name"))
         cells = []
@@ -83,6 +81,16 @@ with open(os.path.join(P, f"{tag}_kernels.md"), "w") as f:
             v = float(col(r, m, "0") or 0); u = uu[hh.index(m)]
             return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
         traffic.setdefault(name, []).append(tobytes("dram__bytes_read.sum") + tobytes("dram__bytes_write.sum"))
+
+head = "| kernel | " + " | ".join(w[1] for w in want) + " | top stalls |\n|---|" + "---:|" * len(want) + "---|\n"
+with open(os.path.join(P, f"{tag}_kernels.md"), "w") as f:
+    f.write(f"# ncu --set full, one frame of synth_1m_4k ({tag})\n\n`ncu --set full --clock-control none --import-source on` on `tools/prof_frame.py synth_1m_4k 2` "
+            "(second frame, direct launches, default = segmented sort). Times under ncu are serialised and slower than in situ.\n\n" + head)
+    process(os.path.join(G, f"prof_{tag}.ncu-rep"), f)
+    rep2 = os.path.join(G, f"prof_{tag}_radix.ncu-rep")
+    if os.path.exists(rep2):
+        f.write("\n## radix sort kernels (`SLPR_FLAG_RADIX_SORT`, the general path: paths of any length)\n\n" + head)
+        process(rep2, f)
 json.dump({"workload": "synth_1m_4k", "source": f"profiles/{tag}_kernels.md (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)",
            "dram_bytes_per_launch": {k: sum(v) / len(v) for k, v in traffic.items()}}, open(os.path.join(P, f"{tag}_traffic.json"), "w"), indent=1)
 print(open(os.path.join(P, f"{tag}_launches.md")).read()); print(open(os.path.join(P, f"{tag}_kernels.md")).read())

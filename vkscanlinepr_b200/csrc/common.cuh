@@ -17,7 +17,9 @@ struct FrameParams {
     int width, height;
     int band_y0, band_y1;  // scanline rows [y0,y1) this context renders
     int cull;              // 1 when the band is a strict subset of the frame
-    int pad[3];
+    int stat_mid;      // paths of 129..512 fragments   } k_path_stats, every frame and in both sort modes:
+    int stat_big;      // paths of 513..4096 fragments  } the host picks the sort from them
+    int stat_huge;     // paths of more than 4096 fragments (radix sort only)
 };
 
 // Device-resident counters (zeroed at the start of every frame).
@@ -31,7 +33,9 @@ struct FrameCounters {
     int sort_fallback; // segmented sort met a path with more than SEG_BLOCK_MAX fragments
     int n_big_segments;  // paths queued for k_segsort_block
     int n_pieces;      // monotone pieces walked this frame (k_piece_emit)
-    int pad[3];
+    int stat_mid;      // paths of 129..512 fragments   } k_path_stats, every frame and in both sort modes:
+    int stat_big;      // paths of 513..4096 fragments  } the host picks the sort from them
+    int stat_huge;     // paths of more than 4096 fragments (radix sort only)
 };
 
 // Key geometry for the compact 64-bit sort key (path | row rank | cell x), see DESIGN.md.

@@ -189,6 +189,27 @@ __device__ __forceinline__ bool warp_sort_segment32(const uint64_t *__restrict__
     return true;
 }
 
+// Path-size statistics for the host's choice between the two sorts (slpr.cu: choose_sort_mode).
+__global__ void __launch_bounds__(256) k_path_stats(const int *__restrict__ seg, uint32_t n_paths, FrameCounters *__restrict__ ctr,
+                                                    int capacity) {
+    if (ctr->n_fragments > capacity) return;
+    int mid = 0, big = 0, huge = 0;
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n_paths; p += gridDim.x * blockDim.x) {
+        const int n = seg[p + 1] - seg[p];
+        mid += (n > 128 && n <= SEG_WARP_MAX);
+        big += (n > SEG_WARP_MAX && n <= SEG_BLOCK_MAX);
+        huge += (n > SEG_BLOCK_MAX);
+    }
+    mid = __reduce_add_sync(0xFFFFFFFFu, mid);
+    big = __reduce_add_sync(0xFFFFFFFFu, big);
+    huge = __reduce_add_sync(0xFFFFFFFFu, huge);
+    if ((threadIdx.x & 31) == 0) {
+        if (mid) atomicAdd(&ctr->stat_mid, mid);
+        if (big) atomicAdd(&ctr->stat_big, big);
+        if (huge) atomicAdd(&ctr->stat_huge, huge);
+    }
+}
+
 constexpr int SEG_CHUNK = 8;  // consecutive paths per warp trip (one contiguous run of fragments)
 
 __global__ void __launch_bounds__(256) k_segsort_warp(const int *__restrict__ seg, uint32_t n_paths,

@@ -428,7 +428,8 @@ static int enqueue_frame(slpr_ctx *c, cudaStream_t s, bool timed, int &launches)
     launches += 3;
     if (timed) CU(cudaEventRecord(c->ev[5], s));
     k_segments_tap<<<grid_for(c, (long long)c->nc + 1, 256, 8), 256, 0, s>>>(c->nc, c->P, c->d_cpath, c->d_offset, c->d_seg_tap);
-    ++launches;
+    k_path_stats<<<grid_for(c, c->P, 256, 4), 256, 0, s>>>(c->d_seg_tap, c->P, c->d_ctr, c->cap);
+    launches += 2;
     // ---- sort
     int cur = 0;
     if (!c->radix_mode) {  // every path sorted on chip, one read + one write of the pairs (segsort.cuh)
@@ -556,6 +557,21 @@ extern "C" int slpr_render(slpr_ctx *c) {
 }
 
 // Wait for the frame; if it overflowed the fragment capacity, grow and render it again.
+// Which sort is cheaper for the frame just rendered? Microsecond models fitted to the B200 measurements
+// in profiles/README.md: the radix sort costs a fixed ~8 us per pass plus ~8.3 ps per fragment and pass; the
+// segmented sort streams the pairs once (~9.4 ps per fragment) but pays ~25 us when warps have to sort paths
+// of 129..512 fragments and ~45 us per wave of 2 x #SM paths of 513..4096 fragments (one block each).
+// Small scenes with a few long paths are therefore sorted by radix, big scenes of small paths segmented.
+static bool segmented_sort_pays(const slpr_ctx *c, const FrameCounters &k) {
+    if (k.stat_huge) return false;
+    const double nf = (double)k.n_fragments;
+    const double t_radix = 15.0 + nf * 3.7e-6 + c->passes * (8.0 + nf * 8.3e-6);
+    const double waves = std::ceil((double)k.stat_big / (2.0 * c->num_sms));
+    const double t_seg = 12.0 + nf * 9.4e-6 + (k.stat_mid ? 25.0 : 0.0) + (k.stat_big ? 40.0 + 45.0 * waves : 0.0);
+    // hysteresis: leave the current mode only for a clear win
+    return c->radix_mode ? (t_seg * 1.25 < t_radix) : (t_seg < t_radix * 1.25);
+}
+
 static int finish_frame(slpr_ctx *c) {
     if (!c->frame_pending && !c->frame_done) return fail(SLPR_ERR_STATE, "no frame has been rendered");
     CU(cudaSetDevice(c->device));
@@ -570,7 +586,17 @@ static int finish_frame(slpr_ctx *c) {
             if (rc2) return rc2;
             continue;
         }
-        if (!c->h_ctr->overflow) { c->frame_done = true; return SLPR_OK; }
+        if (!c->h_ctr->overflow) {
+            if (!(c->flags & (SLPR_FLAG_RADIX_SORT | SLPR_FLAG_SEGMENTED_SORT))) {
+                const bool seg = segmented_sort_pays(c, *c->h_ctr);
+                if (seg == c->radix_mode) {  // the other sort suits this scene and view better: use it from the next frame on
+                    c->radix_mode = !seg;
+                    c->graph_valid = c->graph2_valid = false;
+                }
+            }
+            c->frame_done = true;
+            return SLPR_OK;
+        }
         const long long nf = c->h_ctr->n_fragments;
         int rc = alloc_capacity(c, (int)std::min<long long>(nf + nf / 4 + 65536, (1ll << 29) - 1));
         if (rc) return rc;

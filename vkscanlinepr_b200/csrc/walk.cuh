@@ -61,7 +61,10 @@ __device__ __forceinline__ void bucket_bases(const uint32_t *__restrict__ hist, 
 }
 
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_piece_emit(const FrameParams *__restrict__ P, uint32_t n_curves,
+#ifndef SLPR_PE_MIN_BLOCKS
+#define SLPR_PE_MIN_BLOCKS 1
+#endif
+__global__ void __launch_bounds__(256, SLPR_PE_MIN_BLOCKS) k_piece_emit(const FrameParams *__restrict__ P, uint32_t n_curves,
                                                     const uint32_t *__restrict__ curve_type,
                                                     const uint32_t *__restrict__ curve_pos_map,
                                                     const uint32_t *__restrict__ curve_path,
@@ -138,11 +141,13 @@ struct FragStore {
     uint64_t pk;
     uint32_t pv0, pv1, pv2;
     int f_first;
+    bool direct;  // (kernel-uniform) few groups per warp: the frame is bound by its longest pieces, not by stores —
+                  // plain stores keep the per-crossing instruction count down (line-heavy scenes: -20 %)
     __device__ __forceinline__ void put(int f, uint64_t k, uint32_t v, uint64_t *__restrict__ key64, uint32_t *__restrict__ val) {
-#if !SLPR_WALK_PAIR
-        key64[f] = k; val[f] = v;
-        return;
-#endif
+        if (!SLPR_WALK_PAIR || direct) {
+            key64[f] = k; val[f] = v;
+            return;
+        }
         if (f & 1) {
             if (f > f_first) *reinterpret_cast<ulonglong2 *>(key64 + f - 1) = make_ulonglong2(pk, k);
             else key64[f] = k;
@@ -162,9 +167,7 @@ struct FragStore {
     }
     // after the piece's last fragment
     __device__ __forceinline__ void flush(int f_last, uint64_t *__restrict__ key64, uint32_t *__restrict__ val) {
-#if !SLPR_WALK_PAIR
-        return;
-#endif
+        if (!SLPR_WALK_PAIR || direct) return;
         if (!(f_last & 1)) key64[f_last] = pk;
         const int q = f_last & 3, base = f_last - q;
         if (q != 3) {
@@ -218,19 +221,17 @@ __global__ void __launch_bounds__(WALK_THREADS, SLPR_WALK_MIN_BLOCKS) k_walk(con
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    // tickets are taken two groups ahead so that neither the atomic nor the record fetch is waited for
-    uint32_t g_cur = 0, g_next = 0;
-    if (lane == 0) {
-        g_cur = take_ticket(tmp.group_counter);
-        g_next = take_ticket(tmp.group_counter);
-    }
-    g_cur = __shfl_sync(0xFFFFFFFFu, g_cur, 0);
-    g_next = __shfl_sync(0xFFFFFFFFu, g_next, 0);
+    // Groups are taken two ahead so that neither the ticket atomic nor the record fetch is waited for.
+    // The first two rounds are dealt statically (warp w: groups w and w + #warps): groups are sorted
+    // longest first, and a warp holding two CONSECUTIVE tickets would walk the two longest groups one
+    // after the other — on a scene bound by its longest pieces that doubles the frame time.
+    const uint32_t n_warps = gridDim.x * (WALK_THREADS / 32);
+    uint32_t g_cur = blockIdx.x * (WALK_THREADS / 32) + warp, g_next = g_cur + n_warps;
     stage_group(g_cur, 0);
     for (int st = 0;; st ^= 1) {
         if ((unsigned long long)g_cur * 32ull >= n_pieces) break;  // tickets only grow: nothing left for this warp
         uint32_t g_after = 0;
-        if (lane == 0) g_after = take_ticket(tmp.group_counter);
+        if (lane == 0) g_after = take_ticket(tmp.group_counter) + 2u * n_warps;
         stage_group(g_next, st ^ 1);
         asm volatile("cp.async.wait_group 1;" ::: "memory");
         __syncwarp();
@@ -264,6 +265,7 @@ __global__ void __launch_bounds__(WALK_THREADS, SLPR_WALK_MIN_BLOCKS) k_walk(con
         g_next = __shfl_sync(0xFFFFFFFFu, g_after, 0);
         FragStore fs;
         fs.pk = 0; fs.pv0 = fs.pv1 = fs.pv2 = 0; fs.f_first = pcnt;
+        fs.direct = (unsigned long long)n_pieces <= 64ull * n_warps;  // at most two groups per warp
         float tx = t0_ms, ty = t0_ms;  // point_coords slots 8, 9 (MI1:304-305)
         int i_inte_last = (int)f2u(-1.0f);
         bool have_prev = false;
