@@ -147,6 +147,7 @@ def main():
     ap.add_argument("--workload", default="synth_1m_4k")
     ap.add_argument("--mode", default="frames", choices=["frames", "bands"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gather", action="store_true", help="bands mode: leave every band on its GPU (no NCCL gather)")
     ap.add_argument("--no-radix-leg", action="store_true", help="skip timing the radix sort beside the segmented sort")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -189,29 +190,54 @@ def main():
         y0 = rank * rows_per
         y1 = H if rank == world - 1 else y0 + rows_per
         r.set_band(y0, y1)
-        frame = torch.empty((H, W, 4), dtype=torch.uint8, device="cuda")
-        r.set_target(frame.data_ptr(), W * 4)
-        band_view = frame[H - y1:H - y0]  # image rows of this band (y flip)
-        gather_list = None
-        sizes = [((H if g == world - 1 else (g + 1) * rows_per) - g * rows_per) for g in range(world)]
+        # Pipelined gather: every rank renders its band straight into frame buffer i & 1 (two captured graphs,
+        # slpr_set_target); the band of frame i then travels to rank 0 (one NCCL group of send/recv over NVLink,
+        # on NCCL's own stream) while frame i+1 is rendered into the other buffer. A buffer is reused only after
+        # the transfer that read / wrote it two frames earlier has finished. Rank 0 receives in place: no copies.
+        if rank == 0:
+            frames2 = [torch.empty((H, W, 4), dtype=torch.uint8, device="cuda") for _ in range(2)]
+        else:  # senders only need their own band, twice
+            bands2 = [torch.empty((y1 - y0, W, 4), dtype=torch.uint8, device="cuda") for _ in range(2)]
+        pending = [[], []]
+        step_no = [0]
+
+    def band_target(slot):
+        """(pointer the context renders to so that its band lands in the buffer of `slot`, the band view)"""
+        if rank == 0:
+            return frames2[slot].data_ptr(), frames2[slot][H - y1:H - y0]
+        # the context addresses a full frame: offset the base so that image rows [H-y1, H-y0) hit the band buffer
+        return bands2[slot].data_ptr() - (H - y1) * W * 4, bands2[slot]
+
+    def drain(slot):
+        for q in pending[slot]:
+            q.wait()
+        pending[slot] = []
 
     def step():
         r.setMVP(rows)
+        if bands:
+            slot = step_no[0] & 1
+            step_no[0] += 1
+            drain(slot)  # the transfer of frame i-2 used this buffer
+            ptr, view = band_target(slot)
+            r.set_target(ptr, W * 4)
         r.render()
-        if bands:  # gather the bands to rank 0 (NVLink): rank 0 receives straight into the frame
+        if bands and not args.no_gather:
             if rank == 0:
-                reqs = []
+                ops = []
                 for g in range(1, world):
                     gy0 = g * rows_per
                     gy1 = H if g == world - 1 else gy0 + rows_per
-                    reqs.append(dist.irecv(frame[H - gy1:H - gy0], src=g))
-                for q in reqs:
-                    q.wait()
+                    ops.append(dist.P2POp(dist.irecv, frames2[slot][H - gy1:H - gy0], g))
+                pending[slot] = dist.batch_isend_irecv(ops)  # one NCCL group: the receives run concurrently
             else:
-                dist.send(band_view, dst=0)
+                pending[slot] = dist.batch_isend_irecv([dist.P2POp(dist.isend, view, 0)])
 
     for _ in range(Wm):
         step()
+    if bands:
+        drain(0)
+        drain(1)
     r.synchronize()
     cnt = r.counts()
     info = r.sort_info()
@@ -231,6 +257,9 @@ def main():
     e0.record(stream)
     for _ in range(K):
         step()
+    if bands:  # every band of every timed frame has arrived before the clock stops
+        drain(0)
+        drain(1)
     e1.record(stream)
     barrier()
     ms_total = e0.elapsed_time(e1)
@@ -246,6 +275,20 @@ def main():
     frames_total = K if bands else K * world
     ms_per_step = ms_total / K
     mpix = frames_total * W * H / (ms_total * 1e-3) / 1e6
+
+    band_check = None
+    if bands and rank == 0 and not args.no_gather:  # the assembled frame against the same frame rendered whole on this GPU
+        full = make_ctx(0)
+        ref_frame = torch.empty((H, W, 4), dtype=torch.uint8, device="cuda")
+        full.set_target(ref_frame.data_ptr(), W * 4)
+        full.render()
+        full.synchronize()
+        last = frames2[(step_no[0] - 1) & 1]
+        diff = int((last.view(torch.int32) != ref_frame.view(torch.int32)).sum().item())
+        band_check = {"pixels_differing": diff, "pixels": W * H,
+                      "note": "0 unless the scene has a winding residue (DESIGN.md section 5)"}
+        full.close()
+        del ref_frame
 
     # ---- e2e: the public calls with HOST buffers (matrix in, RGBA8 frame out to pinned memory).
     #      Headline: the pipelined frame-sequence call (slpr_submit_to_host: the copy of frame i overlaps the
@@ -380,12 +423,14 @@ def main():
                        "points": sc.n_points, "fragments": cnt["n_fragments"], "records": cnt["n_out_frag"] + cnt["n_span"],
                        "scene_sha256": sc.sha256()[:16], "sort": r.sort_mode(), "sort_key_bits": info["key_bits"],
                        "radix_passes_if_radix": info["passes"],
-                       "parallelism": ("bands%d+nccl-gather" % world) if bands else ("frames-dp%d" % world),
+                       "parallelism": (("bands%d" % world) + ("+no-gather" if args.no_gather else "+pipelined-nccl-gather")) if bands else ("frames-dp%d" % world),
                        "l2": "per-frame working set (fragments x 44 B + 33 MB frame) exceeds the 126 MB L2; no flush needed",
                        "frame_replay": "cuda-graph"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
             "stage_ms": stage_avg,
         }
+        if band_check is not None:
+            out["bands_vs_full_frame"] = band_check
         print(json.dumps(out))
     r.close()
     if dist is not None:

@@ -159,6 +159,22 @@ SLPR_API int slpr_debug_copy(slpr_ctx *ctx, int which, void *dst, size_t bytes);
  * fills min(n, SLPR_STAGE_COUNT) slots. New: the reference has no timers. */
 SLPR_API int slpr_stage_ms(slpr_ctx *ctx, float *ms, int n);
 
+/* ---- Exact row bands across GPUs (new; csrc/bands.cuh) --------------------------------
+ * The reference's winding scan is one unsegmented prefix sum over all fragments (SR.cpp:479-506), so a band of
+ * rows needs the winding sums of the other bands' fragments that sort before its own. Per frame and per band:
+ *   slpr_render_band_begin   transform .. sort of this band; leaves 3 * n_paths int32 (per-path sums of the
+ *                            winding deltas: normal rows | outside the frame | row 0) in dev_sums; returns after
+ *                            the stream has drained (capacity growth and sort selection are settled here)
+ *   (caller)                 all-gather of dev_sums over the bands into dev_gathered [n_bands][3 * n_paths],
+ *                            bands ordered by rows, on the context's stream or ordered after it (NCCL all-gather)
+ *   slpr_render_band_end     corrections, spans, draw records, pixels of the band (asynchronous, like slpr_render)
+ * slpr_set_band first; slpr_set_band_exchange(ctx, NULL, NULL, 0, 0) returns to independent bands, which are
+ * exact only for scenes whose per-path winding sums vanish. */
+SLPR_API int slpr_band_exchange_ints(slpr_ctx *ctx, size_t *ints_per_band);
+SLPR_API int slpr_set_band_exchange(slpr_ctx *ctx, int32_t *dev_sums, const int32_t *dev_gathered, int n_bands, int band);
+SLPR_API int slpr_render_band_begin(slpr_ctx *ctx);
+SLPR_API int slpr_render_band_end(slpr_ctx *ctx);
+
 /* Sort geometry of the last frame: key bits, number of 8-bit radix passes, bytes of one key. */
 SLPR_API int slpr_sort_info(slpr_ctx *ctx, uint32_t *key_bits, uint32_t *passes, uint32_t *key_bytes);
 /* Which sort the context uses: 0 = segmented one-pass sort (csrc/segsort.cuh), 1 = onesweep radix

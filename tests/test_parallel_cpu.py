@@ -67,9 +67,41 @@ def _worker(rank, world, port, q):
         mine[PAR.frames_of_rank(16, rank, world)] = 1
         dist.all_reduce(mine)
         ok = ok and bool((mine == 1).all())
+        ok = ok and _exact_band_windings(rank, world, dist, torch)
         q.put((rank, ok))
     finally:
         dist.destroy_process_group()
+
+
+def _exact_band_windings(rank, world, dist, torch):
+    """The exchange step of exact row bands (csrc/bands.cuh) on oracle data: every rank keeps the fragments
+    of its rows, all-gathers its per-path winding sums, and must recover the FULL frame's winding number at
+    each of its fragments as local scan + correction — on a scene with a winding residue."""
+    from oracle import oracle_py as O
+    W = H = 192
+    sc = S.synth_scene(160, W, H, 6.0, 30.0, seed=0x5CA71E01)
+    ref = O.render(sc, S.identity_rows(), W, H, do_fill=False)
+    assert ref["wn"][-1] != 0, "the test scene must have a winding residue"
+    sk, si = ref["skey"], ref["sidx"]
+    path_s, d_s, wn = ref["path"][si].astype(np.int64), ref["wind"][si].astype(np.int64), ref["wn"][:-1]
+    invalid = sk.view(np.uint32) == 0xFFFEFFFE
+    y = (sk.view(np.uint32) >> 16).astype(np.int64) - 0x7FFF
+    cls = np.where(invalid, 1, np.where(y == 0, 2, 0))  # normal rows | outside the frame | row 0
+    bands = PAR.band_rows(H, world)
+    owner = np.zeros(len(sk), dtype=np.int64)           # fragments outside the frame: band 0 (any single owner works)
+    for r, (y0, y1) in enumerate(bands):
+        owner[~invalid & (y >= y0) & (y < y1)] = r
+    mine = owner == rank
+    P = sc.n_paths
+    sums = np.zeros((3, P), dtype=np.int32)
+    np.add.at(sums, (cls[mine], path_s[mine]), d_s[mine].astype(np.int32))
+    gathered = torch.zeros((world, 3 * P), dtype=torch.int32)
+    dist.all_gather_into_tensor(gathered.view(-1), torch.from_numpy(sums.reshape(-1)))
+    corr_n, corr_z = PAR.band_corrections(gathered.numpy().reshape(world, 3, P), rank)
+    local = np.cumsum(np.where(mine, d_s, 0)) - np.where(mine, d_s, 0)  # exclusive scan of this band's own deltas
+    check = mine & (cls != 1)
+    corr = np.where(cls == 2, corr_z[path_s], corr_n[path_s])
+    return bool(np.array_equal((local + corr)[check].astype(np.int32), wn[check]))
 
 
 def test_gloo_band_gather_and_frame_partition():

@@ -201,6 +201,56 @@ def test_row_bands_equal_full_frame():
         assert np.array_equal(full, ref["rgba"]), f"G={G}"
 
 
+def test_exact_row_bands_with_exchange():
+    """SURVEY §8e with a winding residue: G band contexts (one GPU here, one per GPU in production) render
+    the two halves of the frame around an all-gather of their per-path winding sums (csrc/bands.cuh); the
+    assembled frame must be the full frame, bit for bit, on scenes where independent bands are NOT exact."""
+    import torch
+    from vkscanlinepr_b200 import parallel as PAR
+    tig, vp = util.golden_scene("tiger")
+    cases = [(S.synth_scene(2000, 512, 512, 6.0, 30.0, seed=0x5CA71E01), S.identity_rows(), 512, 512, 3),
+             (S.synth_scene(3000, 640, 360, 4.0, 60.0, seed=0x5CA71E02), S.identity_rows(), 640, 360, 8),
+             (tig, S.fit_rows(vp, 640, 480), 640, 480, 4)]
+    for sc, rows, W, H, G in cases:
+        ref = O.render(sc, rows, W, H)
+        P = sc.n_paths
+        bands = PAR.band_rows(H, G)
+        frame = torch.zeros((H, W, 4), dtype=torch.uint8, device="cuda")
+        gathered = torch.zeros((G, 3 * P), dtype=torch.int32, device="cuda")
+        sums = [torch.zeros(3 * P, dtype=torch.int32, device="cuda") for _ in range(G)]
+        ctxs = []
+        for g, (y0, y1) in enumerate(bands):
+            c = V.ScanlineRasterizer(0, 0).initialize(None, W, H)
+            c.loadVG(sc)
+            c.setMVP(rows)
+            c.set_band(y0, y1)
+            c.set_target(frame.data_ptr(), W * 4)
+            assert c.band_exchange_ints() == 3 * P
+            c.set_band_exchange(sums[g].data_ptr(), gathered.data_ptr(), G, g)
+            ctxs.append(c)
+        with pytest.raises(RuntimeError):
+            ctxs[0].render()  # a configured exchange needs the two-step call
+        for _ in range(2):  # the second frame replays the captured graphs
+            frame.zero_()
+            torch.cuda.synchronize()
+            for c in ctxs:
+                c.render_band_begin()  # returns with the band's sums complete
+            gathered.copy_(torch.stack(sums))  # stands in for the NCCL all-gather
+            torch.cuda.synchronize()
+            for c in ctxs:
+                c.render_band_end()
+            for c in ctxs:
+                c.synchronize()
+            got = frame.cpu().numpy()
+            assert np.array_equal(got, ref["rgba"]), f"{int((got != ref['rgba']).any(axis=2).sum())} pixels differ ({G} bands)"
+        if ref["wn"][-1] != 0:  # with a residue, independent bands are expected to differ: the exchange is what fixes it
+            ctxs[G - 1].set_band_exchange(0, 0, 0, 0)
+            ctxs[G - 1].render()
+            ctxs[G - 1].synchronize()
+        for c in ctxs:
+            c.close()
+
+
 def test_error_paths():
     r = V.ScanlineRasterizer(0, 0).initialize(None, 64, 64)
     with pytest.raises(V.SlprError):

@@ -222,6 +222,21 @@ class ScanlineRasterizer:
     def set_target(self, dev_ptr, stride_bytes):
         _check(lib().slpr_set_target(self._h, C.c_void_p(dev_ptr), C.c_size_t(stride_bytes)))
 
+    def band_exchange_ints(self):
+        n = C.c_size_t()
+        _check(lib().slpr_band_exchange_ints(self._h, C.byref(n)))
+        return int(n.value)
+
+    def set_band_exchange(self, dev_sums, dev_gathered, n_bands, band):
+        """Exact row bands (include/slpr.h): device pointers of the int32 buffers [3P] and [n_bands][3P]."""
+        _check(lib().slpr_set_band_exchange(self._h, C.c_void_p(dev_sums), C.c_void_p(dev_gathered), int(n_bands), int(band)))
+
+    def render_band_begin(self):
+        _check(lib().slpr_render_band_begin(self._h))
+
+    def render_band_end(self):
+        _check(lib().slpr_render_band_end(self._h))
+
     def framebuffer(self):
         p = C.c_void_p(); s = C.c_size_t()
         _check(lib().slpr_framebuffer(self._h, C.byref(p), C.byref(s)))

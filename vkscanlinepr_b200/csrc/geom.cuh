@@ -148,7 +148,15 @@ __global__ void __launch_bounds__(256) k_monotonize_count(const FrameParams *__r
         CurvePts cp;
         load_points(type, curve_pos_map[c], tpos, cp);
         uint32_t n_cuts = 0;
-        const bool visible = !path_invisible(path_visible[curve_path[c]]);  // MI0:260-261
+        bool culled = false;  // band mode: a curve whose control-point box misses the band is skipped like an invisible one
+        if (cull) {
+            const uint32_t np = type & 7u;
+            float ymin = cp.y[0], ymax = cp.y[0];
+            for (uint32_t i = 1; i < 4; ++i)
+                if (i < np) { ymin = fminf(ymin, cp.y[i]); ymax = fmaxf(ymax, cp.y[i]); }
+            culled = (ymax < band_lo) || (ymin >= band_hi);
+        }
+        const bool visible = !culled && !path_invisible(path_visible[curve_path[c]]);  // MI0:260-261
         float tq[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
         float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
         if (visible) {
@@ -189,15 +197,6 @@ __global__ void __launch_bounds__(256) k_monotonize_count(const FrameParams *__r
         cut_cache[5 * c + 3] = q3;
         cut_cache[5 * c + 4] = u2f(n_cuts);
         if (visible) { tq[n_cuts] = 1.f; ++n_cuts; }  // MI0:374-377
-
-        bool culled = false;
-        if (cull) {
-            const uint32_t np = type & 7u;
-            float ymin = cp.y[0], ymax = cp.y[0];
-            for (uint32_t i = 1; i < 4; ++i)
-                if (i < np) { ymin = fminf(ymin, cp.y[i]); ymax = fmaxf(ymax, cp.y[i]); }
-            culled = (ymax < band_lo) || (ymin >= band_hi);
-        }
 
         float p0x = cp.x[0], p0y = cp.y[0];
         int pcnt = 0;
@@ -299,7 +298,12 @@ __device__ __forceinline__ void make_fragment(const FragEnv &P, const KeyLayout 
         if (pfy == ply) wn = 0;  // GF:190-199
         else if (pfy < wn_y && wn_y <= ply) wn = -1;
         else if (ply < wn_y && wn_y <= pfy) wn = 1;
-        if (P.cull && valid && (pos_y < P.band_y0 || pos_y >= P.band_y1)) { valid = false; wn = 0; }  // band mode (new)
+        if (P.cull) {  // band mode (new): every fragment belongs to exactly one band; rows outside the frame go to the
+                       // band at that frame edge. A fragment of another band keeps its slot but carries nothing.
+            const bool below = raw_y < P.band_y0 && P.band_y0 > 0;
+            const bool above = raw_y >= P.band_y1 && P.band_y1 < height;
+            if (below || above) { valid = false; wn = 0; }
+        }
     }
     key_out = pack_key(L, pidx, valid, pos_x, pos_y);
     val_out = (uint32_t)f | (rule_bit << 29) | ((uint32_t)(wn + 1) << 30);

@@ -24,6 +24,7 @@
 #include "raster.cuh"
 #include "scan.cuh"
 #include "segsort.cuh"
+#include "bands.cuh"
 #include "spans.cuh"
 #include "walk.cuh"
 
@@ -133,6 +134,20 @@ struct slpr_ctx {
     cudaGraphExec_t gexec = nullptr;   // graph of the frame for `graph_fb`
     cudaGraphExec_t gexec2 = nullptr;  // and for the second framebuffer
     bool graph_valid = false, graph2_valid = false;
+    // frames rendered into caller-owned targets (slpr_set_target): one captured graph per target, two kept,
+    // so that a caller can alternate between two frame buffers (bench.py --mode bands) without re-capturing
+    struct TargetGraph { uint8_t *target = nullptr; size_t stride = 0; cudaGraphExec_t ge = nullptr; bool valid = false; uint64_t used = 0; int launches = 0; } tgraph[2];
+    uint64_t tgraph_clock = 0;
+    // exact row bands (bands.cuh): caller-owned exchange buffers, scratch, and the graph of the first half
+    int *x_sums = nullptr;            // [3][P] this band's per-path winding sums (written by render_band_begin)
+    const int *x_gathered = nullptr;  // [n_ranks][3][P] all bands' sums (read by render_band_end)
+    int x_ranks = 0, x_rank = 0;
+    int *x_d = nullptr, *x_e = nullptr, *x_corr = nullptr;  // [P], [P+1], [2][P]
+    unsigned char *x_scan_temp = nullptr;                  // ticket + tile states of the path scan
+    size_t x_scan_bytes = 0;
+    cudaGraphExec_t gexec_a = nullptr;
+    bool graph_a_valid = false, band_begun = false;
+    int launches_a = 0;
     cudaEvent_t ev[SLPR_STAGE_COUNT + 1] = {};
     bool stage_times_valid = false;
     uint64_t launches = 0;
@@ -143,6 +158,11 @@ struct slpr_ctx {
     unsigned char *d_prim_temp = nullptr;
     size_t prim_temp_bytes = 0;
 };
+
+static void invalidate_graphs(slpr_ctx *c) {
+    c->graph_valid = c->graph2_valid = c->graph_a_valid = false;
+    for (auto &t : c->tgraph) t.valid = false;
+}
 
 static void free_capacity(slpr_ctx *c) {
     cudaFree(c->d_inter); c->d_inter = nullptr;
@@ -156,11 +176,24 @@ static void free_capacity(slpr_ctx *c) {
     cudaFree(c->d_temp); c->d_temp = nullptr;
     if (c->gexec) { cudaGraphExecDestroy(c->gexec); c->gexec = nullptr; }
     if (c->gexec2) { cudaGraphExecDestroy(c->gexec2); c->gexec2 = nullptr; }
-    c->graph_valid = c->graph2_valid = false;
+    for (auto &t : c->tgraph)
+        if (t.ge) { cudaGraphExecDestroy(t.ge); t.ge = nullptr; }
+    invalidate_graphs(c);
     c->cap = 0;
 }
 
+static void free_exchange(slpr_ctx *c) {
+    cudaFree(c->x_d); cudaFree(c->x_e); cudaFree(c->x_corr); cudaFree(c->x_scan_temp);
+    c->x_d = c->x_e = c->x_corr = nullptr;
+    c->x_scan_temp = nullptr;
+    c->x_sums = nullptr; c->x_gathered = nullptr;
+    c->x_ranks = c->x_rank = 0;
+    c->band_begun = false;
+    if (c->gexec_a) { cudaGraphExecDestroy(c->gexec_a); c->gexec_a = nullptr; }
+}
+
 static void free_scene(slpr_ctx *c) {
+    free_exchange(c);
     cudaFree(c->d_pos); cudaFree(c->d_pos_path); cudaFree(c->d_cpm); cudaFree(c->d_ctype); cudaFree(c->d_cpath);
     cudaFree(c->d_frule); cudaFree(c->d_finfo); cudaFree(c->d_tpos); cudaFree(c->d_pvis); cudaFree(c->d_cut);
     cudaFree(c->d_count); cudaFree(c->d_offset); cudaFree(c->d_seg_tap);
@@ -374,7 +407,6 @@ extern "C" int slpr_set_band(slpr_ctx *c, uint32_t y0, uint32_t y1) {
 extern "C" int slpr_set_target(slpr_ctx *c, void *dev_rgba, size_t stride_bytes) {
     if (!c) return fail(SLPR_ERR_INVALID, "null context");
     if (dev_rgba && stride_bytes < (size_t)c->W * 4) return fail(SLPR_ERR_INVALID, "slpr_set_target: stride smaller than a row");
-    if (c->target != dev_rgba || c->target_stride != stride_bytes) c->graph_valid = c->graph2_valid = false;
     c->target = reinterpret_cast<uint8_t *>(dev_rgba);
     c->target_stride = stride_bytes;
     return SLPR_OK;
@@ -408,11 +440,11 @@ static int enqueue_count_phase(slpr_ctx *c, cudaStream_t s, bool timed, int &lau
     return SLPR_OK;
 }
 
-static int enqueue_frame(slpr_ctx *c, cudaStream_t s, bool timed, int &launches) {
+// First half of the frame: everything up to and including the sort (the fragments of this band in the
+// reference's order). With a band exchange configured it also leaves the per-path winding sums in x_sums.
+static int enqueue_front(slpr_ctx *c, cudaStream_t s, bool timed, int &launches) {
     int rc = enqueue_count_phase(c, s, timed, launches);
     if (rc) return rc;
-    const bool taps = (c->flags & SLPR_FLAG_TAPS) != 0;
-    const int wide = c->num_sms * 8;
     FragTaps ft{c->t_key32, c->t_path, c->t_wind};
     k_piece_emit<<<grid_for(c, c->nc, 256, 8), 256, 0, s>>>(c->d_params, c->nc, c->d_ctype, c->d_cpm, c->d_cpath, c->d_frule, c->d_tpos, c->d_cut,
                                                              c->d_offset, c->d_slots, c->d_ctr, c->cap, c->d_bucket_hist,
@@ -430,6 +462,11 @@ static int enqueue_frame(slpr_ctx *c, cudaStream_t s, bool timed, int &launches)
     k_segments_tap<<<grid_for(c, (long long)c->nc + 1, 256, 8), 256, 0, s>>>(c->nc, c->P, c->d_cpath, c->d_offset, c->d_seg_tap);
     k_path_stats<<<grid_for(c, c->P, 256, 4), 256, 0, s>>>(c->d_seg_tap, c->P, c->d_ctr, c->cap);
     launches += 2;
+    if (c->x_sums) {  // before the sort: the radix sort reuses buffer 0
+        k_band_sums<<<grid_for(c, (long long)c->P * 32, 256, 8), 256, 0, s>>>(c->d_seg_tap, c->P, c->d_key[0], c->d_val[0], c->d_ctr,
+                                                                             c->cap, c->L, c->x_sums);
+        ++launches;
+    }
     // ---- sort
     int cur = 0;
     if (!c->radix_mode) {  // every path sorted on chip, one read + one write of the pairs (segsort.cuh)
@@ -457,6 +494,27 @@ static int enqueue_frame(slpr_ctx *c, cudaStream_t s, bool timed, int &launches)
     }
     c->sorted_buf = cur;
     if (timed) CU(cudaEventRecord(c->ev[7], s));
+    CU(cudaGetLastError());
+    return SLPR_OK;
+}
+
+// Second half: winding prefix, spans, draw records, pixels. With a band exchange configured it starts by
+// turning the gathered sums of all bands into this band's winding corrections.
+static int enqueue_back(slpr_ctx *c, cudaStream_t s, bool timed, int &launches) {
+    const bool taps = (c->flags & SLPR_FLAG_TAPS) != 0;
+    const int wide = c->num_sms * 8;
+    const int cur = c->sorted_buf;
+    const int *corr = nullptr;
+    if (c->x_sums) {
+        CU(cudaMemsetAsync(c->x_scan_temp, 0, c->x_scan_bytes, s));
+        k_band_other<<<grid_for(c, c->P, 256, 8), 256, 0, s>>>(c->x_gathered, c->P, c->x_ranks, c->x_rank, c->x_d);
+        ScanI32Op op{c->x_d, c->x_e, (long long)c->P, nullptr, 0, nullptr};
+        ScanTemp t{reinterpret_cast<unsigned long long *>(c->x_scan_temp + 256), reinterpret_cast<int *>(c->x_scan_temp)};
+        k_lookback_scan<ScanI32Op><<<grid_for(c, (long long)(c->P / SCAN_TILE_MIN + 2), 1, 8), SCAN_THREADS, 0, s>>>(op, t);
+        k_band_corr<<<grid_for(c, c->P, 256, 8), 256, 0, s>>>(c->x_gathered, c->x_e, c->P, c->x_ranks, c->x_rank, c->x_corr);
+        launches += 3;
+        corr = c->x_corr;
+    }
     // ---- winding scan + mark + flag scan + emit: one kernel, two chained look-backs
     SpanTaps stp{c->d_wn, c->t_sidx, c->t_skey32, c->t_flags, c->t_scan3};
     SpanTemp stmp{c->d_wsum, c->d_status[1], c->d_status[2], c->d_tickets + 1};
@@ -467,7 +525,7 @@ static int enqueue_frame(slpr_ctx *c, cudaStream_t s, bool timed, int &launches)
 #endif
     if (timed) CU(cudaEventRecord(c->ev[8], s));
     k_spans<<<c->num_sms * std::max(1, c->span_blocks_per_sm), SP_THREADS, SP_STAGE_BYTES, s>>>(c->d_key[cur], c->d_val[cur], c->d_finfo, c->d_rec, c->d_ctr,
-                                                  c->L, (int)c->W, (int)c->H, c->cap, stp, stmp);
+                                                  c->L, (int)c->W, (int)c->H, c->cap, stp, stmp, corr, c->P);
     ++launches;
     if (taps) {
         k_scan3_fixup<<<wide, 256, 0, s>>>(c->d_ctr, c->cap, c->t_scan3);
@@ -485,6 +543,12 @@ static int enqueue_frame(slpr_ctx *c, cudaStream_t s, bool timed, int &launches)
     CU(cudaMemcpyAsync(c->h_ctr, c->d_ctr, sizeof(FrameCounters), cudaMemcpyDeviceToHost, s));
     CU(cudaGetLastError());
     return SLPR_OK;
+}
+
+static int enqueue_frame(slpr_ctx *c, cudaStream_t s, bool timed, int &launches) {
+    int rc = enqueue_front(c, s, timed, launches);
+    if (rc) return rc;
+    return enqueue_back(c, s, timed, launches);
 }
 
 static int size_buffers_from_count(slpr_ctx *c) {
@@ -514,6 +578,7 @@ static int size_buffers_from_count(slpr_ctx *c) {
 extern "C" int slpr_render(slpr_ctx *c) {
     if (!c) return fail(SLPR_ERR_INVALID, "null context");
     if (!c->scene_loaded) return fail(SLPR_ERR_STATE, "slpr_render: no scene loaded (call slpr_load_scene first)");
+    if (c->x_sums) return fail(SLPR_ERR_STATE, "slpr_render: a band exchange is configured; use slpr_render_band_begin / _end");
     CU(cudaSetDevice(c->device));
     if (c->cap == 0) {
         int rc = size_buffers_from_count(c);
@@ -530,8 +595,20 @@ extern "C" int slpr_render(slpr_ctx *c) {
         c->stage_times_valid = true;
     } else {
         const bool second = !c->target && c->fb_cur == c->d_fb2 && c->d_fb2;
-        cudaGraphExec_t &ge = second ? c->gexec2 : c->gexec;
-        bool &valid = second ? c->graph2_valid : c->graph_valid;
+        slpr_ctx::TargetGraph *tg = nullptr;
+        if (c->target) {  // the entry of this target, else the least recently used one
+            for (auto &t : c->tgraph)
+                if (t.valid && t.target == c->target && t.stride == c->target_stride) tg = &t;
+            if (!tg) {
+                tg = (c->tgraph[0].used <= c->tgraph[1].used) ? &c->tgraph[0] : &c->tgraph[1];
+                tg->valid = false;
+                tg->target = c->target;
+                tg->stride = c->target_stride;
+            }
+            tg->used = ++c->tgraph_clock;
+        }
+        cudaGraphExec_t &ge = tg ? tg->ge : (second ? c->gexec2 : c->gexec);
+        bool &valid = tg ? tg->valid : (second ? c->graph2_valid : c->graph_valid);
         if (!valid) {
             if (ge) { cudaGraphExecDestroy(ge); ge = nullptr; }
             cudaGraph_t g = nullptr;
@@ -581,7 +658,7 @@ static int finish_frame(slpr_ctx *c) {
         if (c->h_ctr->sort_fallback && !c->radix_mode && !c->h_ctr->overflow) {
             // a path outgrew the segmented sort: this scene uses the radix sort from now on; redo the frame
             c->radix_mode = true;
-            c->graph_valid = c->graph2_valid = false;
+            invalidate_graphs(c);
             int rc2 = slpr_render(c);
             if (rc2) return rc2;
             continue;
@@ -591,7 +668,7 @@ static int finish_frame(slpr_ctx *c) {
                 const bool seg = segmented_sort_pays(c, *c->h_ctr);
                 if (seg == c->radix_mode) {  // the other sort suits this scene and view better: use it from the next frame on
                     c->radix_mode = !seg;
-                    c->graph_valid = c->graph2_valid = false;
+                    invalidate_graphs(c);
                 }
             }
             c->frame_done = true;
@@ -742,6 +819,126 @@ extern "C" int slpr_sort_info(slpr_ctx *c, uint32_t *key_bits, uint32_t *passes,
     if (key_bits) *key_bits = (uint32_t)c->key_bits;
     if (passes) *passes = (uint32_t)c->passes;
     if (key_bytes) *key_bytes = 8;
+    return SLPR_OK;
+}
+
+// ---- exact row bands across GPUs (bands.cuh) ---------------------------------------------------
+extern "C" int slpr_band_exchange_ints(slpr_ctx *c, size_t *ints_per_band) {
+    if (!c || !ints_per_band) return fail(SLPR_ERR_INVALID, "slpr_band_exchange_ints: null argument");
+    if (!c->scene_loaded) return fail(SLPR_ERR_STATE, "slpr_band_exchange_ints: no scene loaded");
+    *ints_per_band = 3 * (size_t)c->P;
+    return SLPR_OK;
+}
+
+extern "C" int slpr_set_band_exchange(slpr_ctx *c, int32_t *dev_sums, const int32_t *dev_gathered, int n_bands, int band) {
+    if (!c) return fail(SLPR_ERR_INVALID, "null context");
+    if (!c->scene_loaded) return fail(SLPR_ERR_STATE, "slpr_set_band_exchange: no scene loaded");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    invalidate_graphs(c);
+    free_exchange(c);
+    if (!dev_sums && !dev_gathered) return SLPR_OK;  // back to independent bands / full frames
+    if (!dev_sums || !dev_gathered || n_bands < 1 || band < 0 || band >= n_bands)
+        return fail(SLPR_ERR_INVALID, "slpr_set_band_exchange: need both buffers and 0 <= band < n_bands");
+    if (c->flags & SLPR_FLAG_NO_GRAPH) return fail(SLPR_ERR_UNSUPPORTED, "slpr_set_band_exchange: not available with SLPR_FLAG_NO_GRAPH");
+    const size_t P = std::max<size_t>(c->P, 1);
+    CU(cudaMalloc(&c->x_d, P * 4));
+    CU(cudaMalloc(&c->x_e, (P + 4) * 4));
+    CU(cudaMalloc(&c->x_corr, 2 * P * 4));
+    c->x_scan_bytes = 256 + (P / SCAN_TILE_MIN + 2) * 8;
+    CU(cudaMalloc(&c->x_scan_temp, c->x_scan_bytes));
+    c->x_sums = dev_sums;
+    c->x_gathered = dev_gathered;
+    c->x_ranks = n_bands;
+    c->x_rank = band;
+    return SLPR_OK;
+}
+
+// One captured graph of `enqueue` on the context's stream, re-captured when `valid` is false.
+template <class F>
+static int launch_graph(slpr_ctx *c, cudaGraphExec_t &ge, bool &valid, int &n_launches, F enqueue) {
+    if (!valid) {
+        if (ge) { cudaGraphExecDestroy(ge); ge = nullptr; }
+        cudaGraph_t g = nullptr;
+        CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        int l = 0;
+        int rc = enqueue(l);
+        cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+        if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+        if (e != cudaSuccess) return fail(SLPR_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+        e = cudaGraphInstantiate(&ge, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) return fail(SLPR_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+        n_launches = l;
+        valid = true;
+    }
+    CU(cudaGraphLaunch(ge, c->stream));
+    c->launches += n_launches;
+    return SLPR_OK;
+}
+
+extern "C" int slpr_render_band_begin(slpr_ctx *c) {
+    if (!c) return fail(SLPR_ERR_INVALID, "null context");
+    if (!c->x_sums) return fail(SLPR_ERR_STATE, "slpr_render_band_begin: call slpr_set_band_exchange first");
+    CU(cudaSetDevice(c->device));
+    if (c->cap == 0) {
+        int rc = size_buffers_from_count(c);
+        if (rc) return rc;
+    }
+    for (int attempt = 0; attempt < 4; ++attempt) {
+        k_set_params<<<1, 1, 0, c->stream>>>(c->d_params, c->hp);
+        ++c->launches;
+        int rc = launch_graph(c, c->gexec_a, c->graph_a_valid, c->launches_a, [&](int &l) {
+            int r = enqueue_front(c, c->stream, false, l);
+            if (r) return r;
+            CU(cudaMemcpyAsync(c->h_ctr, c->d_ctr, sizeof(FrameCounters), cudaMemcpyDeviceToHost, c->stream));
+            return (int)SLPR_OK;
+        });
+        if (rc) return rc;
+        // the exchange happens outside the library, so capacity and sort mode are settled here, before it
+        CU(cudaStreamSynchronize(c->stream));
+        if (c->h_ctr->overflow) {
+            const long long nf = c->h_ctr->n_fragments;
+            rc = alloc_capacity(c, (int)std::min<long long>(nf + nf / 4 + 65536, (1ll << 29) - 1));
+            if (rc) return rc;
+            continue;
+        }
+        if (c->h_ctr->sort_fallback && !c->radix_mode) {
+            c->radix_mode = true;
+            invalidate_graphs(c);
+            continue;
+        }
+        c->band_begun = true;
+        return SLPR_OK;
+    }
+    return fail(SLPR_ERR_STATE, "band kept overflowing its fragment buffers");
+}
+
+extern "C" int slpr_render_band_end(slpr_ctx *c) {
+    if (!c) return fail(SLPR_ERR_INVALID, "null context");
+    if (!c->x_sums || !c->band_begun) return fail(SLPR_ERR_STATE, "slpr_render_band_end: no band in flight (slpr_render_band_begin first)");
+    CU(cudaSetDevice(c->device));
+    c->band_begun = false;
+    const bool second = !c->target && c->fb_cur == c->d_fb2 && c->d_fb2;
+    slpr_ctx::TargetGraph *tg = nullptr;
+    if (c->target) {
+        for (auto &t : c->tgraph)
+            if (t.valid && t.target == c->target && t.stride == c->target_stride) tg = &t;
+        if (!tg) {
+            tg = (c->tgraph[0].used <= c->tgraph[1].used) ? &c->tgraph[0] : &c->tgraph[1];
+            tg->valid = false;
+            tg->target = c->target;
+            tg->stride = c->target_stride;
+        }
+        tg->used = ++c->tgraph_clock;
+    }
+    cudaGraphExec_t &ge = tg ? tg->ge : (second ? c->gexec2 : c->gexec);
+    bool &valid = tg ? tg->valid : (second ? c->graph2_valid : c->graph_valid);
+    int rc = launch_graph(c, ge, valid, tg ? tg->launches : c->launches_per_frame, [&](int &l) { return enqueue_back(c, c->stream, false, l); });
+    if (rc) return rc;
+    c->stage_times_valid = false;
+    c->frame_pending = true;
+    c->frame_done = false;
     return SLPR_OK;
 }
 

@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(SP_THREADS, SP_BLOCKS) k_spans(const uint64_t 
                                                          const uint32_t *__restrict__ fill_info,
                                                          int4 *__restrict__ records, FrameCounters *__restrict__ ctr,
                                                          KeyLayout L, int width, int height, int capacity, SpanTaps taps,
-                                                         SpanTemp tmp) {
+                                                         SpanTemp tmp, const int *__restrict__ band_corr, uint32_t n_paths) {
     __shared__ uint32_t s_warp[SP_THREADS / 32];
     __shared__ unsigned long long s_prefix;
     __shared__ long long s_tile;
@@ -248,7 +248,9 @@ __global__ void __launch_bounds__(SP_THREADS, SP_BLOCKS) k_spans(const uint64_t 
                         frag = (!oob && k[j] != k[j + 1]) ? 1u : 0u;  // MARK:69-77 (the compact key holds the path)
                         const bool even_odd = (rpack >> j) & 1u;  // fill_rule[path] == 1
                         // MARK:82 (rule values other than 0/1 never set the flag there; the loader only produces 0/1)
-                        const bool wn_flag = even_odd ? ((wn & 1) != 0) : (wn != 0);
+                        // exact row bands (bands.cuh): the deltas of the other bands' fragments that sort before this one
+                        const int wf = band_corr ? wn + band_corr[(b.y == 0 ? n_paths : 0u) + b.path] : wn;
+                        const bool wn_flag = even_odd ? ((wf & 1) != 0) : (wf != 0);
                         span = (a.y == b.y && (a.x + FRAG_SIZE) < b.x && a.path == b.path && wn_flag) ? 1u : 0u;  // MARK:84
                     }
                     fmask |= frag << j;

@@ -1,9 +1,13 @@
 """Multi-GPU host logic (new work; the reference is single-device — SURVEY §8e).
 
-The path shards two ways and has NO exchange step inside the algorithm:
-  * row bands  — rank r renders scanline rows [y0, y1) of one frame (slpr_set_band); the only
-    communication is the gather of the finished RGBA8 bands to rank 0 (NCCL send/recv over NVLink,
-    or direct stores into a peer-mapped frame through slpr_set_target);
+The path shards two ways:
+  * row bands  — rank r renders scanline rows [y0, y1) of one frame (slpr_set_band). The reference's
+    winding scan is one prefix sum over ALL fragments, so the bands exchange one thing: per-path sums
+    of their winding deltas (3 * n_paths int32 per band, all-gather; csrc/bands.cuh) between the two
+    halves of the frame (render_bands_exact). The finished RGBA8 bands are then gathered to rank 0
+    (NCCL send/recv over NVLink, or direct stores into a peer-mapped frame through slpr_set_target).
+    Without the exchange (plain render() on a band) the result is exact only for scenes whose per-path
+    winding sums vanish;
   * frame batches — frame f goes to rank f mod world; nothing is exchanged.
 One process per GPU, torch.distributed for the plumbing. These helpers are backend-agnostic so the
 host logic is covered on CPU with gloo (tests/test_parallel_cpu.py).
@@ -57,3 +61,25 @@ def gather_bands(frame, bands, rank, world, dist, dst=0):
 def scatter_frames(n_frames, world):
     """Which rank renders which frame, as an int array (frame-parallel batches)."""
     return np.arange(n_frames) % world
+
+
+def render_bands_exact(rasterizer, sums, gathered, dist):
+    """One exact band of a frame on this rank: first half, all-gather of the per-path winding sums, second
+    half. `sums` [3P] and `gathered` [world, 3P] are int32 tensors on the rasterizer's device, registered once
+    with rasterizer.set_band_exchange(sums.data_ptr(), gathered.data_ptr(), world, rank); the collective must
+    be ordered after the rasterizer's stream (make it torch's current stream)."""
+    rasterizer.render_band_begin()
+    dist.all_gather_into_tensor(gathered.view(-1), sums)
+    rasterizer.render_band_end()
+
+
+def band_corrections(gathered, band):
+    """numpy restatement of k_band_other + scan + k_band_corr (csrc/bands.cuh) for tests: gathered is
+    [n_bands, 3, P] (normal rows | outside the frame | row 0); returns (corrN, corrZ) of `band`."""
+    g = np.asarray(gathered, dtype=np.int64)
+    others = np.delete(g, band, axis=0)
+    d = others.sum(axis=(0, 1))                                   # total - mine, per path
+    e = np.concatenate(([0], np.cumsum(d)[:-1])) if d.size else d  # exclusive scan over paths
+    corr_n = e + g[:band, 0].sum(axis=0)
+    corr_z = e + others[:, 0].sum(axis=0) + others[:, 1].sum(axis=0)
+    return corr_n.astype(np.int32), corr_z.astype(np.int32)
