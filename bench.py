@@ -147,6 +147,7 @@ def main():
     ap.add_argument("--workload", default="synth_1m_4k")
     ap.add_argument("--mode", default="frames", choices=["frames", "bands"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--independent-bands", action="store_true", help="bands mode: no winding-sum exchange (exact only without winding residues)")
     ap.add_argument("--no-gather", action="store_true", help="bands mode: leave every band on its GPU (no NCCL gather)")
     ap.add_argument("--no-radix-leg", action="store_true", help="skip timing the radix sort beside the segmented sort")
     args = ap.parse_args()
@@ -157,6 +158,7 @@ def main():
 
     import torch
     import vkscanlinepr_b200 as V
+    from vkscanlinepr_b200 import parallel as PAR
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -200,6 +202,12 @@ def main():
             bands2 = [torch.empty((y1 - y0, W, 4), dtype=torch.uint8, device="cuda") for _ in range(2)]
         pending = [[], []]
         step_no = [0]
+        # exact bands: per-path winding sums are all-gathered between the two halves of the frame (csrc/bands.cuh)
+        x_sums = torch.zeros(3 * sc.n_paths, dtype=torch.int32, device="cuda")
+        x_gathered = torch.zeros((world, 3 * sc.n_paths), dtype=torch.int32, device="cuda")
+        comm_stream = torch.cuda.Stream()
+        if not args.independent_bands:
+            r.set_band_exchange(x_sums.data_ptr(), x_gathered.data_ptr(), world, rank)
 
     def band_target(slot):
         """(pointer the context renders to so that its band lands in the buffer of `slot`, the band view)"""
@@ -221,7 +229,12 @@ def main():
             drain(slot)  # the transfer of frame i-2 used this buffer
             ptr, view = band_target(slot)
             r.set_target(ptr, W * 4)
-        r.render()
+            if not args.independent_bands:
+                PAR.render_bands_exact(r, x_sums, x_gathered, dist, comm_stream)
+            else:
+                r.render()
+        else:
+            r.render()
         if bands and not args.no_gather:
             if rank == 0:
                 ops = []
@@ -423,7 +436,8 @@ def main():
                        "points": sc.n_points, "fragments": cnt["n_fragments"], "records": cnt["n_out_frag"] + cnt["n_span"],
                        "scene_sha256": sc.sha256()[:16], "sort": r.sort_mode(), "sort_key_bits": info["key_bits"],
                        "radix_passes_if_radix": info["passes"],
-                       "parallelism": (("bands%d" % world) + ("+no-gather" if args.no_gather else "+pipelined-nccl-gather")) if bands else ("frames-dp%d" % world),
+                       "parallelism": (("bands%d" % world) + ("+independent" if args.independent_bands else "+nccl-allgather-of-winding-sums")
+                                        + ("+no-gather" if args.no_gather else "+pipelined-nccl-gather")) if bands else ("frames-dp%d" % world),
                        "l2": "per-frame working set (fragments x 44 B + 33 MB frame) exceeds the 126 MB L2; no flush needed",
                        "frame_replay": "cuda-graph"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,

@@ -162,11 +162,13 @@ SLPR_API int slpr_stage_ms(slpr_ctx *ctx, float *ms, int n);
 /* ---- Exact row bands across GPUs (new; csrc/bands.cuh) --------------------------------
  * The reference's winding scan is one unsegmented prefix sum over all fragments (SR.cpp:479-506), so a band of
  * rows needs the winding sums of the other bands' fragments that sort before its own. Per frame and per band:
- *   slpr_render_band_begin   transform .. sort of this band; leaves 3 * n_paths int32 (per-path sums of the
- *                            winding deltas: normal rows | outside the frame | row 0) in dev_sums; returns after
- *                            the stream has drained (capacity growth and sort selection are settled here)
+ *   slpr_render_band_begin   transform .. fragments of this band, then its sort; leaves 3 * n_paths int32
+ *                            (per-path sums of the winding deltas: normal rows | outside the frame | row 0) in
+ *                            dev_sums and returns as soon as THEY are complete (capacity growth and sort
+ *                            selection are settled here); the sort is still running on the context's stream
  *   (caller)                 all-gather of dev_sums over the bands into dev_gathered [n_bands][3 * n_paths],
- *                            bands ordered by rows, on the context's stream or ordered after it (NCCL all-gather)
+ *                            bands ordered by rows — on another stream, so that it overlaps the sort; the
+ *                            context's stream must wait for it before the next call (NCCL all-gather)
  *   slpr_render_band_end     corrections, spans, draw records, pixels of the band (asynchronous, like slpr_render)
  * slpr_set_band first; slpr_set_band_exchange(ctx, NULL, NULL, 0, 0) returns to independent bands, which are
  * exact only for scenes whose per-path winding sums vanish. */

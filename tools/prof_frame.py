@@ -16,6 +16,10 @@ sc, rows, W, H = bench.load_workload(wl)
 r = V.ScanlineRasterizer(0, flags).initialize(None, W, H)
 r.loadVG(sc)
 r.setMVP(rows)
+if os.environ.get("SLPR_BAND"):  # e.g. SLPR_BAND=3/8: render only band 3 of 8 (independent bands)
+    from vkscanlinepr_b200 import parallel as PAR
+    b, n = (int(x) for x in os.environ["SLPR_BAND"].split("/"))
+    r.set_band(*PAR.band_rows(H, n)[b])
 for _ in range(frames):
     r.render()
     r.synchronize()

@@ -20,6 +20,8 @@ struct FrameParams {
     int stat_mid;      // paths of 129..512 fragments   } k_path_stats, every frame and in both sort modes:
     int stat_big;      // paths of 513..4096 fragments  } the host picks the sort from them
     int stat_huge;     // paths of more than 4096 fragments (radix sort only)
+    int n_live;        // band mode: curves whose path comes near the band (k_band_live)
+    int pad[3];
 };
 
 // Device-resident counters (zeroed at the start of every frame).
@@ -36,6 +38,8 @@ struct FrameCounters {
     int stat_mid;      // paths of 129..512 fragments   } k_path_stats, every frame and in both sort modes:
     int stat_big;      // paths of 513..4096 fragments  } the host picks the sort from them
     int stat_huge;     // paths of more than 4096 fragments (radix sort only)
+    int n_live;        // band mode: curves whose path comes near the band (k_band_live)
+    int pad[3];
 };
 
 // Key geometry for the compact 64-bit sort key (path | row rank | cell x), see DESIGN.md.

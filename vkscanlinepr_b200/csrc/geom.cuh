@@ -13,10 +13,17 @@ namespace slpr {
 // over the lanes of the warp that hit the same path (points of a path are contiguous), then one
 // atomicOr per distinct path per warp.
 // ------------------------------------------------------------------------------------------------
+// Monotone map float -> uint32 (a < b  <=>  float_order(a) < float_order(b); NaNs land at the two ends).
+__device__ __forceinline__ uint32_t float_order(float f) {
+    const uint32_t b = f2u(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
 __global__ void __launch_bounds__(256) k_transform(const FrameParams *__restrict__ P, uint32_t n_points,
                                                    const float2 *__restrict__ pos,
                                                    const uint32_t *__restrict__ pos_path,
-                                                   float2 *__restrict__ tpos, int *__restrict__ path_visible) {
+                                                   float2 *__restrict__ tpos, int *__restrict__ path_visible,
+                                                   const uint8_t *__restrict__ path_live) {
     const float m0x = P->rows[0], m0y = P->rows[1], m0z = P->rows[2], m0w = P->rows[3];
     const float m1x = P->rows[4], m1y = P->rows[5], m1z = P->rows[6], m1w = P->rows[7];
     const float m3x = P->rows[12], m3y = P->rows[13], m3z = P->rows[14], m3w = P->rows[15];
@@ -24,8 +31,13 @@ __global__ void __launch_bounds__(256) k_transform(const FrameParams *__restrict
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t n_round = (n_points + 31u) & ~31u;  // keep whole warps in the loop for the shuffles
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
-        const bool live = i < n_points;
+        bool live = i < n_points;
         uint32_t flag = 0, pidx = 0xFFFFFFFFu;
+        if (live && path_live) {  // band mode: the points of a path that cannot reach the band are not needed
+            pidx = pos_path[i];
+            live = path_live[pidx] != 0;
+            if (!live) pidx = 0xFFFFFFFFu;
+        }
         if (live) {
             const float2 p = pos[i];
             // dot(vec4(x,y,0,1), m) evaluated left to right (TP:41-46)
@@ -56,7 +68,8 @@ __global__ void __launch_bounds__(256) k_transform(const FrameParams *__restrict
         }
         const uint32_t peers = __match_any_sync(0xFFFFFFFFu, pidx);
         const uint32_t red = __reduce_or_sync(peers, flag);
-        if (live && (lane_id() == (uint32_t)(__ffs(peers) - 1))) atomicOr(&path_visible[pidx], (int)red);
+        const bool leader = live && (lane_id() == (uint32_t)(__ffs(peers) - 1));
+        if (leader) atomicOr(&path_visible[pidx], (int)red);
     }
 }
 
@@ -122,6 +135,87 @@ __device__ __forceinline__ void load_points(uint32_t type, uint32_t po, const fl
 // ------------------------------------------------------------------------------------------------
 constexpr int WALK_BUCKETS = 64;
 
+// Band mode: the per-curve kernels (k_monotonize_count, k_piece_emit, k_piece_fix) walk a compacted list of
+// the curves whose path comes near the band instead of all curves — with 8 bands 7 of 8 curves are dead, and
+// scattered among live ones they would leave the warps of those kernels 1/8 full. Work item w -> curve.
+struct LiveCurves {
+    const uint32_t *list;         // nullptr: every curve is live (full frame)
+    const FrameCounters *ctr;
+    __device__ __forceinline__ uint32_t count(uint32_t n_curves) const { return list ? (uint32_t)ctr->n_live : n_curves; }
+    __device__ __forceinline__ uint32_t curve(uint32_t w) const { return list ? list[w] : w; }
+};
+
+// Band mode, per path: can any control point of the path come near the band? Decided from the path's box in
+// OBJECT space (static, computed by slpr_load_scene): the four corners go through the frame's matrix exactly
+// like points do; a projective map with w > 0 keeps the box convex, so every transformed control point lies
+// between the smallest and largest corner row (up to rounding, covered by the margin). Conservative: a corner
+// with w <= 0 or a NaN keeps the path alive. Dead paths skip k_transform and every per-curve kernel.
+__global__ void __launch_bounds__(256) k_path_cull(const FrameParams *__restrict__ P, uint32_t n_paths,
+                                                   const float4 *__restrict__ path_obj_box, uint8_t *__restrict__ path_live) {
+    const float m1x = P->rows[4], m1y = P->rows[5], m1z = P->rows[6], m1w = P->rows[7];
+    const float m3x = P->rows[12], m3y = P->rows[13], m3z = P->rows[14], m3w = P->rows[15];
+    const float lo = (P->band_y0 > 0) ? (float)(P->band_y0 - 3) : -3.0e38f;       // per-curve margin 1 px + 2 px for rounding
+    const float hi = (P->band_y1 < P->height) ? (float)(P->band_y1 + 3) : 3.0e38f;
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n_paths; p += gridDim.x * blockDim.x) {
+        const float4 b = path_obj_box[p];  // xmin, ymin, xmax, ymax; an empty path has xmin > xmax
+        bool alive = true;
+        if (b.x <= b.z) {
+            float ymin = 3.0e38f, ymax = -3.0e38f;
+            bool safe = true;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float x = (k & 1) ? b.z : b.x, y = (k & 2) ? b.w : b.y;
+                const float oy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, m1x), __fmul_rn(y, m1y)), __fmul_rn(0.0f, m1z)), __fmul_rn(1.0f, m1w));
+                const float ow = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, m3x), __fmul_rn(y, m3y)), __fmul_rn(0.0f, m3z)), __fmul_rn(1.0f, m3w));
+                const float v = __fdiv_rn(oy, ow);
+                safe = safe && (ow > 0.0f) && (v == v);
+                ymin = fminf(ymin, v);
+                ymax = fmaxf(ymax, v);
+            }
+            alive = !safe || !(ymax < lo || ymin >= hi);
+        } else {
+            alive = false;  // no points, hence no curves
+        }
+        path_live[p] = alive ? 1 : 0;
+    }
+}
+
+// Compacts the curves of live paths into `list` (arbitrary order) and zeroes the count of the others. A warp
+// classifies 32 x LIVE_CHUNK consecutive curves and reserves its part of the list with ONE atomic.
+constexpr int LIVE_CHUNK = 16;
+__global__ void __launch_bounds__(256) k_band_live(uint32_t n_curves, const uint32_t *__restrict__ curve_path,
+                                                   const uint8_t *__restrict__ path_live, int *__restrict__ count,
+                                                   uint32_t *__restrict__ list, FrameCounters *__restrict__ ctr) {
+    const uint32_t lane = lane_id();
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t n_chunks = (n_curves + 32 * LIVE_CHUNK - 1) / (32 * LIVE_CHUNK);
+    for (uint32_t ch = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ch < n_chunks; ch += warps) {
+        const uint32_t c0 = ch * 32 * LIVE_CHUNK;
+        uint32_t mask[LIVE_CHUNK];
+        uint32_t total = 0;
+#pragma unroll
+        for (int j = 0; j < LIVE_CHUNK; ++j) {
+            const uint32_t c = c0 + j * 32 + lane;
+            bool alive = false;
+            if (c < n_curves) {
+                alive = path_live[curve_path[c]] != 0;
+                if (!alive) count[c] = 0;
+            }
+            mask[j] = __ballot_sync(0xFFFFFFFFu, alive);
+            total += __popc(mask[j]);
+        }
+        if (total == 0) continue;
+        uint32_t base = 0;
+        if (lane == 0) base = (uint32_t)atomicAdd(&ctr->n_live, (int)total);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+#pragma unroll
+        for (int j = 0; j < LIVE_CHUNK; ++j) {
+            if ((mask[j] >> lane) & 1u) list[base + __popc(mask[j] & ((1u << lane) - 1))] = c0 + j * 32 + lane;
+            base += __popc(mask[j]);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) k_monotonize_count(const FrameParams *__restrict__ P, uint32_t n_curves,
                                                           const uint32_t *__restrict__ curve_type,
                                                           const uint32_t *__restrict__ curve_pos_map,
@@ -129,21 +223,23 @@ __global__ void __launch_bounds__(256) k_monotonize_count(const FrameParams *__r
                                                           const float2 *__restrict__ tpos,
                                                           const int *__restrict__ path_visible,
                                                           float *__restrict__ cut_cache, int *__restrict__ count,
-                                                          uint32_t *__restrict__ slots, uint32_t *__restrict__ bucket_hist) {
-    __shared__ uint32_t s_cnt[WALK_BUCKETS], s_base[WALK_BUCKETS];
+                                                          uint32_t *__restrict__ slots, uint32_t *__restrict__ block_cnt,
+                                                          LiveCurves live) {
+    // Pieces are ranked inside (block, length bucket) with shared-memory atomics only; the block's 64 counts
+    // go to block_cnt[bucket][block] at the end and k_bucket_scan turns them into positions. (One global
+    // atomicAdd per block iteration and bucket on 64 addresses serialised in L2: 0.1 ms at 4 M curves.)
+    __shared__ uint32_t s_cnt[WALK_BUCKETS];
+    if (threadIdx.x < WALK_BUCKETS) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
     const int width = P->width, height = P->height;
     const bool cull = P->cull != 0;
     // Only interior band edges cull: beyond the frame edges the reference still emits (invalid-key)
     // fragments whose winding deltas pair up across curves of a path (sampling rows -1 and H'+3).
     const float band_lo = (P->band_y0 > 0) ? (float)(P->band_y0 - 1) : -3.0e38f;
     const float band_hi = (P->band_y1 < P->height) ? (float)(P->band_y1 + 1) : 3.0e38f;
-    const uint32_t n_round = (n_curves + blockDim.x - 1) / blockDim.x * blockDim.x;  // whole blocks iterate (barriers)
-    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n_round; c += gridDim.x * blockDim.x) {
-        if (threadIdx.x < WALK_BUCKETS) s_cnt[threadIdx.x] = 0;
-        __syncthreads();
-        uint32_t slot[5] = {0u, 0u, 0u, 0u, 0u};
-        uint32_t n_pieces = 0;
-        if (c < n_curves) {
+    const uint32_t n_work = live.count(n_curves);
+    for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n_work; w += gridDim.x * blockDim.x) {
+        const uint32_t c = live.curve(w);
         const uint32_t type = curve_type[c];
         CurvePts cp;
         load_points(type, curve_pos_map[c], tpos, cp);
@@ -217,23 +313,60 @@ __global__ void __launch_bounds__(256) k_monotonize_count(const FrameParams *__r
             p0x = p1x; p0y = p1y;
             if (!culled) {  // file the piece under its length bucket (a scheduling hint only)
                 const uint32_t b = (uint32_t)min(1 + nx + ny, WALK_BUCKETS - 1);
-                const uint32_t lr = atomicAdd(&s_cnt[b], 1u);
-                const uint32_t sl = (b << 26) | lr;
-                if (i == 0) slot[0] = sl; else if (i == 1) slot[1] = sl; else if (i == 2) slot[2] = sl;
-                else if (i == 3) slot[3] = sl; else slot[4] = sl;
+                slots[5 * c + i] = (b << 26) | atomicAdd(&s_cnt[b], 1u);  // rank inside (this block, bucket b)
             }
         }
-        n_pieces = culled ? 0u : n_cuts;
         count[c] = culled ? 0 : pcnt;
+    }
+    __syncthreads();
+    if (threadIdx.x < WALK_BUCKETS) block_cnt[threadIdx.x * gridDim.x + blockIdx.x] = s_cnt[threadIdx.x];
+}
+
+// block_cnt[bucket][block] -> exclusive prefix over the blocks (in place) and bucket_hist[bucket] = total.
+// One block per bucket; every thread takes BS_ITEMS consecutive entries (n_blocks <= 8 x #SM <= 1024 x BS_ITEMS).
+constexpr int BS_ITEMS = 4;
+__global__ void __launch_bounds__(1024) k_bucket_scan(uint32_t *__restrict__ block_cnt, uint32_t n_blocks,
+                                                      uint32_t *__restrict__ bucket_hist) {
+    __shared__ uint32_t s_w[32];
+    __shared__ uint32_t s_total;
+    uint32_t *row = block_cnt + (size_t)blockIdx.x * n_blocks;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < n_blocks; base += blockDim.x * BS_ITEMS) {  // one trip on every current GPU
+        const uint32_t i0 = base + threadIdx.x * BS_ITEMS;
+        uint32_t v[BS_ITEMS], sum = 0;
+#pragma unroll
+        for (int k = 0; k < BS_ITEMS; ++k) { v[k] = (i0 + k < n_blocks) ? row[i0 + k] : 0u; sum += v[k]; }
+        uint32_t incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if ((int)lane >= d) incl += o;
+        }
+        if (lane == 31) s_w[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t w = s_w[lane];
+            uint32_t wi = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, wi, d);
+                if ((int)lane >= d) wi += o;
+            }
+            s_w[lane] = wi - w;  // exclusive offset of each warp; lane 31 of warp 0 keeps the total below
+            if (lane == 31) s_total = carry + wi;
         }
         __syncthreads();
-        if (threadIdx.x < WALK_BUCKETS && s_cnt[threadIdx.x])
-            s_base[threadIdx.x] = atomicAdd(&bucket_hist[threadIdx.x], s_cnt[threadIdx.x]);
-        __syncthreads();
+        uint32_t run = carry + s_w[warp] + incl - sum;
 #pragma unroll
-        for (uint32_t i = 0; i < 5; ++i)
-            if (i < n_pieces) slots[5 * c + i] = (slot[i] & 0xFC000000u) | (s_base[slot[i] >> 26] + (slot[i] & 0x03FFFFFFu));
+        for (int k = 0; k < BS_ITEMS; ++k) {
+            if (i0 + k < n_blocks) row[i0 + k] = run;
+            run += v[k];
+        }
+        carry = s_total;
+        __syncthreads();
     }
+    if (threadIdx.x == 0) bucket_hist[blockIdx.x] = carry;
 }
 
 struct FragTaps {

@@ -77,6 +77,11 @@ struct slpr_ctx {
              *d_finfo = nullptr;
     float2 *d_tpos = nullptr;
     int *d_pvis = nullptr;
+    uint32_t *d_block_cnt = nullptr;  // [WALK_BUCKETS][mono_blocks] pieces per (length bucket, k_monotonize_count block)
+    int mono_blocks = 0;
+    uint32_t *d_live = nullptr;  // [nc] band mode: curves whose path comes near the band (k_band_live)
+    float4 *d_pobj = nullptr;    // [P] object-space box of each path's control points (static)
+    uint8_t *d_plive = nullptr;  // [P] band mode: the path can reach the band (k_path_cull)
     float *d_cut = nullptr;
     int *d_count = nullptr, *d_offset = nullptr, *d_seg_tap = nullptr;  // d_seg_tap: [P+1] sort segment table (always built)
     int *d_big = nullptr;              // [P] paths queued for the block-level segmented sort
@@ -145,9 +150,10 @@ struct slpr_ctx {
     int *x_d = nullptr, *x_e = nullptr, *x_corr = nullptr;  // [P], [P+1], [2][P]
     unsigned char *x_scan_temp = nullptr;                  // ticket + tile states of the path scan
     size_t x_scan_bytes = 0;
-    cudaGraphExec_t gexec_a = nullptr;
-    bool graph_a_valid = false, band_begun = false;
-    int launches_a = 0;
+    cudaGraphExec_t gexec_a = nullptr, gexec_s = nullptr;  // fragments | sort (the back half uses the per-target graphs)
+    bool graph_a_valid = false, graph_s_valid = false, band_begun = false;
+    int launches_a = 0, launches_s = 0;
+    cudaEvent_t x_event = nullptr;  // sums and counters of the band in flight are complete
     cudaEvent_t ev[SLPR_STAGE_COUNT + 1] = {};
     bool stage_times_valid = false;
     uint64_t launches = 0;
@@ -160,7 +166,7 @@ struct slpr_ctx {
 };
 
 static void invalidate_graphs(slpr_ctx *c) {
-    c->graph_valid = c->graph2_valid = c->graph_a_valid = false;
+    c->graph_valid = c->graph2_valid = c->graph_a_valid = c->graph_s_valid = false;
     for (auto &t : c->tgraph) t.valid = false;
 }
 
@@ -190,18 +196,20 @@ static void free_exchange(slpr_ctx *c) {
     c->x_ranks = c->x_rank = 0;
     c->band_begun = false;
     if (c->gexec_a) { cudaGraphExecDestroy(c->gexec_a); c->gexec_a = nullptr; }
+    if (c->gexec_s) { cudaGraphExecDestroy(c->gexec_s); c->gexec_s = nullptr; }
+    if (c->x_event) { cudaEventDestroy(c->x_event); c->x_event = nullptr; }
 }
 
 static void free_scene(slpr_ctx *c) {
     free_exchange(c);
     cudaFree(c->d_pos); cudaFree(c->d_pos_path); cudaFree(c->d_cpm); cudaFree(c->d_ctype); cudaFree(c->d_cpath);
-    cudaFree(c->d_frule); cudaFree(c->d_finfo); cudaFree(c->d_tpos); cudaFree(c->d_pvis); cudaFree(c->d_cut);
+    cudaFree(c->d_frule); cudaFree(c->d_finfo); cudaFree(c->d_tpos); cudaFree(c->d_pvis); cudaFree(c->d_pobj); cudaFree(c->d_plive); cudaFree(c->d_live); cudaFree(c->d_block_cnt); cudaFree(c->d_cut);
     cudaFree(c->d_count); cudaFree(c->d_offset); cudaFree(c->d_seg_tap);
     cudaFree(c->d_big); c->d_big = nullptr;
     cudaFree(c->d_slots); cudaFree(c->d_pieces); cudaFree(c->d_boundary); cudaFree(c->d_fixflag);
     c->d_slots = nullptr; c->d_pieces = nullptr; c->d_boundary = nullptr; c->d_fixflag = nullptr;
     c->d_pos = nullptr; c->d_pos_path = c->d_cpm = c->d_ctype = c->d_cpath = c->d_frule = c->d_finfo = nullptr;
-    c->d_tpos = nullptr; c->d_pvis = nullptr; c->d_cut = nullptr; c->d_count = c->d_offset = c->d_seg_tap = nullptr;
+    c->d_tpos = nullptr; c->d_pvis = nullptr; c->d_pobj = nullptr; c->d_plive = nullptr; c->d_live = nullptr; c->d_block_cnt = nullptr; c->d_cut = nullptr; c->d_count = c->d_offset = c->d_seg_tap = nullptr;
     c->scene_loaded = false;
 }
 
@@ -365,6 +373,21 @@ extern "C" int slpr_load_scene(slpr_ctx *c, const float *pos_xy, const uint32_t 
     if ((rc = upload(&c->d_finfo, fill_rgba8, n_paths))) return rc;
     CU(cudaMalloc(&c->d_tpos, std::max<size_t>(n_points, 1) * sizeof(float2)));
     CU(cudaMalloc(&c->d_pvis, std::max<size_t>(n_paths, 1) * 4));
+    {   // object-space box of every path (band mode culls whole paths with it)
+        std::vector<float4> box(std::max<size_t>(n_paths, 1), make_float4(3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f));
+        for (uint32_t i = 0; i < n_points; ++i) {
+            float4 &b = box[pos_path[i]];
+            const float x = pos_xy[2 * i], y = pos_xy[2 * i + 1];
+            if (!(x == x) || !(y == y)) { b = make_float4(-3.0e38f, -3.0e38f, 3.0e38f, 3.0e38f); continue; }  // NaN: never culled
+            b.x = std::min(b.x, x); b.y = std::min(b.y, y); b.z = std::max(b.z, x); b.w = std::max(b.w, y);
+        }
+        CU(cudaMalloc(&c->d_pobj, box.size() * sizeof(float4)));
+        CU(cudaMemcpy(c->d_pobj, box.data(), box.size() * sizeof(float4), cudaMemcpyHostToDevice));
+        CU(cudaMalloc(&c->d_plive, std::max<size_t>(n_paths, 1)));
+    }
+    CU(cudaMalloc(&c->d_live, std::max<size_t>(n_curves, 1) * 4));
+    c->mono_blocks = (int)std::max<long long>(1, std::min<long long>(((long long)n_curves + 255) / 256, (long long)c->num_sms * 8));
+    CU(cudaMalloc(&c->d_block_cnt, (size_t)WALK_BUCKETS * c->mono_blocks * 4));
     CU(cudaMalloc(&c->d_cut, std::max<size_t>(n_curves, 1) * 5 * 4));
     CU(cudaMalloc(&c->d_count, ((size_t)n_curves + 4) * 4));
     CU(cudaMalloc(&c->d_offset, ((size_t)n_curves + 4) * 4));
@@ -399,8 +422,10 @@ extern "C" int slpr_set_band(slpr_ctx *c, uint32_t y0, uint32_t y1) {
     if (!c) return fail(SLPR_ERR_INVALID, "null context");
     if (y0 >= y1 || y1 > c->H || (y0 & 1) || ((y1 & 1) && y1 != c->H))
         return fail(SLPR_ERR_INVALID, "slpr_set_band: need even 0 <= y_begin < y_end <= height (got %u,%u)", y0, y1);
+    const int cull = (y0 != 0 || y1 != c->H) ? 1 : 0;
+    if (cull != c->hp.cull) invalidate_graphs(c);  // the band-mode kernels take one more table (path row boxes)
     c->hp.band_y0 = (int)y0; c->hp.band_y1 = (int)y1;
-    c->hp.cull = (y0 != 0 || y1 != c->H) ? 1 : 0;
+    c->hp.cull = cull;
     return SLPR_OK;
 }
 
@@ -424,13 +449,26 @@ static int enqueue_count_phase(slpr_ctx *c, cudaStream_t s, bool timed, int &lau
     CU(cudaMemsetAsync(c->d_temp, 0, c->temp_bytes, s));
     CU(cudaMemsetAsync(c->d_pvis, 0, std::max<size_t>(c->P, 1) * 4, s));
     if (timed) CU(cudaEventRecord(c->ev[0], s));
-    k_transform<<<grid_for(c, c->np, 256, 8), 256, 0, s>>>(c->d_params, c->np, c->d_pos, c->d_pos_path, c->d_tpos, c->d_pvis);
+    const uint8_t *plive = c->hp.cull ? c->d_plive : nullptr;
+    if (plive) {
+        k_path_cull<<<grid_for(c, c->P, 256, 8), 256, 0, s>>>(c->d_params, c->P, c->d_pobj, c->d_plive);
+        ++launches;
+    }
+    k_transform<<<grid_for(c, c->np, 256, 8), 256, 0, s>>>(c->d_params, c->np, c->d_pos, c->d_pos_path, c->d_tpos, c->d_pvis, plive);
     ++launches;
     if (timed) CU(cudaEventRecord(c->ev[1], s));
-    k_monotonize_count<<<grid_for(c, c->nc, 256, 8), 256, 0, s>>>(c->d_params, c->nc, c->d_ctype, c->d_cpm, c->d_cpath,
+    LiveCurves live{nullptr, c->d_ctr};
+    if (plive) {
+        k_band_live<<<grid_for(c, ((long long)c->nc + LIVE_CHUNK - 1) / LIVE_CHUNK, 256, 8), 256, 0, s>>>(c->nc, c->d_cpath, plive, c->d_count,
+                                                                                                     c->d_live, c->d_ctr);
+        ++launches;
+        live.list = c->d_live;
+    }
+    k_monotonize_count<<<c->mono_blocks, 256, 0, s>>>(c->d_params, c->nc, c->d_ctype, c->d_cpm, c->d_cpath,
                                                                    c->d_tpos, c->d_pvis, c->d_cut, c->d_count, c->d_slots,
-                                                                   c->d_bucket_hist);
-    ++launches;
+                                                                   c->d_block_cnt, live);
+    k_bucket_scan<<<WALK_BUCKETS, 1024, 0, s>>>(c->d_block_cnt, (uint32_t)c->mono_blocks, c->d_bucket_hist);
+    launches += 2;
     if (timed) CU(cudaEventRecord(c->ev[2], s));
     ScanI32Op op1{c->d_count, c->d_offset, (long long)c->nc, &c->d_ctr->n_fragments, c->cap, &c->d_ctr->overflow};
     k_lookback_scan<ScanI32Op><<<grid_for(c, (long long)c->nc / 16 + 1, SCAN_THREADS, 8), SCAN_THREADS, 0, s>>>(
@@ -440,22 +478,25 @@ static int enqueue_count_phase(slpr_ctx *c, cudaStream_t s, bool timed, int &lau
     return SLPR_OK;
 }
 
-// First half of the frame: everything up to and including the sort (the fragments of this band in the
-// reference's order). With a band exchange configured it also leaves the per-path winding sums in x_sums.
-static int enqueue_front(slpr_ctx *c, cudaStream_t s, bool timed, int &launches) {
+// The frame in three pieces: enqueue_fragments (transform .. fragment generation; with a band exchange
+// configured it also leaves the per-path winding sums in x_sums), enqueue_sort, enqueue_back.
+static int enqueue_fragments(slpr_ctx *c, cudaStream_t s, bool timed, int &launches) {
     int rc = enqueue_count_phase(c, s, timed, launches);
     if (rc) return rc;
     FragTaps ft{c->t_key32, c->t_path, c->t_wind};
     k_piece_emit<<<grid_for(c, c->nc, 256, 8), 256, 0, s>>>(c->d_params, c->nc, c->d_ctype, c->d_cpm, c->d_cpath, c->d_frule, c->d_tpos, c->d_cut,
                                                              c->d_offset, c->d_slots, c->d_ctr, c->cap, c->d_bucket_hist,
-                                                             c->d_pieces);
+                                                             PieceRanks{c->d_block_cnt, (uint32_t)c->mono_blocks},
+                                                             LiveCurves{c->hp.cull ? c->d_live : nullptr, c->d_ctr}, c->d_pieces);
     if (timed) CU(cudaEventRecord(c->ev[4], s));
     k_walk<<<c->num_sms * std::max(1, c->walk_blocks_per_sm), WALK_THREADS, 0, s>>>(
         c->d_params, c->d_pieces, c->d_ctr, c->cap, WalkTemp{c->d_bucket_hist, c->d_tickets + 3 + RS_MAX_PASSES},
         c->L, c->d_key[0], c->d_val[0], ft, c->d_inter, c->d_boundary, c->d_fixflag);
     k_piece_fix<<<grid_for(c, c->nc, 256, 8), 256, 0, s>>>(c->d_params, c->nc, c->d_ctype, c->d_cpm, c->d_cpath, c->d_frule, c->d_tpos,
                                                               c->d_cut, c->d_offset, c->d_slots, c->d_ctr, c->cap,
-                                                              c->d_bucket_hist, c->d_pieces, c->d_boundary, c->d_fixflag, c->L, c->d_key[0],
+                                                              c->d_bucket_hist, PieceRanks{c->d_block_cnt, (uint32_t)c->mono_blocks},
+                                                              LiveCurves{c->hp.cull ? c->d_live : nullptr, c->d_ctr}, c->d_pieces,
+                                                              c->d_boundary, c->d_fixflag, c->L, c->d_key[0],
                                                               c->d_val[0], ft);
     launches += 3;
     if (timed) CU(cudaEventRecord(c->ev[5], s));
@@ -467,7 +508,11 @@ static int enqueue_front(slpr_ctx *c, cudaStream_t s, bool timed, int &launches)
                                                                              c->cap, c->L, c->x_sums);
         ++launches;
     }
-    // ---- sort
+    CU(cudaGetLastError());
+    return SLPR_OK;
+}
+
+static int enqueue_sort(slpr_ctx *c, cudaStream_t s, bool timed, int &launches) {
     int cur = 0;
     if (!c->radix_mode) {  // every path sorted on chip, one read + one write of the pairs (segsort.cuh)
         if (timed) CU(cudaEventRecord(c->ev[6], s));
@@ -546,7 +591,9 @@ static int enqueue_back(slpr_ctx *c, cudaStream_t s, bool timed, int &launches) 
 }
 
 static int enqueue_frame(slpr_ctx *c, cudaStream_t s, bool timed, int &launches) {
-    int rc = enqueue_front(c, s, timed, launches);
+    int rc = enqueue_fragments(c, s, timed, launches);
+    if (rc) return rc;
+    rc = enqueue_sort(c, s, timed, launches);
     if (rc) return rc;
     return enqueue_back(c, s, timed, launches);
 }
@@ -847,6 +894,7 @@ extern "C" int slpr_set_band_exchange(slpr_ctx *c, int32_t *dev_sums, const int3
     CU(cudaMalloc(&c->x_corr, 2 * P * 4));
     c->x_scan_bytes = 256 + (P / SCAN_TILE_MIN + 2) * 8;
     CU(cudaMalloc(&c->x_scan_temp, c->x_scan_bytes));
+    CU(cudaEventCreateWithFlags(&c->x_event, cudaEventDisableTiming));
     c->x_sums = dev_sums;
     c->x_gathered = dev_gathered;
     c->x_ranks = n_bands;
@@ -889,21 +937,27 @@ extern "C" int slpr_render_band_begin(slpr_ctx *c) {
         k_set_params<<<1, 1, 0, c->stream>>>(c->d_params, c->hp);
         ++c->launches;
         int rc = launch_graph(c, c->gexec_a, c->graph_a_valid, c->launches_a, [&](int &l) {
-            int r = enqueue_front(c, c->stream, false, l);
+            int r = enqueue_fragments(c, c->stream, false, l);
             if (r) return r;
             CU(cudaMemcpyAsync(c->h_ctr, c->d_ctr, sizeof(FrameCounters), cudaMemcpyDeviceToHost, c->stream));
             return (int)SLPR_OK;
         });
         if (rc) return rc;
-        // the exchange happens outside the library, so capacity and sort mode are settled here, before it
-        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaEventRecord(c->x_event, c->stream));
+        // the sort does not need the other bands: it runs while the caller exchanges the sums
+        rc = launch_graph(c, c->gexec_s, c->graph_s_valid, c->launches_s, [&](int &l) { return enqueue_sort(c, c->stream, false, l); });
+        if (rc) return rc;
+        // The exchange happens outside the library, so capacity and sort mode are settled here, before it.
+        // Only the sums (and counters) are waited for; the sort is still running when this returns.
+        CU(cudaEventSynchronize(c->x_event));
         if (c->h_ctr->overflow) {
             const long long nf = c->h_ctr->n_fragments;
             rc = alloc_capacity(c, (int)std::min<long long>(nf + nf / 4 + 65536, (1ll << 29) - 1));
             if (rc) return rc;
             continue;
         }
-        if (c->h_ctr->sort_fallback && !c->radix_mode) {
+        if (c->h_ctr->stat_huge && !c->radix_mode) {  // a path too long for the segmented sort (k_path_stats): sort again by radix
+            CU(cudaStreamSynchronize(c->stream));
             c->radix_mode = true;
             invalidate_graphs(c);
             continue;

@@ -36,9 +36,18 @@ struct WalkTemp {
     int *group_counter;           // zeroed per frame
 };
 
-// position of (bucket, rank) in the length-sorted piece array: longest bucket first
-__device__ __forceinline__ uint32_t piece_position(const uint32_t *s_dbase, uint32_t slot) {
-    return s_dbase[slot >> 26] + (slot & 0x03FFFFFFu);
+// Where the pieces were ranked: k_monotonize_count's launch shape (256 threads per block, grid-stride) and
+// the exclusive per-(bucket, block) prefix from k_bucket_scan.
+struct PieceRanks {
+    const uint32_t *block_base;  // [WALK_BUCKETS][n_blocks]
+    uint32_t n_blocks;
+};
+
+// position of a piece in the length-sorted piece array (longest bucket first): bucket start + pieces of
+// the same bucket ranked by earlier blocks + rank inside its block
+__device__ __forceinline__ uint32_t piece_position(const uint32_t *s_dbase, const PieceRanks &pr, uint32_t work_item, uint32_t slot) {
+    const uint32_t bucket = slot >> 26, blk = (work_item >> 8) % pr.n_blocks;  // the block that ranked work item w (LiveCurves)
+    return s_dbase[bucket] + pr.block_base[bucket * pr.n_blocks + blk] + (slot & 0x03FFFFFFu);
 }
 
 __device__ __forceinline__ void bucket_bases(const uint32_t *__restrict__ hist, uint32_t *s_dbase, uint32_t *s_total) {
@@ -72,14 +81,17 @@ __global__ void __launch_bounds__(256, SLPR_PE_MIN_BLOCKS) k_piece_emit(const Fr
                                                     const float2 *__restrict__ tpos, const float *__restrict__ cut_cache,
                                                     const int *__restrict__ offsets, const uint32_t *__restrict__ slots,
                                                     FrameCounters *__restrict__ ctr, int capacity,
-                                                    const uint32_t *__restrict__ bucket_hist, PieceRec *__restrict__ pieces) {
+                                                    const uint32_t *__restrict__ bucket_hist, PieceRanks ranks,
+                                                    LiveCurves live, PieceRec *__restrict__ pieces) {
     __shared__ uint32_t s_dbase[WALK_BUCKETS];
     __shared__ uint32_t s_total;
     if (ctr->n_fragments > capacity) return;
     bucket_bases(bucket_hist, s_dbase, &s_total);
     if (blockIdx.x == 0 && threadIdx.x == 0) ctr->n_pieces = (int)s_total;
     const int width = P->width, height = P->height;
-    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n_curves; c += gridDim.x * blockDim.x) {
+    const uint32_t n_work = live.count(n_curves);
+    for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n_work; w += gridDim.x * blockDim.x) {
+        const uint32_t c = live.curve(w);
         int pcnt = offsets[c];
         if (offsets[c + 1] == pcnt) continue;  // invisible or band-culled
         const uint32_t type = curve_type[c];
@@ -115,7 +127,7 @@ __global__ void __launch_bounds__(256, SLPR_PE_MIN_BLOCKS) k_piece_emit(const Fr
                                u2f(path_rule));
             r.m = make_uint4((uint32_t)n_x | ((uint32_t)n_y << 15) | (xfwd ? 0u : 1u << 30) | (yfwd ? 0u : 1u << 31), c,
                              (uint32_t)pcnt, (type & 0xFFu) | (piece << 8) | ((type > 0xFFu) ? 0x80u : 0u));
-            pieces[piece_position(s_dbase, slots[5 * c + piece])] = r;
+            pieces[piece_position(s_dbase, ranks, w, slots[5 * c + piece])] = r;
             pcnt += n_x + n_y + 1;
             t0_ms = t1_ms; p0x = p1x; p0y = p1y;  // MI1:442-443
         }
@@ -409,7 +421,7 @@ __global__ void __launch_bounds__(256) k_piece_fix(const FrameParams *__restrict
                                                      const float2 *__restrict__ tpos, const float *__restrict__ cut_cache,
                                                      const int *__restrict__ offsets, const uint32_t *__restrict__ slots,
                                                      const FrameCounters *__restrict__ ctr, int capacity,
-                                                     const uint32_t *__restrict__ bucket_hist,
+                                                     const uint32_t *__restrict__ bucket_hist, PieceRanks ranks, LiveCurves live,
                                                      const PieceRec *__restrict__ pieces, const float2 *__restrict__ boundary,
                                                      const uint8_t *__restrict__ fixflag, KeyLayout L, uint64_t *__restrict__ key64, uint32_t *__restrict__ val,
                                                      FragTaps taps) {
@@ -418,7 +430,9 @@ __global__ void __launch_bounds__(256) k_piece_fix(const FrameParams *__restrict
     if (ctr->n_fragments > capacity) return;
     bucket_bases(bucket_hist, s_dbase, &s_total);
     const FragEnv env = load_frag_env(P);
-    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n_curves; c += gridDim.x * blockDim.x) {
+    const uint32_t n_work = live.count(n_curves);
+    for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n_work; w += gridDim.x * blockDim.x) {
+        const uint32_t c = live.curve(w);
         if (offsets[c + 1] == offsets[c]) continue;
         const uint32_t n_cuts = f2u(cut_cache[5 * c + 4]) + 1u;
         bool any = false;
@@ -431,7 +445,7 @@ __global__ void __launch_bounds__(256) k_piece_fix(const FrameParams *__restrict
         load_points(type, curve_pos_map[c], tpos, cp);
         for (uint32_t piece = 0; piece + 1 < n_cuts; ++piece) {
             if (!fixflag[5 * c + piece + 1]) continue;
-            const uint4 m = pieces[piece_position(s_dbase, slots[5 * c + piece])].m;
+            const uint4 m = pieces[piece_position(s_dbase, ranks, w, slots[5 * c + piece])].m;
             const int n_loop = (int)(m.x & 0x7FFFu) + (int)((m.x >> 15) & 0x7FFFu) + 1;
             const int f = (int)m.z + n_loop - 1;  // last record of the piece
             // GF:99-104: t0 from this record, t1 from the next record of the curve

@@ -63,13 +63,21 @@ def scatter_frames(n_frames, world):
     return np.arange(n_frames) % world
 
 
-def render_bands_exact(rasterizer, sums, gathered, dist):
-    """One exact band of a frame on this rank: first half, all-gather of the per-path winding sums, second
-    half. `sums` [3P] and `gathered` [world, 3P] are int32 tensors on the rasterizer's device, registered once
-    with rasterizer.set_band_exchange(sums.data_ptr(), gathered.data_ptr(), world, rank); the collective must
-    be ordered after the rasterizer's stream (make it torch's current stream)."""
+def render_bands_exact(rasterizer, sums, gathered, dist, comm_stream=None):
+    """One exact band of a frame on this rank: fragments + sort, all-gather of the per-path winding sums,
+    second half. `sums` [3P] and `gathered` [world, 3P] are int32 tensors on the rasterizer's device,
+    registered once with rasterizer.set_band_exchange(sums.data_ptr(), gathered.data_ptr(), world, rank).
+    render_band_begin returns when the sums are complete while the sort is still running on the rasterizer's
+    stream (torch's current stream); the collective is issued from `comm_stream` so that it overlaps the
+    sort, and the current stream waits for it before the second half."""
+    import torch
     rasterizer.render_band_begin()
-    dist.all_gather_into_tensor(gathered.view(-1), sums)
+    if comm_stream is not None and gathered.is_cuda:
+        with torch.cuda.stream(comm_stream):
+            work = dist.all_gather_into_tensor(gathered.view(-1), sums, async_op=True)
+        work.wait()  # orders the CURRENT stream after the collective; the host does not block
+    else:
+        dist.all_gather_into_tensor(gathered.view(-1), sums)
     rasterizer.render_band_end()
 
 
