@@ -148,6 +148,7 @@ def main():
     ap.add_argument("--mode", default="frames", choices=["frames", "bands"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--independent-bands", action="store_true", help="bands mode: no winding-sum exchange (exact only without winding residues)")
+    ap.add_argument("--rank0-share", type=float, default=1.0, help="bands mode: rank 0 renders this fraction of an equal band (it also receives the gathered frame)")
     ap.add_argument("--no-gather", action="store_true", help="bands mode: leave every band on its GPU (no NCCL gather)")
     ap.add_argument("--no-radix-leg", action="store_true", help="skip timing the radix sort beside the segmented sort")
     args = ap.parse_args()
@@ -188,9 +189,8 @@ def main():
     bands = args.mode == "bands" and world > 1
     frame = None
     if bands:
-        rows_per = (H // world) & ~1
-        y0 = rank * rows_per
-        y1 = H if rank == world - 1 else y0 + rows_per
+        band_list = PAR.band_rows(H, world, args.rank0_share)
+        y0, y1 = band_list[rank]
         r.set_band(y0, y1)
         # Pipelined gather: every rank renders its band straight into frame buffer i & 1 (two captured graphs,
         # slpr_set_target); the band of frame i then travels to rank 0 (one NCCL group of send/recv over NVLink,
@@ -239,8 +239,7 @@ def main():
             if rank == 0:
                 ops = []
                 for g in range(1, world):
-                    gy0 = g * rows_per
-                    gy1 = H if g == world - 1 else gy0 + rows_per
+                    gy0, gy1 = band_list[g]
                     ops.append(dist.P2POp(dist.irecv, frames2[slot][H - gy1:H - gy0], g))
                 pending[slot] = dist.batch_isend_irecv(ops)  # one NCCL group: the receives run concurrently
             else:
@@ -437,7 +436,8 @@ def main():
                        "scene_sha256": sc.sha256()[:16], "sort": r.sort_mode(), "sort_key_bits": info["key_bits"],
                        "radix_passes_if_radix": info["passes"],
                        "parallelism": (("bands%d" % world) + ("+independent" if args.independent_bands else "+nccl-allgather-of-winding-sums")
-                                        + ("+no-gather" if args.no_gather else "+pipelined-nccl-gather")) if bands else ("frames-dp%d" % world),
+                                        + ("+no-gather" if args.no_gather else "+pipelined-nccl-gather")
+                                        + ("" if args.rank0_share == 1.0 else "+rank0-share-%.2f" % args.rank0_share)) if bands else ("frames-dp%d" % world),
                        "l2": "per-frame working set (fragments x 44 B + 33 MB frame) exceeds the 126 MB L2; no flush needed",
                        "frame_replay": "cuda-graph"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,

@@ -48,33 +48,32 @@ __global__ void __launch_bounds__(256) k_band_sums(const int *__restrict__ seg, 
     }
 }
 
-// gathered: [n_ranks][3][P]
+// gathered: [n_ranks][3][P]. One pass over the gathered sums: d[p] (scanned next) and the two per-path terms
+// of the corrections, so that k_band_corr only adds the scan.
 __global__ void __launch_bounds__(256) k_band_other(const int *__restrict__ gathered, uint32_t n_paths, int n_ranks, int rank,
-                                                    int *__restrict__ d) {
+                                                    int *__restrict__ d, int *__restrict__ corr) {
     for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n_paths; p += gridDim.x * blockDim.x) {
-        int s = 0;
+        int all = 0, below = 0, others = 0;
         for (int r = 0; r < n_ranks; ++r) {
             if (r == rank) continue;
             const int *g = gathered + (size_t)r * 3 * n_paths;
-            s += g[p] + g[n_paths + p] + g[2 * (size_t)n_paths + p];
+            const int a = g[p], inv = g[n_paths + p], z = g[2 * (size_t)n_paths + p];
+            all += a + inv + z;
+            others += a + inv;
+            if (r < rank) below += a;
         }
-        d[p] = s;
+        d[p] = all;
+        corr[p] = below;
+        corr[n_paths + p] = others;
     }
 }
 
 // corr: [2][P] = corrN | corrZ; e = exclusive scan of d
-__global__ void __launch_bounds__(256) k_band_corr(const int *__restrict__ gathered, const int *__restrict__ e, uint32_t n_paths,
-                                                   int n_ranks, int rank, int *__restrict__ corr) {
+__global__ void __launch_bounds__(256) k_band_corr(const int *__restrict__ e, uint32_t n_paths, int *__restrict__ corr) {
     for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n_paths; p += gridDim.x * blockDim.x) {
-        int below = 0, others = 0;
-        for (int r = 0; r < n_ranks; ++r) {
-            if (r == rank) continue;
-            const int *g = gathered + (size_t)r * 3 * n_paths;
-            if (r < rank) below += g[p];
-            others += g[p] + g[n_paths + p];
-        }
-        corr[p] = e[p] + below;
-        corr[n_paths + p] = e[p] + others;
+        const int v = e[p];
+        corr[p] += v;
+        corr[n_paths + p] += v;
     }
 }
 

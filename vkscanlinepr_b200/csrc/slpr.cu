@@ -552,11 +552,11 @@ static int enqueue_back(slpr_ctx *c, cudaStream_t s, bool timed, int &launches) 
     const int *corr = nullptr;
     if (c->x_sums) {
         CU(cudaMemsetAsync(c->x_scan_temp, 0, c->x_scan_bytes, s));
-        k_band_other<<<grid_for(c, c->P, 256, 8), 256, 0, s>>>(c->x_gathered, c->P, c->x_ranks, c->x_rank, c->x_d);
+        k_band_other<<<grid_for(c, c->P, 256, 8), 256, 0, s>>>(c->x_gathered, c->P, c->x_ranks, c->x_rank, c->x_d, c->x_corr);
         ScanI32Op op{c->x_d, c->x_e, (long long)c->P, nullptr, 0, nullptr};
         ScanTemp t{reinterpret_cast<unsigned long long *>(c->x_scan_temp + 256), reinterpret_cast<int *>(c->x_scan_temp)};
         k_lookback_scan<ScanI32Op><<<grid_for(c, (long long)(c->P / SCAN_TILE_MIN + 2), 1, 8), SCAN_THREADS, 0, s>>>(op, t);
-        k_band_corr<<<grid_for(c, c->P, 256, 8), 256, 0, s>>>(c->x_gathered, c->x_e, c->P, c->x_ranks, c->x_rank, c->x_corr);
+        k_band_corr<<<grid_for(c, c->P, 256, 8), 256, 0, s>>>(c->x_e, c->P, c->x_corr);
         launches += 3;
         corr = c->x_corr;
     }

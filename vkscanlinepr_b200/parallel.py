@@ -15,9 +15,10 @@ host logic is covered on CPU with gloo (tests/test_parallel_cpu.py).
 import numpy as np
 
 
-def band_rows(height, world):
+def band_rows(height, world, first_share=1.0):
     """Even-aligned scanline-row bands [(y0, y1)] covering [0, height): fragments are 2 px tall, so a band
-    edge must be even (slpr_set_band); the last band takes the remainder."""
+    edge must be even (slpr_set_band); the last band takes the remainder. `first_share` < 1 gives band 0 that
+    fraction of an equal share (the rank that also receives the gathered frame renders less)."""
     if world < 1 or height < 1:
         raise ValueError("world and height must be positive")
     per = (height // world) & ~1
@@ -25,7 +26,12 @@ def band_rows(height, world):
         if world > 1:
             raise ValueError(f"height {height} is too small for {world} even-aligned bands")
         return [(0, height)]
-    return [(r * per, height if r == world - 1 else (r + 1) * per) for r in range(world)]
+    if world == 1 or first_share == 1.0:
+        return [(r * per, height if r == world - 1 else (r + 1) * per) for r in range(world)]
+    first = max(2, int(per * first_share) & ~1)
+    rest = ((height - first) // (world - 1)) & ~1
+    edges = [0, first] + [first + k * rest for k in range(1, world - 1)] + [height]
+    return [(edges[r], edges[r + 1]) for r in range(world)]
 
 
 def image_rows(height, y0, y1):
