@@ -11,6 +11,8 @@ the north-star target is quoted on. Metric: Mpixel/s (= W*H / frame time), ms_pe
 N > 1 (torchrun, one process per GPU): frame-parallel — every rank renders its own K frames of the
 resident scene, no data-path collective ("scaling": "weak"). `--mode bands` instead splits ONE
 frame into N row bands and gathers them to rank 0 with NCCL (BASELINE cfg4; "strong").
+`--mode anim` is BASELINE cfg5: a 256-frame animation (per-frame affine matrices, scene.anim_rows) of the
+workload, frame f on rank f mod N; step i of rank r renders frame r + i*N (use --steps 256/N for one cycle).
 
 `--impl reference` times the reference's algorithm on the host cores (the oracle port: the
 reference has no CPU implementation and cannot run without Vulkan), same workload and metric.
@@ -145,7 +147,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="synth_1m_4k")
-    ap.add_argument("--mode", default="frames", choices=["frames", "bands"])
+    ap.add_argument("--mode", default="frames", choices=["frames", "bands", "anim"])
+    ap.add_argument("--anim-frames", type=int, default=256, help="anim mode: length of the animation cycle (BASELINE cfg5: 256)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--independent-bands", action="store_true", help="bands mode: no winding-sum exchange (exact only without winding residues)")
     ap.add_argument("--rank0-share", type=float, default=1.0, help="bands mode: rank 0 renders this fraction of an equal band (it also receives the gathered frame)")
@@ -186,6 +189,21 @@ def main():
         return r
 
     r = make_ctx(0)
+    anim = args.mode == "anim"
+    if anim:
+        from vkscanlinepr_b200 import scene as S
+        base64 = np.asarray(rows, np.float64)
+        my_frames = list(range(rank, args.anim_frames, world)) or [0]
+        anim_mats = [np.ascontiguousarray((S.anim_rows(f, W, H, args.anim_frames).astype(np.float64) @ base64).astype(np.float32))
+                     for f in my_frames]
+        anim_step = [0]
+        # one untimed pass over this rank's frames, waited for frame by frame: the fragment buffers grow to the
+        # largest frame of the cycle and the sort mode settles, so no timed frame has to be rendered twice
+        for m in anim_mats:
+            r.setMVP(m)
+            r.render()
+            r.synchronize()
+        anim_frag = []
     bands = args.mode == "bands" and world > 1
     frame = None
     if bands:
@@ -222,7 +240,11 @@ def main():
         pending[slot] = []
 
     def step():
-        r.setMVP(rows)
+        if anim:
+            r.setMVP(anim_mats[anim_step[0] % len(anim_mats)])
+            anim_step[0] += 1
+        else:
+            r.setMVP(rows)
         if bands:
             slot = step_no[0] & 1
             step_no[0] += 1
@@ -288,6 +310,18 @@ def main():
     ms_per_step = ms_total / K
     mpix = frames_total * W * H / (ms_total * 1e-3) / 1e6
 
+    anim_info = None
+    if anim:
+        # every frame of this rank once more, waited for: the fragment counts of the cycle
+        for m in anim_mats:
+            r.setMVP(m)
+            r.render()
+            anim_frag.append(r.counts()["n_fragments"])
+        anim_info = {"frames_in_cycle": args.anim_frames, "frames_of_this_rank": len(anim_mats),
+                     "fragments_min": int(min(anim_frag)), "fragments_max": int(max(anim_frag)),
+                     "fragments_mean": float(np.mean(anim_frag))}
+        anim_step[0] = 0
+
     band_check = None
     if bands and rank == 0 and not args.no_gather:  # the assembled frame against the same frame rendered whole on this GPU
         full = make_ctx(0)
@@ -317,16 +351,20 @@ def main():
             r.render_to_host(rows_host, host_np)
         barrier()
         sync_s = time.perf_counter() - t0
+        def rows_of(i):
+            return anim_mats[i % len(anim_mats)] if anim else rows_host
         for i in range(4):
-            r.submit_to_host(rows_host, hosts[i & 1].numpy())
+            r.submit_to_host(rows_of(i), hosts[i & 1].numpy())
         r.wait_host()
         barrier()
+        redone0 = r.pipeline_redone()
         t0 = time.perf_counter()
         for i in range(K):
-            r.submit_to_host(rows_host, hosts[i & 1].numpy())
+            r.submit_to_host(rows_of(i), hosts[i & 1].numpy())
         r.wait_host()
         barrier()
         e2e_s = time.perf_counter() - t0
+        e2e_redone = r.pipeline_redone() - redone0
         if dist is not None:
             t = torch.tensor([e2e_s, sync_s], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -336,7 +374,8 @@ def main():
                "what": "slpr_submit_to_host per frame + slpr_wait_host: TransPosIn rows from host, render, RGBA8 frame "
                        "to pinned host memory, copy of frame i overlapped with rendering of frame i+1",
                "blocking_call": {"value": frames_total * W * H / sync_s / 1e6, "ms_per_step": sync_s / K * 1e3,
-                                 "what": "slpr_render_to_host (set_mvp + render + readback, synchronous per frame)"}}
+                                 "what": "slpr_render_to_host (set_mvp + render + readback, synchronous per frame)"},
+               "frames_rendered_twice": int(e2e_redone)}
     else:
         e2e = None
 
@@ -344,7 +383,7 @@ def main():
     #      steps, on the launching stream. The headline object is the kernel with the largest share
     #      of the frame; the sort and the scans (the north star's HBM-bound stages) are listed too.
     roof = stage_avg = None
-    if rank == 0 and not bands:
+    if rank == 0 and not bands and not anim:
         def stage_times(flags):
             ri = make_ctx(flags)
             for _ in range(3):
@@ -355,11 +394,11 @@ def main():
                 ri.render()
                 for k, v in ri.stage_ms().items():
                     acc[k] = acc.get(k, 0.0) + v
-            out = {k: v / K for k, v in acc.items()}, ri.sort_mode(), ri.n_pieces(), ri.sort_info()
+            out = {k: v / K for k, v in acc.items()}, ri.sort_mode(), ri.n_pieces(), ri.sort_info(), ri.fill_fused()
             ri.close()
             return out
 
-        stage_avg, mode, n_pieces, _ = stage_times(V.FLAG_NO_GRAPH)
+        stage_avg, mode, n_pieces, _, fused = stage_times(V.FLAG_NO_GRAPH)
         nf = cnt["n_fragments"]
         nrec = cnt["n_out_frag"] + cnt["n_span"]
         peak, peak_src = peaks()
@@ -379,9 +418,12 @@ def main():
             "walk": entry("k_walk", n_pieces * 64 + nf * (kb + 4) + n_pieces * 9, stage_avg["walk"],
                           note="issue-bound, not HBM-bound: 2/3 of its instructions are the reference's 24-step fp32 "
                                "bisection, reproduced operation for operation (no FMA); see DESIGN.md"),
-            "spans": entry("k_spans", nf * (kb + 4) + nrec * 16, stage_avg["span_emit"]),
-            "fill": entry("k_fill_cells", nrec * 16, stage_avg["fill_cells"]),
+            "spans": entry("k_spans", nf * (kb + 4) + nrec * 16, stage_avg["span_emit"],
+                           note="also marks the cells of every record (stage 5 coverage fused in: ~2.4 L2 atomics per record)"
+                           if fused else None),
         }
+        if not fused:
+            kernels["fill"] = entry("k_fill_cells", nrec * 16, stage_avg["fill_cells"])
         if mode == "segmented":  # one read + one write of every pair
             kernels["sort"] = entry("k_segsort_warp", nf * 2 * (kb + 4), stage_avg["sort_passes"])
         else:                    # 2*(K+4) B per fragment per pass
@@ -400,7 +442,7 @@ def main():
                           "frac": scan_bytes / (scan_ms * 1e-3) / 1e9 / peak}}
         if mode == "segmented" and not args.no_radix_leg:
             # the general sort (paths of any length), timed on the same frame for comparison
-            st_r, _, _, info_r = stage_times(V.FLAG_NO_GRAPH | V.FLAG_RADIX_SORT)
+            st_r, _, _, info_r, _ = stage_times(V.FLAG_NO_GRAPH | V.FLAG_RADIX_SORT)
             pass_ms = st_r["sort_passes"] / info_r["passes"]
             pass_bytes = nf * 2 * (info_r["key_bytes"] + 4)
             tr = ncu_traffic("k_onesweep", args.workload) or (None, None)
@@ -417,10 +459,11 @@ def main():
         cores = O.num_threads()
         ts = []
         t_budget = time.perf_counter()
+        cpu_rows = anim_mats[min(37, len(anim_mats) - 1)] if anim else rows
         while len(ts) < 3 and (time.perf_counter() - t_budget) < 20.0:
-            dt, ref = cpu_frame(sc, rows, W, H)
+            dt, ref = cpu_frame(sc, cpu_rows, W, H)
             ts.append(dt)
-        r.render_to_host(rows_host, host_np)
+        r.render_to_host(np.ascontiguousarray(cpu_rows, dtype=np.float32), host_np)
         ok = bool(np.array_equal(host_np, ref["rgba"])) and ref["n_fragments"] == cnt["n_fragments"]
         cpu = {"value": W * H / min(ts) / 1e6, "unit": "Mpixel/s", "cores": cores, "kind": "port",
                "sample": f"{len(ts)} full frame(s) of {args.workload}, best; all {cores} OpenMP threads",
@@ -433,11 +476,12 @@ def main():
             "vs_baseline": None, "dtype": "f32+i32", "data": "synthetic",
             "config": {"workload": args.workload, "width": W, "height": H, "curves": sc.n_curves, "paths": sc.n_paths,
                        "points": sc.n_points, "fragments": cnt["n_fragments"], "records": cnt["n_out_frag"] + cnt["n_span"],
-                       "scene_sha256": sc.sha256()[:16], "sort": r.sort_mode(), "sort_key_bits": info["key_bits"],
+                       "scene_sha256": sc.sha256()[:16], "sort": r.sort_mode(), "fill": "fused into k_spans" if r.fill_fused() else "k_fill_cells", "sort_key_bits": info["key_bits"],
                        "radix_passes_if_radix": info["passes"],
                        "parallelism": (("bands%d" % world) + ("+independent" if args.independent_bands else "+nccl-allgather-of-winding-sums")
                                         + ("+no-gather" if args.no_gather else "+pipelined-nccl-gather")
-                                        + ("" if args.rank0_share == 1.0 else "+rank0-share-%.2f" % args.rank0_share)) if bands else ("frames-dp%d" % world),
+                                        + ("" if args.rank0_share == 1.0 else "+rank0-share-%.2f" % args.rank0_share)) if bands
+                                       else (("anim%d-frame-f-on-rank-f-mod-%d" % (args.anim_frames, world)) if anim else ("frames-dp%d" % world)),
                        "l2": "per-frame working set (fragments x 44 B + 33 MB frame) exceeds the 126 MB L2; no flush needed",
                        "frame_replay": "cuda-graph"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
@@ -445,6 +489,8 @@ def main():
         }
         if band_check is not None:
             out["bands_vs_full_frame"] = band_check
+        if anim_info is not None:
+            out["anim"] = anim_info
         print(json.dumps(out))
     r.close()
     if dist is not None:

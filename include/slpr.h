@@ -50,7 +50,11 @@ enum {
      * (csrc/radix.cuh) for small scenes with long paths; a path of more than 4096 fragments always means radix.
      * RADIX_SORT: always radix. SEGMENTED_SORT: segmented whenever no path exceeds 4096 fragments. */
     SLPR_FLAG_RADIX_SORT = 1u << 3,
-    SLPR_FLAG_SEGMENTED_SORT = 1u << 4
+    SLPR_FLAG_SEGMENTED_SORT = 1u << 4,
+    /* Stage-5 coverage. Default: by frame size (slpr_fill_mode). FUSED_FILL: the span kernel always marks the cells
+     * of its draw records itself; SEPARATE_FILL: always a separate pass over the records. Same pixels. */
+    SLPR_FLAG_FUSED_FILL = 1u << 5,
+    SLPR_FLAG_SEPARATE_FILL = 1u << 6
 };
 
 /* Buffers that slpr_debug_copy() can return. Layouts are the reference's:
@@ -143,6 +147,12 @@ SLPR_API int slpr_render_to_host(slpr_ctx *ctx, const float rows[16], uint8_t *r
  * asynchronous copy) holds the frame after slpr_wait_host(); use two host buffers alternately. */
 SLPR_API int slpr_submit_to_host(slpr_ctx *ctx, const float rows[16], uint8_t *rgba, size_t stride_bytes);
 SLPR_API int slpr_wait_host(slpr_ctx *ctx);
+/* A frame of a sequence can outgrow the fragment buffers sized from earlier frames (or a path the on-chip sort);
+ * that is only known once it ran. The pipelined path checks every frame's device counters when its slot comes
+ * round again and in slpr_wait_host, and renders such a frame again into the caller's buffer (the reference
+ * sizes its buffers with a host read-back in the middle of every frame instead, scanline_rasterizer.cpp:355-369).
+ * Returns how many frames had to be rendered twice so far. */
+SLPR_API uint64_t slpr_pipeline_redone(slpr_ctx *ctx);
 
 /* Device pointer of the last rendered frame (RGBA8) and its row stride. Does not synchronise. */
 SLPR_API int slpr_framebuffer(slpr_ctx *ctx, void **dev_rgba, size_t *stride_bytes);
@@ -182,6 +192,10 @@ SLPR_API int slpr_sort_info(slpr_ctx *ctx, uint32_t *key_bits, uint32_t *passes,
 /* Which sort the context uses: 0 = segmented one-pass sort (csrc/segsort.cuh), 1 = onesweep radix
  * sort (SLPR_FLAG_RADIX_SORT, or a path had more than 4096 fragments). */
 SLPR_API int slpr_sort_mode(slpr_ctx *ctx, int *mode);
+/* Where the cells of the draw records are marked (stage 5, scanlinepr.vert/.frag): 1 = inside the span kernel
+ * (big frames), 0 = by a separate pass over the records (small frames). Chosen per scene and view from the
+ * fragment count; the pixels are the same either way. */
+SLPR_API int slpr_fill_mode(slpr_ctx *ctx, int *fused);
 /* Monotone pieces walked by the last frame (64-byte piece records read by k_walk). */
 SLPR_API int slpr_walk_info(slpr_ctx *ctx, uint32_t *n_pieces);
 

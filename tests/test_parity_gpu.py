@@ -59,6 +59,13 @@ def assert_frame_parity(sc, rows, W, H):
         assert np.array_equal(g.tap(t), ref[ORACLE_NAME[t]]), f"radix sort: tap {t} differs"
     assert np.array_equal(g.readback(), ref["rgba"])
     g.close()
+    # stage-5 coverage both ways: marked by the span kernel itself (big frames) or by a separate pass (small ones)
+    for flag, fused in ((V.FLAG_FUSED_FILL, True), (V.FLAG_SEPARATE_FILL, False)):
+        h = render_gpu(sc, rows, W, H, flag)
+        assert np.array_equal(h.readback(), ref["rgba"]), f"fill fused={fused}"
+        assert h.fill_fused() == fused
+        assert np.array_equal(h.tap("records"), ref["records"])
+        h.close()
     return ref
 
 
@@ -284,4 +291,35 @@ def test_pipelined_submit_to_host():
     r.wait_host()
     for i, (b, ref) in enumerate(zip(bufs, refs)):
         assert np.array_equal(b, ref), f"frame {i}"
+    r.close()
+
+
+def test_pipelined_animation_outgrows_buffers():
+    """cfg5-style sequence through slpr_submit_to_host whose fragment count grows several-fold between frames
+    (zoom in): frames that outgrow the buffers sized from earlier frames are found from their device counters and
+    rendered again — every frame must still land in its host buffer identical to the oracle's."""
+    import torch
+    sc, vp = util.golden_scene("tiger")
+    W, H = 640, 480
+    fit = S.fit_rows(vp, W, H)
+
+    def zoom(s):
+        m = np.eye(4, dtype=np.float32)
+        m[0, 0] = m[1, 1] = s
+        m[0, 3] = W * 0.5 * (1 - s)
+        m[1, 3] = H * 0.5 * (1 - s)
+        return np.asarray(m @ fit, np.float32)
+
+    mats = [zoom(s) for s in (0.08, 0.1, 0.6, 0.7, 2.5, 0.3, 6.0, 6.0, 1.0)]
+    refs = [O.render(sc, m, W, H) for m in mats]
+    assert max(r["n_fragments"] for r in refs) > 3 * refs[0]["n_fragments"]
+    r = V.ScanlineRasterizer(0, 0).initialize(None, W, H)
+    r.loadVG(sc)
+    bufs = [torch.empty((H, W, 4), dtype=torch.uint8, pin_memory=True).numpy() for _ in mats]
+    for m, b in zip(mats, bufs):
+        r.submit_to_host(m, b)
+    r.wait_host()
+    for i, (b, ref) in enumerate(zip(bufs, refs)):
+        assert np.array_equal(b, ref["rgba"]), f"frame {i}"
+    assert r.pipeline_redone() >= 1
     r.close()

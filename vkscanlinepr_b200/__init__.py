@@ -22,6 +22,7 @@ LIB_PATH = os.environ.get("SLPR_LIB") or os.path.join(_HERE, "libslpr.so")  # SL
 _LIB = None
 
 FLAG_TAPS, FLAG_CONTRACT_FMA, FLAG_NO_GRAPH, FLAG_RADIX_SORT, FLAG_SEGMENTED_SORT = 1, 2, 4, 8, 16
+FLAG_FUSED_FILL, FLAG_SEPARATE_FILL = 32, 64
 TAPS = dict(transformed_pos=0, path_visible=1, cut_cache=2, curve_count=3, curve_offset=4, intersection=5,
             key=6, path=7, winding=8, sorted_key=9, sorted_index=10, winding_scan=11, flags=12,
             flag_scan=13, records=14, segments=15)
@@ -63,6 +64,8 @@ def lib():
         L.slpr_destroy.argtypes = [C.c_void_p]
         L.slpr_launch_count.restype = C.c_uint64
         L.slpr_launch_count.argtypes = [C.c_void_p]
+        L.slpr_pipeline_redone.restype = C.c_uint64
+        L.slpr_pipeline_redone.argtypes = [C.c_void_p]
         L.slpr_vg_load_rvg.restype = C.c_void_p
         L.slpr_vg_load_rvg.argtypes = [C.c_char_p]
         L.slpr_vg_from_arrays.restype = C.c_void_p
@@ -213,6 +216,10 @@ class ScanlineRasterizer:
     def wait_host(self):
         _check(lib().slpr_wait_host(self._h))
 
+    def pipeline_redone(self):
+        """Frames the pipelined path rendered twice (they outgrew buffers sized from earlier frames)."""
+        return int(lib().slpr_pipeline_redone(self._h))
+
     def set_band(self, y0, y1):
         _check(lib().slpr_set_band(self._h, C.c_uint32(y0), C.c_uint32(y1)))
 
@@ -259,6 +266,11 @@ class ScanlineRasterizer:
         m = C.c_int()
         _check(lib().slpr_sort_mode(self._h, C.byref(m)))
         return "radix" if m.value else "segmented"
+
+    def fill_fused(self):
+        m = C.c_int()
+        _check(lib().slpr_fill_mode(self._h, C.byref(m)))
+        return bool(m.value)
 
     def n_pieces(self):
         n = C.c_uint32()

@@ -86,6 +86,7 @@ struct slpr_ctx {
     int *d_count = nullptr, *d_offset = nullptr, *d_seg_tap = nullptr;  // d_seg_tap: [P+1] sort segment table (always built)
     int *d_big = nullptr;              // [P] paths queued for the block-level segmented sort
     bool radix_mode = false;           // false: one-pass segmented sort; true: onesweep radix sort
+    bool fill_fused = false;           // true: k_spans marks the cells itself (no k_fill_cells), see choose_fill_mode
     uint32_t *d_slots = nullptr;       // [5*nc] (length bucket << 26 | rank) of every monotone piece
     PieceRec *d_pieces = nullptr;      // [5*nc] piece records in length-sorted order
     float2 *d_boundary = nullptr;      // [5*nc] first / last emitted parameter of every piece
@@ -132,6 +133,16 @@ struct slpr_ctx {
     cudaEvent_t ev_rendered[2] = {}, ev_copied[2] = {};
     bool copy_pending[2] = {false, false};
     unsigned pipe_frame = 0;
+    // what each of the two pipeline slots holds, so that a frame found invalid after the fact (it outgrew the
+    // fragment buffers, or a path outgrew the segmented sort) can be rendered again into the caller's buffer
+    struct PipeSlot {
+        float rows[16];
+        uint8_t *rgba = nullptr;
+        size_t stride = 0;
+        bool in_flight = false, was_radix = false;
+        FrameCounters *h = nullptr;  // pinned: this frame's counters, copied right behind its kernels
+    } pslot[2];
+    uint64_t pipe_redone = 0;          // frames the pipelined path had to render twice
     size_t fb_stride = 0;
     uint8_t *target = nullptr;
     size_t target_stride = 0;
@@ -293,8 +304,9 @@ extern "C" slpr_ctx *slpr_create(int device, uint32_t width, uint32_t height, ui
     for (auto &ev : c->ev) ok = ok && cudaEventCreate(&ev) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_onesweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->walk_blocks_per_sm, k_walk, WALK_THREADS, 0) == cudaSuccess;
-    ok = ok && cudaFuncSetAttribute(k_spans, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_STAGE_BYTES) == cudaSuccess;
-    ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->span_blocks_per_sm, k_spans, SP_THREADS, SP_STAGE_BYTES) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_spans<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_STAGE_BYTES) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_spans<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_STAGE_BYTES) == cudaSuccess;
+    ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->span_blocks_per_sm, k_spans<true>, SP_THREADS, SP_STAGE_BYTES) == cudaSuccess;
     if (!ok) {
         fail(SLPR_ERR_CUDA, "slpr_create: device setup failed: %s", cudaGetErrorString(cudaGetLastError()));
         slpr_destroy(c);
@@ -314,7 +326,7 @@ extern "C" void slpr_destroy(slpr_ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     free_capacity(c);
     free_scene(c);
-    cudaFree(c->d_params); cudaFreeHost(c->h_ctr); cudaFree(c->d_cells); cudaFree(c->d_fb); cudaFree(c->d_fb2); cudaFree(c->d_prim_temp);
+    cudaFree(c->d_params); cudaFreeHost(c->h_ctr); cudaFreeHost(c->pslot[0].h); cudaFreeHost(c->pslot[1].h); cudaFree(c->d_cells); cudaFree(c->d_fb); cudaFree(c->d_fb2); cudaFree(c->d_prim_temp);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     for (int i = 0; i < 2; ++i) { if (c->ev_rendered[i]) cudaEventDestroy(c->ev_rendered[i]); if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]); }
     for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
@@ -569,8 +581,13 @@ static int enqueue_back(slpr_ctx *c, cudaStream_t s, bool timed, int &launches) 
     launches += 2;
 #endif
     if (timed) CU(cudaEventRecord(c->ev[8], s));
-    k_spans<<<c->num_sms * std::max(1, c->span_blocks_per_sm), SP_THREADS, SP_STAGE_BYTES, s>>>(c->d_key[cur], c->d_val[cur], c->d_finfo, c->d_rec, c->d_ctr,
-                                                  c->L, (int)c->W, (int)c->H, c->cap, stp, stmp, corr, c->P);
+    const int span_grid = c->num_sms * std::max(1, c->span_blocks_per_sm);
+    if (c->fill_fused)
+        k_spans<true><<<span_grid, SP_THREADS, SP_STAGE_BYTES, s>>>(c->d_key[cur], c->d_val[cur], c->d_finfo, c->d_rec, c->d_ctr, c->L, (int)c->W,
+                                                                    (int)c->H, c->cap, stp, stmp, corr, c->P, c->d_cells, c->cw);
+    else
+        k_spans<false><<<span_grid, SP_THREADS, SP_STAGE_BYTES, s>>>(c->d_key[cur], c->d_val[cur], c->d_finfo, c->d_rec, c->d_ctr, c->L, (int)c->W,
+                                                                     (int)c->H, c->cap, stp, stmp, corr, c->P, c->d_cells, c->cw);
     ++launches;
     if (taps) {
         k_scan3_fixup<<<wide, 256, 0, s>>>(c->d_ctr, c->cap, c->t_scan3);
@@ -580,10 +597,13 @@ static int enqueue_back(slpr_ctx *c, cudaStream_t s, bool timed, int &launches) 
     // ---- pixels
     uint8_t *fb = c->target ? c->target : c->fb_cur;
     const size_t stride = c->target ? c->target_stride : c->fb_stride;
-    k_fill_cells<<<wide, 256, 0, s>>>(c->d_params, c->d_ctr, c->cap, c->d_rec, c->d_cells, c->cw);
+    if (!c->fill_fused) {  // small frames: a grid-wide pass over the records spreads the few wide spans better
+        k_fill_cells<<<wide, 256, 0, s>>>(c->d_params, c->d_ctr, c->cap, c->d_rec, c->d_cells, c->cw);
+        ++launches;
+    }
     if (timed) CU(cudaEventRecord(c->ev[10], s));
     k_resolve<<<wide, 256, 0, s>>>(c->d_params, c->d_rec, c->d_cells, c->cw, fb, stride);
-    launches += 2;
+    ++launches;
     if (timed) CU(cudaEventRecord(c->ev[11], s));
     CU(cudaMemcpyAsync(c->h_ctr, c->d_ctr, sizeof(FrameCounters), cudaMemcpyDeviceToHost, s));
     CU(cudaGetLastError());
@@ -596,6 +616,20 @@ static int enqueue_frame(slpr_ctx *c, cudaStream_t s, bool timed, int &launches)
     rc = enqueue_sort(c, s, timed, launches);
     if (rc) return rc;
     return enqueue_back(c, s, timed, launches);
+}
+
+// Where are the cells of the draw records marked? Fused into k_spans the 16-byte records are not read back
+// (-0.03 ms at 18 M records, -0.8 ms at 146 M), but a frame of a few hundred thousand records occupies only a few
+// dozen span tiles, whose warps then fill its wide spans one after the other (+0.1 ms on tiger at 4K): measured on
+// the B200, profiles/README.md. Hysteresis keeps an animation from flipping (a flip re-captures the graph).
+#ifndef SLPR_FILL_FUSED
+#define SLPR_FILL_FUSED -1 /* -1: by frame size; 0 / 1: forced (experiments) */
+#endif
+static bool choose_fill_mode(const slpr_ctx *c, long long n_fragments) {
+    if (SLPR_FILL_FUSED >= 0) return SLPR_FILL_FUSED != 0;
+    if (c->flags & SLPR_FLAG_FUSED_FILL) return true;
+    if (c->flags & SLPR_FLAG_SEPARATE_FILL) return false;
+    return c->fill_fused ? (n_fragments > (3ll << 19)) : (n_fragments > (1ll << 21));
 }
 
 static int size_buffers_from_count(slpr_ctx *c) {
@@ -619,6 +653,7 @@ static int size_buffers_from_count(slpr_ctx *c) {
         rc = alloc_capacity(c, (int)std::min<long long>(want, (1ll << 29) - 1));
         if (rc) return rc;
     }
+    c->fill_fused = choose_fill_mode(c, nf);
     return SLPR_OK;
 }
 
@@ -718,6 +753,10 @@ static int finish_frame(slpr_ctx *c) {
                     invalidate_graphs(c);
                 }
             }
+            if (choose_fill_mode(c, c->h_ctr->n_fragments) != c->fill_fused) {  // from the next frame on
+                c->fill_fused = !c->fill_fused;
+                invalidate_graphs(c);
+            }
             c->frame_done = true;
             return SLPR_OK;
         }
@@ -760,6 +799,38 @@ extern "C" int slpr_render_to_host(slpr_ctx *c, const float rows[16], uint8_t *r
 // Pipelined end-to-end path: frame i renders into one of two framebuffers while frame i-1 is still
 // being copied to the host on a second stream. The pixels of a submitted frame are valid in `rgba`
 // after slpr_wait_host() (or after the second-next submit returns).
+// A frame can turn out invalid only after it ran (its fragments outgrew the buffers sized from earlier frames,
+// or one of its paths outgrew the segmented sort — both common in an animation that zooms in). Its counters
+// are copied into the slot right behind its kernels; they are looked at when the slot comes round again and in
+// slpr_wait_host, and an invalid frame is then rendered again, synchronously, into the caller's buffer.
+static bool slot_invalid(const slpr_ctx::PipeSlot &p) {
+    return p.in_flight && (p.h->overflow || (p.h->sort_fallback && !p.was_radix));
+}
+
+static int pipe_recover(slpr_ctx *c, int first_slot) {
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaStreamSynchronize(c->copy_stream));
+    c->frame_pending = false;
+    c->copy_pending[0] = c->copy_pending[1] = false;
+    uint8_t *const fb_keep = c->fb_cur;
+    for (int i = 0; i < 2; ++i) {  // older frame first
+        slpr_ctx::PipeSlot &p = c->pslot[(first_slot + i) & 1];
+        const bool bad = slot_invalid(p);
+        p.in_flight = false;
+        if (!bad) continue;
+        c->fb_cur = ((first_slot + i) & 1) ? c->d_fb2 : c->d_fb;
+        int rc = slpr_set_mvp(c, p.rows);
+        if (!rc) rc = slpr_render(c);
+        if (!rc) rc = finish_frame(c);  // grows the buffers / switches the sort until the frame is whole
+        if (rc) { c->fb_cur = fb_keep; return rc; }
+        CU(cudaMemcpy2DAsync(p.rgba, p.stride, c->fb_cur, c->fb_stride, (size_t)c->W * 4, c->H, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        ++c->pipe_redone;
+    }
+    c->fb_cur = fb_keep;
+    return SLPR_OK;
+}
+
 extern "C" int slpr_submit_to_host(slpr_ctx *c, const float rows[16], uint8_t *rgba, size_t stride_bytes) {
     if (!c || !rows || !rgba) return fail(SLPR_ERR_INVALID, "slpr_submit_to_host: null argument");
     if (stride_bytes < (size_t)c->W * 4) return fail(SLPR_ERR_INVALID, "slpr_submit_to_host: stride smaller than a row");
@@ -771,9 +842,19 @@ extern "C" int slpr_submit_to_host(slpr_ctx *c, const float rows[16], uint8_t *r
         for (int i = 0; i < 2; ++i) {
             CU(cudaEventCreateWithFlags(&c->ev_rendered[i], cudaEventDisableTiming));
             CU(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
+            CU(cudaMallocHost(&c->pslot[i].h, sizeof(FrameCounters)));
         }
     }
     const int k = (int)(c->pipe_frame++ & 1u);
+    slpr_ctx::PipeSlot &slot = c->pslot[k];
+    if (slot.in_flight) {  // the frame submitted two calls ago: finished long since; was it whole?
+        CU(cudaEventSynchronize(c->ev_rendered[k]));
+        if (slot_invalid(slot)) {
+            int rc = pipe_recover(c, k);
+            if (rc) return rc;
+        }
+        slot.in_flight = false;
+    }
     if (c->copy_pending[k]) {  // the copy that last read this framebuffer must be done before it is rendered into again
         CU(cudaStreamWaitEvent(c->stream, c->ev_copied[k], 0));
         c->copy_pending[k] = false;
@@ -782,9 +863,9 @@ extern "C" int slpr_submit_to_host(slpr_ctx *c, const float rows[16], uint8_t *r
     int rc = slpr_set_mvp(c, rows);
     if (!rc) rc = slpr_render(c);
     if (rc) return rc;
-    if (c->h_ctr->overflow) {  // an earlier frame outgrew the fragment buffers: grow them and redo this frame now
-        if ((rc = finish_frame(c))) return rc;
-    }
+    memcpy(slot.rows, rows, sizeof slot.rows);
+    slot.rgba = rgba; slot.stride = stride_bytes; slot.was_radix = c->radix_mode; slot.in_flight = true;
+    CU(cudaMemcpyAsync(slot.h, c->d_ctr, sizeof(FrameCounters), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaEventRecord(c->ev_rendered[k], c->stream));
     CU(cudaStreamWaitEvent(c->copy_stream, c->ev_rendered[k], 0));
     CU(cudaMemcpy2DAsync(rgba, stride_bytes, c->fb_cur, c->fb_stride, (size_t)c->W * 4, c->H, cudaMemcpyDeviceToHost, c->copy_stream));
@@ -796,11 +877,14 @@ extern "C" int slpr_submit_to_host(slpr_ctx *c, const float rows[16], uint8_t *r
 extern "C" int slpr_wait_host(slpr_ctx *c) {
     if (!c) return fail(SLPR_ERR_INVALID, "null context");
     CU(cudaSetDevice(c->device));
-    int rc = c->frame_pending ? finish_frame(c) : SLPR_OK;
-    if (c->copy_stream) CU(cudaStreamSynchronize(c->copy_stream));
-    c->copy_pending[0] = c->copy_pending[1] = false;
+    if (!c->copy_stream) return c->frame_pending ? finish_frame(c) : SLPR_OK;
+    // every submitted frame whole and in its host buffer: redo the (at most two) frames still unchecked
+    int rc = pipe_recover(c, (int)(c->pipe_frame & 1u));
+    if (!rc) c->frame_done = true;
     return rc;
 }
+
+extern "C" uint64_t slpr_pipeline_redone(slpr_ctx *c) { return c ? c->pipe_redone : 0; }
 
 extern "C" int slpr_framebuffer(slpr_ctx *c, void **dev_rgba, size_t *stride_bytes) {
     if (!c || !dev_rgba || !stride_bytes) return fail(SLPR_ERR_INVALID, "slpr_framebuffer: null argument");
@@ -999,6 +1083,12 @@ extern "C" int slpr_render_band_end(slpr_ctx *c) {
 extern "C" int slpr_sort_mode(slpr_ctx *c, int *mode) {
     if (!c || !mode) return fail(SLPR_ERR_INVALID, "slpr_sort_mode: null argument");
     *mode = c->radix_mode ? 1 : 0;
+    return SLPR_OK;
+}
+
+extern "C" int slpr_fill_mode(slpr_ctx *c, int *fused) {
+    if (!c || !fused) return fail(SLPR_ERR_INVALID, "slpr_fill_mode: null argument");
+    *fused = c->fill_fused ? 1 : 0;
     return SLPR_OK;
 }
 

@@ -13,6 +13,7 @@
 #pragma once
 #include "geom.cuh"
 #include "scan.cuh"
+#include "raster.cuh"
 
 namespace slpr {
 
@@ -126,12 +127,14 @@ __device__ __forceinline__ KeyFields decode_key(const KeyLayout &L, uint64_t k) 
     return f;
 }
 
+template <bool FILL>
 __global__ void __launch_bounds__(SP_THREADS, SP_BLOCKS) k_spans(const uint64_t *__restrict__ skey,
                                                          const uint32_t *__restrict__ sval,
                                                          const uint32_t *__restrict__ fill_info,
                                                          int4 *__restrict__ records, FrameCounters *__restrict__ ctr,
                                                          KeyLayout L, int width, int height, int capacity, SpanTaps taps,
-                                                         SpanTemp tmp, const int *__restrict__ band_corr, uint32_t n_paths) {
+                                                         SpanTemp tmp, const int *__restrict__ band_corr, uint32_t n_paths,
+                                                         uint32_t *__restrict__ cells, int cw) {
     __shared__ uint32_t s_warp[SP_THREADS / 32];
     __shared__ unsigned long long s_prefix;
     __shared__ long long s_tile;
@@ -373,7 +376,43 @@ __global__ void __launch_bounds__(SP_THREADS, SP_BLOCKS) k_spans(const uint64_t 
 #if SLPR_SP_STAGE
         __syncwarp();
         if (!SLPR_SP_NOSTORE) {
-            for (uint32_t q = (uint32_t)lane; q < wtot; q += 32) {
+            // Stage 5 coverage fused in with FILL (big frames: slpr.cu fill_fused): the record's index
+            // is known here, so the cells it covers are marked right away — atomicMax(cell, record index + 1),
+            // fire and forget — and the 16-byte records are not read back by k_fill_cells. Narrow records by
+            // their own lane, wide spans by the whole warp (same split as k_fill_cells).
+            if (FILL) for (uint32_t q0 = 0; q0 < wtot; q0 += 32) {
+                const uint32_t q = q0 + (uint32_t)lane;
+                int cx0 = 0, ncell = 0, cy = 0;
+                uint32_t prio = 0;
+                if (q < wtot) {
+                    const uint32_t pos = wp[q], w1 = wp[SP_WARP_RECORDS + q], ord = w1 >> 16;
+                    records[gbase + q] = make_int4((int)pos, (int)(w1 & 0xFFFFu), (int)wp[2 * SP_WARP_RECORDS + q],
+                                                   ord ? warp_frag_base + (int)ord : 0);
+                    const int X = (int)(pos & 0xFFFFu), Y = (int)pos >> 16;  // VERT:27
+                    if (Y >= 0 && Y < height) {
+                        cx0 = X >> 1;
+                        ncell = min((X + (int)(w1 & 0xFFFFu)) >> 1, cw) - cx0;
+                        cy = Y >> 1;
+                    }
+                    prio = (uint32_t)(gbase + q) + 1u;
+                }
+                if (ncell > 0 && ncell <= SLPR_FILL_NARROW) {
+                    uint32_t *row = cells + (size_t)cy * cw + cx0;
+                    for (int c = 0; c < ncell; ++c) atomicMax(row + c, prio);
+                }
+                uint32_t wide = __ballot_sync(0xFFFFFFFFu, ncell > SLPR_FILL_NARROW);
+                while (wide) {
+                    const int src = __ffs(wide) - 1;
+                    wide &= wide - 1;
+                    const int s_cx0 = __shfl_sync(0xFFFFFFFFu, cx0, src);
+                    const int s_n = __shfl_sync(0xFFFFFFFFu, ncell, src);
+                    const int s_cy = __shfl_sync(0xFFFFFFFFu, cy, src);
+                    const uint32_t s_prio = __shfl_sync(0xFFFFFFFFu, prio, src);
+                    uint32_t *row = cells + (size_t)s_cy * cw + s_cx0;
+                    for (int c = lane; c < s_n; c += 32) atomicMax(row + c, s_prio);
+                }
+            }
+            else for (uint32_t q = (uint32_t)lane; q < wtot; q += 32) {
                 const uint32_t w1 = wp[SP_WARP_RECORDS + q], ord = w1 >> 16;
                 records[gbase + q] = make_int4((int)wp[q], (int)(w1 & 0xFFFFu), (int)wp[2 * SP_WARP_RECORDS + q],
                                                ord ? warp_frag_base + (int)ord : 0);
