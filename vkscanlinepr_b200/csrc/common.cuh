@@ -17,7 +17,7 @@ struct FrameParams {
     int width, height;
     int band_y0, band_y1;  // scanline rows [y0,y1) this context renders
     int cull;              // 1 when the band is a strict subset of the frame
-    int stat_mid;      // paths of 129..512 fragments   } k_path_stats, every frame and in both sort modes:
+    int stat_mid;      // paths of 129..512 fragments   } k_path_segments, every frame and in both sort modes:
     int stat_big;      // paths of 513..4096 fragments  } the host picks the sort from them
     int stat_huge;     // paths of more than 4096 fragments (radix sort only)
     int n_live;        // band mode: curves whose path comes near the band (k_band_live)
@@ -35,11 +35,12 @@ struct FrameCounters {
     int sort_fallback; // segmented sort met a path with more than SEG_BLOCK_MAX fragments
     int n_big_segments;  // paths queued for k_segsort_block
     int n_pieces;      // monotone pieces walked this frame (k_piece_emit)
-    int stat_mid;      // paths of 129..512 fragments   } k_path_stats, every frame and in both sort modes:
+    int stat_mid;      // paths of 129..512 fragments   } k_path_segments, every frame and in both sort modes:
     int stat_big;      // paths of 513..4096 fragments  } the host picks the sort from them
     int stat_huge;     // paths of more than 4096 fragments (radix sort only)
     int n_live;        // band mode: curves whose path comes near the band (k_band_live)
-    int pad[3];
+    int n_fix;         // pieces whose predecessor's boundary fragment must be redone (k_walk -> k_piece_fix)
+    int pad[2];
 };
 
 // Key geometry for the compact 64-bit sort key (path | row rank | cell x), see DESIGN.md.

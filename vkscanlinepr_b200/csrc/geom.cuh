@@ -473,16 +473,4 @@ __device__ __forceinline__ void eval_point(uint32_t type, const CurvePts &cp, fl
     }
 }
 
-// Sort segment table (gen_fragment.comp:226-244) for the tap: seg[j] = first record of the first
-// curve whose path is >= j; seg[n_paths] = nf. Derived from the scanned curve offsets.
-__global__ void k_segments_tap(uint32_t n_curves, uint32_t n_paths, const uint32_t *__restrict__ curve_path,
-                               const int *__restrict__ offsets, int *__restrict__ seg) {
-    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c <= n_curves; c += gridDim.x * blockDim.x) {
-        const uint32_t lo = (c == 0) ? 0u : curve_path[c - 1] + 1u;
-        const uint32_t hi = (c == n_curves) ? n_paths : curve_path[c];
-        const int v = offsets[c];
-        for (uint32_t j = lo; j <= hi && j <= n_paths; ++j) seg[j] = v;
-    }
-}
-
 }  // namespace slpr

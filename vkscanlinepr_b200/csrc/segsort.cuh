@@ -189,16 +189,26 @@ __device__ __forceinline__ bool warp_sort_segment32(const uint64_t *__restrict__
     return true;
 }
 
-// Path-size statistics for the host's choice between the two sorts (slpr.cu: choose_sort_mode).
-__global__ void __launch_bounds__(256) k_path_stats(const int *__restrict__ seg, uint32_t n_paths, FrameCounters *__restrict__ ctr,
-                                                    int capacity) {
+// Sort segment table (gen_fragment.comp:226-244): seg[p] = first record of the first curve whose path is >= p,
+// seg[n_paths] = nf — read off the scanned curve offsets through the scene's static table of every path's first
+// curve (slpr_load_scene) — and, in the same pass, the path-size statistics for the host's choice between the two
+// sorts (slpr.cu: segmented_sort_pays).
+__global__ void __launch_bounds__(256) k_path_segments(const uint32_t *__restrict__ path_first_curve, uint32_t n_paths,
+                                                       const int *__restrict__ offsets, int *__restrict__ seg,
+                                                       FrameCounters *__restrict__ ctr, int capacity) {
     if (ctr->n_fragments > capacity) return;
     int mid = 0, big = 0, huge = 0;
-    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n_paths; p += gridDim.x * blockDim.x) {
-        const int n = seg[p + 1] - seg[p];
-        mid += (n > 128 && n <= SEG_WARP_MAX);
-        big += (n > SEG_WARP_MAX && n <= SEG_BLOCK_MAX);
-        huge += (n > SEG_BLOCK_MAX);
+    const uint32_t n_round = (n_paths + 1u + 31u) & ~31u;  // whole warps stay in the loop for the reductions
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n_round; p += gridDim.x * blockDim.x) {
+        if (p > n_paths) continue;
+        const int s0 = offsets[path_first_curve[p]];
+        seg[p] = s0;
+        if (p < n_paths) {
+            const int n = offsets[path_first_curve[p + 1]] - s0;
+            mid += (n > 128 && n <= SEG_WARP_MAX);
+            big += (n > SEG_WARP_MAX && n <= SEG_BLOCK_MAX);
+            huge += (n > SEG_BLOCK_MAX);
+        }
     }
     mid = __reduce_add_sync(0xFFFFFFFFu, mid);
     big = __reduce_add_sync(0xFFFFFFFFu, big);

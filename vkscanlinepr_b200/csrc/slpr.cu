@@ -81,6 +81,7 @@ struct slpr_ctx {
     int mono_blocks = 0;
     uint32_t *d_live = nullptr;  // [nc] band mode: curves whose path comes near the band (k_band_live)
     float4 *d_pobj = nullptr;    // [P] object-space box of each path's control points (static)
+    uint32_t *d_pfc = nullptr;   // [P+1] first curve whose path is >= p (static; [P] = n_curves)
     uint8_t *d_plive = nullptr;  // [P] band mode: the path can reach the band (k_path_cull)
     float *d_cut = nullptr;
     int *d_count = nullptr, *d_offset = nullptr, *d_seg_tap = nullptr;  // d_seg_tap: [P+1] sort segment table (always built)
@@ -90,7 +91,7 @@ struct slpr_ctx {
     uint32_t *d_slots = nullptr;       // [5*nc] (length bucket << 26 | rank) of every monotone piece
     PieceRec *d_pieces = nullptr;      // [5*nc] piece records in length-sorted order
     float2 *d_boundary = nullptr;      // [5*nc] first / last emitted parameter of every piece
-    uint8_t *d_fixflag = nullptr;      // [5*nc] piece whose predecessor's boundary fragment must be redone
+    uint4 *d_fixlist = nullptr;        // [4*nc] pieces whose predecessor's boundary fragment must be redone (k_walk -> k_piece_fix)
 
     // frame state
     FrameParams hp{};
@@ -124,8 +125,8 @@ struct slpr_ctx {
     KeyLayout L{};
     int key_bits = 0, passes = 0, sorted_buf = 0;
 
-    uint32_t *d_cells = nullptr;
-    int cw = 0, ch = 0;
+    uint32_t *d_cells = nullptr, *d_cells4 = nullptr;  // coverage grids (raster.cuh CellGrids)
+    int cw = 0, ch = 0, cw4 = 0;
     uint8_t *d_fb = nullptr;
     uint8_t *d_fb2 = nullptr;          // second framebuffer of the pipelined host path (lazy)
     uint8_t *fb_cur = nullptr;         // framebuffer the next frame renders into (d_fb unless pipelining)
@@ -214,13 +215,13 @@ static void free_exchange(slpr_ctx *c) {
 static void free_scene(slpr_ctx *c) {
     free_exchange(c);
     cudaFree(c->d_pos); cudaFree(c->d_pos_path); cudaFree(c->d_cpm); cudaFree(c->d_ctype); cudaFree(c->d_cpath);
-    cudaFree(c->d_frule); cudaFree(c->d_finfo); cudaFree(c->d_tpos); cudaFree(c->d_pvis); cudaFree(c->d_pobj); cudaFree(c->d_plive); cudaFree(c->d_live); cudaFree(c->d_block_cnt); cudaFree(c->d_cut);
+    cudaFree(c->d_frule); cudaFree(c->d_finfo); cudaFree(c->d_tpos); cudaFree(c->d_pvis); cudaFree(c->d_pobj); cudaFree(c->d_pfc); cudaFree(c->d_plive); cudaFree(c->d_live); cudaFree(c->d_block_cnt); cudaFree(c->d_cut);
     cudaFree(c->d_count); cudaFree(c->d_offset); cudaFree(c->d_seg_tap);
     cudaFree(c->d_big); c->d_big = nullptr;
-    cudaFree(c->d_slots); cudaFree(c->d_pieces); cudaFree(c->d_boundary); cudaFree(c->d_fixflag);
-    c->d_slots = nullptr; c->d_pieces = nullptr; c->d_boundary = nullptr; c->d_fixflag = nullptr;
+    cudaFree(c->d_slots); cudaFree(c->d_pieces); cudaFree(c->d_boundary); cudaFree(c->d_fixlist);
+    c->d_slots = nullptr; c->d_pieces = nullptr; c->d_boundary = nullptr; c->d_fixlist = nullptr;
     c->d_pos = nullptr; c->d_pos_path = c->d_cpm = c->d_ctype = c->d_cpath = c->d_frule = c->d_finfo = nullptr;
-    c->d_tpos = nullptr; c->d_pvis = nullptr; c->d_pobj = nullptr; c->d_plive = nullptr; c->d_live = nullptr; c->d_block_cnt = nullptr; c->d_cut = nullptr; c->d_count = c->d_offset = c->d_seg_tap = nullptr;
+    c->d_tpos = nullptr; c->d_pvis = nullptr; c->d_pobj = nullptr; c->d_pfc = nullptr; c->d_plive = nullptr; c->d_live = nullptr; c->d_block_cnt = nullptr; c->d_cut = nullptr; c->d_count = c->d_offset = c->d_seg_tap = nullptr;
     c->scene_loaded = false;
 }
 
@@ -298,6 +299,9 @@ extern "C" slpr_ctx *slpr_create(int device, uint32_t width, uint32_t height, ui
     c->cw = (int)(width + 1) / 2; c->ch = (int)(height + 1) / 2;
     ok = ok && cudaMalloc(&c->d_cells, (size_t)c->cw * c->ch * 4) == cudaSuccess;
     ok = ok && cudaMemset(c->d_cells, 0, (size_t)c->cw * c->ch * 4) == cudaSuccess;
+    c->cw4 = (c->cw + 3) / 4;
+    ok = ok && cudaMalloc(&c->d_cells4, (size_t)c->cw4 * c->ch * 4) == cudaSuccess;
+    ok = ok && cudaMemset(c->d_cells4, 0, (size_t)c->cw4 * c->ch * 4) == cudaSuccess;
     c->fb_stride = (size_t)width * 4;
     ok = ok && cudaMalloc(&c->d_fb, c->fb_stride * height) == cudaSuccess;
     c->fb_cur = c->d_fb;
@@ -326,7 +330,7 @@ extern "C" void slpr_destroy(slpr_ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     free_capacity(c);
     free_scene(c);
-    cudaFree(c->d_params); cudaFreeHost(c->h_ctr); cudaFreeHost(c->pslot[0].h); cudaFreeHost(c->pslot[1].h); cudaFree(c->d_cells); cudaFree(c->d_fb); cudaFree(c->d_fb2); cudaFree(c->d_prim_temp);
+    cudaFree(c->d_params); cudaFreeHost(c->h_ctr); cudaFreeHost(c->pslot[0].h); cudaFreeHost(c->pslot[1].h); cudaFree(c->d_cells); cudaFree(c->d_cells4); cudaFree(c->d_fb); cudaFree(c->d_fb2); cudaFree(c->d_prim_temp);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     for (int i = 0; i < 2; ++i) { if (c->ev_rendered[i]) cudaEventDestroy(c->ev_rendered[i]); if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]); }
     for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
@@ -393,6 +397,14 @@ extern "C" int slpr_load_scene(slpr_ctx *c, const float *pos_xy, const uint32_t 
             if (!(x == x) || !(y == y)) { b = make_float4(-3.0e38f, -3.0e38f, 3.0e38f, 3.0e38f); continue; }  // NaN: never culled
             b.x = std::min(b.x, x); b.y = std::min(b.y, y); b.z = std::max(b.z, x); b.w = std::max(b.w, y);
         }
+        // first curve of every path (curve_path is non-decreasing): the per-frame segment table is offsets[] read through it
+        std::vector<uint32_t> pfc((size_t)n_paths + 1);
+        uint32_t cur = 0;
+        for (uint32_t p = 0; p <= n_paths; ++p) {
+            while (cur < n_curves && curve_path[cur] < p) ++cur;
+            pfc[p] = cur;
+        }
+        if ((rc = upload(&c->d_pfc, pfc.data(), pfc.size()))) return rc;
         CU(cudaMalloc(&c->d_pobj, box.size() * sizeof(float4)));
         CU(cudaMemcpy(c->d_pobj, box.data(), box.size() * sizeof(float4), cudaMemcpyHostToDevice));
         CU(cudaMalloc(&c->d_plive, std::max<size_t>(n_paths, 1)));
@@ -406,7 +418,7 @@ extern "C" int slpr_load_scene(slpr_ctx *c, const float *pos_xy, const uint32_t 
     CU(cudaMalloc(&c->d_slots, std::max<size_t>(n_curves, 1) * 5 * 4));
     CU(cudaMalloc(&c->d_pieces, std::max<size_t>(n_curves, 1) * 5 * sizeof(PieceRec)));
     CU(cudaMalloc(&c->d_boundary, std::max<size_t>(n_curves, 1) * 5 * sizeof(float2)));
-    CU(cudaMalloc(&c->d_fixflag, std::max<size_t>(n_curves, 1) * 5));
+    CU(cudaMalloc(&c->d_fixlist, std::max<size_t>(n_curves, 1) * 4 * sizeof(uint4)));  // a curve has at most 4 pieces after its first
     CU(cudaMalloc(&c->d_seg_tap, ((size_t)n_paths + 1) * 4));
     CU(cudaMalloc(&c->d_big, std::max<size_t>(n_paths, 1) * 4));
     c->radix_mode = (c->flags & SLPR_FLAG_RADIX_SORT) != 0;
@@ -503,18 +515,13 @@ static int enqueue_fragments(slpr_ctx *c, cudaStream_t s, bool timed, int &launc
     if (timed) CU(cudaEventRecord(c->ev[4], s));
     k_walk<<<c->num_sms * std::max(1, c->walk_blocks_per_sm), WALK_THREADS, 0, s>>>(
         c->d_params, c->d_pieces, c->d_ctr, c->cap, WalkTemp{c->d_bucket_hist, c->d_tickets + 3 + RS_MAX_PASSES},
-        c->L, c->d_key[0], c->d_val[0], ft, c->d_inter, c->d_boundary, c->d_fixflag);
-    k_piece_fix<<<grid_for(c, c->nc, 256, 8), 256, 0, s>>>(c->d_params, c->nc, c->d_ctype, c->d_cpm, c->d_cpath, c->d_frule, c->d_tpos,
-                                                              c->d_cut, c->d_offset, c->d_slots, c->d_ctr, c->cap,
-                                                              c->d_bucket_hist, PieceRanks{c->d_block_cnt, (uint32_t)c->mono_blocks},
-                                                              LiveCurves{c->hp.cull ? c->d_live : nullptr, c->d_ctr}, c->d_pieces,
-                                                              c->d_boundary, c->d_fixflag, c->L, c->d_key[0],
-                                                              c->d_val[0], ft);
+        c->L, c->d_key[0], c->d_val[0], ft, c->d_inter, c->d_boundary, c->d_fixlist);
+    k_piece_fix<<<8, 256, 0, s>>>(c->d_params, c->d_ctype, c->d_cpm, c->d_cpath, c->d_frule, c->d_tpos, c->d_ctr, c->cap, c->d_boundary,
+                                  c->d_fixlist, c->L, c->d_key[0], c->d_val[0], ft);
     launches += 3;
     if (timed) CU(cudaEventRecord(c->ev[5], s));
-    k_segments_tap<<<grid_for(c, (long long)c->nc + 1, 256, 8), 256, 0, s>>>(c->nc, c->P, c->d_cpath, c->d_offset, c->d_seg_tap);
-    k_path_stats<<<grid_for(c, c->P, 256, 4), 256, 0, s>>>(c->d_seg_tap, c->P, c->d_ctr, c->cap);
-    launches += 2;
+    k_path_segments<<<grid_for(c, (long long)c->P + 1, 256, 4), 256, 0, s>>>(c->d_pfc, c->P, c->d_offset, c->d_seg_tap, c->d_ctr, c->cap);
+    ++launches;
     if (c->x_sums) {  // before the sort: the radix sort reuses buffer 0
         k_band_sums<<<grid_for(c, (long long)c->P * 32, 256, 8), 256, 0, s>>>(c->d_seg_tap, c->P, c->d_key[0], c->d_val[0], c->d_ctr,
                                                                              c->cap, c->L, c->x_sums);
@@ -582,12 +589,13 @@ static int enqueue_back(slpr_ctx *c, cudaStream_t s, bool timed, int &launches) 
 #endif
     if (timed) CU(cudaEventRecord(c->ev[8], s));
     const int span_grid = c->num_sms * std::max(1, c->span_blocks_per_sm);
+    const CellGrids grids{c->d_cells, c->d_cells4, c->cw, c->cw4};
     if (c->fill_fused)
         k_spans<true><<<span_grid, SP_THREADS, SP_STAGE_BYTES, s>>>(c->d_key[cur], c->d_val[cur], c->d_finfo, c->d_rec, c->d_ctr, c->L, (int)c->W,
-                                                                    (int)c->H, c->cap, stp, stmp, corr, c->P, c->d_cells, c->cw);
+                                                                    (int)c->H, c->cap, stp, stmp, corr, c->P, grids);
     else
         k_spans<false><<<span_grid, SP_THREADS, SP_STAGE_BYTES, s>>>(c->d_key[cur], c->d_val[cur], c->d_finfo, c->d_rec, c->d_ctr, c->L, (int)c->W,
-                                                                     (int)c->H, c->cap, stp, stmp, corr, c->P, c->d_cells, c->cw);
+                                                                     (int)c->H, c->cap, stp, stmp, corr, c->P, grids);
     ++launches;
     if (taps) {
         k_scan3_fixup<<<wide, 256, 0, s>>>(c->d_ctr, c->cap, c->t_scan3);
@@ -598,11 +606,11 @@ static int enqueue_back(slpr_ctx *c, cudaStream_t s, bool timed, int &launches) 
     uint8_t *fb = c->target ? c->target : c->fb_cur;
     const size_t stride = c->target ? c->target_stride : c->fb_stride;
     if (!c->fill_fused) {  // small frames: a grid-wide pass over the records spreads the few wide spans better
-        k_fill_cells<<<wide, 256, 0, s>>>(c->d_params, c->d_ctr, c->cap, c->d_rec, c->d_cells, c->cw);
+        k_fill_cells<<<wide, 256, 0, s>>>(c->d_params, c->d_ctr, c->cap, c->d_rec, grids);
         ++launches;
     }
     if (timed) CU(cudaEventRecord(c->ev[10], s));
-    k_resolve<<<wide, 256, 0, s>>>(c->d_params, c->d_rec, c->d_cells, c->cw, fb, stride);
+    k_resolve<<<wide, 256, 0, s>>>(c->d_params, c->d_rec, grids, fb, stride);
     ++launches;
     if (timed) CU(cudaEventRecord(c->ev[11], s));
     CU(cudaMemcpyAsync(c->h_ctr, c->d_ctr, sizeof(FrameCounters), cudaMemcpyDeviceToHost, s));
@@ -1040,7 +1048,7 @@ extern "C" int slpr_render_band_begin(slpr_ctx *c) {
             if (rc) return rc;
             continue;
         }
-        if (c->h_ctr->stat_huge && !c->radix_mode) {  // a path too long for the segmented sort (k_path_stats): sort again by radix
+        if (c->h_ctr->stat_huge && !c->radix_mode) {  // a path too long for the segmented sort (k_path_segments): sort again by radix
             CU(cudaStreamSynchronize(c->stream));
             c->radix_mode = true;
             invalidate_graphs(c);

@@ -16,8 +16,8 @@
 //                  the current group is walked; every emitted record
 //                  also closes the fragment that began at the previous record (gen_fragment fused,
 //                  the (curve, tbits) intersection records are only a debug tap now);
-//   k_piece_fix    one thread per curve: re-emits the boundary fragment of the rare pieces whose successor
-//                  did not start exactly at its t0 (only possible after the MI0:340 cut-order slip).
+//   k_piece_fix    re-emits the boundary fragment of the rare pieces whose successor did not start exactly
+//                  at its t0 (only possible after the MI0:340 cut-order slip); k_walk lists them.
 // The arithmetic of every step is the reference's, operation for operation.
 #pragma once
 #include "geom.cuh"
@@ -201,11 +201,11 @@ constexpr int WALK_UNROLL = SLPR_WALK_UNROLL;  // bisection steps per loop trip
 
 __global__ void __launch_bounds__(WALK_THREADS, SLPR_WALK_MIN_BLOCKS) k_walk(const FrameParams *__restrict__ P,
                                                        const PieceRec *__restrict__ pieces,
-                                                       const FrameCounters *__restrict__ ctr, int capacity, WalkTemp tmp,
+                                                       FrameCounters *__restrict__ ctr, int capacity, WalkTemp tmp,
                                                        KeyLayout L, uint64_t *__restrict__ key64,
                                                        uint32_t *__restrict__ val, FragTaps taps,
                                                        int2 *__restrict__ inter, float2 *__restrict__ boundary,
-                                                       uint8_t *__restrict__ fixflag) {
+                                                       uint4 *__restrict__ fixlist) {
     const int nf_total = ctr->n_fragments;
     if (nf_total > capacity) return;
     if (taps.key32 && blockIdx.x == 0 && threadIdx.x == 0 && nf_total > 0) taps.key32[nf_total] = -1;  // GF:240
@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(WALK_THREADS, SLPR_WALK_MIN_BLOCKS) k_walk(con
         //      record is its start parameter t0 = this piece's tagged t1 (MI1:304-305,442) in every case
         //      but one: when the MI0:340 slip leaves the cuts out of order, a bisection can land below t0.
         //      So the boundary fragment is emitted here with t1 = (t1_ms without tag bits), and a piece
-        //      whose first record does not match its t0 raises a flag for k_piece_fix to redo its
+        //      whose first record does not match its t0 is listed for k_piece_fix, which redoes its
         //      predecessor's boundary fragment from the recorded parameters.
         if (active) {
             float tcl = u2f(f2u(t1_ms) & 0xFFFFFFFCu);
@@ -407,57 +407,44 @@ __global__ void __launch_bounds__(WALK_THREADS, SLPR_WALK_MIN_BLOCKS) k_walk(con
             fs.put(pcnt - 1, k, v, key64, val);
             fs.flush(pcnt - 1, key64, val);
             boundary[5 * c + piece] = make_float2(u2f(first_bits), u2f(last_bits));
-            fixflag[5 * c + piece] = (piece > 0 && (first_bits & 0xFFFFFFFCu) != (f2u(t0_ms) & 0xFFFFFFFCu)) ? 1 : 0;
+            if (piece > 0 && (first_bits & 0xFFFFFFFCu) != (f2u(t0_ms) & 0xFFFFFFFCu))  // rare: a few dozen per million curves
+                fixlist[atomicAdd(&ctr->n_fix, 1)] = make_uint4(c, piece, (uint32_t)fs.f_first, 0u);
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_piece_fix(const FrameParams *__restrict__ P, uint32_t n_curves,
-                                                     const uint32_t *__restrict__ curve_type,
-                                                     const uint32_t *__restrict__ curve_pos_map,
-                                                     const uint32_t *__restrict__ curve_path,
-                                                     const uint32_t *__restrict__ fill_rule,
-                                                     const float2 *__restrict__ tpos, const float *__restrict__ cut_cache,
-                                                     const int *__restrict__ offsets, const uint32_t *__restrict__ slots,
-                                                     const FrameCounters *__restrict__ ctr, int capacity,
-                                                     const uint32_t *__restrict__ bucket_hist, PieceRanks ranks, LiveCurves live,
-                                                     const PieceRec *__restrict__ pieces, const float2 *__restrict__ boundary,
-                                                     const uint8_t *__restrict__ fixflag, KeyLayout L, uint64_t *__restrict__ key64, uint32_t *__restrict__ val,
-                                                     FragTaps taps) {
-    __shared__ uint32_t s_dbase[WALK_BUCKETS];
-    __shared__ uint32_t s_total;
+// One thread per listed piece (curve, piece >= 1, its first record): the fragment between the last
+// record of the piece before it and its own first record, from the parameters both pieces recorded. Runs after
+// k_walk, when every piece of the frame has left its boundary parameters.
+__global__ void __launch_bounds__(256) k_piece_fix(const FrameParams *__restrict__ P, const uint32_t *__restrict__ curve_type,
+                                                   const uint32_t *__restrict__ curve_pos_map,
+                                                   const uint32_t *__restrict__ curve_path, const uint32_t *__restrict__ fill_rule,
+                                                   const float2 *__restrict__ tpos, const FrameCounters *__restrict__ ctr, int capacity,
+                                                   const float2 *__restrict__ boundary, const uint4 *__restrict__ fixlist, KeyLayout L,
+                                                   uint64_t *__restrict__ key64, uint32_t *__restrict__ val, FragTaps taps) {
     if (ctr->n_fragments > capacity) return;
-    bucket_bases(bucket_hist, s_dbase, &s_total);
+    const int n_fix = ctr->n_fix;
+    if (n_fix == 0) return;  // the common case
     const FragEnv env = load_frag_env(P);
-    const uint32_t n_work = live.count(n_curves);
-    for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n_work; w += gridDim.x * blockDim.x) {
-        const uint32_t c = live.curve(w);
-        if (offsets[c + 1] == offsets[c]) continue;
-        const uint32_t n_cuts = f2u(cut_cache[5 * c + 4]) + 1u;
-        bool any = false;
-        for (uint32_t piece = 1; piece < n_cuts; ++piece) any |= fixflag[5 * c + piece] != 0;
-        if (!any) continue;  // the common case: nothing to redo
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_fix; i += gridDim.x * blockDim.x) {
+        const uint4 e = fixlist[i];
+        const uint32_t c = e.x, piece = e.y;
         const uint32_t type = curve_type[c];
         const uint32_t pidx = curve_path[c];
         const uint32_t rule_bit = fill_rule[pidx] == 1u ? 1u : 0u;
         CurvePts cp;
         load_points(type, curve_pos_map[c], tpos, cp);
-        for (uint32_t piece = 0; piece + 1 < n_cuts; ++piece) {
-            if (!fixflag[5 * c + piece + 1]) continue;
-            const uint4 m = pieces[piece_position(s_dbase, ranks, w, slots[5 * c + piece])].m;
-            const int n_loop = (int)(m.x & 0x7FFFu) + (int)((m.x >> 15) & 0x7FFFu) + 1;
-            const int f = (int)m.z + n_loop - 1;  // last record of the piece
-            // GF:99-104: t0 from this record, t1 from the next record of the curve
-            float t0 = u2f(f2u(boundary[5 * c + piece].y) & 0xFFFFFFFCu);
-            float t1 = u2f(f2u(boundary[5 * c + piece + 1].x) & 0xFFFFFFFCu);
-            t0 = (t0 < 0.0f) ? 0.0f : t0;
-            t1 = (t1 < 0.0f) ? 0.0f : t1;
-            float ax, ay, bx, by;
-            eval_point(type, cp, t0, ax, ay);
-            eval_point(type, cp, t1, bx, by);
-            emit_fragment(env, L, f, pidx, rule_bit, t0, t1, ax, ay, bx, by, key64, val, taps);
-        }
+        const int f = (int)e.z - 1;  // last record of the piece before: a curve's records are consecutive
+        // GF:99-104: t0 from that record, t1 from the next record of the curve
+        float t0 = u2f(f2u(boundary[5 * c + piece - 1].y) & 0xFFFFFFFCu);
+        float t1 = u2f(f2u(boundary[5 * c + piece].x) & 0xFFFFFFFCu);
+        t0 = (t0 < 0.0f) ? 0.0f : t0;
+        t1 = (t1 < 0.0f) ? 0.0f : t1;
+        float ax, ay, bx, by;
+        eval_point(type, cp, t0, ax, ay);
+        eval_point(type, cp, t1, bx, by);
+        emit_fragment(env, L, f, pidx, rule_bit, t0, t1, ax, ay, bx, by, key64, val, taps);
     }
 }
 
