@@ -125,8 +125,8 @@ struct slpr_ctx {
     KeyLayout L{};
     int key_bits = 0, passes = 0, sorted_buf = 0;
 
-    uint32_t *d_cells = nullptr, *d_cells4 = nullptr;  // coverage grids (raster.cuh CellGrids)
-    int cw = 0, ch = 0, cw4 = 0;
+    uint32_t *d_cells = nullptr;
+    int cw = 0, ch = 0;
     uint8_t *d_fb = nullptr;
     uint8_t *d_fb2 = nullptr;          // second framebuffer of the pipelined host path (lazy)
     uint8_t *fb_cur = nullptr;         // framebuffer the next frame renders into (d_fb unless pipelining)
@@ -299,9 +299,6 @@ extern "C" slpr_ctx *slpr_create(int device, uint32_t width, uint32_t height, ui
     c->cw = (int)(width + 1) / 2; c->ch = (int)(height + 1) / 2;
     ok = ok && cudaMalloc(&c->d_cells, (size_t)c->cw * c->ch * 4) == cudaSuccess;
     ok = ok && cudaMemset(c->d_cells, 0, (size_t)c->cw * c->ch * 4) == cudaSuccess;
-    c->cw4 = (c->cw + 3) / 4;
-    ok = ok && cudaMalloc(&c->d_cells4, (size_t)c->cw4 * c->ch * 4) == cudaSuccess;
-    ok = ok && cudaMemset(c->d_cells4, 0, (size_t)c->cw4 * c->ch * 4) == cudaSuccess;
     c->fb_stride = (size_t)width * 4;
     ok = ok && cudaMalloc(&c->d_fb, c->fb_stride * height) == cudaSuccess;
     c->fb_cur = c->d_fb;
@@ -330,7 +327,7 @@ extern "C" void slpr_destroy(slpr_ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     free_capacity(c);
     free_scene(c);
-    cudaFree(c->d_params); cudaFreeHost(c->h_ctr); cudaFreeHost(c->pslot[0].h); cudaFreeHost(c->pslot[1].h); cudaFree(c->d_cells); cudaFree(c->d_cells4); cudaFree(c->d_fb); cudaFree(c->d_fb2); cudaFree(c->d_prim_temp);
+    cudaFree(c->d_params); cudaFreeHost(c->h_ctr); cudaFreeHost(c->pslot[0].h); cudaFreeHost(c->pslot[1].h); cudaFree(c->d_cells); cudaFree(c->d_fb); cudaFree(c->d_fb2); cudaFree(c->d_prim_temp);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     for (int i = 0; i < 2; ++i) { if (c->ev_rendered[i]) cudaEventDestroy(c->ev_rendered[i]); if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]); }
     for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
@@ -589,13 +586,12 @@ static int enqueue_back(slpr_ctx *c, cudaStream_t s, bool timed, int &launches) 
 #endif
     if (timed) CU(cudaEventRecord(c->ev[8], s));
     const int span_grid = c->num_sms * std::max(1, c->span_blocks_per_sm);
-    const CellGrids grids{c->d_cells, c->d_cells4, c->cw, c->cw4};
     if (c->fill_fused)
         k_spans<true><<<span_grid, SP_THREADS, SP_STAGE_BYTES, s>>>(c->d_key[cur], c->d_val[cur], c->d_finfo, c->d_rec, c->d_ctr, c->L, (int)c->W,
-                                                                    (int)c->H, c->cap, stp, stmp, corr, c->P, grids);
+                                                                    (int)c->H, c->cap, stp, stmp, corr, c->P, c->d_cells, c->cw);
     else
         k_spans<false><<<span_grid, SP_THREADS, SP_STAGE_BYTES, s>>>(c->d_key[cur], c->d_val[cur], c->d_finfo, c->d_rec, c->d_ctr, c->L, (int)c->W,
-                                                                     (int)c->H, c->cap, stp, stmp, corr, c->P, grids);
+                                                                     (int)c->H, c->cap, stp, stmp, corr, c->P, c->d_cells, c->cw);
     ++launches;
     if (taps) {
         k_scan3_fixup<<<wide, 256, 0, s>>>(c->d_ctr, c->cap, c->t_scan3);
@@ -606,11 +602,11 @@ static int enqueue_back(slpr_ctx *c, cudaStream_t s, bool timed, int &launches) 
     uint8_t *fb = c->target ? c->target : c->fb_cur;
     const size_t stride = c->target ? c->target_stride : c->fb_stride;
     if (!c->fill_fused) {  // small frames: a grid-wide pass over the records spreads the few wide spans better
-        k_fill_cells<<<wide, 256, 0, s>>>(c->d_params, c->d_ctr, c->cap, c->d_rec, grids);
+        k_fill_cells<<<wide, 256, 0, s>>>(c->d_params, c->d_ctr, c->cap, c->d_rec, c->d_cells, c->cw);
         ++launches;
     }
     if (timed) CU(cudaEventRecord(c->ev[10], s));
-    k_resolve<<<wide, 256, 0, s>>>(c->d_params, c->d_rec, grids, fb, stride);
+    k_resolve<<<wide, 256, 0, s>>>(c->d_params, c->d_rec, c->d_cells, c->cw, fb, stride);
     ++launches;
     if (timed) CU(cudaEventRecord(c->ev[11], s));
     CU(cudaMemcpyAsync(c->h_ctr, c->d_ctr, sizeof(FrameCounters), cudaMemcpyDeviceToHost, s));

@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(SP_THREADS, SP_BLOCKS) k_spans(const uint64_t 
                                                          int4 *__restrict__ records, FrameCounters *__restrict__ ctr,
                                                          KeyLayout L, int width, int height, int capacity, SpanTaps taps,
                                                          SpanTemp tmp, const int *__restrict__ band_corr, uint32_t n_paths,
-                                                         CellGrids grids) {
+                                                         uint32_t *__restrict__ cells, int cw) {
     __shared__ uint32_t s_warp[SP_THREADS / 32];
     __shared__ unsigned long long s_prefix;
     __shared__ long long s_tile;
@@ -391,12 +391,26 @@ __global__ void __launch_bounds__(SP_THREADS, SP_BLOCKS) k_spans(const uint64_t 
                     const int X = (int)(pos & 0xFFFFu), Y = (int)pos >> 16;  // VERT:27
                     if (Y >= 0 && Y < height) {
                         cx0 = X >> 1;
-                        ncell = min((X + (int)(w1 & 0xFFFFu)) >> 1, grids.cw) - cx0;
+                        ncell = min((X + (int)(w1 & 0xFFFFu)) >> 1, cw) - cx0;
                         cy = Y >> 1;
                     }
                     prio = (uint32_t)(gbase + q) + 1u;
                 }
-                mark_records_warp(grids, cy, cx0, ncell, prio, lane);
+                if (ncell > 0 && ncell <= SLPR_FILL_NARROW) {
+                    uint32_t *row = cells + (size_t)cy * cw + cx0;
+                    for (int c = 0; c < ncell; ++c) atomicMax(row + c, prio);
+                }
+                uint32_t wide = __ballot_sync(0xFFFFFFFFu, ncell > SLPR_FILL_NARROW);
+                while (wide) {
+                    const int src = __ffs(wide) - 1;
+                    wide &= wide - 1;
+                    const int s_cx0 = __shfl_sync(0xFFFFFFFFu, cx0, src);
+                    const int s_n = __shfl_sync(0xFFFFFFFFu, ncell, src);
+                    const int s_cy = __shfl_sync(0xFFFFFFFFu, cy, src);
+                    const uint32_t s_prio = __shfl_sync(0xFFFFFFFFu, prio, src);
+                    uint32_t *row = cells + (size_t)s_cy * cw + s_cx0;
+                    for (int c = lane; c < s_n; c += 32) atomicMax(row + c, s_prio);
+                }
             }
             else for (uint32_t q = (uint32_t)lane; q < wtot; q += 32) {
                 const uint32_t w1 = wp[SP_WARP_RECORDS + q], ord = w1 >> 16;
