@@ -125,6 +125,16 @@ def test_synthetic_scene_parity():
     assert_frame_parity(sc, S.identity_rows(), 1024, 768)
 
 
+def test_cubics_with_cuts_out_of_order():
+    """Hundreds of cubics with four monotonic cuts (MI0:340 leaves the fourth unsorted): pieces that end below
+    their start, whose boundary fragments k_piece_fix re-emits from the parameters k_walk leaves for it."""
+    sc = util.looping_cubics_scene()
+    ref = assert_frame_parity(sc, S.identity_rows(), 512, 384)
+    ncuts = ref["cut_cache"].reshape(-1, 5)[:, 4].copy().view(np.uint32)
+    assert (ncuts == 4).sum() >= 100
+    assert_frame_parity(sc, S.anim_rows(29, 512, 384), 512, 384)
+
+
 def test_sort_modes_by_path_size():
     """Segmented sort: warp network (paths up to 512 fragments), block network (up to 4096), and the
     switch to the radix sort when a path is longer than that or when the host's cost model prefers it.

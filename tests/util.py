@@ -113,3 +113,27 @@ def edge_scene():
     return S.Scene(np.array(pos, np.float32), np.array(pos_path, np.uint32), np.array(cpm, np.uint32),
                    np.array(ctype, np.uint32), np.array(cpath, np.uint32), np.array([0, 1, 0, 0, 0, 1], np.uint32),
                    np.array([0xFF0000FF, 0xFF00FF00, 0xFFFF0000, 0xFF00FFFF, 0xFFFFFFFF, 0xFF808080], np.uint32), "edge")
+
+
+def looping_cubics_scene(n_paths=600, width=512, height=384, seed=7):
+    """Paths of one S-shaped or looping cubic closed by a line, control points scattered over (and beyond) the
+    frame: many cubics with three and four monotonic cuts, i.e. plenty of pieces left out of order by the
+    MI0:340 slip — the case in which a piece's first record differs from its start parameter."""
+    rng = np.random.default_rng(seed)
+    pos, pos_path, cpm, ctype, cpath = [], [], [], [], []
+    for p in range(n_paths):
+        cx, cy = rng.uniform(0, width), rng.uniform(0, height)
+        r = rng.uniform(10, 90)
+        pts = [(cx + rng.uniform(-r, r), cy + rng.uniform(-r, r)) for _ in range(4)]
+        if p % 3 == 0:  # force the S shape of edge_scene(): x and y both turn twice
+            pts = [(cx - r, cy - r), (cx + 1.6 * r, cy - 1.2 * r), (cx - 1.5 * r, cy + 1.1 * r), (cx + r, cy + 0.7 * r)]
+        cpm.append(len(pos)); ctype.append(S.CUBIC); cpath.append(p)
+        for q in pts:
+            pos.append(q); pos_path.append(p)
+        cpm.append(len(pos)); ctype.append(S.LINE); cpath.append(p)
+        for q in (pts[3], pts[0]):
+            pos.append(q); pos_path.append(p)
+    col = (0xFF000000 | rng.integers(0, 1 << 24, n_paths)).astype(np.uint32)
+    return S.Scene(np.array(pos, np.float32), np.array(pos_path, np.uint32), np.array(cpm, np.uint32),
+                   np.array(ctype, np.uint32), np.array(cpath, np.uint32), (np.arange(n_paths) & 1).astype(np.uint32),
+                   col, "looping_cubics")

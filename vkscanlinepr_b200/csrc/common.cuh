@@ -40,7 +40,8 @@ struct FrameCounters {
     int stat_huge;     // paths of more than 4096 fragments (radix sort only)
     int n_live;        // band mode: curves whose path comes near the band (k_band_live)
     int n_fix;         // pieces whose predecessor's boundary fragment must be redone (k_walk -> k_piece_fix)
-    int pad[2];
+    int fix_missed;    // invariant check of k_walk's conditional boundary stores (always 0)
+    int pad[1];
 };
 
 // Key geometry for the compact 64-bit sort key (path | row rank | cell x), see DESIGN.md.

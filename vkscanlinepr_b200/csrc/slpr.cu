@@ -750,6 +750,7 @@ static int finish_frame(slpr_ctx *c) {
             continue;
         }
         if (!c->h_ctr->overflow) {
+            if (c->h_ctr->fix_missed) return fail(SLPR_ERR_STATE, "internal: a piece started below its start parameter without ending below it");
             if (!(c->flags & (SLPR_FLAG_RADIX_SORT | SLPR_FLAG_SEGMENTED_SORT))) {
                 const bool seg = segmented_sort_pays(c, *c->h_ctr);
                 if (seg == c->radix_mode) {  // the other sort suits this scene and view better: use it from the next frame on

@@ -125,8 +125,16 @@ __global__ void __launch_bounds__(256, SLPR_PE_MIN_BLOCKS) k_piece_emit(const Fr
             // MI1:301-302; the grid lines are clamped to [0, dim + 2] whenever they are used (count > 0)
             r.tt = make_float4(t0_ms, t1_ms, u2f(((uint32_t)(xfwd ? xb : xe) & 0xFFFFu) | ((uint32_t)(yfwd ? yb : ye) << 16)),
                                u2f(path_rule));
+            // Does the NEXT piece of the curve end below its start (cuts left out of order by the MI0:340 slip)? Only
+            // then can its first record differ from its start parameter, and only then does k_piece_fix need this
+            // piece's last parameter: the piece is told to leave it (bit 16). Conservative in the two tag bits.
+            uint32_t next_unordered = 0;
+            if (piece + 1 < n_cuts) {
+                const float next_raw = (piece + 2 == n_cuts) ? 1.f : (piece == 0) ? q1 : (piece == 1) ? q2 : q3;
+                next_unordered = ((f2u(next_raw) & 0xFFFFFFFCu) <= (f2u(t1_ms) | 3u)) ? 1u : 0u;
+            }
             r.m = make_uint4((uint32_t)n_x | ((uint32_t)n_y << 15) | (xfwd ? 0u : 1u << 30) | (yfwd ? 0u : 1u << 31), c,
-                             (uint32_t)pcnt, (type & 0xFFu) | (piece << 8) | ((type > 0xFFu) ? 0x80u : 0u));
+                             (uint32_t)pcnt, (type & 0xFFu) | (piece << 8) | ((type > 0xFFu) ? 0x80u : 0u) | (next_unordered << 16));
             pieces[piece_position(s_dbase, ranks, w, slots[5 * c + piece])] = r;
             pcnt += n_x + n_y + 1;
             t0_ms = t1_ms; p0x = p1x; p0y = p1y;  // MI1:442-443
@@ -254,7 +262,7 @@ __global__ void __launch_bounds__(WALK_THREADS, SLPR_WALK_MIN_BLOCKS) k_walk(con
         CurvePts cp;
         float t0_ms = 0.f, t1_ms = 0.f, x = 0.f, y = 0.f, dx = 2.f, dy = 2.f;
         int n_x = 0, n_y = 0, n_loop = -2, pcnt = 0;
-        uint32_t c = 0, type = T_LINE, piece = 0, pidx = 0, rule_bit = 0;
+        uint32_t c = 0, type = T_LINE, piece = 0, pidx = 0, rule_bit = 0, keep_last = 0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) { cp.x[i] = 0.f; cp.y[i] = 0.f; }
         if (active) {
@@ -269,7 +277,8 @@ __global__ void __launch_bounds__(WALK_THREADS, SLPR_WALK_MIN_BLOCKS) k_walk(con
             dx = (m.x & (1u << 30)) ? -2.f : 2.f; dy = (m.x & (1u << 31)) ? -2.f : 2.f;
             c = m.y; pcnt = (int)m.z;
             type = (m.w & 0x80u) ? 0xFFFFu : (m.w & 0x7Fu);  // types above 0xFF only need to be "other"
-            piece = m.w >> 8;
+            piece = (m.w >> 8) & 0xFFu;
+            keep_last = (m.w >> 16) & 1u;
             n_loop = n_x + n_y + 1;
         }
         __syncwarp();  // every lane has read its record: the stage may be refilled two groups from now
@@ -406,9 +415,15 @@ __global__ void __launch_bounds__(WALK_THREADS, SLPR_WALK_MIN_BLOCKS) k_walk(con
             make_fragment(env, L, pcnt - 1, pidx, rule_bit, prev_t, tcl, prev_x, prev_y, ex, ey, k, v, taps);
             fs.put(pcnt - 1, k, v, key64, val);
             fs.flush(pcnt - 1, key64, val);
-            boundary[5 * c + piece] = make_float2(u2f(first_bits), u2f(last_bits));
-            if (piece > 0 && (first_bits & 0xFFFFFFFCu) != (f2u(t0_ms) & 0xFFFFFFFCu))  // rare: a few dozen per million curves
-                fixlist[atomicAdd(&ctr->n_fix, 1)] = make_uint4(c, piece, (uint32_t)fs.f_first, 0u);
+            // The first / last parameters are only left behind where k_piece_fix can need them: a piece that ends
+            // below its start (every parameter it emits otherwise lies at or above its start: midpoints of a bracket
+            // [t0, t1 >= t0], closed-form line crossings clamped into it) and the piece before such a piece.
+            const bool unordered = piece > 0 && (f2u(t1_ms) & 0xFFFFFFFCu) <= (f2u(t0_ms) | 3u);
+            if (unordered || keep_last) boundary[5 * c + piece] = make_float2(u2f(first_bits), u2f(last_bits));
+            if (piece > 0 && (first_bits & 0xFFFFFFFCu) != (f2u(t0_ms) & 0xFFFFFFFCu)) {  // rare: a few dozen per million curves
+                if (unordered) fixlist[atomicAdd(&ctr->n_fix, 1)] = make_uint4(c, piece, (uint32_t)fs.f_first, 0u);
+                else ctr->fix_missed = 1;  // cannot happen (see above); the host refuses the frame if it does
+            }
         }
     }
 }
