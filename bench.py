@@ -97,8 +97,9 @@ def ncu_traffic(kernel, workload):
     for f in sorted(os.listdir(pdir)) if os.path.isdir(pdir) else []:
         if f.endswith("_traffic.json"):
             d = json.load(open(os.path.join(pdir, f)))
-            if d.get("workload") == workload and kernel in d.get("dram_bytes_per_launch", {}):
-                best = (d["dram_bytes_per_launch"][kernel], f)
+            for k, v in d.get("dram_bytes_per_launch", {}).items():  # "k_spans<1>" is k_spans with the fill fused in
+                if d.get("workload") == workload and (k == kernel or k.startswith(kernel + "<")):
+                    best = (v, f)
     return best
 
 

@@ -54,7 +54,11 @@ enum {
     /* Stage-5 coverage. Default: by frame size (slpr_fill_mode). FUSED_FILL: the span kernel always marks the cells
      * of its draw records itself; SEPARATE_FILL: always a separate pass over the records. Same pixels. */
     SLPR_FLAG_FUSED_FILL = 1u << 5,
-    SLPR_FLAG_SEPARATE_FILL = 1u << 6
+    SLPR_FLAG_SEPARATE_FILL = 1u << 6,
+    /* Order in which the monotone pieces are walked (a scheduling choice, results are identical): by default pieces
+     * are walked longest first, and on scenes of more than two million curves the short ones also window by window
+     * of consecutive curves (less HBM traffic). WINDOWED_WALK forces eight windows on any scene (tests). */
+    SLPR_FLAG_WINDOWED_WALK = 1u << 7
 };
 
 /* Buffers that slpr_debug_copy() can return. Layouts are the reference's:

@@ -125,6 +125,24 @@ def test_synthetic_scene_parity():
     assert_frame_parity(sc, S.identity_rows(), 1024, 768)
 
 
+def test_windowed_walk_order():
+    """The walk's piece order is a scheduling choice (csrc/geom.cuh PieceLayout): windows of consecutive curves
+    (the default on scenes of more than two million curves, forced here) must give the same buffers."""
+    for sc, W, H in ((S.synth_scene(4096, 1024, 768, 6.0, 30.0, seed=0x5CA71E01), 1024, 768),
+                     (util.looping_cubics_scene(), 512, 384), (util.golden_scene("tiger")[0], 640, 480)):
+        rows = S.identity_rows() if sc.name != "tiger" else S.fit_rows(util.golden_scene("tiger")[1], W, H)
+        ref = O.render(sc, rows, W, H)
+        for flags in (V.FLAG_WINDOWED_WALK | V.FLAG_TAPS | V.FLAG_NO_GRAPH, V.FLAG_WINDOWED_WALK):
+            r = render_gpu(sc, rows, W, H, flags)
+            assert r.counts() == {k: ref[k] for k in ("n_fragments", "n_out_frag", "n_span")}
+            if flags & V.FLAG_TAPS:
+                for t in ("intersection", "path", "winding", "sorted_key", "sorted_index", "winding_scan"):
+                    assert np.array_equal(r.tap(t), ref[ORACLE_NAME[t]]), f"tap {t} differs"
+            assert np.array_equal(r.tap("records"), ref["records"])
+            assert np.array_equal(r.readback(), ref["rgba"])
+            r.close()
+
+
 def test_cubics_with_cuts_out_of_order():
     """Hundreds of cubics with four monotonic cuts (MI0:340 leaves the fourth unsorted): pieces that end below
     their start, whose boundary fragments k_piece_fix re-emits from the parameters k_walk leaves for it."""

@@ -134,6 +134,47 @@ __device__ __forceinline__ void load_points(uint32_t type, uint32_t po, const fl
 // of equal length in the same warp: slots[5c+k] = bucket << 26 | rank.
 // ------------------------------------------------------------------------------------------------
 constexpr int WALK_BUCKETS = 64;
+// Pieces are laid out for the walk longest first. On big scenes the short pieces (the bulk) are in addition grouped
+// by window of consecutive curves: first every piece of more than `long_min` records, by length; then window
+// after window, inside a window by length again. A window's pieces — and so its fragments, which neighbour each
+// other in the fragment arrays — are then walked within a few tens of microseconds of each other, so the 32-byte
+// sectors two pieces share are completed in L2 instead of being written to HBM half empty and read back.
+// Measured (profiles/README.md): k_walk's DRAM traffic 666 -> 455 MB per 4K frame with every piece windowed, but
+// the kernel is bound by instruction issue, and groups of long pieces that start with their window instead of
+// with the frame leave a tail: +2..8 % at 1 M curves, -2 % at 4 M curves (where a frame's fragments are 13 x
+// the L2). So the host windows the pieces of up to WALK_LONG records on scenes of more than WALK_WINDOWED_CURVES
+// curves and keeps one global longest-first order (long_min = 0) otherwise.
+constexpr int WALK_MAX_WINDOWS = 64;
+#ifndef SLPR_WALK_WINDOW
+#define SLPR_WALK_WINDOW 131072
+#endif
+constexpr int WALK_WINDOW_CURVES = SLPR_WALK_WINDOW;
+#ifndef SLPR_WALK_LONG
+#define SLPR_WALK_LONG 16
+#endif
+constexpr uint32_t WALK_LONG = SLPR_WALK_LONG;
+#ifndef SLPR_WALK_WINDOWED_CURVES
+#define SLPR_WALK_WINDOWED_CURVES 2000000
+#endif
+constexpr long long WALK_WINDOWED_CURVES = SLPR_WALK_WINDOWED_CURVES;
+constexpr int WALK_VBUCKETS_MAX = (WALK_MAX_WINDOWS + 1) * WALK_BUCKETS;
+struct PieceLayout {
+    uint32_t n_blocks;       // blocks of k_monotonize_count; block b ranks the work items [b * ipb, (b + 1) * ipb)
+    uint32_t n_windows;      // windows of blocks_per_window consecutive blocks
+    uint32_t blocks_per_window;
+    uint32_t long_min;       // pieces of more than this many records are laid out before all windows (0: every piece)
+    __device__ __forceinline__ uint32_t items_per_block(uint32_t n_work) const {
+        return (((n_work + n_blocks - 1) / n_blocks) + 255u) & ~255u;
+    }
+    __device__ __forceinline__ uint32_t n_vbuckets() const { return (n_windows + 1u) * WALK_BUCKETS; }
+    // virtual bucket of (window, length bucket); pieces are laid out in DESCENDING virtual bucket order
+    __device__ __forceinline__ uint32_t vbucket_of_window(uint32_t win, uint32_t bucket) const {
+        return bucket > long_min ? n_windows * WALK_BUCKETS + bucket : (n_windows - 1u - win) * WALK_BUCKETS + bucket;
+    }
+    __device__ __forceinline__ uint32_t vbucket(uint32_t block, uint32_t bucket) const {
+        return vbucket_of_window(block / blocks_per_window, bucket);
+    }
+};
 
 // Band mode: the per-curve kernels (k_monotonize_count, k_piece_emit, k_piece_fix) walk a compacted list of
 // the curves whose path comes near the band instead of all curves — with 8 bands 7 of 8 curves are dead, and
@@ -224,7 +265,7 @@ __global__ void __launch_bounds__(256) k_monotonize_count(const FrameParams *__r
                                                           const int *__restrict__ path_visible,
                                                           float *__restrict__ cut_cache, int *__restrict__ count,
                                                           uint32_t *__restrict__ slots, uint32_t *__restrict__ block_cnt,
-                                                          LiveCurves live) {
+                                                          LiveCurves live, PieceLayout lay) {
     // Pieces are ranked inside (block, length bucket) with shared-memory atomics only; the block's 64 counts
     // go to block_cnt[bucket][block] at the end and k_bucket_scan turns them into positions. (One global
     // atomicAdd per block iteration and bucket on 64 addresses serialised in L2: 0.1 ms at 4 M curves.)
@@ -238,7 +279,9 @@ __global__ void __launch_bounds__(256) k_monotonize_count(const FrameParams *__r
     const float band_lo = (P->band_y0 > 0) ? (float)(P->band_y0 - 1) : -3.0e38f;
     const float band_hi = (P->band_y1 < P->height) ? (float)(P->band_y1 + 1) : 3.0e38f;
     const uint32_t n_work = live.count(n_curves);
-    for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n_work; w += gridDim.x * blockDim.x) {
+    const uint32_t ipb = lay.items_per_block(n_work);  // a contiguous run of work items per block (PieceLayout)
+    const uint32_t w_end = min(n_work, (blockIdx.x + 1u) * ipb);
+    for (uint32_t w = blockIdx.x * ipb + threadIdx.x; w < w_end; w += blockDim.x) {
         const uint32_t c = live.curve(w);
         const uint32_t type = curve_type[c];
         CurvePts cp;
@@ -322,22 +365,27 @@ __global__ void __launch_bounds__(256) k_monotonize_count(const FrameParams *__r
     if (threadIdx.x < WALK_BUCKETS) block_cnt[threadIdx.x * gridDim.x + blockIdx.x] = s_cnt[threadIdx.x];
 }
 
-// block_cnt[bucket][block] -> exclusive prefix over the blocks (in place) and bucket_hist[bucket] = total.
-// One block per bucket; every thread takes BS_ITEMS consecutive entries (n_blocks <= 8 x #SM <= 1024 x BS_ITEMS).
-constexpr int BS_ITEMS = 4;
-__global__ void __launch_bounds__(1024) k_bucket_scan(uint32_t *__restrict__ block_cnt, uint32_t n_blocks,
-                                                      uint32_t *__restrict__ bucket_hist) {
-    __shared__ uint32_t s_w[32];
-    __shared__ uint32_t s_total;
-    uint32_t *row = block_cnt + (size_t)blockIdx.x * n_blocks;
+// block_cnt[bucket][block] -> exclusive prefix over the blocks of the same window — over all blocks for the long
+// buckets — (in place) and vhist[virtual bucket] = number of pieces in it. Grid (WALK_BUCKETS, n_windows).
+__global__ void __launch_bounds__(128) k_bucket_scan(uint32_t *__restrict__ block_cnt, PieceLayout lay, uint32_t *__restrict__ vhist) {
+    __shared__ uint32_t s_w[4];
+    const uint32_t bucket = blockIdx.x, win = blockIdx.y;
+    const bool is_long = bucket > lay.long_min;
+    uint32_t b0 = win * lay.blocks_per_window, b1 = min(lay.n_blocks, b0 + lay.blocks_per_window);
+    if (is_long) {  // one run over all blocks, done by the block of window 0; the per-window slots stay empty
+        if (threadIdx.x == 0) vhist[(lay.n_windows - 1u - win) * WALK_BUCKETS + bucket] = 0u;
+        if (win != 0) return;
+        b0 = 0; b1 = lay.n_blocks;
+    } else if (win == 0 && threadIdx.x == 0) {
+        vhist[lay.n_windows * WALK_BUCKETS + bucket] = 0u;  // the long slot of a short bucket
+    }
+    uint32_t *row = block_cnt + (size_t)bucket * lay.n_blocks;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t carry = 0;
-    for (uint32_t base = 0; base < n_blocks; base += blockDim.x * BS_ITEMS) {  // one trip on every current GPU
-        const uint32_t i0 = base + threadIdx.x * BS_ITEMS;
-        uint32_t v[BS_ITEMS], sum = 0;
-#pragma unroll
-        for (int k = 0; k < BS_ITEMS; ++k) { v[k] = (i0 + k < n_blocks) ? row[i0 + k] : 0u; sum += v[k]; }
-        uint32_t incl = sum;
+    for (uint32_t base = b0; base < b1; base += blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = (i < b1) ? row[i] : 0u;
+        uint32_t incl = v;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
@@ -345,28 +393,17 @@ __global__ void __launch_bounds__(1024) k_bucket_scan(uint32_t *__restrict__ blo
         }
         if (lane == 31) s_w[warp] = incl;
         __syncthreads();
-        if (warp == 0) {
-            const uint32_t w = s_w[lane];
-            uint32_t wi = w;
+        uint32_t before = 0, total = 0;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, wi, d);
-                if ((int)lane >= d) wi += o;
-            }
-            s_w[lane] = wi - w;  // exclusive offset of each warp; lane 31 of warp 0 keeps the total below
-            if (lane == 31) s_total = carry + wi;
+        for (uint32_t k = 0; k < 4; ++k) {
+            if (k < warp) before += s_w[k];
+            total += s_w[k];
         }
-        __syncthreads();
-        uint32_t run = carry + s_w[warp] + incl - sum;
-#pragma unroll
-        for (int k = 0; k < BS_ITEMS; ++k) {
-            if (i0 + k < n_blocks) row[i0 + k] = run;
-            run += v[k];
-        }
-        carry = s_total;
+        if (i < b1) row[i] = carry + before + incl - v;
+        carry += total;
         __syncthreads();
     }
-    if (threadIdx.x == 0) bucket_hist[blockIdx.x] = carry;
+    if (threadIdx.x == 0) vhist[lay.vbucket_of_window(win, bucket)] = carry;
 }
 
 struct FragTaps {

@@ -79,6 +79,8 @@ struct slpr_ctx {
     int *d_pvis = nullptr;
     uint32_t *d_block_cnt = nullptr;  // [WALK_BUCKETS][mono_blocks] pieces per (length bucket, k_monotonize_count block)
     int mono_blocks = 0;
+    uint32_t *d_vhist = nullptr;      // [(windows + 1) * WALK_BUCKETS] pieces per virtual bucket (geom.cuh PieceLayout)
+    PieceLayout lay{};
     uint32_t *d_live = nullptr;  // [nc] band mode: curves whose path comes near the band (k_band_live)
     float4 *d_pobj = nullptr;    // [P] object-space box of each path's control points (static)
     uint32_t *d_pfc = nullptr;   // [P+1] first curve whose path is >= p (static; [P] = n_curves)
@@ -117,7 +119,6 @@ struct slpr_ctx {
     FrameCounters *d_ctr = nullptr;
     int *d_tickets = nullptr;  // 3 scan tickets + RS_MAX_PASSES sort tickets + 1 curve-walk work counter
     uint32_t *d_hist = nullptr;
-    uint32_t *d_bucket_hist = nullptr;  // [WALK_BUCKETS] pieces per length bucket
     unsigned long long *d_status[3] = {nullptr, nullptr, nullptr};
     uint32_t *d_lookback = nullptr;
     int sort_tiles_cap = 0;
@@ -215,13 +216,13 @@ static void free_exchange(slpr_ctx *c) {
 static void free_scene(slpr_ctx *c) {
     free_exchange(c);
     cudaFree(c->d_pos); cudaFree(c->d_pos_path); cudaFree(c->d_cpm); cudaFree(c->d_ctype); cudaFree(c->d_cpath);
-    cudaFree(c->d_frule); cudaFree(c->d_finfo); cudaFree(c->d_tpos); cudaFree(c->d_pvis); cudaFree(c->d_pobj); cudaFree(c->d_pfc); cudaFree(c->d_plive); cudaFree(c->d_live); cudaFree(c->d_block_cnt); cudaFree(c->d_cut);
+    cudaFree(c->d_frule); cudaFree(c->d_finfo); cudaFree(c->d_tpos); cudaFree(c->d_pvis); cudaFree(c->d_pobj); cudaFree(c->d_pfc); cudaFree(c->d_plive); cudaFree(c->d_live); cudaFree(c->d_block_cnt); cudaFree(c->d_vhist); cudaFree(c->d_cut);
     cudaFree(c->d_count); cudaFree(c->d_offset); cudaFree(c->d_seg_tap);
     cudaFree(c->d_big); c->d_big = nullptr;
     cudaFree(c->d_slots); cudaFree(c->d_pieces); cudaFree(c->d_boundary); cudaFree(c->d_fixlist);
     c->d_slots = nullptr; c->d_pieces = nullptr; c->d_boundary = nullptr; c->d_fixlist = nullptr;
     c->d_pos = nullptr; c->d_pos_path = c->d_cpm = c->d_ctype = c->d_cpath = c->d_frule = c->d_finfo = nullptr;
-    c->d_tpos = nullptr; c->d_pvis = nullptr; c->d_pobj = nullptr; c->d_pfc = nullptr; c->d_plive = nullptr; c->d_live = nullptr; c->d_block_cnt = nullptr; c->d_cut = nullptr; c->d_count = c->d_offset = c->d_seg_tap = nullptr;
+    c->d_tpos = nullptr; c->d_pvis = nullptr; c->d_pobj = nullptr; c->d_pfc = nullptr; c->d_plive = nullptr; c->d_live = nullptr; c->d_block_cnt = nullptr; c->d_vhist = nullptr; c->d_cut = nullptr; c->d_count = c->d_offset = c->d_seg_tap = nullptr;
     c->scene_loaded = false;
 }
 
@@ -252,7 +253,6 @@ static int alloc_capacity(slpr_ctx *c, int cap) {
     size_t off = 0;
     const size_t o_ctr = off; off += align_up(sizeof(FrameCounters), 256);
     const size_t o_tick = off; off += align_up((3 + RS_MAX_PASSES + 1) * sizeof(int), 256);
-    const size_t o_bhist = off; off += align_up(WALK_BUCKETS * sizeof(uint32_t), 256);
     const size_t o_hist = off; off += align_up((size_t)RS_MAX_PASSES * RS_BINS * 4, 256);
     size_t o_status[3];
     for (int i = 0; i < 3; ++i) { o_status[i] = off; off += align_up(scan_tiles[i] * 8, 256); }
@@ -263,7 +263,6 @@ static int alloc_capacity(slpr_ctx *c, int cap) {
     c->d_ctr = reinterpret_cast<FrameCounters *>(c->d_temp + o_ctr);
     c->d_tickets = reinterpret_cast<int *>(c->d_temp + o_tick);
     c->d_hist = reinterpret_cast<uint32_t *>(c->d_temp + o_hist);
-    c->d_bucket_hist = reinterpret_cast<uint32_t *>(c->d_temp + o_bhist);
     for (int i = 0; i < 3; ++i) c->d_status[i] = reinterpret_cast<unsigned long long *>(c->d_temp + o_status[i]);
     c->d_lookback = reinterpret_cast<uint32_t *>(c->d_temp + o_lb);
     c->cap = cap;
@@ -409,6 +408,14 @@ extern "C" int slpr_load_scene(slpr_ctx *c, const float *pos_xy, const uint32_t 
     CU(cudaMalloc(&c->d_live, std::max<size_t>(n_curves, 1) * 4));
     c->mono_blocks = (int)std::max<long long>(1, std::min<long long>(((long long)n_curves + 255) / 256, (long long)c->num_sms * 8));
     CU(cudaMalloc(&c->d_block_cnt, (size_t)WALK_BUCKETS * c->mono_blocks * 4));
+    c->lay.n_blocks = (uint32_t)c->mono_blocks;
+    c->lay.n_windows = (uint32_t)std::max<long long>(1, std::min<long long>(((long long)n_curves + WALK_WINDOW_CURVES - 1) / WALK_WINDOW_CURVES,
+                                                                               std::min<long long>(WALK_MAX_WINDOWS, c->mono_blocks)));
+    c->lay.long_min = WALK_LONG;
+    if (c->flags & SLPR_FLAG_WINDOWED_WALK) c->lay.n_windows = (uint32_t)std::min(8, c->mono_blocks);
+    else if ((long long)n_curves <= WALK_WINDOWED_CURVES) { c->lay.n_windows = 1; c->lay.long_min = 0; }  // one longest-first order
+    c->lay.blocks_per_window = (c->lay.n_blocks + c->lay.n_windows - 1) / c->lay.n_windows;
+    CU(cudaMalloc(&c->d_vhist, (size_t)WALK_VBUCKETS_MAX * 4));
     CU(cudaMalloc(&c->d_cut, std::max<size_t>(n_curves, 1) * 5 * 4));
     CU(cudaMalloc(&c->d_count, ((size_t)n_curves + 4) * 4));
     CU(cudaMalloc(&c->d_offset, ((size_t)n_curves + 4) * 4));
@@ -487,8 +494,8 @@ static int enqueue_count_phase(slpr_ctx *c, cudaStream_t s, bool timed, int &lau
     }
     k_monotonize_count<<<c->mono_blocks, 256, 0, s>>>(c->d_params, c->nc, c->d_ctype, c->d_cpm, c->d_cpath,
                                                                    c->d_tpos, c->d_pvis, c->d_cut, c->d_count, c->d_slots,
-                                                                   c->d_block_cnt, live);
-    k_bucket_scan<<<WALK_BUCKETS, 1024, 0, s>>>(c->d_block_cnt, (uint32_t)c->mono_blocks, c->d_bucket_hist);
+                                                                   c->d_block_cnt, live, c->lay);
+    k_bucket_scan<<<dim3(WALK_BUCKETS, c->lay.n_windows), 128, 0, s>>>(c->d_block_cnt, c->lay, c->d_vhist);
     launches += 2;
     if (timed) CU(cudaEventRecord(c->ev[2], s));
     ScanI32Op op1{c->d_count, c->d_offset, (long long)c->nc, &c->d_ctr->n_fragments, c->cap, &c->d_ctr->overflow};
@@ -506,12 +513,12 @@ static int enqueue_fragments(slpr_ctx *c, cudaStream_t s, bool timed, int &launc
     if (rc) return rc;
     FragTaps ft{c->t_key32, c->t_path, c->t_wind};
     k_piece_emit<<<grid_for(c, c->nc, 256, 8), 256, 0, s>>>(c->d_params, c->nc, c->d_ctype, c->d_cpm, c->d_cpath, c->d_frule, c->d_tpos, c->d_cut,
-                                                             c->d_offset, c->d_slots, c->d_ctr, c->cap, c->d_bucket_hist,
-                                                             PieceRanks{c->d_block_cnt, (uint32_t)c->mono_blocks},
+                                                             c->d_offset, c->d_slots, c->d_ctr, c->cap,
+                                                             PieceRanks{c->d_block_cnt, c->d_vhist, c->lay},
                                                              LiveCurves{c->hp.cull ? c->d_live : nullptr, c->d_ctr}, c->d_pieces);
     if (timed) CU(cudaEventRecord(c->ev[4], s));
     k_walk<<<c->num_sms * std::max(1, c->walk_blocks_per_sm), WALK_THREADS, 0, s>>>(
-        c->d_params, c->d_pieces, c->d_ctr, c->cap, WalkTemp{c->d_bucket_hist, c->d_tickets + 3 + RS_MAX_PASSES},
+        c->d_params, c->d_pieces, c->d_ctr, c->cap, WalkTemp{c->d_tickets + 3 + RS_MAX_PASSES},
         c->L, c->d_key[0], c->d_val[0], ft, c->d_inter, c->d_boundary, c->d_fixlist);
     k_piece_fix<<<8, 256, 0, s>>>(c->d_params, c->d_ctype, c->d_cpm, c->d_cpath, c->d_frule, c->d_tpos, c->d_ctr, c->cap, c->d_boundary,
                                   c->d_fixlist, c->L, c->d_key[0], c->d_val[0], ft);

@@ -32,40 +32,52 @@ struct __align__(16) PieceRec {
 };
 
 struct WalkTemp {
-    const uint32_t *bucket_hist;  // [WALK_BUCKETS] pieces per length bucket (from k_monotonize_count)
     int *group_counter;           // zeroed per frame
 };
 
-// Where the pieces were ranked: k_monotonize_count's launch shape (256 threads per block, grid-stride) and
-// the exclusive per-(bucket, block) prefix from k_bucket_scan.
+// Where the pieces were ranked: k_monotonize_count's launch shape (PieceLayout) and the exclusive per-(bucket,
+// block) prefix inside the block's window from k_bucket_scan.
 struct PieceRanks {
     const uint32_t *block_base;  // [WALK_BUCKETS][n_blocks]
-    uint32_t n_blocks;
+    const uint32_t *vhist;       // [(n_windows + 1) * WALK_BUCKETS] pieces per virtual bucket (PieceLayout)
+    PieceLayout lay;
 };
 
-// position of a piece in the length-sorted piece array (longest bucket first): bucket start + pieces of
-// the same bucket ranked by earlier blocks + rank inside its block
-__device__ __forceinline__ uint32_t piece_position(const uint32_t *s_dbase, const PieceRanks &pr, uint32_t work_item, uint32_t slot) {
-    const uint32_t bucket = slot >> 26, blk = (work_item >> 8) % pr.n_blocks;  // the block that ranked work item w (LiveCurves)
-    return s_dbase[bucket] + pr.block_base[bucket * pr.n_blocks + blk] + (slot & 0x03FFFFFFu);
+// position of a piece in the piece array (descending virtual bucket, PieceLayout): start of its virtual bucket +
+// pieces of the same bucket ranked by earlier blocks (of its window, if short) + rank inside its block
+__device__ __forceinline__ uint32_t piece_position(const uint32_t *s_vbase, const PieceRanks &pr, uint32_t block, uint32_t slot) {
+    const uint32_t bucket = slot >> 26;
+    return s_vbase[pr.lay.vbucket(block, bucket)] + pr.block_base[bucket * pr.lay.n_blocks + block] + (slot & 0x03FFFFFFu);
 }
 
-__device__ __forceinline__ void bucket_bases(const uint32_t *__restrict__ hist, uint32_t *s_dbase, uint32_t *s_total) {
-    // descending exclusive scan of the 64 bucket counts, by one warp
-    if (threadIdx.x < 32) {
-        const uint32_t l = threadIdx.x;
-        const uint32_t hi = hist[WALK_BUCKETS - 1 - l], lo = hist[WALK_BUCKETS - 1 - (l + 32)];  // reversed order
-        uint32_t a = hi, b = lo;
+// descending exclusive scan of the (at most WALK_VBUCKETS_MAX) virtual bucket counts by one block of 256 threads
+__device__ __forceinline__ void vbucket_bases(const PieceRanks &pr, uint32_t *s_vbase, uint32_t *s_total) {
+    __shared__ uint32_t s_part[8];
+    const uint32_t nv = pr.lay.n_vbuckets();                   // a multiple of 64
+    const uint32_t per = (nv + 255u) / 256u;                   // consecutive entries (in descending order) per thread
+    const uint32_t first = threadIdx.x * per;                  // rank of this thread's first entry, 0 = highest index
+    uint32_t sum = 0;
+    for (uint32_t k = 0; k < per; ++k)
+        if (first + k < nv) sum += pr.vhist[nv - 1u - (first + k)];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = sum;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t oa = __shfl_up_sync(0xFFFFFFFFu, a, d), ob = __shfl_up_sync(0xFFFFFFFFu, b, d);
-            if ((int)l >= d) { a += oa; b += ob; }
-        }
-        const uint32_t first_half = __shfl_sync(0xFFFFFFFFu, a, 31);
-        s_dbase[WALK_BUCKETS - 1 - l] = a - hi;
-        s_dbase[WALK_BUCKETS - 1 - (l + 32)] = first_half + b - lo;
-        if (l == 31) *s_total = first_half + b;
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if ((int)lane >= d) incl += o;
     }
+    if (lane == 31) s_part[warp] = incl;
+    __syncthreads();
+    uint32_t run = incl - sum;
+    for (uint32_t k = 0; k < warp; ++k) run += s_part[k];
+    for (uint32_t k = 0; k < per; ++k) {
+        if (first + k < nv) {
+            const uint32_t idx = nv - 1u - (first + k);
+            s_vbase[idx] = run;
+            run += pr.vhist[idx];
+        }
+    }
+    if (threadIdx.x == 255) *s_total = run;
     __syncthreads();
 }
 
@@ -80,16 +92,16 @@ __global__ void __launch_bounds__(256, SLPR_PE_MIN_BLOCKS) k_piece_emit(const Fr
                                                     const uint32_t *__restrict__ fill_rule,
                                                     const float2 *__restrict__ tpos, const float *__restrict__ cut_cache,
                                                     const int *__restrict__ offsets, const uint32_t *__restrict__ slots,
-                                                    FrameCounters *__restrict__ ctr, int capacity,
-                                                    const uint32_t *__restrict__ bucket_hist, PieceRanks ranks,
+                                                    FrameCounters *__restrict__ ctr, int capacity, PieceRanks ranks,
                                                     LiveCurves live, PieceRec *__restrict__ pieces) {
-    __shared__ uint32_t s_dbase[WALK_BUCKETS];
+    __shared__ uint32_t s_vbase[WALK_VBUCKETS_MAX];
     __shared__ uint32_t s_total;
     if (ctr->n_fragments > capacity) return;
-    bucket_bases(bucket_hist, s_dbase, &s_total);
+    vbucket_bases(ranks, s_vbase, &s_total);
     if (blockIdx.x == 0 && threadIdx.x == 0) ctr->n_pieces = (int)s_total;
     const int width = P->width, height = P->height;
     const uint32_t n_work = live.count(n_curves);
+    const uint32_t ipb = ranks.lay.items_per_block(n_work);
     for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n_work; w += gridDim.x * blockDim.x) {
         const uint32_t c = live.curve(w);
         int pcnt = offsets[c];
@@ -135,7 +147,7 @@ __global__ void __launch_bounds__(256, SLPR_PE_MIN_BLOCKS) k_piece_emit(const Fr
             }
             r.m = make_uint4((uint32_t)n_x | ((uint32_t)n_y << 15) | (xfwd ? 0u : 1u << 30) | (yfwd ? 0u : 1u << 31), c,
                              (uint32_t)pcnt, (type & 0xFFu) | (piece << 8) | ((type > 0xFFu) ? 0x80u : 0u) | (next_unordered << 16));
-            pieces[piece_position(s_dbase, ranks, w, slots[5 * c + piece])] = r;
+            pieces[piece_position(s_vbase, ranks, w / ipb, slots[5 * c + piece])] = r;
             pcnt += n_x + n_y + 1;
             t0_ms = t1_ms; p0x = p1x; p0y = p1y;  // MI1:442-443
         }
@@ -220,11 +232,7 @@ __global__ void __launch_bounds__(WALK_THREADS, SLPR_WALK_MIN_BLOCKS) k_walk(con
     const uint32_t lane = lane_id();
     const uint32_t warp = threadIdx.x >> 5;
     __shared__ uint4 s_stage[WALK_THREADS / 32][2][128];  // per warp: two groups of 32 records (2 KB each)
-    uint32_t n_pieces = 0;
-    {
-        const uint32_t h = tmp.bucket_hist[lane] + tmp.bucket_hist[lane + 32];
-        n_pieces = __reduce_add_sync(0xFFFFFFFFu, h);
-    }
+    const uint32_t n_pieces = (uint32_t)ctr->n_pieces;  // k_piece_emit
     const FragEnv env = load_frag_env(P);
     const uint32_t n_chunks = n_pieces * 4u;  // 16-byte chunks in the record array
     // group g's records -> stage st, one commit group per call (empty past the end)
