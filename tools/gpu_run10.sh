@@ -1,0 +1,13 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
+mkdir -p gpurun_out
+echo "=== pytest gpu"; timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -4
+echo "=== stages main"; timeout 300 python tools/prof_frame.py synth_1m_4k 6 2>&1 | tail -1 | cut -c100-
+for wl in synth_1m_4k synth_16k; do timeout 120 python tools/lat_frame.py $wl 30 2>&1 | tail -1; done
+for v in $(ls vkscanlinepr_b200/variants | sed "s/libslpr_//;s/.so//"); do
+  export SLPR_LIB=$PWD/vkscanlinepr_b200/variants/libslpr_$v.so
+  echo "=== variant $v"
+  timeout 120 python tools/prof_frame.py synth_1m_4k 6 2>&1 | tail -1 | cut -c100-
+  for wl in synth_1m_4k synth_16k; do timeout 120 python tools/lat_frame.py $wl 30 2>&1 | tail -1; done
+done
+unset SLPR_LIB

@@ -138,12 +138,13 @@ struct SegIdxBits {
 // inside the path — half the shuffle traffic of the 64-bit network. A path covers a small part of the
 // frame, so the relative row|x almost always fits in 32 - log2(32 R) bits at any resolution; when it
 // does not (warp-uniform test) the 64-bit network sorts the segment instead. A fragment's index is its
-// position, so (row|x, position) is the reference's (key, index) order; the value word is fetched
-// again (an L1 hit) from the position the sorted word names.
+// position, so (row|x, position) is the reference's (key, index) order. The value words are loaded together
+// with the keys (one exposure to HBM latency per path instead of two: the kernel waits on loads half of its
+// time) and parked in the warp's slice of shared memory, from where the sorted positions pick them.
 template <int R>
 __device__ __forceinline__ bool warp_sort_segment32(const uint64_t *__restrict__ key_in, const uint32_t *__restrict__ val_in,
                                                     uint64_t *__restrict__ key_out, uint32_t *__restrict__ val_out, int b, int n,
-                                                    int yx_bits, int lane) {
+                                                    int yx_bits, int lane, uint32_t *__restrict__ s_val) {
     constexpr int IB = SegIdxBits<R>::value;
     static_assert(R == 1 || R == 2 || R == 4 || R == 8 || R == 16, "R must be 1, 2, 4, 8 or 16");
     const uint64_t mask = (1ull << yx_bits) - 1;
@@ -156,6 +157,7 @@ __device__ __forceinline__ bool warp_sort_segment32(const uint64_t *__restrict__
         e[r] = 0u;
         if (j < n) {
             const uint64_t k = key_in[b + j];
+            s_val[j] = val_in[b + j];
             path_bits = k & ~mask;
             e[r] = (uint32_t)(k & mask);
             mn = min(mn, e[r]);
@@ -163,7 +165,7 @@ __device__ __forceinline__ bool warp_sort_segment32(const uint64_t *__restrict__
         }
     }
     mn = __reduce_min_sync(0xFFFFFFFFu, mn);
-    mx = __reduce_max_sync(0xFFFFFFFFu, mx);
+    mx = __reduce_max_sync(0xFFFFFFFFu, mx);  // (also orders the s_val stores before the reads below)
     if (((mx - mn) >> (32 - IB)) != 0u) {  // the path spans too much of the frame for a 32-bit word
         if constexpr (R > 8) return false;  // 32 registers of 64-bit words: left to the block kernel
         else {
@@ -178,14 +180,16 @@ __device__ __forceinline__ bool warp_sort_segment32(const uint64_t *__restrict__
         e[r] = (j < n) ? (((e[r] - mn) << IB) | (uint32_t)j) : 0xFFFFFFFFu;
     }
     warp_bitonic<R, uint32_t>(e, lane);
+    __syncwarp();
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const int j = r * 32 + lane;
         if (j < n) {
             key_out[b + j] = path_bits | (uint64_t)(mn + (e[r] >> IB));
-            val_out[b + j] = val_in[b + (e[r] & ((1u << IB) - 1))];
+            val_out[b + j] = s_val[e[r] & ((1u << IB) - 1)];
         }
     }
+    __syncwarp();  // the slice is rewritten by the warp's next path
     return true;
 }
 
@@ -227,8 +231,10 @@ __global__ void __launch_bounds__(256) k_segsort_warp(const int *__restrict__ se
                                                       uint64_t *__restrict__ key_out, uint32_t *__restrict__ val_out,
                                                       FrameCounters *__restrict__ ctr, int capacity, int yx_bits,
                                                       int *__restrict__ big_list) {
+    __shared__ uint32_t s_vals[256 / 32][SEG_WARP_MAX];  // values of the path a warp is sorting
     if (ctr->n_fragments > capacity) return;
     const int lane = threadIdx.x & 31;
+    uint32_t *const s_val = s_vals[threadIdx.x >> 5];
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
     const uint32_t n_chunks = (n_paths + SEG_CHUNK - 1) / SEG_CHUNK;
     for (uint32_t ch = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ch < n_chunks; ch += warps) {
@@ -243,11 +249,11 @@ __global__ void __launch_bounds__(256) k_segsort_warp(const int *__restrict__ se
             bool done = true;
             if (n == 1) {
                 if (lane == 0) { key_out[b] = key_in[b]; val_out[b] = val_in[b]; }
-            } else if (n <= 32) warp_sort_segment32<1>(key_in, val_in, key_out, val_out, b, n, yx_bits, lane);
-            else if (n <= 64) warp_sort_segment32<2>(key_in, val_in, key_out, val_out, b, n, yx_bits, lane);
-            else if (n <= 128) warp_sort_segment32<4>(key_in, val_in, key_out, val_out, b, n, yx_bits, lane);
-            else if (n <= 256) done = warp_sort_segment32<8>(key_in, val_in, key_out, val_out, b, n, yx_bits, lane);
-            else if (n <= SEG_WARP_MAX) done = warp_sort_segment32<16>(key_in, val_in, key_out, val_out, b, n, yx_bits, lane);
+            } else if (n <= 32) warp_sort_segment32<1>(key_in, val_in, key_out, val_out, b, n, yx_bits, lane, s_val);
+            else if (n <= 64) warp_sort_segment32<2>(key_in, val_in, key_out, val_out, b, n, yx_bits, lane, s_val);
+            else if (n <= 128) warp_sort_segment32<4>(key_in, val_in, key_out, val_out, b, n, yx_bits, lane, s_val);
+            else if (n <= 256) done = warp_sort_segment32<8>(key_in, val_in, key_out, val_out, b, n, yx_bits, lane, s_val);
+            else if (n <= SEG_WARP_MAX) done = warp_sort_segment32<16>(key_in, val_in, key_out, val_out, b, n, yx_bits, lane, s_val);
             else done = false;
             if (!done && lane == 0) {
                 if (n > SEG_BLOCK_MAX) ctr->sort_fallback = 1;  // the host re-renders with the radix sort

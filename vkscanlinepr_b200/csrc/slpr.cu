@@ -512,7 +512,7 @@ static int enqueue_fragments(slpr_ctx *c, cudaStream_t s, bool timed, int &launc
     int rc = enqueue_count_phase(c, s, timed, launches);
     if (rc) return rc;
     FragTaps ft{c->t_key32, c->t_path, c->t_wind};
-    k_piece_emit<<<grid_for(c, c->nc, 256, 8), 256, 0, s>>>(c->d_params, c->nc, c->d_ctype, c->d_cpm, c->d_cpath, c->d_frule, c->d_tpos, c->d_cut,
+    k_piece_emit<<<c->mono_blocks, 256, 0, s>>>(c->d_params, c->nc, c->d_ctype, c->d_cpm, c->d_cpath, c->d_frule, c->d_tpos, c->d_cut,
                                                              c->d_offset, c->d_slots, c->d_ctr, c->cap,
                                                              PieceRanks{c->d_block_cnt, c->d_vhist, c->lay},
                                                              LiveCurves{c->hp.cull ? c->d_live : nullptr, c->d_ctr}, c->d_pieces);

@@ -43,13 +43,6 @@ struct PieceRanks {
     PieceLayout lay;
 };
 
-// position of a piece in the piece array (descending virtual bucket, PieceLayout): start of its virtual bucket +
-// pieces of the same bucket ranked by earlier blocks (of its window, if short) + rank inside its block
-__device__ __forceinline__ uint32_t piece_position(const uint32_t *s_vbase, const PieceRanks &pr, uint32_t block, uint32_t slot) {
-    const uint32_t bucket = slot >> 26;
-    return s_vbase[pr.lay.vbucket(block, bucket)] + pr.block_base[bucket * pr.lay.n_blocks + block] + (slot & 0x03FFFFFFu);
-}
-
 // descending exclusive scan of the (at most WALK_VBUCKETS_MAX) virtual bucket counts by one block of 256 threads
 __device__ __forceinline__ void vbucket_bases(const PieceRanks &pr, uint32_t *s_vbase, uint32_t *s_total) {
     __shared__ uint32_t s_part[8];
@@ -95,17 +88,28 @@ __global__ void __launch_bounds__(256, SLPR_PE_MIN_BLOCKS) k_piece_emit(const Fr
                                                     FrameCounters *__restrict__ ctr, int capacity, PieceRanks ranks,
                                                     LiveCurves live, PieceRec *__restrict__ pieces) {
     __shared__ uint32_t s_vbase[WALK_VBUCKETS_MAX];
+    __shared__ uint32_t s_pos[WALK_BUCKETS];
     __shared__ uint32_t s_total;
     if (ctr->n_fragments > capacity) return;
     vbucket_bases(ranks, s_vbase, &s_total);
     if (blockIdx.x == 0 && threadIdx.x == 0) ctr->n_pieces = (int)s_total;
+    // This block walks the work items the block of the same index ranked in k_monotonize_count (same launch
+    // shape), so one 64-entry table — where this block's pieces of every length start — places all its pieces
+    // without a global look-up per piece.
+    if (threadIdx.x < WALK_BUCKETS)
+        s_pos[threadIdx.x] = s_vbase[ranks.lay.vbucket(blockIdx.x, threadIdx.x)] + ranks.block_base[threadIdx.x * ranks.lay.n_blocks + blockIdx.x];
+    __syncthreads();
     const int width = P->width, height = P->height;
     const uint32_t n_work = live.count(n_curves);
     const uint32_t ipb = ranks.lay.items_per_block(n_work);
-    for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n_work; w += gridDim.x * blockDim.x) {
+    const uint32_t w_end = min(n_work, (blockIdx.x + 1u) * ipb);
+    for (uint32_t w = blockIdx.x * ipb + threadIdx.x; w < w_end; w += blockDim.x) {
         const uint32_t c = live.curve(w);
         int pcnt = offsets[c];
         if (offsets[c + 1] == pcnt) continue;  // invisible or band-culled
+        uint32_t slot[5];  // all five up front (those past the curve's last piece are never used)
+#pragma unroll
+        for (int k = 0; k < 5; ++k) slot[k] = slots[5 * c + k];
         const uint32_t type = curve_type[c];
         const uint32_t pidx = curve_path[c];
         // MARK:82 only distinguishes rule 1 (even-odd) from the rest
@@ -147,7 +151,8 @@ __global__ void __launch_bounds__(256, SLPR_PE_MIN_BLOCKS) k_piece_emit(const Fr
             }
             r.m = make_uint4((uint32_t)n_x | ((uint32_t)n_y << 15) | (xfwd ? 0u : 1u << 30) | (yfwd ? 0u : 1u << 31), c,
                              (uint32_t)pcnt, (type & 0xFFu) | (piece << 8) | ((type > 0xFFu) ? 0x80u : 0u) | (next_unordered << 16));
-            pieces[piece_position(s_vbase, ranks, w / ipb, slots[5 * c + piece])] = r;
+            const uint32_t sl = (piece == 0) ? slot[0] : (piece == 1) ? slot[1] : (piece == 2) ? slot[2] : (piece == 3) ? slot[3] : slot[4];
+            pieces[s_pos[sl >> 26] + (sl & 0x03FFFFFFu)] = r;
             pcnt += n_x + n_y + 1;
             t0_ms = t1_ms; p0x = p1x; p0y = p1y;  // MI1:442-443
         }
