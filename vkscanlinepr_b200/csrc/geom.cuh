@@ -164,7 +164,7 @@ struct PieceLayout {
     uint32_t blocks_per_window;
     uint32_t long_min;       // pieces of more than this many records are laid out before all windows (0: every piece)
     __device__ __forceinline__ uint32_t items_per_block(uint32_t n_work) const {
-        return (((n_work + n_blocks - 1) / n_blocks) + 255u) & ~255u;
+        return (((n_work + n_blocks - 1) / n_blocks) + 31u) & ~31u;  // whole warps; every block gets work
     }
     __device__ __forceinline__ uint32_t n_vbuckets() const { return (n_windows + 1u) * WALK_BUCKETS; }
     // virtual bucket of (window, length bucket); pieces are laid out in DESCENDING virtual bucket order
@@ -366,9 +366,11 @@ __global__ void __launch_bounds__(256) k_monotonize_count(const FrameParams *__r
 }
 
 // block_cnt[bucket][block] -> exclusive prefix over the blocks of the same window — over all blocks for the long
-// buckets — (in place) and vhist[virtual bucket] = number of pieces in it. Grid (WALK_BUCKETS, n_windows).
-__global__ void __launch_bounds__(128) k_bucket_scan(uint32_t *__restrict__ block_cnt, PieceLayout lay, uint32_t *__restrict__ vhist) {
-    __shared__ uint32_t s_w[4];
+// buckets — (in place) and vhist[virtual bucket] = number of pieces in it. Grid (WALK_BUCKETS, n_windows), 128 or
+// 1024 threads.
+__global__ void __launch_bounds__(1024) k_bucket_scan(uint32_t *__restrict__ block_cnt, PieceLayout lay, uint32_t *__restrict__ vhist) {
+    __shared__ uint32_t s_w[32];
+    const uint32_t n_warps = blockDim.x >> 5;  // 4 with many windows, 32 when one run covers every block
     const uint32_t bucket = blockIdx.x, win = blockIdx.y;
     const bool is_long = bucket > lay.long_min;
     uint32_t b0 = win * lay.blocks_per_window, b1 = min(lay.n_blocks, b0 + lay.blocks_per_window);
@@ -394,8 +396,7 @@ __global__ void __launch_bounds__(128) k_bucket_scan(uint32_t *__restrict__ bloc
         if (lane == 31) s_w[warp] = incl;
         __syncthreads();
         uint32_t before = 0, total = 0;
-#pragma unroll
-        for (uint32_t k = 0; k < 4; ++k) {
+        for (uint32_t k = 0; k < n_warps; ++k) {
             if (k < warp) before += s_w[k];
             total += s_w[k];
         }

@@ -495,7 +495,7 @@ static int enqueue_count_phase(slpr_ctx *c, cudaStream_t s, bool timed, int &lau
     k_monotonize_count<<<c->mono_blocks, 256, 0, s>>>(c->d_params, c->nc, c->d_ctype, c->d_cpm, c->d_cpath,
                                                                    c->d_tpos, c->d_pvis, c->d_cut, c->d_count, c->d_slots,
                                                                    c->d_block_cnt, live, c->lay);
-    k_bucket_scan<<<dim3(WALK_BUCKETS, c->lay.n_windows), 128, 0, s>>>(c->d_block_cnt, c->lay, c->d_vhist);
+    k_bucket_scan<<<dim3(WALK_BUCKETS, c->lay.n_windows), c->lay.blocks_per_window > 256 ? 1024 : 128, 0, s>>>(c->d_block_cnt, c->lay, c->d_vhist);
     launches += 2;
     if (timed) CU(cudaEventRecord(c->ev[2], s));
     ScanI32Op op1{c->d_count, c->d_offset, (long long)c->nc, &c->d_ctr->n_fragments, c->cap, &c->d_ctr->overflow};
