@@ -234,6 +234,20 @@ def test_row_bands_equal_full_frame():
             assert r.counts()["n_fragments"] <= ref["n_fragments"]
             r.close()
         assert np.array_equal(full, ref["rgba"]), f"G={G}"
+    # the same scene with its points stored curve by curve in reverse order: points are no longer grouped by path, so
+    # band mode falls back from the per-path pass (k_band_paths) to the per-point / per-curve passes
+    order = np.concatenate([np.arange(m, m + (t & 7)) for m, t in zip(sc.curve_pos_map[::-1], sc.curve_type[::-1])])
+    new_map = np.zeros(sc.n_curves, np.uint32)
+    new_map[::-1] = np.concatenate([[0], np.cumsum((sc.curve_type[::-1] & 7))[:-1]]).astype(np.uint32)
+    shuffled = S.Scene(sc.pos[order], sc.pos_path[order], new_map, sc.curve_type, sc.curve_path, sc.fill_rule, sc.fill_info, "shuffled")
+    assert (np.diff(shuffled.pos_path.astype(np.int64)) < 0).any()
+    for g in range(4):
+        y0, y1 = g * H // 4, (g + 1) * H // 4
+        r = V.ScanlineRasterizer(0, 0).initialize(None, W, H)
+        r.loadVG(shuffled); r.setMVP(rows); r.set_band(y0, y1); r.render()
+        full[H - y1:H - y0] = r.readback()[H - y1:H - y0]
+        r.close()
+    assert np.array_equal(full, ref["rgba"]), "points not grouped by path"
 
 
 def test_exact_row_bands_with_exchange():

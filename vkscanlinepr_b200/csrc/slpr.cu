@@ -84,6 +84,7 @@ struct slpr_ctx {
     uint32_t *d_live = nullptr;  // [nc] band mode: curves whose path comes near the band (k_band_live)
     float4 *d_pobj = nullptr;    // [P] object-space box of each path's control points (static)
     uint32_t *d_pfc = nullptr;   // [P+1] first curve whose path is >= p (static; [P] = n_curves)
+    uint32_t *d_pfp = nullptr;   // [P+1] first point whose path is >= p, when the points are grouped by path (else null)
     uint8_t *d_plive = nullptr;  // [P] band mode: the path can reach the band (k_path_cull)
     float *d_cut = nullptr;
     int *d_count = nullptr, *d_offset = nullptr, *d_seg_tap = nullptr;  // d_seg_tap: [P+1] sort segment table (always built)
@@ -216,13 +217,13 @@ static void free_exchange(slpr_ctx *c) {
 static void free_scene(slpr_ctx *c) {
     free_exchange(c);
     cudaFree(c->d_pos); cudaFree(c->d_pos_path); cudaFree(c->d_cpm); cudaFree(c->d_ctype); cudaFree(c->d_cpath);
-    cudaFree(c->d_frule); cudaFree(c->d_finfo); cudaFree(c->d_tpos); cudaFree(c->d_pvis); cudaFree(c->d_pobj); cudaFree(c->d_pfc); cudaFree(c->d_plive); cudaFree(c->d_live); cudaFree(c->d_block_cnt); cudaFree(c->d_vhist); cudaFree(c->d_cut);
+    cudaFree(c->d_frule); cudaFree(c->d_finfo); cudaFree(c->d_tpos); cudaFree(c->d_pvis); cudaFree(c->d_pobj); cudaFree(c->d_pfc); cudaFree(c->d_pfp); cudaFree(c->d_plive); cudaFree(c->d_live); cudaFree(c->d_block_cnt); cudaFree(c->d_vhist); cudaFree(c->d_cut);
     cudaFree(c->d_count); cudaFree(c->d_offset); cudaFree(c->d_seg_tap);
     cudaFree(c->d_big); c->d_big = nullptr;
     cudaFree(c->d_slots); cudaFree(c->d_pieces); cudaFree(c->d_boundary); cudaFree(c->d_fixlist);
     c->d_slots = nullptr; c->d_pieces = nullptr; c->d_boundary = nullptr; c->d_fixlist = nullptr;
     c->d_pos = nullptr; c->d_pos_path = c->d_cpm = c->d_ctype = c->d_cpath = c->d_frule = c->d_finfo = nullptr;
-    c->d_tpos = nullptr; c->d_pvis = nullptr; c->d_pobj = nullptr; c->d_pfc = nullptr; c->d_plive = nullptr; c->d_live = nullptr; c->d_block_cnt = nullptr; c->d_vhist = nullptr; c->d_cut = nullptr; c->d_count = c->d_offset = c->d_seg_tap = nullptr;
+    c->d_tpos = nullptr; c->d_pvis = nullptr; c->d_pobj = nullptr; c->d_pfc = nullptr; c->d_pfp = nullptr; c->d_plive = nullptr; c->d_live = nullptr; c->d_block_cnt = nullptr; c->d_vhist = nullptr; c->d_cut = nullptr; c->d_count = c->d_offset = c->d_seg_tap = nullptr;
     c->scene_loaded = false;
 }
 
@@ -401,6 +402,19 @@ extern "C" int slpr_load_scene(slpr_ctx *c, const float *pos_xy, const uint32_t 
             pfc[p] = cur;
         }
         if ((rc = upload(&c->d_pfc, pfc.data(), pfc.size()))) return rc;
+        // and, when the points are grouped by path (loadVG's flattening always does), its first point: band mode then
+        // only touches the paths that reach the band (k_band_paths)
+        bool grouped = true;
+        for (uint32_t i = 1; i < n_points && grouped; ++i) grouped = pos_path[i] >= pos_path[i - 1];
+        if (grouped) {
+            std::vector<uint32_t> pfp((size_t)n_paths + 1);
+            uint32_t pt = 0;
+            for (uint32_t p = 0; p <= n_paths; ++p) {
+                while (pt < n_points && pos_path[pt] < p) ++pt;
+                pfp[p] = pt;
+            }
+            if ((rc = upload(&c->d_pfp, pfp.data(), pfp.size()))) return rc;
+        }
         CU(cudaMalloc(&c->d_pobj, box.size() * sizeof(float4)));
         CU(cudaMemcpy(c->d_pobj, box.data(), box.size() * sizeof(float4), cudaMemcpyHostToDevice));
         CU(cudaMalloc(&c->d_plive, std::max<size_t>(n_paths, 1)));
@@ -477,20 +491,30 @@ static int enqueue_count_phase(slpr_ctx *c, cudaStream_t s, bool timed, int &lau
     CU(cudaMemsetAsync(c->d_temp, 0, c->temp_bytes, s));
     CU(cudaMemsetAsync(c->d_pvis, 0, std::max<size_t>(c->P, 1) * 4, s));
     if (timed) CU(cudaEventRecord(c->ev[0], s));
-    const uint8_t *plive = c->hp.cull ? c->d_plive : nullptr;
-    if (plive) {
-        k_path_cull<<<grid_for(c, c->P, 256, 8), 256, 0, s>>>(c->d_params, c->P, c->d_pobj, c->d_plive);
-        ++launches;
-    }
-    k_transform<<<grid_for(c, c->np, 256, 8), 256, 0, s>>>(c->d_params, c->np, c->d_pos, c->d_pos_path, c->d_tpos, c->d_pvis, plive);
-    ++launches;
-    if (timed) CU(cudaEventRecord(c->ev[1], s));
+    const bool band = c->hp.cull != 0;
     LiveCurves live{nullptr, c->d_ctr};
-    if (plive) {
-        k_band_live<<<grid_for(c, ((long long)c->nc + LIVE_CHUNK - 1) / LIVE_CHUNK, 256, 8), 256, 0, s>>>(c->nc, c->d_cpath, plive, c->d_count,
-                                                                                                     c->d_live, c->d_ctr);
+    if (band && c->d_pfp) {  // one pass over the paths: cull, transform the live ones, list their curves
+        CU(cudaMemsetAsync(c->d_count, 0, (size_t)c->nc * 4, s));  // k_monotonize_count only writes the live curves
+        k_band_paths<<<grid_for(c, c->P, 256, 8), 256, 0, s>>>(c->d_params, c->P, c->d_pobj, c->d_pfp, c->d_pfc, c->d_pos, c->d_tpos, c->d_pvis,
+                                                                c->d_live, c->d_ctr);
         ++launches;
+        if (timed) CU(cudaEventRecord(c->ev[1], s));
         live.list = c->d_live;
+    } else {
+        const uint8_t *plive = band ? c->d_plive : nullptr;
+        if (plive) {
+            k_path_cull<<<grid_for(c, c->P, 256, 8), 256, 0, s>>>(c->d_params, c->P, c->d_pobj, c->d_plive);
+            ++launches;
+        }
+        k_transform<<<grid_for(c, c->np, 256, 8), 256, 0, s>>>(c->d_params, c->np, c->d_pos, c->d_pos_path, c->d_tpos, c->d_pvis, plive);
+        ++launches;
+        if (timed) CU(cudaEventRecord(c->ev[1], s));
+        if (plive) {
+            k_band_live<<<grid_for(c, ((long long)c->nc + LIVE_CHUNK - 1) / LIVE_CHUNK, 256, 8), 256, 0, s>>>(c->nc, c->d_cpath, plive, c->d_count,
+                                                                                                         c->d_live, c->d_ctr);
+            ++launches;
+            live.list = c->d_live;
+        }
     }
     k_monotonize_count<<<c->mono_blocks, 256, 0, s>>>(c->d_params, c->nc, c->d_ctype, c->d_cpm, c->d_cpath,
                                                                    c->d_tpos, c->d_pvis, c->d_cut, c->d_count, c->d_slots,
