@@ -766,6 +766,24 @@ static bool segmented_sort_pays(const slpr_ctx *c, const FrameCounters &k) {
     return c->radix_mode ? (t_seg * 1.25 < t_radix) : (t_seg < t_radix * 1.25);
 }
 
+// After a whole frame: which sort and which coverage pass suit this scene and view, from the frame's counters
+// (used from the next frame on; a change re-captures the graph).
+static int settle_modes(slpr_ctx *c, const FrameCounters &k) {
+    if (k.fix_missed) return fail(SLPR_ERR_STATE, "internal: a piece started below its start parameter without ending below it");
+    if (!(c->flags & (SLPR_FLAG_RADIX_SORT | SLPR_FLAG_SEGMENTED_SORT))) {
+        const bool seg = segmented_sort_pays(c, k);
+        if (seg == c->radix_mode) {  // the other sort suits this scene and view better
+            c->radix_mode = !seg;
+            invalidate_graphs(c);
+        }
+    }
+    if (choose_fill_mode(c, k.n_fragments) != c->fill_fused) {
+        c->fill_fused = !c->fill_fused;
+        invalidate_graphs(c);
+    }
+    return SLPR_OK;
+}
+
 static int finish_frame(slpr_ctx *c) {
     if (!c->frame_pending && !c->frame_done) return fail(SLPR_ERR_STATE, "no frame has been rendered");
     CU(cudaSetDevice(c->device));
@@ -781,18 +799,8 @@ static int finish_frame(slpr_ctx *c) {
             continue;
         }
         if (!c->h_ctr->overflow) {
-            if (c->h_ctr->fix_missed) return fail(SLPR_ERR_STATE, "internal: a piece started below its start parameter without ending below it");
-            if (!(c->flags & (SLPR_FLAG_RADIX_SORT | SLPR_FLAG_SEGMENTED_SORT))) {
-                const bool seg = segmented_sort_pays(c, *c->h_ctr);
-                if (seg == c->radix_mode) {  // the other sort suits this scene and view better: use it from the next frame on
-                    c->radix_mode = !seg;
-                    invalidate_graphs(c);
-                }
-            }
-            if (choose_fill_mode(c, c->h_ctr->n_fragments) != c->fill_fused) {  // from the next frame on
-                c->fill_fused = !c->fill_fused;
-                invalidate_graphs(c);
-            }
+            int rc = settle_modes(c, *c->h_ctr);
+            if (rc) return rc;
             c->frame_done = true;
             return SLPR_OK;
         }
@@ -887,6 +895,9 @@ extern "C" int slpr_submit_to_host(slpr_ctx *c, const float rows[16], uint8_t *r
         CU(cudaEventSynchronize(c->ev_rendered[k]));
         if (slot_invalid(slot)) {
             int rc = pipe_recover(c, k);
+            if (rc) return rc;
+        } else if (slot.was_radix == c->radix_mode) {  // (not while a mode change is still working its way through the pipeline)
+            int rc = settle_modes(c, *slot.h);
             if (rc) return rc;
         }
         slot.in_flight = false;
