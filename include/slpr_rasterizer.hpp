@@ -194,6 +194,15 @@ public:
         readback(img.data(), (size_t)_width * 4);
         return img;
     }
+    // Frame sequences: setMVP + render + copy to (pinned) host memory, the copy of one frame overlapping the
+    // rendering of the next; every submitted frame is whole and in its buffer after waitFrames().
+    void submitFrame(const glm::mat4 &m, uint8_t *rgba, size_t stride_bytes) {
+        need_ctx();
+        float rows[16];
+        for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) rows[4 * i + j] = m[i][j];
+        check(slpr_submit_to_host(_ctx, rows, rgba, stride_bytes));
+    }
+    void waitFrames() { need_ctx(); check(slpr_wait_host(_ctx)); }
     void setBand(uint32_t y_begin, uint32_t y_end) { need_ctx(); check(slpr_set_band(_ctx, y_begin, y_end)); }
     void counts(uint32_t &n_fragments, uint32_t &n_out_fragments, uint32_t &n_spans) {
         need_ctx(); check(slpr_get_counts(_ctx, &n_fragments, &n_out_fragments, &n_spans));
