@@ -373,6 +373,8 @@ extern "C" int slpr_load_scene(slpr_ctx *c, const float *pos_xy, const uint32_t 
         if (pos_path[i] >= n_paths) return fail(SLPR_ERR_INVALID, "slpr_load_scene: point %u has path %u >= n_paths", i, pos_path[i]);
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
+    if (c->copy_stream) CU(cudaStreamSynchronize(c->copy_stream));
+    for (int i = 0; i < 2; ++i) { c->pslot[i].in_flight = false; c->copy_pending[i] = false; }  // frames of the old scene are not looked at again
     free_capacity(c);
     free_scene(c);
     c->np = n_points; c->nc = n_curves; c->P = n_paths;
