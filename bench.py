@@ -311,6 +311,22 @@ def main():
     ms_per_step = ms_total / K
     mpix = frames_total * W * H / (ms_total * 1e-3) / 1e6
 
+    # ---- per-frame distribution (median / p10 / p90), in a second loop of K frames with one event
+    #      per frame so that the timed region above stays exactly K back-to-back steps
+    frame_dist = None
+    if rank == 0 and not bands:
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+        evs[0].record(stream)
+        for i in range(K):
+            step()
+            evs[i + 1].record(stream)
+        torch.cuda.synchronize()
+        per = np.array([evs[i].elapsed_time(evs[i + 1]) for i in range(K)])
+        frame_dist = {"median": float(np.median(per)), "p10": float(np.percentile(per, 10)), "p90": float(np.percentile(per, 90)),
+                      "max": float(per.max()), "frames": K}
+    if dist is not None:
+        dist.barrier()
+
     anim_info = None
     if anim:
         # every frame of this rank once more, waited for: the fragment counts of the cycle
@@ -486,7 +502,7 @@ def main():
                        "l2": "per-frame working set (fragments x 44 B + 33 MB frame) exceeds the 126 MB L2; no flush needed",
                        "frame_replay": "cuda-graph"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
-            "stage_ms": stage_avg,
+            "stage_ms": stage_avg, "frame_ms": frame_dist,
         }
         if band_check is not None:
             out["bands_vs_full_frame"] = band_check
