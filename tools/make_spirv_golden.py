@@ -140,6 +140,9 @@ def cases():
     yield "tiger14", sub, rows, 144, 112
     # synthetic blobs: cubics with 0-4 cuts incl. three, mixed fill rules
     yield "synth48", S.synth_scene(48, 128, 96, 6.0, 22.0, seed=11), S.identity_rows(), 128, 96
+    # S-shaped and looping cubics, control points beyond the frame: several curves with four monotonic cuts, i.e.
+    # pieces that end below their start (MI0:340) and whose first record is not their start parameter
+    yield "loops", util.looping_cubics_scene(14, 96, 72, seed=5), S.identity_rows(), 96, 72
 
 
 def main():
