@@ -143,6 +143,12 @@ def cases():
     # S-shaped and looping cubics, control points beyond the frame: several curves with four monotonic cuts, i.e.
     # pieces that end below their start (MI0:340) and whose first record is not their start parameter
     yield "loops", util.looping_cubics_scene(14, 96, 72, seed=5), S.identity_rows(), 96, 72
+    # a projective matrix (w depends on x and y: the division of TP:53-54 and the left-to-right dot products matter)
+    persp = np.array([[1.0, 0.1, 0, 2.0], [-0.05, 1.0, 0, 1.0], [0, 0, 1, 0], [0.0015, 0.002, 0, 1.0]], np.float32)
+    yield "persp", S.synth_scene(20, 96, 80, 6.0, 20.0, seed=23), persp, 96, 80
+    # odd frame size (the last cell column / row is half outside: clamps of GF:177-178, MARK:45) and a frame smaller
+    # than the scene, so that paths are cut by every edge
+    yield "odd", S.synth_scene(28, 120, 90, 6.0, 24.0, seed=31), S.identity_rows(), 97, 61
 
 
 def main():
