@@ -136,7 +136,8 @@ namespace Galaxysailing {
 class CudaVGRasterizer : public VGRasterizer {
 public:
     explicit CudaVGRasterizer(int device = 0, uint32_t flags = 0) : _device(device), _flags(flags) {}
-    ~CudaVGRasterizer() override { slpr_destroy(_ctx); }
+    // (no `override`: the reference's VGRasterizer declares no virtual destructor, core/rasterizer.h:9-20)
+    ~CudaVGRasterizer() { slpr_destroy(_ctx); }
     CudaVGRasterizer(const CudaVGRasterizer &) = delete;
     CudaVGRasterizer &operator=(const CudaVGRasterizer &) = delete;
 

@@ -24,8 +24,14 @@ def build(force=False):
 
 def build_ref():
     """Compile the reference's own RVG parser (oracle/_ref/rvg_dump) when /root/reference exists."""
-    subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
+    subprocess.check_call(["make", "-C", _HERE, "ref", "ref_driver"], stdout=subprocess.DEVNULL)
     p = os.path.join(_HERE, "_ref", "rvg_dump")
+    return p if os.path.exists(p) else None
+
+
+def ref_driver():
+    """oracle/_ref/slpr_render_ref: the headless driver compiled against the reference's own headers and parser."""
+    p = os.path.join(_HERE, "_ref", "slpr_render_ref")
     return p if os.path.exists(p) else None
 
 

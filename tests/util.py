@@ -137,3 +137,35 @@ def looping_cubics_scene(n_paths=600, width=512, height=384, seed=7):
     return S.Scene(np.array(pos, np.float32), np.array(pos_path, np.uint32), np.array(cpm, np.uint32),
                    np.array(ctype, np.uint32), np.array(cpath, np.uint32), (np.arange(n_paths) & 1).astype(np.uint32),
                    col, "looping_cubics")
+
+
+def write_rvg(container, path):
+    """RVG text (the subset the reference's parser reads: M / L / C / Z, solid paints) of a golden container: one
+    `element` per path, a new `M` wherever a curve does not start where the previous one ended. Numbers are printed
+    with 9 significant digits so that sscanf("%f") reads back the same floats."""
+    c = container
+    n_paths, n_curves = len(c.path_curve), len(c.curve_type)
+    fmt = lambda p: f"{float(p[0]):.9g},{float(p[1]):.9g}"
+    with open(path, "w") as f:
+        f.write(f"viewport {c.vp[0]:.9g},{c.vp[1]:.9g} {c.vp[2]:.9g},{c.vp[3]:.9g}\n")
+        f.write(f"window {c.vp[0]:.9g},{c.vp[1]:.9g} {c.vp[2]:.9g},{c.vp[3]:.9g}\nscene dyn_identity\n")
+        for p in range(n_paths):
+            c0 = int(c.path_curve[p])
+            c1 = int(c.path_curve[p + 1]) if p + 1 < n_paths else n_curves
+            if c1 <= c0:
+                continue
+            cmds, last = [], None
+            for k in range(c0, c1):
+                t = int(c.curve_type[k])
+                npt = 2 if t == S.LINE else 4 if t == S.CUBIC else 0
+                if npt == 0:
+                    continue
+                pts = c.pos[int(c.curve_pos[k]):int(c.curve_pos[k]) + npt]
+                if last is None or tuple(pts[0]) != last:
+                    cmds.append("M " + fmt(pts[0]))
+                cmds.append(("L " + fmt(pts[1])) if npt == 2 else ("C " + " ".join(fmt(q) for q in pts[1:])))
+                last = tuple(pts[-1])
+            rule = "ofill" if int(c.fill_rule[p]) == S.EVEN_ODD else "nzfill"
+            col = ",".join(f"{float(v):.9g}" for v in c.fill_color[p])
+            f.write(f"  1 element {rule} dyn_concrete 0,0 0,0 0,0: {' '.join(cmds)} dyn_identity dyn_paint "
+                    f"{float(c.fill_opacity[p]) if float(c.fill_opacity[p]) > 0 else 1:.9g} solid rgba({col})\n")

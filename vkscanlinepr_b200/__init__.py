@@ -41,9 +41,13 @@ def build(force=False, verbose=False):
     srcs.append(os.path.join(_HERE, "..", "include", "slpr.h"))
     stale = (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
     if force or stale:
-        r = subprocess.run(["make", "-C", src_dir, "../libslpr.so"], capture_output=True, text=True)
+        before = os.path.getmtime(LIB_PATH) if os.path.exists(LIB_PATH) else 0.0
+        r = subprocess.run(["make", "-C", src_dir] + (["-B"] if force else []) + ["../libslpr.so"], capture_output=True, text=True)
         if r.returncode != 0:
             raise SlprError("building libslpr.so failed:\n" + r.stdout + r.stderr)
+        if not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) <= before:
+            raise SlprError("libslpr.so is older than its sources but `make` did not rebuild it "
+                            "(a source file missing from csrc/Makefile's dependencies?):\n" + r.stdout + r.stderr)
         if verbose:
             print(r.stdout)
     return LIB_PATH

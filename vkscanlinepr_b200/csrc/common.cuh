@@ -44,6 +44,13 @@ struct FrameCounters {
     int pad[1];
 };
 
+// The back half of a frame (winding prefix, spans, coverage) must not touch the sorted buffers of a frame the
+// host is going to render again: one whose fragments outgrew the buffers (overflow; nothing was generated) or one
+// with a path too long for the segmented sort (sort_fallback: the sorted buffers are partly unwritten).
+__device__ __forceinline__ bool frame_void(const FrameCounters *ctr, int capacity) {
+    return ctr->overflow != 0 || ctr->n_fragments > capacity || ctr->sort_fallback != 0;
+}
+
 // Key geometry for the compact 64-bit sort key (path | row rank | cell x), see DESIGN.md.
 struct KeyLayout {
     int bits_x, bits_y, bits_path;

@@ -21,7 +21,7 @@ __global__ void __launch_bounds__(256) k_fill_cells(const FrameParams *__restric
                                                     const FrameCounters *__restrict__ ctr, int capacity,
                                                     const int4 *__restrict__ records, uint32_t *__restrict__ cells,
                                                     int cw) {
-    if (ctr->n_fragments > capacity) return;
+    if (frame_void(ctr, capacity)) return;
     const int nrec = ctr->n_records;
     const int nround = (nrec + 31) & ~31;
     const int height = P->height;

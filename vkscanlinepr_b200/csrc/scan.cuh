@@ -160,8 +160,10 @@ struct ScanI32Op {
     }
     __device__ void finish(long long n, unsigned long long total) const {
         out[n] = (int)total;
-        if (total_out) *total_out = (int)total;
-        if (overflow_out && (long long)(int)total > (long long)capacity) *overflow_out = 1;
+        // the exact (62-bit) total decides; a total beyond int32 is reported as INT_MAX so that every
+        // `n_fragments > capacity` guard downstream still fires
+        if (total_out) *total_out = (total > 0x7FFFFFFFull) ? 0x7FFFFFFF : (int)total;
+        if (overflow_out && total > (unsigned long long)(capacity < 0 ? 0 : capacity)) *overflow_out = 1;
     }
 };
 

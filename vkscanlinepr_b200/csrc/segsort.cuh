@@ -90,7 +90,7 @@ __device__ __forceinline__ void warp_bitonic(W (&e)[R], int lane) {
                 }
             }
             // partner in lane ^ j: the five shuffle stages of a phase are unrolled (compile-time lane masks), the
-            // phase loop is not — measured 21.8 -> ? ps per fragment on paths of 129..256 fragments
+            // phase loop is not
 #pragma unroll
             for (int j = 16; j > 0; j >>= 1) {
                 if (j >= k) continue;  // phase k starts at j = k / 2

@@ -234,6 +234,10 @@ static int alloc_capacity(slpr_ctx *c, int cap) {
     for (int i = 0; i < 2; ++i) {
         CU(cudaMalloc(&c->d_key[i], n * 8));
         CU(cudaMalloc(&c->d_val[i], n * 4));
+        // never hand uninitialised pairs to a kernel: a frame that is abandoned half way (overflow, sort fall-back)
+        // leaves these partly unwritten, and the keys index per-path tables
+        CU(cudaMemsetAsync(c->d_key[i], 0, n * 8, c->stream));
+        CU(cudaMemsetAsync(c->d_val[i], 0, n * 4, c->stream));
     }
     CU(cudaMalloc(&c->d_rec, (2 * n + 1) * sizeof(int4)));
     CU(cudaMalloc(&c->d_wsum, (n / SP_TILE + 4) * sizeof(int)));
@@ -807,6 +811,7 @@ static int finish_frame(slpr_ctx *c) {
             return SLPR_OK;
         }
         const long long nf = c->h_ctr->n_fragments;
+        if (nf < 0 || nf >= (1ll << 29) - (1ll << 26)) return fail(SLPR_ERR_INVALID, "frame has %lld fragments; limit is 2^29", nf);
         int rc = alloc_capacity(c, (int)std::min<long long>(nf + nf / 4 + 65536, (1ll << 29) - 1));
         if (rc) return rc;
         rc = slpr_render(c);
@@ -1085,6 +1090,7 @@ extern "C" int slpr_render_band_begin(slpr_ctx *c) {
         CU(cudaEventSynchronize(c->x_event));
         if (c->h_ctr->overflow) {
             const long long nf = c->h_ctr->n_fragments;
+            if (nf < 0 || nf >= (1ll << 29) - (1ll << 26)) return fail(SLPR_ERR_INVALID, "band has %lld fragments; limit is 2^29", nf);
             rc = alloc_capacity(c, (int)std::min<long long>(nf + nf / 4 + 65536, (1ll << 29) - 1));
             if (rc) return rc;
             continue;

@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(SP_THREADS, SP_BLOCKS) k_spans(const uint64_t 
     extern __shared__ uint32_t s_stage[];  // [warps][3][SP_WARP_RECORDS]
 #endif
     const int nf = ctr->n_fragments;
-    if (nf > capacity) return;
+    if (frame_void(ctr, capacity)) return;
     const long long n = nf;
     const long long ntiles = (n == 0) ? 1 : (n + SP_TILE - 1) / SP_TILE;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -434,7 +434,7 @@ __global__ void __launch_bounds__(SP_THREADS) k_wsum(const uint32_t *__restrict_
                                                      int capacity, int *__restrict__ wsum) {
     __shared__ int s_w[SP_THREADS / 32];
     const int nf = ctr->n_fragments;
-    if (nf > capacity) return;
+    if (frame_void(ctr, capacity)) return;
     const long long n = nf;
     const long long ntiles = (n == 0) ? 1 : (n + SP_TILE - 1) / SP_TILE;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -468,7 +468,7 @@ __global__ void __launch_bounds__(1024) k_wscan(FrameCounters *__restrict__ ctr,
     __shared__ int s_w[32];
     __shared__ int s_carry;
     const int nf = ctr->n_fragments;
-    if (nf > capacity) return;
+    if (frame_void(ctr, capacity)) return;
     const long long n = nf;
     const int ntiles = (int)((n == 0) ? 1 : (n + SP_TILE - 1) / SP_TILE);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -513,7 +513,7 @@ __global__ void __launch_bounds__(1024) k_wscan(FrameCounters *__restrict__ ctr,
 // reference's single scan over the concatenated [frag | span] flag array (SR.cpp:545-573).
 __global__ void k_scan3_fixup(const FrameCounters *__restrict__ ctr, int capacity, int *__restrict__ scan3) {
     const int nf = ctr->n_fragments;
-    if (nf > capacity) return;
+    if (frame_void(ctr, capacity)) return;
     const int add = ctr->n_out_frag;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= nf; i += gridDim.x * blockDim.x) scan3[nf + i] += add;
 }
