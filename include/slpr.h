@@ -58,7 +58,11 @@ enum {
     /* Order in which the monotone pieces are walked (a scheduling choice, results are identical): by default pieces
      * are walked longest first, and on scenes of more than two million curves the short ones also window by window
      * of consecutive curves (less HBM traffic). WINDOWED_WALK forces eight windows on any scene (tests). */
-    SLPR_FLAG_WINDOWED_WALK = 1u << 7
+    SLPR_FLAG_WINDOWED_WALK = 1u << 7,
+    /* Keep the reference's draw records (output_buf, gen_merged_fragment_and_span.comp:77,102) readable through
+     * slpr_debug_copy(SLPR_TAP_RECORDS). Without it a big frame never writes them: the span kernel marks the
+     * coverage grid directly (16 B per record of HBM traffic saved). Implied by SLPR_FLAG_TAPS. */
+    SLPR_FLAG_RECORDS = 1u << 8
 };
 
 /* Buffers that slpr_debug_copy() can return. Layouts are the reference's:

@@ -79,9 +79,10 @@ def _arr(ptr, n, dtype):
 STAGE_NAMES = ("transform", "monotonize", "scan1", "intersect", "gen_fragment", "sort", "spans", "fill")
 
 
-def render(scene, rows, width, height, do_fill=True, threads=None):
+def render(scene, rows, width, height, do_fill=True, threads=None, keep=None):
     """Run the whole oracle frame. `scene` has the 7 flat loadVG arrays (see scene.Scene).
-    Returns a dict of every intermediate buffer (numpy copies)."""
+    Returns a dict of every intermediate buffer (numpy copies); `keep` (a set of names) limits the copies to
+    those buffers — on frames of 10^8 fragments the full set is tens of gigabytes."""
     L = lib()
     if threads:
         L.orc_set_num_threads(int(threads))
@@ -94,25 +95,27 @@ def render(scene, rows, width, height, do_fill=True, threads=None):
     f = fp.contents
     nf = f.n_fragments
     no = f.n_out_frag + f.n_span
-    out = dict(
-        n_fragments=nf, n_out_frag=f.n_out_frag, n_span=f.n_span,
-        tpos=_arr(f.tpos, 2 * s.n_points, np.float32).reshape(-1, 2),
-        path_visible=_arr(f.path_visible, s.n_paths, np.int32),
-        cut_cache=_arr(f.cut_cache, 5 * s.n_curves, np.float32).reshape(-1, 5),
-        curve_count=_arr(f.curve_count, s.n_curves, np.int32),
-        curve_offset=_arr(f.curve_offset, s.n_curves + 1, np.int32),
-        inter=_arr(f.inter, 2 * nf, np.int32).reshape(-1, 2),
-        key=_arr(f.key, nf, np.int32), idx=_arr(f.idx, nf, np.int32),
-        path=_arr(f.path, nf, np.int32), wind=_arr(f.wind, nf, np.int32),
-        seg=_arr(f.seg, s.n_paths + 1, np.int32),
-        skey=_arr(f.skey, nf, np.int32), sidx=_arr(f.sidx, nf, np.int32),
-        swind=_arr(f.swind, nf, np.int32), wn=_arr(f.wn, nf + 1, np.int32),
-        flags=_arr(f.flags, 2 * nf, np.int32), scan3=_arr(f.scan3, 2 * nf + 1, np.int32),
-        records=_arr(f.records, 4 * no, np.int32).reshape(-1, 4),
-        ms=dict(zip(STAGE_NAMES, list(f.ms))),
+    out = dict(n_fragments=nf, n_out_frag=f.n_out_frag, n_span=f.n_span, ms=dict(zip(STAGE_NAMES, list(f.ms))))
+    buffers = dict(
+        tpos=lambda: _arr(f.tpos, 2 * s.n_points, np.float32).reshape(-1, 2),
+        path_visible=lambda: _arr(f.path_visible, s.n_paths, np.int32),
+        cut_cache=lambda: _arr(f.cut_cache, 5 * s.n_curves, np.float32).reshape(-1, 5),
+        curve_count=lambda: _arr(f.curve_count, s.n_curves, np.int32),
+        curve_offset=lambda: _arr(f.curve_offset, s.n_curves + 1, np.int32),
+        inter=lambda: _arr(f.inter, 2 * nf, np.int32).reshape(-1, 2),
+        key=lambda: _arr(f.key, nf, np.int32), idx=lambda: _arr(f.idx, nf, np.int32),
+        path=lambda: _arr(f.path, nf, np.int32), wind=lambda: _arr(f.wind, nf, np.int32),
+        seg=lambda: _arr(f.seg, s.n_paths + 1, np.int32),
+        skey=lambda: _arr(f.skey, nf, np.int32), sidx=lambda: _arr(f.sidx, nf, np.int32),
+        swind=lambda: _arr(f.swind, nf, np.int32), wn=lambda: _arr(f.wn, nf + 1, np.int32),
+        flags=lambda: _arr(f.flags, 2 * nf, np.int32), scan3=lambda: _arr(f.scan3, 2 * nf + 1, np.int32),
+        records=lambda: _arr(f.records, 4 * no, np.int32).reshape(-1, 4),
     )
     if do_fill:
-        out["rgba"] = _arr(f.rgba, 4 * width * height, np.uint8).reshape(height, width, 4)
+        buffers["rgba"] = lambda: _arr(f.rgba, 4 * width * height, np.uint8).reshape(height, width, 4)
+    for name, get in buffers.items():
+        if keep is None or name in keep:
+            out[name] = get()
     L.orc_frame_free(fp)
     return out
 

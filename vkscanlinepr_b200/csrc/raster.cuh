@@ -4,8 +4,9 @@
 // record wins; the clear colour is white (SR.cpp:622); image row = H-1-scanline row (VERT:44).
 //
 // All record coordinates are even, so coverage is resolved on the 2x2-pixel cell grid:
-//   k_fill_cells    atomicMax(cell, record index + 1)  — deterministic "later record wins"
-//   k_resolve       cell -> colour of that record (or white), 2x2 pixels, 128-bit stores; also
+//   k_fill_cells    atomicMax(cell, record index + 1)  — deterministic "later record wins" (small frames); on big
+//                   frames k_spans marks the cells itself, with path + 1 (spans.cuh)
+//   k_resolve       cell -> colour of that record / path (or white), 2x2 pixels, 128-bit stores; also
 //                   re-zeroes the cell grid for the next frame.
 // The cell grid of a 4K frame is 8 MB and stays L2-resident between the two kernels.
 #pragma once
@@ -57,8 +58,12 @@ __global__ void __launch_bounds__(256) k_fill_cells(const FrameParams *__restric
     }
 }
 
-// One thread resolves two horizontally adjacent cells = 4 pixels on 2 image rows.
+// One thread resolves two horizontally adjacent cells = 4 pixels on 2 image rows. A cell holds 0 (empty) or, + 1,
+// the index of the last record that covers it (BY_PATH false: marked by k_fill_cells) or the highest path that
+// covers it (BY_PATH true: marked by k_spans<true, .>); its colour is that record's / that path's.
+template <bool BY_PATH>
 __global__ void __launch_bounds__(256) k_resolve(const FrameParams *__restrict__ P, const int4 *__restrict__ records,
+                                                 const uint32_t *__restrict__ fill_info,
                                                  uint32_t *__restrict__ cells, int cw, uint8_t *__restrict__ fb,
                                                  size_t stride_bytes) {
     const int width = P->width, height = P->height;
@@ -75,7 +80,7 @@ __global__ void __launch_bounds__(256) k_resolve(const FrameParams *__restrict__
             col[k] = 0xFFFFFFFFu;  // clear colour (1,1,1,1), SR.cpp:622
             if (cx + k < cw) {
                 const uint32_t v = cp[k];
-                if (v) { col[k] = (uint32_t)records[v - 1].z; cp[k] = 0; }  // colour bytes R,G,B,A = fill_info (VERT:8-10)
+                if (v) { col[k] = BY_PATH ? fill_info[v - 1] : (uint32_t)records[v - 1].z; cp[k] = 0; }  // colour bytes R,G,B,A = fill_info (VERT:8-10)
             }
         }
         const int px = cx * 2;

@@ -179,6 +179,10 @@ struct slpr_ctx {
     size_t prim_temp_bytes = 0;
 };
 
+// The 16-byte draw records (output_buf of gen_merged_fragment_and_span.comp) are written when the caller asked for
+// them (SLPR_FLAG_RECORDS, or taps) and whenever coverage is a separate pass over them (small frames).
+static bool want_records(const slpr_ctx *c) { return (c->flags & (SLPR_FLAG_RECORDS | SLPR_FLAG_TAPS)) != 0; }
+
 static void invalidate_graphs(slpr_ctx *c) {
     c->graph_valid = c->graph2_valid = c->graph_a_valid = c->graph_s_valid = false;
     for (auto &t : c->tgraph) t.valid = false;
@@ -239,7 +243,7 @@ static int alloc_capacity(slpr_ctx *c, int cap) {
         CU(cudaMemsetAsync(c->d_key[i], 0, n * 8, c->stream));
         CU(cudaMemsetAsync(c->d_val[i], 0, n * 4, c->stream));
     }
-    CU(cudaMalloc(&c->d_rec, (2 * n + 1) * sizeof(int4)));
+    // draw records (32 B per fragment of capacity): allocated by ensure_records() when a frame will write them
     CU(cudaMalloc(&c->d_wsum, (n / SP_TILE + 4) * sizeof(int)));
     if (c->flags & SLPR_FLAG_TAPS) {
         CU(cudaMalloc(&c->d_wn, (n + 4) * 4));
@@ -309,9 +313,9 @@ extern "C" slpr_ctx *slpr_create(int device, uint32_t width, uint32_t height, ui
     for (auto &ev : c->ev) ok = ok && cudaEventCreate(&ev) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_onesweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->walk_blocks_per_sm, k_walk, WALK_THREADS, 0) == cudaSuccess;
-    ok = ok && cudaFuncSetAttribute(k_spans<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_STAGE_BYTES) == cudaSuccess;
-    ok = ok && cudaFuncSetAttribute(k_spans<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_STAGE_BYTES) == cudaSuccess;
-    ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->span_blocks_per_sm, k_spans<true>, SP_THREADS, SP_STAGE_BYTES) == cudaSuccess;
+    for (auto fn : {k_spans<false, true, false>, k_spans<true, true, false>, k_spans<true, false, false>, k_spans<false, true, true>, k_spans<true, true, true>})
+        ok = ok && cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_STAGE_BYTES) == cudaSuccess;
+    ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->span_blocks_per_sm, k_spans<true, false, false>, SP_THREADS, SP_STAGE_BYTES) == cudaSuccess;
     if (!ok) {
         fail(SLPR_ERR_CUDA, "slpr_create: device setup failed: %s", cudaGetErrorString(cudaGetLastError()));
         slpr_destroy(c);
@@ -486,6 +490,13 @@ extern "C" int slpr_set_target(slpr_ctx *c, void *dev_rgba, size_t stride_bytes)
 }
 
 // ------------------------------------------------------------------------------------------------
+// Before a frame is enqueued (never inside a stream capture): the record buffer, if this frame writes records.
+static int ensure_records(slpr_ctx *c) {
+    if (c->d_rec || (c->fill_fused && !want_records(c))) return SLPR_OK;
+    CU(cudaMalloc(&c->d_rec, (2 * (size_t)c->cap + 1) * sizeof(int4)));
+    return SLPR_OK;
+}
+
 static int grid_for(const slpr_ctx *c, long long work_items, int threads, int per_sm) {
     long long blocks = (work_items + threads - 1) / threads;
     const long long cap = (long long)c->num_sms * per_sm;
@@ -623,12 +634,10 @@ static int enqueue_back(slpr_ctx *c, cudaStream_t s, bool timed, int &launches) 
 #endif
     if (timed) CU(cudaEventRecord(c->ev[8], s));
     const int span_grid = c->num_sms * std::max(1, c->span_blocks_per_sm);
-    if (c->fill_fused)
-        k_spans<true><<<span_grid, SP_THREADS, SP_STAGE_BYTES, s>>>(c->d_key[cur], c->d_val[cur], c->d_finfo, c->d_rec, c->d_ctr, c->L, (int)c->W,
-                                                                    (int)c->H, c->cap, stp, stmp, corr, c->P, c->d_cells, c->cw);
-    else
-        k_spans<false><<<span_grid, SP_THREADS, SP_STAGE_BYTES, s>>>(c->d_key[cur], c->d_val[cur], c->d_finfo, c->d_rec, c->d_ctr, c->L, (int)c->W,
-                                                                     (int)c->H, c->cap, stp, stmp, corr, c->P, c->d_cells, c->cw);
+    auto spans = taps ? (c->fill_fused ? k_spans<true, true, true> : k_spans<false, true, true>)
+                      : !c->fill_fused ? k_spans<false, true, false> : (want_records(c) ? k_spans<true, true, false> : k_spans<true, false, false>);
+    spans<<<span_grid, SP_THREADS, SP_STAGE_BYTES, s>>>(c->d_key[cur], c->d_val[cur], c->d_finfo, c->d_rec, c->d_ctr, c->L, (int)c->W, (int)c->H,
+                                                       c->cap, stp, stmp, corr, c->P, c->d_cells, c->cw);
     ++launches;
     if (taps) {
         k_scan3_fixup<<<wide, 256, 0, s>>>(c->d_ctr, c->cap, c->t_scan3);
@@ -643,7 +652,8 @@ static int enqueue_back(slpr_ctx *c, cudaStream_t s, bool timed, int &launches) 
         ++launches;
     }
     if (timed) CU(cudaEventRecord(c->ev[10], s));
-    k_resolve<<<wide, 256, 0, s>>>(c->d_params, c->d_rec, c->d_cells, c->cw, fb, stride);
+    if (c->fill_fused) k_resolve<true><<<wide, 256, 0, s>>>(c->d_params, c->d_rec, c->d_finfo, c->d_cells, c->cw, fb, stride);
+    else k_resolve<false><<<wide, 256, 0, s>>>(c->d_params, c->d_rec, c->d_finfo, c->d_cells, c->cw, fb, stride);
     ++launches;
     if (timed) CU(cudaEventRecord(c->ev[11], s));
     CU(cudaMemcpyAsync(c->h_ctr, c->d_ctr, sizeof(FrameCounters), cudaMemcpyDeviceToHost, s));
@@ -707,6 +717,7 @@ extern "C" int slpr_render(slpr_ctx *c) {
         int rc = size_buffers_from_count(c);
         if (rc) return rc;
     }
+    { int rc = ensure_records(c); if (rc) return rc; }
     k_set_params<<<1, 1, 0, c->stream>>>(c->d_params, c->hp);
     ++c->launches;
     if (c->flags & SLPR_FLAG_NO_GRAPH) {
@@ -980,7 +991,9 @@ extern "C" int slpr_debug_copy(slpr_ctx *c, int which, void *dst, size_t bytes) 
         case SLPR_TAP_WINDING_SCAN: src = c->d_wn; avail = (nf + 1) * 4; tap = true; break;
         case SLPR_TAP_FLAGS: src = c->t_flags; avail = 2 * nf * 4; tap = true; break;
         case SLPR_TAP_FLAG_SCAN: src = c->t_scan3; avail = (2 * nf + 1) * 4; tap = true; break;
-        case SLPR_TAP_RECORDS: src = c->d_rec; avail = no * 16; break;
+        case SLPR_TAP_RECORDS:
+            if (!want_records(c)) return fail(SLPR_ERR_STATE, "slpr_debug_copy: the draw records need SLPR_FLAG_RECORDS (or SLPR_FLAG_TAPS)");
+            src = c->d_rec; avail = no * 16; break;
         case SLPR_TAP_SEGMENTS: src = c->d_seg_tap; avail = ((size_t)c->P + 1) * 4; break;
         default: return fail(SLPR_ERR_INVALID, "slpr_debug_copy: unknown buffer %d", which);
     }
@@ -1072,6 +1085,7 @@ extern "C" int slpr_render_band_begin(slpr_ctx *c) {
         if (rc) return rc;
     }
     for (int attempt = 0; attempt < 4; ++attempt) {
+        { int rc = ensure_records(c); if (rc) return rc; }
         k_set_params<<<1, 1, 0, c->stream>>>(c->d_params, c->hp);
         ++c->launches;
         int rc = launch_graph(c, c->gexec_a, c->graph_a_valid, c->launches_a, [&](int &l) {

@@ -127,7 +127,12 @@ __device__ __forceinline__ KeyFields decode_key(const KeyLayout &L, uint64_t k) 
     return f;
 }
 
-template <bool FILL>
+// FILL: the kernel marks the cells its records cover itself (stage 5 coverage fused in) — with the record's PATH
+//       (+1), not its index: records are emitted in path order and a path has one colour, so "the later record
+//       wins" (opaque overwrite in primitive order, SR.cpp:893-895) is "the highest path wins", and k_resolve
+//       finds the colour in fill_info[path]. Nobody then reads the 16-byte draw records, so they are
+// REC:  only written when asked for (SLPR_FLAG_RECORDS / taps), or for the separate coverage pass (!FILL).
+template <bool FILL, bool REC, bool TAPS>
 __global__ void __launch_bounds__(SP_THREADS, SP_BLOCKS) k_spans(const uint64_t *__restrict__ skey,
                                                          const uint32_t *__restrict__ sval,
                                                          const uint32_t *__restrict__ fill_info,
@@ -173,7 +178,7 @@ __global__ void __launch_bounds__(SP_THREADS, SP_BLOCKS) k_spans(const uint64_t 
                 for (int e = 0; e < 4; ++e) {
                     dpack |= (v[e] >> 30) << (2 * (j + e));
                     rpack |= ((v[e] >> 29) & 1u) << (j + e);
-                    if (taps.sidx) taps.sidx[i0 + j + e] = (int)(v[e] & VAL_INDEX_MASK);
+                    if (TAPS && taps.sidx) taps.sidx[i0 + j + e] = (int)(v[e] & VAL_INDEX_MASK);
                 }
             }
         } else {
@@ -184,7 +189,7 @@ __global__ void __launch_bounds__(SP_THREADS, SP_BLOCKS) k_spans(const uint64_t 
                 const uint32_t v = in ? sval[i0 + j] : (1u << 30);
                 dpack |= (v >> 30) << (2 * j);
                 rpack |= ((v >> 29) & 1u) << j;
-                if (in && taps.sidx) taps.sidx[i0 + j] = (int)(v & VAL_INDEX_MASK);
+                if (TAPS && in && taps.sidx) taps.sidx[i0 + j] = (int)(v & VAL_INDEX_MASK);
             }
         }
         {   // key of the element before this thread's run: neighbour lane, or global for lane 0
@@ -226,7 +231,7 @@ __global__ void __launch_bounds__(SP_THREADS, SP_BLOCKS) k_spans(const uint64_t 
                 if (!SLPR_SP_WPRE && tile == ntiles - 1) {
                     const int wtotal = (int)(uint32_t)(excl + total);
                     ctr->wn_total = wtotal;
-                    if (taps.wn) taps.wn[n] = wtotal;
+                    if (TAPS && taps.wn) taps.wn[n] = wtotal;
                 }
             }
         }
@@ -242,7 +247,7 @@ __global__ void __launch_bounds__(SP_THREADS, SP_BLOCKS) k_spans(const uint64_t 
             for (int j = 0; j < SP_ITEMS; ++j) {
                 const KeyFields b = decode_key(L, k[j + 1]);
                 if (i0 + j < n) {
-                    if (taps.wn) taps.wn[i0 + j] = wn;
+                    if (TAPS && taps.wn) taps.wn[i0 + j] = wn;
                     const bool oob = (b.x < 0 || b.y < 0 || b.x >= width || b.y >= height);  // MARK:45,69
                     uint32_t frag, span = 0;
                     if (i0 + j == 0) {
@@ -258,7 +263,7 @@ __global__ void __launch_bounds__(SP_THREADS, SP_BLOCKS) k_spans(const uint64_t 
                     }
                     fmask |= frag << j;
                     smask |= span << j;
-                    if (taps.flags) {
+                    if (TAPS && taps.flags) {
                         taps.flags[i0 + j] = (int)frag;
                         taps.flags[n + i0 + j] = (int)span;
                         uint32_t pp;
@@ -300,7 +305,7 @@ __global__ void __launch_bounds__(SP_THREADS, SP_BLOCKS) k_spans(const uint64_t 
                     ctr->n_out_frag = nfrag;
                     ctr->n_span = nspan;
                     ctr->n_records = nfrag + nspan;
-                    if (taps.scan3) { taps.scan3[n] = 0; taps.scan3[2 * n] = nspan; }  // + n_out_frag in k_scan3_fixup
+                    if (TAPS && taps.scan3) { taps.scan3[n] = 0; taps.scan3[2 * n] = nspan; }  // + n_out_frag in k_scan3_fixup
                 }
             }
         }
@@ -326,39 +331,33 @@ __global__ void __launch_bounds__(SP_THREADS, SP_BLOCKS) k_spans(const uint64_t 
         const int warp_frag_base = frag_before - wfrag;               // fragments emitted before this warp
         const long long gbase = (long long)frag_before + span_before - slot;
 #endif
-        if (((fmask | smask) || taps.scan3) && !(SLPR_SP_NOSTORE && frag_before >= 0)) {
-            int fillc[SP_ITEMS];  // colours first: eight independent gathers instead of eight dependent ones
-#pragma unroll
-            for (int j = 0; j < SP_ITEMS; ++j) {
-                const uint32_t path = (uint32_t)(k[j + 1] >> (L.bits_x + L.bits_y));
-                fillc[j] = (((fmask | smask) >> j) & 1u) ? (int)fill_info[path] : 0;
-            }
+        if (((fmask | smask) || (TAPS && taps.scan3)) && !(SLPR_SP_NOSTORE && frag_before >= 0)) {
             KeyFields a = decode_key(L, k[0]);
 #pragma unroll
             for (int j = 0; j < SP_ITEMS; ++j) {
                 const KeyFields b = decode_key(L, k[j + 1]);
                 const uint32_t frag = (fmask >> j) & 1u, span = (smask >> j) & 1u;
-                if (taps.scan3 && i0 + j < n) {
+                if (TAPS && taps.scan3 && i0 + j < n) {
                     taps.scan3[i0 + j] = frag_before;
                     taps.scan3[n + i0 + j] = span_before;
                 }
                 if (frag | span) {
-                    const int fill = fillc[j];
 #if SLPR_SP_STAGE
                     if (frag) {  // GEN:77: (y<<16 | x, 2, rgba, inclusive fragment index)
                         wp[slot] = ((uint32_t)b.y << 16) | (uint32_t)b.x;
                         wp[SP_WARP_RECORDS + slot] = 2u | ((uint32_t)(frag_before - warp_frag_base + 1) << 16);
-                        wp[2 * SP_WARP_RECORDS + slot] = (uint32_t)fill;
+                        wp[2 * SP_WARP_RECORDS + slot] = b.path;
                         ++slot;
                     }
                     if (span) {  // GEN:85-102: from the previous fragment's right edge to this fragment
                         const int xs = max(0, a.x + FRAG_SIZE);
                         wp[slot] = ((uint32_t)a.y << 16) | (uint32_t)xs;
                         wp[SP_WARP_RECORDS + slot] = (uint32_t)(b.x - xs) & 0xFFFFu;
-                        wp[2 * SP_WARP_RECORDS + slot] = (uint32_t)fill;
+                        wp[2 * SP_WARP_RECORDS + slot] = b.path;
                         ++slot;
                     }
 #else
+                    const int fill = (int)fill_info[b.path];
                     const int oi = frag_before + span_before;  // GEN:64-66
                     if (frag)  // GEN:77: (y<<16 | x, 2, rgba, inclusive fragment index)
                         records[oi] = make_int4((int)(((uint32_t)b.y << 16) | (uint32_t)b.x), 2, fill, frag_before + 1);
@@ -376,46 +375,45 @@ __global__ void __launch_bounds__(SP_THREADS, SP_BLOCKS) k_spans(const uint64_t 
 #if SLPR_SP_STAGE
         __syncwarp();
         if (!SLPR_SP_NOSTORE) {
-            // Stage 5 coverage fused in with FILL (big frames: slpr.cu fill_fused): the record's index
-            // is known here, so the cells it covers are marked right away — atomicMax(cell, record index + 1),
-            // fire and forget — and the 16-byte records are not read back by k_fill_cells. Narrow records by
-            // their own lane, wide spans by the whole warp (same split as k_fill_cells).
-            if (FILL) for (uint32_t q0 = 0; q0 < wtot; q0 += 32) {
+            // One pass over the warp's staged records, 32 at a time. REC: the record goes out (full 512-byte rows; its
+            // colour is fetched here, one gather per record). FILL: its cells are marked — atomicMax(cell, path + 1),
+            // fire and forget; narrow records by their own lane, wide spans by the whole warp (as k_fill_cells).
+            for (uint32_t q0 = 0; q0 < wtot; q0 += 32) {
                 const uint32_t q = q0 + (uint32_t)lane;
                 int cx0 = 0, ncell = 0, cy = 0;
                 uint32_t prio = 0;
                 if (q < wtot) {
-                    const uint32_t pos = wp[q], w1 = wp[SP_WARP_RECORDS + q], ord = w1 >> 16;
-                    records[gbase + q] = make_int4((int)pos, (int)(w1 & 0xFFFFu), (int)wp[2 * SP_WARP_RECORDS + q],
-                                                   ord ? warp_frag_base + (int)ord : 0);
-                    const int X = (int)(pos & 0xFFFFu), Y = (int)pos >> 16;  // VERT:27
-                    if (Y >= 0 && Y < height) {
-                        cx0 = X >> 1;
-                        ncell = min((X + (int)(w1 & 0xFFFFu)) >> 1, cw) - cx0;
-                        cy = Y >> 1;
+                    const uint32_t pos = wp[q], w1 = wp[SP_WARP_RECORDS + q], ord = w1 >> 16, path = wp[2 * SP_WARP_RECORDS + q];
+                    if (REC)
+                        records[gbase + q] = make_int4((int)pos, (int)(w1 & 0xFFFFu), (int)fill_info[path],
+                                                       ord ? warp_frag_base + (int)ord : 0);
+                    if (FILL) {
+                        const int X = (int)(pos & 0xFFFFu), Y = (int)pos >> 16;  // VERT:27
+                        if (Y >= 0 && Y < height) {
+                            cx0 = X >> 1;
+                            ncell = min((X + (int)(w1 & 0xFFFFu)) >> 1, cw) - cx0;
+                            cy = Y >> 1;
+                        }
+                        prio = path + 1u;
                     }
-                    prio = (uint32_t)(gbase + q) + 1u;
                 }
-                if (ncell > 0 && ncell <= SLPR_FILL_NARROW) {
-                    uint32_t *row = cells + (size_t)cy * cw + cx0;
-                    for (int c = 0; c < ncell; ++c) atomicMax(row + c, prio);
+                if (FILL) {
+                    if (ncell > 0 && ncell <= SLPR_FILL_NARROW) {
+                        uint32_t *row = cells + (size_t)cy * cw + cx0;
+                        for (int c = 0; c < ncell; ++c) atomicMax(row + c, prio);
+                    }
+                    uint32_t wide = __ballot_sync(0xFFFFFFFFu, ncell > SLPR_FILL_NARROW);
+                    while (wide) {
+                        const int src = __ffs(wide) - 1;
+                        wide &= wide - 1;
+                        const int s_cx0 = __shfl_sync(0xFFFFFFFFu, cx0, src);
+                        const int s_n = __shfl_sync(0xFFFFFFFFu, ncell, src);
+                        const int s_cy = __shfl_sync(0xFFFFFFFFu, cy, src);
+                        const uint32_t s_prio = __shfl_sync(0xFFFFFFFFu, prio, src);
+                        uint32_t *row = cells + (size_t)s_cy * cw + s_cx0;
+                        for (int c = lane; c < s_n; c += 32) atomicMax(row + c, s_prio);
+                    }
                 }
-                uint32_t wide = __ballot_sync(0xFFFFFFFFu, ncell > SLPR_FILL_NARROW);
-                while (wide) {
-                    const int src = __ffs(wide) - 1;
-                    wide &= wide - 1;
-                    const int s_cx0 = __shfl_sync(0xFFFFFFFFu, cx0, src);
-                    const int s_n = __shfl_sync(0xFFFFFFFFu, ncell, src);
-                    const int s_cy = __shfl_sync(0xFFFFFFFFu, cy, src);
-                    const uint32_t s_prio = __shfl_sync(0xFFFFFFFFu, prio, src);
-                    uint32_t *row = cells + (size_t)s_cy * cw + s_cx0;
-                    for (int c = lane; c < s_n; c += 32) atomicMax(row + c, s_prio);
-                }
-            }
-            else for (uint32_t q = (uint32_t)lane; q < wtot; q += 32) {
-                const uint32_t w1 = wp[SP_WARP_RECORDS + q], ord = w1 >> 16;
-                records[gbase + q] = make_int4((int)wp[q], (int)(w1 & 0xFFFFu), (int)wp[2 * SP_WARP_RECORDS + q],
-                                               ord ? warp_frag_base + (int)ord : 0);
             }
         }
         __syncwarp();
