@@ -103,10 +103,17 @@ def ncu_traffic(kernel, workload):
     return best
 
 
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_frame(sc, rows, W, H, threads=None):
     from oracle import oracle_py as O
     t = time.perf_counter()
-    r = O.render(sc, rows, W, H, do_fill=True, threads=threads)
+    r = O.render(sc, rows, W, H, do_fill=True, threads=threads, keep={"rgba"})
     return time.perf_counter() - t, r
 
 
@@ -117,6 +124,10 @@ def run_reference(args):
         return
     from oracle import oracle_py as O
     sc, rows, W, H = load_workload(args.workload)
+    # all the host threads this process may use: torchrun exports OMP_NUM_THREADS=1 to its ranks, which would
+    # otherwise make the N > 1 reference lines single-threaded; rank 0 alone runs this arm
+    cores = host_threads()
+    O.lib().orc_set_num_threads(cores)
     cores = O.num_threads()
     t0, _ = cpu_frame(sc, rows, W, H)  # first frame doubles as warm-up and as the size probe
     budget_s = 150.0
@@ -141,6 +152,202 @@ def run_reference(args):
     }))
 
 
+def primitive_rooflines(r, stream, nf, key_bits, peak, iters=10):
+    """The two roofline-graded primitives timed alone through the C ABI (slpr_scan_i32, slpr_sort_pairs) at the
+    frame's sizes: algorithmic bytes (scan 8 B/element; radix sort n * [K + p * 2 * (K + 4)]) / time
+    / measured peak. CUDA events on the launching stream, one pair per call; inputs are larger than L2 or re-created
+    per call (the sort input is copied fresh outside the timed pair: sorting sorted keys would flatter the scatter)."""
+    import torch
+    out = {}
+
+    def timed(fn, prep=None):
+        ms = []
+        for i in range(iters + 3):
+            if prep:
+                prep()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            fn()
+            e1.record(stream)
+            e1.synchronize()
+            if i >= 3:
+                ms.append(e0.elapsed_time(e1))
+        return float(np.median(ms)), float(min(ms))
+
+    for label, n in (("scan_nf", nf), ("scan_2nf", 2 * nf), ("scan_35M", 35_000_000)):
+        a = torch.randint(0, 4, (n,), dtype=torch.int32, device="cuda")
+        b = torch.empty(n + 1, dtype=torch.int32, device="cuda")
+        med, best = timed(lambda: r.scan_i32(a.data_ptr(), b.data_ptr(), n))
+        out[label] = {"kernel": "k_lookback_scan", "n": n, "bytes": 8 * n, "ms": med, "ms_best": best,
+                      "achieved": 8 * n / (med * 1e-3) / 1e9, "frac": 8 * n / (med * 1e-3) / 1e9 / peak}
+        del a, b
+    passes = (key_bits + 7) // 8
+    n = nf
+    k0 = torch.randint(0, 1 << key_bits, (n,), dtype=torch.int64, device="cuda")
+    v0 = torch.arange(n, dtype=torch.int32, device="cuda")
+    k, v, kt, vt = (torch.empty_like(k0), torch.empty_like(v0), torch.empty_like(k0), torch.empty_like(v0))
+
+    def prep():
+        k.copy_(k0)
+        v.copy_(v0)
+
+    med, best = timed(lambda: r.sort_pairs(k.data_ptr(), v.data_ptr(), kt.data_ptr(), vt.data_ptr(), n, key_bits), prep)
+    nbytes = n * (8 + passes * 2 * 12)
+    out["sort_pairs_nf"] = {"kernel": "k_radix_hist + k_onesweep x %d" % passes, "n": n, "key_bits": key_bits, "passes": passes,
+                            "bytes": nbytes, "ms": med, "ms_best": best, "achieved": nbytes / (med * 1e-3) / 1e9,
+                            "frac": nbytes / (med * 1e-3) / 1e9 / peak}
+    return out
+
+
+def d2h_probe(W, H, stream, dist, iters=20):
+    """Host-memory ceiling of the end-to-end path: every rank copies one RGBA8 frame device -> pinned host memory,
+    back to back, all ranks at once; per-rank GB/s (min / mean over ranks). Nothing is rendered."""
+    import torch
+    dev = torch.empty((H, W, 4), dtype=torch.uint8, device="cuda")
+    host = torch.empty((H, W, 4), dtype=torch.uint8, pin_memory=True)
+    for _ in range(3):
+        host.copy_(dev, non_blocking=True)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(iters):
+        host.copy_(dev, non_blocking=True)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    gbs = iters * W * H * 4 / (e0.elapsed_time(e1) * 1e-3) / 1e9
+    if dist is None:
+        return {"per_rank_gbs_min": gbs, "per_rank_gbs_mean": gbs, "aggregate_gbs": gbs}
+    t = torch.tensor([gbs], device="cuda", dtype=torch.float64)
+    lo = t.clone(); dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    sm = t.clone(); dist.all_reduce(sm)
+    return {"per_rank_gbs_min": float(lo.item()), "per_rank_gbs_mean": float(sm.item()) / dist.get_world_size(),
+            "aggregate_gbs": float(sm.item())}
+
+
+class BandRunner:
+    """One frame split into `world` exact row bands, device-side exchange (csrc/bands.cuh second half): per frame ONE
+    graph launch per rank, no host synchronisation, no collective call; the few non-zero per-path winding sums travel
+    as peer stores over NVLink. gather="peer": every band's k_resolve stores its pixels straight into the root's
+    peer-mapped frame buffer (two buffers, alternating); the root orders its stream after the arrival of frame i once
+    frame i+1 is enqueued. gather="none": bands stay on their GPUs."""
+
+    def __init__(self, V, PAR, sc, rows, W, H, rank, world, local_rank, dist, stream, rank0_share=1.0):
+        self.V, self.PAR, self.W, self.H, self.rank, self.world, self.dist, self.stream = V, PAR, W, H, rank, world, dist, stream
+        self.rows = rows
+        self.r = V.ScanlineRasterizer(local_rank, 0).initialize(None, W, H)
+        self.r.set_stream(stream.cuda_stream)
+        self.r.loadVG(sc)
+        self.r.setMVP(rows)
+        self.band_list = PAR.band_rows(H, world, rank0_share)
+        self.r.set_band(*self.band_list[rank])
+        self.peers = PAR.connect_band_peers(self.r, dist, rank, world, root=0, frame_bytes=W * H * 4, n_frames=2)
+        self.seq = 1
+        self.retries = 0
+        self.last_slot = 0
+
+    def _step(self, gather, first):
+        r = self.r
+        if gather == "peer":
+            self.last_slot = self.seq & 1
+            r.set_target(self.peers["frames"][self.last_slot], self.W * 4)
+        else:
+            r.set_target(0, 0)
+        r.setMVP(self.rows)
+        r.render_band(self.seq)
+        if gather == "peer" and self.rank == 0 and not first:
+            r.band_wait_gather(self.seq - 1)
+        self.seq += 1
+
+    def _finish(self, gather):
+        if gather == "peer" and self.rank == 0:
+            self.r.band_wait_gather(self.seq - 1)
+
+    def run(self, K, Wm, gather):
+        import torch
+        for _ in range(max(Wm, 3)):  # waited for one by one: capacities and sort modes settle (a void frame is redone by all)
+            for _ in range(4):
+                self._step(gather, True)
+                self._finish(gather)
+                if not self.PAR.finish_band_frame(self.r, self.dist):
+                    break
+                self.retries += 1
+        self.dist.barrier()
+        torch.cuda.synchronize()
+        l0 = self.r.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(self.stream)
+        for i in range(K):
+            self._step(gather, i == 0)
+        self._finish(gather)
+        e1.record(self.stream)
+        void = self.PAR.finish_band_frame(self.r, self.dist)
+        self.dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        lt = torch.tensor([self.r.launch_count() - l0], device="cuda", dtype=torch.int64)
+        self.dist.all_reduce(lt)
+        nf = torch.tensor([self.r.counts()["n_fragments"]], device="cuda", dtype=torch.int64)
+        nf_max = nf.clone(); self.dist.all_reduce(nf_max, op=self.dist.ReduceOp.MAX)
+        self.dist.all_reduce(nf)
+        return {"ms_per_step": float(t.item()) / K, "steps": K, "launches": int(lt.item()), "void_frame_in_timed_region": bool(void),
+                "fragments_sum_over_bands": int(nf.item()), "fragments_largest_band": int(nf_max.item())}
+
+    def check_against_full_frame(self, sc, K):
+        """Rank 0: the same frame rendered whole on this GPU — its time (the 1-GPU reference of the speed-up) and the
+        number of pixels in which the assembled frame of the last gathered step differs from it."""
+        import torch
+        V = self.V
+        full = V.ScanlineRasterizer(self.r._device, 0).initialize(None, self.W, self.H)
+        full.set_stream(self.stream.cuda_stream)
+        full.loadVG(sc)
+        full.setMVP(self.rows)
+        for _ in range(3):
+            full.render()
+        full.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(self.stream)
+        for _ in range(K):
+            full.render()
+        e1.record(self.stream)
+        full.synchronize()
+        ms = e0.elapsed_time(e1) / K
+        fb, _ = full.framebuffer()
+        diff = full.diff_u32(self.peers["frames"][self.last_slot], fb, self.W * self.H)
+        nf = full.counts()["n_fragments"]
+        full.close()
+        return ms, diff, nf
+
+    def close(self):
+        self.r.close()
+
+
+def bands_peer_report(V, PAR, sc, rows, W, H, rank, world, local_rank, dist, stream, K, Wm, workload, rank0_share=1.0, gather=True):
+    """Resident and gathered exact bands + the 1-GPU full frame on rank 0: the north star's strong-scaling case."""
+    br = BandRunner(V, PAR, sc, rows, W, H, rank, world, local_rank, dist, stream, rank0_share)
+    resident = br.run(K, Wm, "none")
+    gathered = br.run(K, Wm, "peer") if gather else None
+    rep = None
+    ms1 = diff = nf1 = None
+    if rank == 0:
+        ms1, diff, nf1 = br.check_against_full_frame(sc, max(3, min(K, 10))) if gather else (None, None, None)
+    dist.barrier()
+    if rank == 0:
+        rep = {"workload": workload, "width": W, "height": H, "curves": sc.n_curves, "paths": sc.n_paths, "bands": world,
+               "fragments_full_frame": nf1, "ms_1gpu": ms1, "ms_resident": resident["ms_per_step"],
+               "ms_gathered": gathered["ms_per_step"] if gathered else None,
+               "speedup_resident": (ms1 / resident["ms_per_step"]) if ms1 else None,
+               "speedup_gathered": (ms1 / gathered["ms_per_step"]) if (ms1 and gathered) else None,
+               "pixels_differing": diff, "pixels": W * H, "resident": resident, "gathered": gathered, "retried_warmup_frames": br.retries,
+               "exchange": "sparse per-path winding sums stored into peer-mapped mailboxes (CUDA IPC over NVLink), no collective, no host sync",
+               "gather": "k_resolve stores each band straight into rank 0's peer-mapped frame buffer (two buffers, arrival of frame i awaited after frame i+1 is enqueued)",
+               "timing": "CUDA events on each rank's stream around K back-to-back frames, max over ranks"}
+    br.close()
+    return rep
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -155,6 +362,8 @@ def main():
     ap.add_argument("--rank0-share", type=float, default=1.0, help="bands mode: rank 0 renders this fraction of an equal band (it also receives the gathered frame)")
     ap.add_argument("--no-gather", action="store_true", help="bands mode: leave every band on its GPU (no NCCL gather)")
     ap.add_argument("--no-radix-leg", action="store_true", help="skip timing the radix sort beside the segmented sort")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="bands mode: device-side sparse exchange over peer-mapped mailboxes (default) or the host-driven NCCL all-gather of dense sums")
+    ap.add_argument("--no-bands16k", action="store_true", help="N > 1, frames mode: skip the cfg4 row-band leg (bands16k in the JSON line)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -181,6 +390,19 @@ def main():
     # a dedicated (non-default) torch stream: the context launches on it, torch events time it
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
+
+    if args.mode == "bands" and world > 1 and args.exchange == "peer" and not args.independent_bands:
+        rep = bands_peer_report(V, PAR, sc, rows, W, H, rank, world, local_rank, dist, stream, K, Wm, args.workload,
+                                args.rank0_share, gather=not args.no_gather)
+        if rank == 0:
+            ms = rep["ms_gathered"] if rep["ms_gathered"] else rep["ms_resident"]
+            print(json.dumps({"metric": "Mpixel/s", "value": W * H / (ms * 1e-3) / 1e6, "unit": "Mpixel/s", "n_gpus": world, "steps": K,
+                              "warmup": Wm, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                              "dtype": "f32+i32", "data": "synthetic",
+                              "config": {"workload": args.workload, "width": W, "height": H, "parallelism": "bands%d+peer-exchange%s" % (world, "" if args.no_gather else "+peer-store-gather")},
+                              "gpu_launches": (rep["gathered"] or rep["resident"])["launches"], "bands": rep}))
+        dist.destroy_process_group()
+        return
 
     def make_ctx(flags):
         r = V.ScanlineRasterizer(local_rank, flags).initialize(None, W, H)
@@ -392,7 +614,8 @@ def main():
                        "to pinned host memory, copy of frame i overlapped with rendering of frame i+1",
                "blocking_call": {"value": frames_total * W * H / sync_s / 1e6, "ms_per_step": sync_s / K * 1e3,
                                  "what": "slpr_render_to_host (set_mvp + render + readback, synchronous per frame)"},
-               "frames_rendered_twice": int(e2e_redone)}
+               "frames_rendered_twice": int(e2e_redone),
+               "d2h_probe": d2h_probe(W, H, stream, dist)}
     else:
         e2e = None
 
@@ -446,7 +669,11 @@ def main():
         else:                    # 2*(K+4) B per fragment per pass
             kernels["sort"] = entry("k_onesweep", nf * 2 * (kb + 4) * info["passes"], stage_avg["sort_passes"], info["passes"])
         dominant = max(kernels.values(), key=lambda e: e["ms_per_launch"] * e["launches_per_step"])
-        scan_bytes = 8 * (sc.n_curves + nf)                     # scan #1 + winding scan (8 B / element)
+        # In the frame, scan #1 is k_lookback_scan over the curve counts (4 B read + 4 B written per curve); the
+        # winding scan is split: k_wsum + k_wscan only READ the 4-byte values (tile sums; timed here), its in-tile
+        # half runs inside k_spans (timed there). Bytes are the ones these kernels move, not 8 B per element.
+        n_tiles = (nf + 4095) // 4096
+        scan_bytes = 8 * sc.n_curves + 4 * nf + 8 * n_tiles
         scan_ms = stage_avg["scan1"] + stage_avg["wind_scan"]
         roof = {"bound": "hbm", "kernel": dominant["kernel"], "achieved": dominant["achieved"], "peak": peak, "unit": "GB/s",
                 "frac": dominant["frac"], "traffic": dominant["traffic"], "traffic_source": dominant["traffic_source"],
@@ -455,8 +682,15 @@ def main():
                 "note": dominant.get("note"),
                 "timing": "cudaEvent pairs around each stage, direct-launch mode, averaged over the same K steps",
                 "sort_mode": mode, "kernels": kernels,
-                "scans": {"bytes": scan_bytes, "ms": scan_ms, "gbs": scan_bytes / (scan_ms * 1e-3) / 1e9,
-                          "frac": scan_bytes / (scan_ms * 1e-3) / 1e9 / peak}}
+                "scans": {"what": "in-frame: k_lookback_scan over curve counts (8 B/curve) + k_wsum/k_wscan tile sums (4 B/fragment, "
+                                  "read only); the stand-alone scan primitive is under `primitives`",
+                          "bytes": scan_bytes, "ms": scan_ms, "gbs": scan_bytes / (scan_ms * 1e-3) / 1e9,
+                          "frac": scan_bytes / (scan_ms * 1e-3) / 1e9 / peak,
+                          "scan1": {"bytes": 8 * sc.n_curves, "ms": stage_avg["scan1"],
+                                    "frac": 8 * sc.n_curves / (stage_avg["scan1"] * 1e-3) / 1e9 / peak},
+                          "wind_prefix": {"bytes": 4 * nf + 8 * n_tiles, "ms": stage_avg["wind_scan"],
+                                          "frac": (4 * nf + 8 * n_tiles) / (stage_avg["wind_scan"] * 1e-3) / 1e9 / peak}},
+                "primitives": primitive_rooflines(r, stream, nf, info["key_bits"], peak)}
         if mode == "segmented" and not args.no_radix_leg:
             # the general sort (paths of any length), timed on the same frame for comparison
             st_r, _, _, info_r, _ = stage_times(V.FLAG_NO_GRAPH | V.FLAG_RADIX_SORT)
@@ -473,6 +707,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import oracle_py as O
+        O.lib().orc_set_num_threads(host_threads())
         cores = O.num_threads()
         ts = []
         t_budget = time.perf_counter()
@@ -486,6 +721,17 @@ def main():
                "sample": f"{len(ts)} full frame(s) of {args.workload}, best; all {cores} OpenMP threads",
                "ms_per_frame": min(ts) * 1e3, "gpu_frame_matches_oracle": ok}
 
+    sort_now, fused_now = r.sort_mode(), r.fill_fused()
+    bands16k = None
+    if world > 1 and args.mode == "frames" and not args.no_bands16k:
+        # The north star's multi-GPU case in the driver-run line: BASELINE cfg4, one 16384 x 16384 frame
+        # of 4 M curves in `world` exact row bands, band-resident and gathered to rank 0, against the same frame on one GPU.
+        from vkscanlinepr_b200 import scene as S16
+        r.close()
+        r = None
+        sc16 = S16.synth_16k()
+        bands16k = bands_peer_report(V, PAR, sc16, S16.identity_rows(), 16384, 16384, rank, world, local_rank, dist, stream,
+                                     min(K, 20), 3, "synth_16k")
     if rank == 0:
         out = {
             "metric": "Mpixel/s", "value": mpix, "unit": "Mpixel/s", "n_gpus": world, "steps": K, "warmup": Wm,
@@ -493,7 +739,7 @@ def main():
             "vs_baseline": None, "dtype": "f32+i32", "data": "synthetic",
             "config": {"workload": args.workload, "width": W, "height": H, "curves": sc.n_curves, "paths": sc.n_paths,
                        "points": sc.n_points, "fragments": cnt["n_fragments"], "records": cnt["n_out_frag"] + cnt["n_span"],
-                       "scene_sha256": sc.sha256()[:16], "sort": r.sort_mode(), "fill": "fused into k_spans" if r.fill_fused() else "k_fill_cells", "sort_key_bits": info["key_bits"],
+                       "scene_sha256": sc.sha256()[:16], "sort": sort_now, "fill": "fused into k_spans" if fused_now else "k_fill_cells", "sort_key_bits": info["key_bits"],
                        "radix_passes_if_radix": info["passes"],
                        "parallelism": (("bands%d" % world) + ("+independent" if args.independent_bands else "+nccl-allgather-of-winding-sums")
                                         + ("+no-gather" if args.no_gather else "+pipelined-nccl-gather")
@@ -506,10 +752,13 @@ def main():
         }
         if band_check is not None:
             out["bands_vs_full_frame"] = band_check
+        if bands16k is not None:
+            out["bands16k"] = bands16k
         if anim_info is not None:
             out["anim"] = anim_info
         print(json.dumps(out))
-    r.close()
+    if r is not None:
+        r.close()
     if dist is not None:
         dist.destroy_process_group()
 

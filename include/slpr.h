@@ -34,7 +34,8 @@ enum {
     SLPR_ERR_CUDA = 2,        /* CUDA runtime error (message has the CUDA string) */
     SLPR_ERR_STATE = 3,       /* call order violated (e.g. render before load_scene) */
     SLPR_ERR_UNSUPPORTED = 4, /* feature not built (e.g. SLPR_FLAG_CONTRACT_FMA) */
-    SLPR_ERR_IO = 5           /* file / parse error (host scene helpers) */
+    SLPR_ERR_IO = 5,          /* file / parse error (host scene helpers) */
+    SLPR_ERR_RETRY = 6        /* exact bands: the frame is void on some band; render it again on EVERY band (new frame_seq) */
 };
 
 enum {
@@ -194,6 +195,36 @@ SLPR_API int slpr_band_exchange_ints(slpr_ctx *ctx, size_t *ints_per_band);
 SLPR_API int slpr_set_band_exchange(slpr_ctx *ctx, int32_t *dev_sums, const int32_t *dev_gathered, int n_bands, int band);
 SLPR_API int slpr_render_band_begin(slpr_ctx *ctx);
 SLPR_API int slpr_render_band_end(slpr_ctx *ctx);
+
+/* ---- Exact row bands, device-side exchange (new in round 2; csrc/bands.cuh second half) -----------------------
+ * No host hand-over and no collective: every (path, row) of a closed path has winding deltas that cancel, so only
+ * the few paths with a residue carry information. A band stores its non-zero per-path sums straight into a mailbox
+ * in every other band's HBM (peer-mapped over NVLink; CUDA IPC between one-process-per-GPU ranks), followed by a
+ * system-scope flag; every band merges what it received into a sorted break-point table that k_spans consults.
+ * The whole band frame is ONE captured graph, like slpr_render. Set-up, once per context:
+ *   slpr_band_mailbox      allocates this band's mailbox (plain cudaMalloc) and returns its device pointer
+ *   slpr_ipc_export/import turn it into a 64-byte CUDA IPC handle / map another process's allocation on this
+ *                          device (peer access is enabled on demand). Same-process contexts pass pointers directly.
+ *   slpr_set_band_peers    mailboxes[n_bands] as addressable from this device, bands ordered by rows; `root` is the
+ *                          band that collects the frame (its mailbox also receives the "pixels are in place" flags)
+ * Per frame, on every band, the same increasing frame_seq:
+ *   slpr_set_band / slpr_set_target (e.g. the root's frame buffer, allocated with slpr_alloc_device and mapped
+ *   through IPC: k_resolve then stores this band's pixels straight into the root's HBM), slpr_render_band(seq);
+ *   on the root slpr_band_wait_gather(seq) orders its stream after the arrival of every band's pixels.
+ * slpr_synchronize (or any call that finishes the frame) returns SLPR_ERR_RETRY when the frame was void on some
+ * band (a band outgrew its buffers, met a path too long for the segmented sort, or had more than 2048 residue
+ * paths): the state that caused it is already adjusted; render the frame again on every band with a new frame_seq.
+ * A band that never publishes makes the others give up after 2 s (SLPR_ERR_STATE) instead of hanging. */
+SLPR_API int slpr_band_mailbox(slpr_ctx *ctx, void **dev_ptr, size_t *bytes);
+SLPR_API int slpr_alloc_device(slpr_ctx *ctx, size_t bytes, void **dev_ptr); /* cudaMalloc, freed with the context */
+SLPR_API int slpr_ipc_export(slpr_ctx *ctx, void *dev_ptr, unsigned char handle[64]);
+SLPR_API int slpr_ipc_import(slpr_ctx *ctx, const unsigned char handle[64], void **dev_ptr);
+SLPR_API int slpr_set_band_peers(slpr_ctx *ctx, int n_bands, int band, int root, void *const *mailboxes);
+SLPR_API int slpr_render_band(slpr_ctx *ctx, uint32_t frame_seq);
+SLPR_API int slpr_band_wait_gather(slpr_ctx *ctx, uint32_t frame_seq);
+/* Number of differing 32-bit words (RGBA8 pixels) between two device buffers (checks an assembled frame against
+ * the same frame rendered whole, on the device). Waits for the context's stream. */
+SLPR_API int slpr_debug_diff_u32(slpr_ctx *ctx, const void *dev_a, const void *dev_b, size_t n_words, uint64_t *n_diff);
 
 /* Sort geometry of the last frame: key bits, number of 8-bit radix passes, bytes of one key. */
 SLPR_API int slpr_sort_info(slpr_ctx *ctx, uint32_t *key_bits, uint32_t *passes, uint32_t *key_bytes);

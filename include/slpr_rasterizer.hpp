@@ -37,7 +37,8 @@ struct vec4 { union { struct { float x, y, z, w; }; struct { float r, g, b, a; }
               vec4() : x(0), y(0), z(0), w(0) {} vec4(float a_, float b_, float c_, float d_) : x(a_), y(b_), z(c_), w(d_) {}
               float &operator[](int i) { return v[i]; } const float &operator[](int i) const { return v[i]; } };
 struct mat4 { vec4 col[4];  // column-major like glm: m[i] is column i
-              mat4() { for (int i = 0; i < 4; ++i) col[i][i] = 1.f; }
+              mat4() : mat4(1.f) {}
+              explicit mat4(float d) { for (int i = 0; i < 4; ++i) col[i][i] = d; }  // glm::mat4(1.0f) = identity
               vec4 &operator[](int i) { return col[i]; } const vec4 &operator[](int i) const { return col[i]; } };
 inline mat4 transpose(const mat4 &m) { mat4 t; for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) t[i][j] = m[j][i]; return t; }
 }  // namespace glm

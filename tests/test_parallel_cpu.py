@@ -101,7 +101,17 @@ def _exact_band_windings(rank, world, dist, torch):
     local = np.cumsum(np.where(mine, d_s, 0)) - np.where(mine, d_s, 0)  # exclusive scan of this band's own deltas
     check = mine & (cls != 1)
     corr = np.where(cls == 2, corr_z[path_s], corr_n[path_s])
-    return bool(np.array_equal((local + corr)[check].astype(np.int32), wn[check]))
+    ok = bool(np.array_equal((local + corr)[check].astype(np.int32), wn[check]))
+    # the sparse exchange (round 2): only the paths with a non-zero sum travel, and the corrections come from a
+    # sorted break-point table (k_band_merge / band_table_lookup) — same numbers as the dense tables
+    nz = np.nonzero(sums.any(axis=0))[0]
+    mine_entries = np.stack([nz, sums[0, nz], sums[1, nz], sums[2, nz]], axis=1) if len(nz) else np.zeros((0, 4), np.int64)
+    everyone = [None] * world
+    dist.all_gather_object(everyone, mine_entries)
+    table = PAR.sparse_band_table(everyone, rank)
+    assert len(nz) < P // 4 and sum(len(e) for e in everyone) > 0, "the exchange must be sparse, and not empty, on this scene"
+    sparse = np.array([PAR.sparse_band_lookup(table, p, c == 2) for p, c in zip(path_s[check], cls[check])])
+    return ok and bool(np.array_equal(sparse, corr[check]))
 
 
 def test_gloo_band_gather_and_frame_partition():
@@ -116,3 +126,23 @@ def test_gloo_band_gather_and_frame_partition():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_sparse_band_table_equals_dense_corrections():
+    """k_band_merge's break-point table against the dense corrN / corrZ tables, random sums, 5 bands."""
+    rng = np.random.default_rng(11)
+    G, P = 5, 300
+    dense = np.zeros((G, 3, P), np.int64)
+    for r in range(G):
+        hit = rng.choice(P, 12, replace=False)
+        dense[r][:, hit] = rng.integers(-3, 4, (3, 12))
+    entries = []
+    for r in range(G):
+        nz = np.nonzero(dense[r].any(axis=0))[0]
+        entries.append(np.stack([nz, dense[r][0, nz], dense[r][1, nz], dense[r][2, nz]], axis=1))
+    for band in range(G):
+        cn, cz = PAR.band_corrections(dense, band)
+        t = PAR.sparse_band_table(entries, band)
+        assert np.all(np.diff(t[0]) > 0)
+        for p in range(P):
+            assert PAR.sparse_band_lookup(t, p, False) == cn[p] and PAR.sparse_band_lookup(t, p, True) == cz[p]

@@ -474,3 +474,62 @@ def test_long_path_with_default_flags_first_frame():
     for b in bufs:
         assert np.array_equal(b, ref["rgba"])
     r.close()
+
+
+def _render_peer_bands(ctxs, seq0, root_waits=True, max_tries=4):
+    """One frame on all band contexts with the device-side exchange; handles SLPR_ERR_RETRY the way parallel.py does
+    across ranks (everybody renders the frame again with a new frame_seq). Returns the next unused seq."""
+    seq = seq0
+    for _ in range(max_tries):
+        for c in ctxs:
+            c.render_band(seq)
+        if root_waits:
+            ctxs[0].band_wait_gather(seq)
+        retry = False
+        for c in ctxs:
+            try:
+                c.synchronize()
+            except V.SlprRetry:
+                retry = True
+        seq += 1
+        if not retry:
+            return seq
+    raise AssertionError("the band frame stayed void")
+
+
+def test_exact_row_bands_device_side_exchange():
+    """Round 2: the same exactness as test_exact_row_bands_with_exchange with NO host hand-over — sparse per-path sums
+    stored into the other bands' mailboxes, flags, a merged break-point table (csrc/bands.cuh second half). G band
+    contexts on one GPU stand in for G GPUs (their mailboxes are plain pointers here, CUDA IPC mappings in
+    production: tests/test_ipc_gpu.py); they all render into ONE frame buffer, like bands storing into the root's."""
+    import torch
+    from vkscanlinepr_b200 import parallel as PAR
+    tig, vp = util.golden_scene("tiger")
+    cases = [(S.synth_scene(2000, 512, 512, 6.0, 30.0, seed=0x5CA71E01), S.identity_rows(), 512, 512, 3),
+             (S.synth_scene(3000, 640, 360, 4.0, 60.0, seed=0x5CA71E02), S.identity_rows(), 640, 360, 8),
+             (util.looping_cubics_scene(), S.identity_rows(), 512, 384, 4),      # hundreds of residue paths
+             (tig, S.fit_rows(vp, 640, 480), 640, 480, 4)]                       # a path too long for the segmented sort: retry
+    for sc, rows, W, H, G in cases:
+        ref = O.render(sc, rows, W, H, keep={"rgba", "wn"})
+        bands = PAR.band_rows(H, G)
+        frame = torch.zeros((H, W, 4), dtype=torch.uint8, device="cuda")
+        ctxs = []
+        for g, (y0, y1) in enumerate(bands):
+            c = V.ScanlineRasterizer(0, 0).initialize(None, W, H)
+            c.loadVG(sc)
+            c.setMVP(rows)
+            c.set_band(y0, y1)
+            c.set_target(frame.data_ptr(), W * 4)
+            ctxs.append(c)
+        boxes = [c.band_mailbox()[0] for c in ctxs]
+        for g, c in enumerate(ctxs):
+            c.set_band_peers(G, g, 0, boxes)
+        seq = 7
+        for _ in range(3):  # later frames replay the captured graph; mailbox slots alternate
+            frame.zero_()
+            torch.cuda.synchronize()
+            seq = _render_peer_bands(ctxs, seq)
+            got = frame.cpu().numpy()
+            assert np.array_equal(got, ref["rgba"]), f"{sc.name}: {int((got != ref['rgba']).any(axis=2).sum())} pixels differ ({G} bands)"
+        for c in ctxs:
+            c.close()

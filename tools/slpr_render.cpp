@@ -25,7 +25,7 @@ int main(int argc, char **argv) {
         rast.loadVG(vg);                                 // _vgRasterizer->loadVG(_vgContainer)
         // camera: uniform fit of the file's viewport box, centred; the app passes transpose(camera.mv())
         const float sx = w / (vg->vp[2] - vg->vp[0]), sy = h / (vg->vp[3] - vg->vp[1]), s = std::min(sx, sy);
-        glm::mat4 mv;                                    // column-major affine: x' = s*x + tx
+        glm::mat4 mv(1.0f);                              // identity (glm's default constructor leaves it unset); column-major affine: x' = s*x + tx
         mv[0][0] = s; mv[1][1] = s;
         mv[3][0] = (w - s * (vg->vp[2] - vg->vp[0])) * 0.5f - s * vg->vp[0];
         mv[3][1] = (h - s * (vg->vp[3] - vg->vp[1])) * 0.5f - s * vg->vp[1];

@@ -34,6 +34,10 @@ class SlprError(RuntimeError):
     pass
 
 
+class SlprRetry(SlprError):
+    """SLPR_ERR_RETRY: an exact-band frame was void on some band; render it again on every band (new frame_seq)."""
+
+
 def build(force=False, verbose=False):
     """Compile libslpr.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
     src_dir = os.path.join(_HERE, "csrc")
@@ -80,7 +84,7 @@ def lib():
 
 def _check(rc):
     if rc != 0:
-        raise SlprError(f"slpr error {rc}: {lib().slpr_last_error().decode()}")
+        raise (SlprRetry if rc == 6 else SlprError)(f"slpr error {rc}: {lib().slpr_last_error().decode()}")
 
 
 def _p(a):
@@ -247,6 +251,43 @@ class ScanlineRasterizer:
 
     def render_band_end(self):
         _check(lib().slpr_render_band_end(self._h))
+
+    # exact bands, device-side exchange (include/slpr.h; host logic in parallel.py)
+    def band_mailbox(self):
+        p = C.c_void_p(); n = C.c_size_t()
+        _check(lib().slpr_band_mailbox(self._h, C.byref(p), C.byref(n)))
+        return int(p.value), int(n.value)
+
+    def alloc_device(self, nbytes):
+        p = C.c_void_p()
+        _check(lib().slpr_alloc_device(self._h, C.c_size_t(nbytes), C.byref(p)))
+        return int(p.value)
+
+    def ipc_export(self, dev_ptr):
+        h = (C.c_ubyte * 64)()
+        _check(lib().slpr_ipc_export(self._h, C.c_void_p(dev_ptr), h))
+        return bytes(h)
+
+    def ipc_import(self, handle):
+        h = (C.c_ubyte * 64).from_buffer_copy(handle)
+        p = C.c_void_p()
+        _check(lib().slpr_ipc_import(self._h, h, C.byref(p)))
+        return int(p.value)
+
+    def set_band_peers(self, n_bands, band, root, mailboxes):
+        arr = (C.c_void_p * max(1, len(mailboxes)))(*[C.c_void_p(m) for m in mailboxes])
+        _check(lib().slpr_set_band_peers(self._h, int(n_bands), int(band), int(root), arr))
+
+    def render_band(self, frame_seq):
+        _check(lib().slpr_render_band(self._h, C.c_uint32(frame_seq & 0xFFFFFFFF)))
+
+    def band_wait_gather(self, frame_seq):
+        _check(lib().slpr_band_wait_gather(self._h, C.c_uint32(frame_seq & 0xFFFFFFFF)))
+
+    def diff_u32(self, dev_a, dev_b, n_words):
+        n = C.c_uint64()
+        _check(lib().slpr_debug_diff_u32(self._h, C.c_void_p(dev_a), C.c_void_p(dev_b), C.c_size_t(n_words), C.byref(n)))
+        return int(n.value)
 
     def framebuffer(self):
         p = C.c_void_p(); s = C.c_size_t()

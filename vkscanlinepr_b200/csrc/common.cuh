@@ -21,7 +21,8 @@ struct FrameParams {
     int stat_big;      // paths of 513..4096 fragments  } the host picks the sort from them
     int stat_huge;     // paths of more than 4096 fragments (radix sort only)
     int n_live;        // band mode: curves whose path comes near the band (k_band_live)
-    int pad[3];
+    int frame_seq;     // exact bands with the device-side exchange: which frame this is (mailbox slot = seq & 1)
+    int pad[2];
 };
 
 // Device-resident counters (zeroed at the start of every frame).
@@ -41,14 +42,18 @@ struct FrameCounters {
     int n_live;        // band mode: curves whose path comes near the band (k_band_live)
     int n_fix;         // pieces whose predecessor's boundary fragment must be redone (k_walk -> k_piece_fix)
     int fix_missed;    // invariant check of k_walk's conditional boundary stores (always 0)
-    int pad[1];
+    int n_band_entries;  // exact bands: paths of this band with a non-zero winding sum (k_band_sums_sparse)
+    int n_band_bp;       // exact bands: break points in the merged correction table (k_band_merge)
+    int band_void;       // exact bands: 1 = another band's frame was void, 2 = a band never published (timeout),
+                         //              3 = more entries than the merge table holds; the frame must be rendered again
+    int pad[2];
 };
 
 // The back half of a frame (winding prefix, spans, coverage) must not touch the sorted buffers of a frame the
 // host is going to render again: one whose fragments outgrew the buffers (overflow; nothing was generated) or one
 // with a path too long for the segmented sort (sort_fallback: the sorted buffers are partly unwritten).
 __device__ __forceinline__ bool frame_void(const FrameCounters *ctr, int capacity) {
-    return ctr->overflow != 0 || ctr->n_fragments > capacity || ctr->sort_fallback != 0;
+    return ctr->overflow != 0 || ctr->n_fragments > capacity || ctr->sort_fallback != 0 || ctr->band_void != 0;
 }
 
 // Key geometry for the compact 64-bit sort key (path | row rank | cell x), see DESIGN.md.

@@ -168,6 +168,14 @@ struct slpr_ctx {
     bool graph_a_valid = false, graph_s_valid = false, band_begun = false;
     int launches_a = 0, launches_s = 0;
     cudaEvent_t x_event = nullptr;  // sums and counters of the band in flight are complete
+    // exact row bands, device-side sparse exchange (bands.cuh, second half): mailboxes in every band's HBM
+    BandMailbox *p_box = nullptr;     // this band's mailbox (cudaMalloc: exportable through CUDA IPC)
+    BandPeers peers{};                // n_bands == 0: not configured
+    BandEntry *p_list = nullptr;      // [XB_CAP] this band's non-zero per-path sums
+    uint32_t *p_tab_path = nullptr;   // [XB_TOTAL] merged break-point table of the frame
+    int *p_tab_cum = nullptr, *p_tab_n = nullptr, *p_tab_z = nullptr;
+    std::vector<void *> ipc_mapped;   // peer allocations opened with slpr_ipc_import
+    std::vector<void *> dev_allocs;   // slpr_alloc_device
     cudaEvent_t ev[SLPR_STAGE_COUNT + 1] = {};
     bool stage_times_valid = false;
     uint64_t launches = 0;
@@ -333,6 +341,9 @@ extern "C" void slpr_destroy(slpr_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    for (void *p : c->ipc_mapped) cudaIpcCloseMemHandle(p);
+    for (void *p : c->dev_allocs) cudaFree(p);
+    cudaFree(c->p_box); cudaFree(c->p_list); cudaFree(c->p_tab_path); cudaFree(c->p_tab_cum); cudaFree(c->p_tab_n); cudaFree(c->p_tab_z);
     free_capacity(c);
     free_scene(c);
     cudaFree(c->d_params); cudaFreeHost(c->h_ctr); cudaFreeHost(c->pslot[0].h); cudaFreeHost(c->pslot[1].h); cudaFree(c->d_cells); cudaFree(c->d_fb); cudaFree(c->d_fb2); cudaFree(c->d_prim_temp);
@@ -571,6 +582,11 @@ static int enqueue_fragments(slpr_ctx *c, cudaStream_t s, bool timed, int &launc
         k_band_sums<<<grid_for(c, (long long)c->P * 32, 256, 8), 256, 0, s>>>(c->d_seg_tap, c->P, c->d_key[0], c->d_val[0], c->d_ctr,
                                                                              c->cap, c->L, c->x_sums);
         ++launches;
+    } else if (c->peers.n_bands > 0) {  // sparse: only the paths with a residue, stored straight into every band's mailbox
+        k_band_sums_sparse<<<grid_for(c, (long long)c->P * 32, 256, 8), 256, 0, s>>>(c->d_seg_tap, c->P, c->d_key[0], c->d_val[0], c->d_ctr,
+                                                                                    c->cap, c->L, c->p_list);
+        k_band_publish<<<c->peers.n_bands, 256, 0, s>>>(c->d_params, c->d_ctr, c->cap, c->radix_mode ? 1 : 0, c->p_list, c->peers);
+        launches += 2;
     }
     CU(cudaGetLastError());
     return SLPR_OK;
@@ -624,6 +640,12 @@ static int enqueue_back(slpr_ctx *c, cudaStream_t s, bool timed, int &launches) 
         launches += 3;
         corr = c->x_corr;
     }
+    BandTable btab{nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (!c->x_sums && c->peers.n_bands > 0) {
+        btab = BandTable{c->p_tab_path, c->p_tab_cum, c->p_tab_n, c->p_tab_z, &c->d_ctr->n_band_bp};
+        k_band_merge<<<1, XB_MERGE_THREADS, XB_MERGE_SMEM, s>>>(c->d_params, c->d_ctr, c->peers, btab);
+        ++launches;
+    }
     // ---- winding scan + mark + flag scan + emit: one kernel, two chained look-backs
     SpanTaps stp{c->d_wn, c->t_sidx, c->t_skey32, c->t_flags, c->t_scan3};
     SpanTemp stmp{c->d_wsum, c->d_status[1], c->d_status[2], c->d_tickets + 1};
@@ -637,7 +659,7 @@ static int enqueue_back(slpr_ctx *c, cudaStream_t s, bool timed, int &launches) 
     auto spans = taps ? (c->fill_fused ? k_spans<true, true, true> : k_spans<false, true, true>)
                       : !c->fill_fused ? k_spans<false, true, false> : (want_records(c) ? k_spans<true, true, false> : k_spans<true, false, false>);
     spans<<<span_grid, SP_THREADS, SP_STAGE_BYTES, s>>>(c->d_key[cur], c->d_val[cur], c->d_finfo, c->d_rec, c->d_ctr, c->L, (int)c->W, (int)c->H,
-                                                       c->cap, stp, stmp, corr, c->P, c->d_cells, c->cw);
+                                                       c->cap, stp, stmp, corr, c->P, c->d_cells, c->cw, btab);
     ++launches;
     if (taps) {
         k_scan3_fixup<<<wide, 256, 0, s>>>(c->d_ctr, c->cap, c->t_scan3);
@@ -656,6 +678,10 @@ static int enqueue_back(slpr_ctx *c, cudaStream_t s, bool timed, int &launches) 
     else k_resolve<false><<<wide, 256, 0, s>>>(c->d_params, c->d_rec, c->d_finfo, c->d_cells, c->cw, fb, stride);
     ++launches;
     if (timed) CU(cudaEventRecord(c->ev[11], s));
+    if (!c->x_sums && c->peers.n_bands > 0 && c->peers.root != c->peers.me) {  // gather: tell the root this band's pixels are in place
+        k_band_done<<<1, 1, 0, s>>>(c->d_params, c->peers);
+        ++launches;
+    }
     CU(cudaMemcpyAsync(c->h_ctr, c->d_ctr, sizeof(FrameCounters), cudaMemcpyDeviceToHost, s));
     CU(cudaGetLastError());
     return SLPR_OK;
@@ -801,9 +827,39 @@ static int settle_modes(slpr_ctx *c, const FrameCounters &k) {
     return SLPR_OK;
 }
 
+// Exact bands with the device-side exchange: a band cannot redo a frame on its own (the other bands have consumed
+// what it published), so a void frame is reported and the caller renders it again on every band with a new seq.
+static int finish_peer_frame(slpr_ctx *c) {
+    CU(cudaStreamSynchronize(c->stream));
+    c->frame_pending = false;
+    const FrameCounters &k = *c->h_ctr;
+    if (k.overflow) {
+        const long long nf = k.n_fragments;
+        if (nf < 0 || nf >= (1ll << 29) - (1ll << 26)) return fail(SLPR_ERR_INVALID, "band has %lld fragments; limit is 2^29", nf);
+        int rc = alloc_capacity(c, (int)std::min<long long>(nf + nf / 4 + 65536, (1ll << 29) - 1));
+        if (rc) return rc;
+        return fail(SLPR_ERR_RETRY, "band %d outgrew its fragment buffers (now %d): render the frame again on every band", c->peers.me, c->cap);
+    }
+    if (k.stat_huge && !c->radix_mode) {
+        c->radix_mode = true;
+        invalidate_graphs(c);
+        return fail(SLPR_ERR_RETRY, "band %d has a path too long for the segmented sort (now radix): render the frame again on every band", c->peers.me);
+    }
+    if (k.band_void == 2) return fail(SLPR_ERR_STATE, "band %d: another band did not publish its winding sums within the time-out", c->peers.me);
+    if (k.band_void) return fail(SLPR_ERR_RETRY, "band %d: the frame was void on another band (%d): render it again on every band", c->peers.me, k.band_void);
+    if (k.fix_missed) return fail(SLPR_ERR_STATE, "internal: a piece started below its start parameter without ending below it");
+    if (choose_fill_mode(c, k.n_fragments) != c->fill_fused) {  // (the sort mode of a band only ever moves to radix, above)
+        c->fill_fused = !c->fill_fused;
+        invalidate_graphs(c);
+    }
+    c->frame_done = true;
+    return SLPR_OK;
+}
+
 static int finish_frame(slpr_ctx *c) {
     if (!c->frame_pending && !c->frame_done) return fail(SLPR_ERR_STATE, "no frame has been rendered");
     CU(cudaSetDevice(c->device));
+    if (c->peers.n_bands > 0 && !c->x_sums && c->frame_pending) return finish_peer_frame(c);
     for (int attempt = 0; attempt < 4; ++attempt) {
         CU(cudaStreamSynchronize(c->stream));
         c->frame_pending = false;
@@ -1146,6 +1202,120 @@ extern "C" int slpr_render_band_end(slpr_ctx *c) {
     c->stage_times_valid = false;
     c->frame_pending = true;
     c->frame_done = false;
+    return SLPR_OK;
+}
+
+// ---- exact row bands, device-side sparse exchange ---------------------------------------------------------
+extern "C" int slpr_band_mailbox(slpr_ctx *c, void **dev_ptr, size_t *bytes) {
+    if (!c || !dev_ptr) return fail(SLPR_ERR_INVALID, "slpr_band_mailbox: null argument");
+    CU(cudaSetDevice(c->device));
+    if (!c->p_box) {
+        CU(cudaMalloc(&c->p_box, sizeof(BandMailbox)));
+        CU(cudaMemset(c->p_box, 0, sizeof(BandMailbox)));
+        CU(cudaMalloc(&c->p_list, (size_t)XB_CAP * sizeof(BandEntry)));
+        CU(cudaMalloc(&c->p_tab_path, (size_t)XB_TOTAL * 4));
+        CU(cudaMalloc(&c->p_tab_cum, (size_t)XB_TOTAL * 4));
+        CU(cudaMalloc(&c->p_tab_n, (size_t)XB_TOTAL * 4));
+        CU(cudaMalloc(&c->p_tab_z, (size_t)XB_TOTAL * 4));
+        CU(cudaFuncSetAttribute(k_band_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XB_MERGE_SMEM));
+    }
+    *dev_ptr = c->p_box;
+    if (bytes) *bytes = sizeof(BandMailbox);
+    return SLPR_OK;
+}
+
+extern "C" int slpr_alloc_device(slpr_ctx *c, size_t bytes, void **dev_ptr) {
+    if (!c || !dev_ptr || !bytes) return fail(SLPR_ERR_INVALID, "slpr_alloc_device: null argument");
+    CU(cudaSetDevice(c->device));
+    void *p = nullptr;
+    CU(cudaMalloc(&p, bytes));
+    c->dev_allocs.push_back(p);
+    *dev_ptr = p;
+    return SLPR_OK;
+}
+
+extern "C" int slpr_ipc_export(slpr_ctx *c, void *dev_ptr, unsigned char handle[64]) {
+    if (!c || !dev_ptr || !handle) return fail(SLPR_ERR_INVALID, "slpr_ipc_export: null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    CU(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, dev_ptr));
+    memcpy(handle, &h, 64);
+    return SLPR_OK;
+}
+
+extern "C" int slpr_ipc_import(slpr_ctx *c, const unsigned char handle[64], void **dev_ptr) {
+    if (!c || !dev_ptr || !handle) return fail(SLPR_ERR_INVALID, "slpr_ipc_import: null argument");
+    CU(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    void *p = nullptr;
+    CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    c->ipc_mapped.push_back(p);
+    *dev_ptr = p;
+    return SLPR_OK;
+}
+
+extern "C" int slpr_set_band_peers(slpr_ctx *c, int n_bands, int band, int root, void *const *mailboxes) {
+    if (!c) return fail(SLPR_ERR_INVALID, "null context");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    invalidate_graphs(c);
+    if (n_bands == 0) { c->peers = BandPeers{}; return SLPR_OK; }
+    if (!c->p_box) return fail(SLPR_ERR_STATE, "slpr_set_band_peers: call slpr_band_mailbox first");
+    if (c->x_sums) return fail(SLPR_ERR_STATE, "slpr_set_band_peers: a host-driven exchange is configured (slpr_set_band_exchange)");
+    if (!mailboxes || n_bands < 1 || n_bands > XB_MAX_BANDS || band < 0 || band >= n_bands || root < 0 || root >= n_bands)
+        return fail(SLPR_ERR_INVALID, "slpr_set_band_peers: need 1 <= n_bands <= %d, 0 <= band, root < n_bands and the mailboxes", XB_MAX_BANDS);
+    if (mailboxes[band] != (void *)c->p_box) return fail(SLPR_ERR_INVALID, "slpr_set_band_peers: mailboxes[band] must be this context's own mailbox");
+    BandPeers p{};
+    for (int i = 0; i < n_bands; ++i) {
+        if (!mailboxes[i]) return fail(SLPR_ERR_INVALID, "slpr_set_band_peers: mailbox %d is null", i);
+        p.box[i] = reinterpret_cast<BandMailbox *>(mailboxes[i]);
+    }
+    p.n_bands = n_bands; p.me = band; p.root = root;
+    c->peers = p;
+    return SLPR_OK;
+}
+
+extern "C" int slpr_render_band(slpr_ctx *c, uint32_t frame_seq) {
+    if (!c) return fail(SLPR_ERR_INVALID, "null context");
+    if (c->peers.n_bands <= 0) return fail(SLPR_ERR_STATE, "slpr_render_band: call slpr_set_band_peers first");
+    c->hp.frame_seq = (int)frame_seq;
+    return slpr_render(c);
+}
+
+extern "C" int slpr_band_wait_gather(slpr_ctx *c, uint32_t frame_seq) {
+    if (!c) return fail(SLPR_ERR_INVALID, "null context");
+    if (c->peers.n_bands <= 0 || c->peers.root != c->peers.me) return fail(SLPR_ERR_STATE, "slpr_band_wait_gather: only on the root band of a configured exchange");
+    CU(cudaSetDevice(c->device));
+    k_band_wait_done<<<1, 32, 0, c->stream>>>(frame_seq, c->peers, c->d_ctr);
+    ++c->launches;
+    CU(cudaGetLastError());
+    return SLPR_OK;
+}
+
+__global__ void k_count_diff(const uint32_t *__restrict__ a, const uint32_t *__restrict__ b, size_t n, unsigned long long *__restrict__ out) {
+    unsigned long long d = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) d += a[i] != b[i];
+    for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xFFFFFFFFu, d, o);
+    if ((threadIdx.x & 31) == 0 && d) atomicAdd(out, d);
+}
+
+// How many 32-bit words (= RGBA8 pixels) differ between two device buffers: compares an assembled frame with the
+// same frame rendered whole without moving a gigabyte to the host. Synchronous.
+extern "C" int slpr_debug_diff_u32(slpr_ctx *c, const void *dev_a, const void *dev_b, size_t n_words, uint64_t *n_diff) {
+    if (!c || !dev_a || !dev_b || !n_diff) return fail(SLPR_ERR_INVALID, "slpr_debug_diff_u32: null argument");
+    CU(cudaSetDevice(c->device));
+    unsigned long long *d = nullptr;
+    CU(cudaMalloc(&d, 8));
+    CU(cudaMemsetAsync(d, 0, 8, c->stream));
+    k_count_diff<<<c->num_sms * 8, 256, 0, c->stream>>>(reinterpret_cast<const uint32_t *>(dev_a), reinterpret_cast<const uint32_t *>(dev_b), n_words, d);
+    unsigned long long h = 0;
+    cudaError_t e = cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(SLPR_ERR_CUDA, "slpr_debug_diff_u32: %s", cudaGetErrorString(e));
+    *n_diff = h;
     return SLPR_OK;
 }
 

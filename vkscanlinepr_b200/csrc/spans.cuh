@@ -14,6 +14,7 @@
 #include "geom.cuh"
 #include "scan.cuh"
 #include "raster.cuh"
+#include "bands.cuh"
 
 namespace slpr {
 
@@ -139,7 +140,7 @@ __global__ void __launch_bounds__(SP_THREADS, SP_BLOCKS) k_spans(const uint64_t 
                                                          int4 *__restrict__ records, FrameCounters *__restrict__ ctr,
                                                          KeyLayout L, int width, int height, int capacity, SpanTaps taps,
                                                          SpanTemp tmp, const int *__restrict__ band_corr, uint32_t n_paths,
-                                                         uint32_t *__restrict__ cells, int cw) {
+                                                         uint32_t *__restrict__ cells, int cw, BandTable btab) {
     __shared__ uint32_t s_warp[SP_THREADS / 32];
     __shared__ unsigned long long s_prefix;
     __shared__ long long s_tile;
@@ -151,6 +152,7 @@ __global__ void __launch_bounds__(SP_THREADS, SP_BLOCKS) k_spans(const uint64_t 
     const long long n = nf;
     const long long ntiles = (n == 0) ? 1 : (n + SP_TILE - 1) / SP_TILE;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nbp = btab.count ? *btab.count : 0;  // exact bands, sparse exchange: break points of this frame (usually 0)
 
     while (true) {
         if (tid == 0) s_tile = (long long)atomicAdd(tmp.ticket, 1);
@@ -242,6 +244,8 @@ __global__ void __launch_bounds__(SP_THREADS, SP_BLOCKS) k_spans(const uint64_t 
         // ---- flags (MARK:38-93) from the keys and the winding prefix
         uint32_t fmask = 0, smask = 0;
         {
+            uint32_t bt_key = 0xFFFFFFFFu;  // (path << 1 | row 0) of the cached break-point look-up
+            int bt_corr = 0;
             KeyFields a = decode_key(L, k[0]);
 #pragma unroll
             for (int j = 0; j < SP_ITEMS; ++j) {
@@ -257,7 +261,13 @@ __global__ void __launch_bounds__(SP_THREADS, SP_BLOCKS) k_spans(const uint64_t 
                         const bool even_odd = (rpack >> j) & 1u;  // fill_rule[path] == 1
                         // MARK:82 (rule values other than 0/1 never set the flag there; the loader only produces 0/1)
                         // exact row bands (bands.cuh): the deltas of the other bands' fragments that sort before this one
-                        const int wf = band_corr ? wn + band_corr[(b.y == 0 ? n_paths : 0u) + b.path] : wn;
+                        int wf = wn;
+                        if (band_corr) wf += band_corr[(b.y == 0 ? n_paths : 0u) + b.path];
+                        else if (nbp > 0) {
+                            const uint32_t bk = (b.path << 1) | (b.y == 0 ? 1u : 0u);
+                            if (bk != bt_key) { bt_key = bk; bt_corr = band_table_lookup(btab, nbp, b.path, b.y == 0); }
+                            wf += bt_corr;
+                        }
                         const bool wn_flag = even_odd ? ((wf & 1) != 0) : (wf != 0);
                         span = (a.y == b.y && (a.x + FRAG_SIZE) < b.x && a.path == b.path && wn_flag) ? 1u : 0u;  // MARK:84
                     }

@@ -97,3 +97,77 @@ def band_corrections(gathered, band):
     corr_n = e + g[:band, 0].sum(axis=0)
     corr_z = e + others[:, 0].sum(axis=0) + others[:, 1].sum(axis=0)
     return corr_n.astype(np.int32), corr_z.astype(np.int32)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# Exact bands with the device-side sparse exchange (csrc/bands.cuh, second half; include/slpr.h)
+def connect_band_peers(rasterizer, dist, rank, world, root=0, frame_bytes=0, n_frames=2):
+    """Once per rasterizer: every rank allocates its mailbox, the 64-byte CUDA IPC handles are all-gathered over
+    torch.distributed (host plumbing only), every rank maps the others' mailboxes (peer access over NVLink) and
+    registers them (slpr_set_band_peers). With `frame_bytes`, the root also allocates `n_frames` frame buffers and
+    every rank maps them: a band rendered with set_target(frames[i], stride) stores its pixels straight into the
+    root's HBM. Returns {"mailboxes": [...], "frames": [...]} as device pointers valid on this rank's GPU."""
+    own, _ = rasterizer.band_mailbox()
+    mine = {"box": rasterizer.ipc_export(own) if world > 1 else None, "frames": []}
+    frames_local = []
+    if frame_bytes and rank == root:
+        frames_local = [rasterizer.alloc_device(frame_bytes) for _ in range(n_frames)]
+        if world > 1:
+            mine["frames"] = [rasterizer.ipc_export(p) for p in frames_local]
+    if world > 1:
+        everyone = [None] * world
+        dist.all_gather_object(everyone, mine)
+    else:
+        everyone = [mine]
+    boxes = [own if r == rank else rasterizer.ipc_import(everyone[r]["box"]) for r in range(world)]
+    frames = frames_local if rank == root else [rasterizer.ipc_import(h) for h in everyone[root]["frames"]]
+    rasterizer.set_band_peers(world, rank, root, boxes)
+    return {"mailboxes": boxes, "frames": frames}
+
+
+def finish_band_frame(rasterizer, dist=None):
+    """Wait for this rank's band of the frame; True if the frame has to be rendered again on EVERY band (some band
+    outgrew its buffers / changed its sort / had too many residue paths — SLPR_ERR_RETRY), agreed over all ranks."""
+    from . import SlprRetry
+    retry = 0
+    try:
+        rasterizer.synchronize()
+    except SlprRetry:
+        retry = 1
+    if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+        import torch
+        dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+        t = torch.tensor([retry], dtype=torch.int32, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        retry = int(t.item())
+    return bool(retry)
+
+
+def sparse_band_table(entries_per_band, band):
+    """numpy restatement of k_band_merge for tests: entries_per_band[r] = array [[path, a, inv, z], ...] (the non-zero
+    per-path sums band r publishes); returns (path, cum, n, z) of `band`: sorted unique paths of the OTHER bands'
+    entries, cum = inclusive prefix of D = sum(a + inv + z), n = sum over bands below of a, z = sum of (a + inv)."""
+    rows = []
+    for r, e in enumerate(entries_per_band):
+        if r == band:
+            continue
+        for p, a, inv, z in np.asarray(e, dtype=np.int64).reshape(-1, 4):
+            rows.append((p, a + inv + z, a if r < band else 0, a + inv))
+    if not rows:
+        return tuple(np.zeros(0, np.int64) for _ in range(4))
+    rows = np.array(rows, dtype=np.int64)
+    paths = np.unique(rows[:, 0])
+    D = np.array([rows[rows[:, 0] == p, 1].sum() for p in paths])
+    N = np.array([rows[rows[:, 0] == p, 2].sum() for p in paths])
+    Z = np.array([rows[rows[:, 0] == p, 3].sum() for p in paths])
+    return paths, np.cumsum(D), N, Z
+
+
+def sparse_band_lookup(table, path, row0):
+    """band_table_lookup (csrc/bands.cuh): the winding correction of a fragment of `path`."""
+    paths, cum, n, z = table
+    i = int(np.searchsorted(paths, path, side="left"))
+    c = int(cum[i - 1]) if i > 0 else 0
+    if i < len(paths) and paths[i] == path:
+        c += int(z[i] if row0 else n[i])
+    return c
