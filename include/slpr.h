@@ -143,6 +143,10 @@ SLPR_API int slpr_set_target(slpr_ctx *ctx, void *dev_rgba, size_t stride_bytes)
  * the whole frame is enqueued asynchronously on the context's stream, with no host round trip. */
 SLPR_API int slpr_render(slpr_ctx *ctx);
 
+/* Optional: do everything a frame needs that can block the device (buffer sizing, allocations, graph capture and
+ * upload for the current target) without rendering; slpr_render otherwise does it on first use. */
+SLPR_API int slpr_prepare(slpr_ctx *ctx);
+
 /* Headless replacement for acquire/present (vulkan/vk_vg_rasterizer.cpp:424-447): waits for the
  * frame and copies the RGBA8 image (top-left origin, bytes R,G,B,A) to host memory. */
 SLPR_API int slpr_readback(slpr_ctx *ctx, uint8_t *rgba, size_t stride_bytes);

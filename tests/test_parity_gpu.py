@@ -481,6 +481,8 @@ def _render_peer_bands(ctxs, seq0, root_waits=True, max_tries=4):
     across ranks (everybody renders the frame again with a new frame_seq). Returns the next unused seq."""
     seq = seq0
     for _ in range(max_tries):
+        for c in ctxs:   # contexts of ONE process: nothing that blocks the device (sizing, allocation, graph capture) may
+            c.prepare()  # happen while another context's exchange kernel waits for this one (slpr_prepare)
         for c in ctxs:
             c.render_band(seq)
         if root_waits:

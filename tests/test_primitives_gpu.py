@@ -15,7 +15,9 @@ def ctx():
     r.close()
 
 
-@pytest.mark.parametrize("n", [0, 1, 3, 4095, 4096, 4097, 100_003, 20_000_000])
+# (from 2^22 elements on the TMA-pipelined kernel k_scan_tma takes over: whole tiles by bulk copy, a ragged last tile)
+@pytest.mark.parametrize("n", [0, 1, 3, 4095, 4096, 4097, 8191, 8192, 8193, 100_003, (1 << 22) - 1, 1 << 22, (1 << 22) + 8192 * 7,
+                               (1 << 22) + 8192 * 300 + 5, 20_000_000, 35_000_003])
 def test_scan_matches_cumsum(ctx, n):
     import torch
     g = torch.Generator(device="cuda").manual_seed(n + 1)
@@ -27,6 +29,29 @@ def test_scan_matches_cumsum(ctx, n):
     exp = torch.zeros(n + 1, dtype=torch.int64, device="cuda")
     exp[1:] = torch.cumsum(a.to(torch.int64), 0)
     assert torch.equal(out.to(torch.int64), exp)
+
+
+def test_scan_unaligned_pointers_and_in_place(ctx):
+    """Pointers that are not 16-byte aligned fall back to the ticketed kernel; in-place scanning is allowed."""
+    import torch
+    n = (1 << 22) + 1000
+    base = torch.randint(0, 5, (n + 8,), dtype=torch.int32, device="cuda")
+    out = torch.empty(n + 9, dtype=torch.int32, device="cuda")
+    for off_in, off_out in ((1, 0), (0, 3), (2, 2)):
+        a = base[off_in:off_in + n]
+        o = out[off_out:off_out + n + 1]
+        ctx.scan_i32(a.data_ptr(), o.data_ptr(), n)
+        ctx.synchronize()
+        exp = torch.zeros(n + 1, dtype=torch.int64, device="cuda")
+        exp[1:] = torch.cumsum(a.to(torch.int64), 0)
+        assert torch.equal(o.to(torch.int64), exp)
+    buf = torch.zeros(n + 4, dtype=torch.int32, device="cuda")
+    buf[:n] = base[:n]
+    exp = torch.zeros(n + 1, dtype=torch.int64, device="cuda")
+    exp[1:] = torch.cumsum(base[:n].to(torch.int64), 0)
+    ctx.scan_i32(buf.data_ptr(), buf.data_ptr(), n)
+    ctx.synchronize()
+    assert torch.equal(buf[:n + 1].to(torch.int64), exp)
 
 
 def test_scan_wraps_like_int32(ctx):

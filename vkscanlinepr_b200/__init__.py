@@ -204,6 +204,9 @@ class ScanlineRasterizer:
     def render(self):
         _check(lib().slpr_render(self._h))
 
+    def prepare(self):
+        _check(lib().slpr_prepare(self._h))
+
     # -- headless additions ------------------------------------------------------------------
     def readback(self, out=None):
         if out is None:

@@ -68,6 +68,7 @@ struct slpr_ctx {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     int num_sms = NUM_SMS_B200;
     int walk_blocks_per_sm = 7, span_blocks_per_sm = 4;  // resident blocks of the persistent kernels (occupancy API)
+    int scan_tma_blocks_per_sm = 0;                      // k_scan_tma: CTAs that fit an SM (its tiles are dealt round-robin)
 
     // scene (slpr_load_scene)
     bool scene_loaded = false;
@@ -321,6 +322,8 @@ extern "C" slpr_ctx *slpr_create(int device, uint32_t width, uint32_t height, ui
     for (auto &ev : c->ev) ok = ok && cudaEventCreate(&ev) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_onesweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->walk_blocks_per_sm, k_walk, WALK_THREADS, 0) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_scan_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM_BYTES) == cudaSuccess;
+    ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->scan_tma_blocks_per_sm, k_scan_tma, ST_THREADS, ST_SMEM_BYTES) == cudaSuccess;
     for (auto fn : {k_spans<false, true, false>, k_spans<true, true, false>, k_spans<true, false, false>, k_spans<false, true, true>, k_spans<true, true, true>})
         ok = ok && cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_STAGE_BYTES) == cudaSuccess;
     ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->span_blocks_per_sm, k_spans<true, false, false>, SP_THREADS, SP_STAGE_BYTES) == cudaSuccess;
@@ -551,7 +554,7 @@ static int enqueue_count_phase(slpr_ctx *c, cudaStream_t s, bool timed, int &lau
     launches += 2;
     if (timed) CU(cudaEventRecord(c->ev[2], s));
     ScanI32Op op1{c->d_count, c->d_offset, (long long)c->nc, &c->d_ctr->n_fragments, c->cap, &c->d_ctr->overflow};
-    k_lookback_scan<ScanI32Op><<<grid_for(c, (long long)c->nc / 16 + 1, SCAN_THREADS, 8), SCAN_THREADS, 0, s>>>(
+    k_lookback_scan<ScanI32Op><<<grid_for(c, (long long)c->nc / 16 + 1, SCAN_THREADS, ScanI32Op::MIN_BLOCKS), SCAN_THREADS, 0, s>>>(
         op1, ScanTemp{c->d_status[0], c->d_tickets + 0});
     ++launches;
     if (timed) CU(cudaEventRecord(c->ev[3], s));
@@ -635,7 +638,7 @@ static int enqueue_back(slpr_ctx *c, cudaStream_t s, bool timed, int &launches) 
         k_band_other<<<grid_for(c, c->P, 256, 8), 256, 0, s>>>(c->x_gathered, c->P, c->x_ranks, c->x_rank, c->x_d, c->x_corr);
         ScanI32Op op{c->x_d, c->x_e, (long long)c->P, nullptr, 0, nullptr};
         ScanTemp t{reinterpret_cast<unsigned long long *>(c->x_scan_temp + 256), reinterpret_cast<int *>(c->x_scan_temp)};
-        k_lookback_scan<ScanI32Op><<<grid_for(c, (long long)(c->P / SCAN_TILE_MIN + 2), 1, 8), SCAN_THREADS, 0, s>>>(op, t);
+        k_lookback_scan<ScanI32Op><<<grid_for(c, (long long)(c->P / scan_tile<ScanI32Op>() + 1), 1, ScanI32Op::MIN_BLOCKS), SCAN_THREADS, 0, s>>>(op, t);
         k_band_corr<<<grid_for(c, c->P, 256, 8), 256, 0, s>>>(c->x_e, c->P, c->x_corr);
         launches += 3;
         corr = c->x_corr;
@@ -734,58 +737,92 @@ static int size_buffers_from_count(slpr_ctx *c) {
     return SLPR_OK;
 }
 
-extern "C" int slpr_render(slpr_ctx *c) {
+// The captured graph of the frame for the current target / framebuffer (captured and instantiated on first use and
+// whenever a mode, a capacity or the band set-up changed). `launches` receives its kernel count.
+static int frame_graph(slpr_ctx *c, cudaGraphExec_t *ge_out, int *launches) {
+    const bool second = !c->target && c->fb_cur == c->d_fb2 && c->d_fb2;
+    slpr_ctx::TargetGraph *tg = nullptr;
+    if (c->target) {  // the entry of this target, else the least recently used one
+        for (auto &t : c->tgraph)
+            if (t.valid && t.target == c->target && t.stride == c->target_stride) tg = &t;
+        if (!tg) {
+            tg = (c->tgraph[0].used <= c->tgraph[1].used) ? &c->tgraph[0] : &c->tgraph[1];
+            tg->valid = false;
+            tg->target = c->target;
+            tg->stride = c->target_stride;
+        }
+        tg->used = ++c->tgraph_clock;
+    }
+    cudaGraphExec_t &ge = tg ? tg->ge : (second ? c->gexec2 : c->gexec);
+    bool &valid = tg ? tg->valid : (second ? c->graph2_valid : c->graph_valid);
+    int &n = tg ? tg->launches : c->launches_per_frame;
+    if (!valid) {
+        if (ge) { cudaGraphExecDestroy(ge); ge = nullptr; }
+        cudaGraph_t g = nullptr;
+        CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        int l = 0;
+        int rc = enqueue_frame(c, c->stream, false, l);
+        cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+        if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+        if (e != cudaSuccess) return fail(SLPR_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+        e = cudaGraphInstantiate(&ge, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) return fail(SLPR_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+        n = l;
+        valid = true;
+    }
+    *ge_out = ge;
+    *launches = n;
+    return SLPR_OK;
+}
+
+static int render_checks(slpr_ctx *c, const char *who) {
     if (!c) return fail(SLPR_ERR_INVALID, "null context");
-    if (!c->scene_loaded) return fail(SLPR_ERR_STATE, "slpr_render: no scene loaded (call slpr_load_scene first)");
-    if (c->x_sums) return fail(SLPR_ERR_STATE, "slpr_render: a band exchange is configured; use slpr_render_band_begin / _end");
+    if (!c->scene_loaded) return fail(SLPR_ERR_STATE, "%s: no scene loaded (call slpr_load_scene first)", who);
+    if (c->x_sums) return fail(SLPR_ERR_STATE, "%s: a band exchange is configured; use slpr_render_band_begin / _end", who);
     CU(cudaSetDevice(c->device));
     if (c->cap == 0) {
         int rc = size_buffers_from_count(c);
         if (rc) return rc;
     }
-    { int rc = ensure_records(c); if (rc) return rc; }
+    return ensure_records(c);
+}
+
+// Everything a frame needs that can block the device — the counting pre-pass that sizes the buffers, allocations,
+// graph capture, instantiation and upload — without rendering. Optional; slpr_render does the same on demand. Needed
+// when several contexts of ONE process render bands that wait for each other (a spinning exchange kernel of one
+// context would otherwise sit in front of another context's cudaMalloc).
+extern "C" int slpr_prepare(slpr_ctx *c) {
+    int rc = render_checks(c, "slpr_prepare");
+    if (rc) return rc;
+    if (!(c->flags & SLPR_FLAG_NO_GRAPH)) {
+        cudaGraphExec_t ge = nullptr;
+        int n = 0;
+        if ((rc = frame_graph(c, &ge, &n))) return rc;
+        CU(cudaGraphUpload(ge, c->stream));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    return SLPR_OK;
+}
+
+extern "C" int slpr_render(slpr_ctx *c) {
+    int rc = render_checks(c, "slpr_render");
+    if (rc) return rc;
     k_set_params<<<1, 1, 0, c->stream>>>(c->d_params, c->hp);
     ++c->launches;
     if (c->flags & SLPR_FLAG_NO_GRAPH) {
         int l = 0;
-        int rc = enqueue_frame(c, c->stream, true, l);
+        rc = enqueue_frame(c, c->stream, true, l);
         if (rc) return rc;
         c->launches += l;
         c->launches_per_frame = l;
         c->stage_times_valid = true;
     } else {
-        const bool second = !c->target && c->fb_cur == c->d_fb2 && c->d_fb2;
-        slpr_ctx::TargetGraph *tg = nullptr;
-        if (c->target) {  // the entry of this target, else the least recently used one
-            for (auto &t : c->tgraph)
-                if (t.valid && t.target == c->target && t.stride == c->target_stride) tg = &t;
-            if (!tg) {
-                tg = (c->tgraph[0].used <= c->tgraph[1].used) ? &c->tgraph[0] : &c->tgraph[1];
-                tg->valid = false;
-                tg->target = c->target;
-                tg->stride = c->target_stride;
-            }
-            tg->used = ++c->tgraph_clock;
-        }
-        cudaGraphExec_t &ge = tg ? tg->ge : (second ? c->gexec2 : c->gexec);
-        bool &valid = tg ? tg->valid : (second ? c->graph2_valid : c->graph_valid);
-        if (!valid) {
-            if (ge) { cudaGraphExecDestroy(ge); ge = nullptr; }
-            cudaGraph_t g = nullptr;
-            CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-            int l = 0;
-            int rc = enqueue_frame(c, c->stream, false, l);
-            cudaError_t e = cudaStreamEndCapture(c->stream, &g);
-            if (rc) { if (g) cudaGraphDestroy(g); return rc; }
-            if (e != cudaSuccess) return fail(SLPR_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
-            e = cudaGraphInstantiate(&ge, g, 0);
-            cudaGraphDestroy(g);
-            if (e != cudaSuccess) return fail(SLPR_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
-            c->launches_per_frame = l;
-            valid = true;
-        }
+        cudaGraphExec_t ge = nullptr;
+        int n = 0;
+        if ((rc = frame_graph(c, &ge, &n))) return rc;
         CU(cudaGraphLaunch(ge, c->stream));
-        c->launches += c->launches_per_frame;
+        c->launches += n;
         c->stage_times_valid = false;
     }
     c->frame_pending = true;
@@ -1364,11 +1401,19 @@ extern "C" int slpr_scan_i32(slpr_ctx *c, const int32_t *in, int32_t *out, uint6
     if (rc) return rc;
     ScanI32Op op{in, out, (long long)n, nullptr, 0, nullptr};
     ScanTemp t{reinterpret_cast<unsigned long long *>(c->d_prim_temp + 256), reinterpret_cast<int *>(c->d_prim_temp)};
-    k_lookback_scan<ScanI32Op><<<grid_for(c, (long long)tiles, 1, 8), SCAN_THREADS, 0, c->stream>>>(op, t);
+    const bool aligned = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    if (n >= (1ull << 22) && aligned && c->scan_tma_blocks_per_sm > 0) {
+        // big arrays: the TMA-pipelined kernel; its round-robin tiles need every CTA resident
+        const long long nchunks = (long long)((n + ST_TILE - 1) / ST_TILE);
+        const int grid = (int)std::min<long long>(nchunks, (long long)c->num_sms * std::min(c->scan_tma_blocks_per_sm, SLPR_ST_CTAS));
+        k_scan_tma<<<grid, ST_THREADS, ST_SMEM_BYTES, c->stream>>>(op, t);
+    } else
+        k_lookback_scan<ScanI32Op><<<grid_for(c, (long long)(n / scan_tile<ScanI32Op>() + 1), 1, ScanI32Op::MIN_BLOCKS), SCAN_THREADS, 0, c->stream>>>(op, t);
     ++c->launches;
     CU(cudaGetLastError());
     return SLPR_OK;
 }
+
 
 extern "C" int slpr_sort_pairs(slpr_ctx *c, uint64_t *keys, uint32_t *vals, uint64_t *keys_tmp, uint32_t *vals_tmp,
                                uint64_t n, uint32_t key_bits, int *result_in_tmp) {
