@@ -199,12 +199,13 @@ def primitive_rooflines(r, stream, nf, key_bits, peak, iters=10):
     return out
 
 
-def d2h_probe(W, H, stream, dist, iters=20):
+def d2h_probe(W, H, stream, dist, host=None, iters=20):
     """Host-memory ceiling of the end-to-end path: every rank copies one RGBA8 frame device -> pinned host memory,
     back to back, all ranks at once; per-rank GB/s (min / mean over ranks). Nothing is rendered."""
     import torch
     dev = torch.empty((H, W, 4), dtype=torch.uint8, device="cuda")
-    host = torch.empty((H, W, 4), dtype=torch.uint8, pin_memory=True)
+    if host is None:
+        host = torch.empty((H, W, 4), dtype=torch.uint8, pin_memory=True)
     for _ in range(3):
         host.copy_(dev, non_blocking=True)
     torch.cuda.synchronize()
@@ -578,8 +579,19 @@ def main():
     # ---- e2e: the public calls with HOST buffers (matrix in, RGBA8 frame out to pinned memory).
     #      Headline: the pipelined frame-sequence call (slpr_submit_to_host: the copy of frame i overlaps the
     #      rendering of frame i+1; every frame's pixels land in host memory). Also the blocking per-frame call.
-    hosts = [torch.empty((H, W, 4), dtype=torch.uint8, pin_memory=True) for _ in range(2)]
-    host_np = hosts[0].numpy()
+    # host buffers: pinned, and placed on the GPU's NUMA node by the library (slpr_host_alloc; torch-pinned as a fall-back)
+    host_arrays, host_nodes = [], []
+    try:
+        for _ in range(2):
+            a, node = r.host_alloc((H, W, 4))
+            host_arrays.append(a)
+            host_nodes.append(node)
+        host_alloc = "slpr_host_alloc"
+    except Exception:
+        host_arrays = [torch.empty((H, W, 4), dtype=torch.uint8, pin_memory=True).numpy() for _ in range(2)]
+        host_nodes, host_alloc = [-1, -1], "torch pin_memory"
+    hosts = [torch.from_numpy(a) for a in host_arrays]
+    host_np = host_arrays[0]
     rows_host = np.ascontiguousarray(rows, dtype=np.float32)
     if not bands:
         for _ in range(2):
@@ -593,13 +605,13 @@ def main():
         def rows_of(i):
             return anim_mats[i % len(anim_mats)] if anim else rows_host
         for i in range(4):
-            r.submit_to_host(rows_of(i), hosts[i & 1].numpy())
+            r.submit_to_host(rows_of(i), host_arrays[i & 1])
         r.wait_host()
         barrier()
         redone0 = r.pipeline_redone()
         t0 = time.perf_counter()
         for i in range(K):
-            r.submit_to_host(rows_of(i), hosts[i & 1].numpy())
+            r.submit_to_host(rows_of(i), host_arrays[i & 1])
         r.wait_host()
         barrier()
         e2e_s = time.perf_counter() - t0
@@ -615,7 +627,8 @@ def main():
                "blocking_call": {"value": frames_total * W * H / sync_s / 1e6, "ms_per_step": sync_s / K * 1e3,
                                  "what": "slpr_render_to_host (set_mvp + render + readback, synchronous per frame)"},
                "frames_rendered_twice": int(e2e_redone),
-               "d2h_probe": d2h_probe(W, H, stream, dist)}
+               "host_buffers": {"allocator": host_alloc, "numa_node": host_nodes[0], "torch_sees_pinned": bool(hosts[0].is_pinned())},
+               "d2h_probe": {"torch_pinned": d2h_probe(W, H, stream, dist, None), "gpu_numa_node": d2h_probe(W, H, stream, dist, hosts[0])}}
     else:
         e2e = None
 

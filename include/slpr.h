@@ -167,6 +167,13 @@ SLPR_API int slpr_wait_host(slpr_ctx *ctx);
  * Returns how many frames had to be rendered twice so far. */
 SLPR_API uint64_t slpr_pipeline_redone(slpr_ctx *ctx);
 
+/* Pinned host memory for the frames of slpr_submit_to_host / slpr_readback, placed on the NUMA node the context's
+ * GPU is attached to (mbind; *numa_node receives the node, or -1 if the placement could not be applied — the
+ * memory is pinned either way). With one rank per GPU on a two-socket host this keeps every GPU's device-to-host
+ * traffic off the inter-socket link. Freed by slpr_host_free or with the context. */
+SLPR_API int slpr_host_alloc(slpr_ctx *ctx, size_t bytes, void **host_ptr, int *numa_node);
+SLPR_API int slpr_host_free(slpr_ctx *ctx, void *host_ptr);
+
 /* Device pointer of the last rendered frame (RGBA8) and its row stride. Does not synchronise. */
 SLPR_API int slpr_framebuffer(slpr_ctx *ctx, void **dev_rgba, size_t *stride_bytes);
 

@@ -292,6 +292,14 @@ class ScanlineRasterizer:
         _check(lib().slpr_debug_diff_u32(self._h, C.c_void_p(dev_a), C.c_void_p(dev_b), C.c_size_t(n_words), C.byref(n)))
         return int(n.value)
 
+    def host_alloc(self, shape, dtype=np.uint8):
+        """Pinned host array next to this context's GPU (slpr_host_alloc); returns (array, numa node or -1)."""
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p(); node = C.c_int(-1)
+        _check(lib().slpr_host_alloc(self._h, C.c_size_t(nbytes), C.byref(p), C.byref(node)))
+        buf = (C.c_ubyte * nbytes).from_address(p.value)
+        return np.frombuffer(buf, dtype=dtype).reshape(shape), int(node.value)
+
     def framebuffer(self):
         p = C.c_void_p(); s = C.c_size_t()
         _check(lib().slpr_framebuffer(self._h, C.byref(p), C.byref(s)))

@@ -160,32 +160,50 @@ __device__ __forceinline__ int band_table_lookup(const BandTable &t, int nbp, ui
     return c;
 }
 
+// (radix-sort mode only: with the segmented sort k_segsort_warp forms these sums while it has each path in hand)
+// A warp takes 32 listed paths per trip — one lane looks up one path's fragment range — and then sums the non-empty
+// ones together, one after the other.
 __global__ void __launch_bounds__(256) k_band_sums_sparse(const int *__restrict__ seg, uint32_t n_paths,
                                                           const uint64_t *__restrict__ key, const uint32_t *__restrict__ val,
                                                           FrameCounters *__restrict__ ctr, int capacity, KeyLayout L,
-                                                          BandEntry *__restrict__ list) {
+                                                          BandEntry *__restrict__ list, const uint32_t *__restrict__ live_paths) {
     if (ctr->n_fragments > capacity) return;
     const int lane = threadIdx.x & 31;
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
     const uint64_t ymask = (1ull << L.bits_y) - 1;
-    for (uint32_t p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; p < n_paths; p += warps) {
-        const int b = seg[p], e = seg[p + 1];
-        if (e <= b) continue;
-        int a = 0, inv = 0, z = 0;
-        for (int i = b + lane; i < e; i += 32) {
-            const int d = (int)(val[i] >> 30) - 1;
-            if (d == 0) continue;
-            const uint32_t yk = (uint32_t)((key[i] >> L.bits_x) & ymask);
-            if (yk == (uint32_t)L.ny) z += d;
-            else if (yk == (uint32_t)(L.ny - 1)) inv += d;
-            else a += d;
+    const uint32_t n_items = live_paths ? (uint32_t)ctr->n_live_paths : n_paths;
+    const uint32_t n_groups = (n_items + 31u) >> 5;
+    for (uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < n_groups; g += warps) {
+        const uint32_t item = g * 32u + (uint32_t)lane;
+        uint32_t my_p = 0;
+        int my_b = 0, my_e = 0;
+        if (item < n_items) {
+            my_p = live_paths ? live_paths[item] : item;
+            my_b = seg[my_p];
+            my_e = seg[my_p + 1];
         }
-        a = __reduce_add_sync(0xFFFFFFFFu, a);
-        inv = __reduce_add_sync(0xFFFFFFFFu, inv);
-        z = __reduce_add_sync(0xFFFFFFFFu, z);
-        if (lane == 0 && (a | inv | z)) {
-            const int slot = atomicAdd(&ctr->n_band_entries, 1);
-            if (slot < XB_CAP) list[slot] = BandEntry{p, a, inv, z};
+        uint32_t todo = __ballot_sync(0xFFFFFFFFu, my_e > my_b);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const uint32_t p = __shfl_sync(0xFFFFFFFFu, my_p, src);
+            const int b = __shfl_sync(0xFFFFFFFFu, my_b, src), e = __shfl_sync(0xFFFFFFFFu, my_e, src);
+            int a = 0, inv = 0, z = 0;
+            for (int i = b + lane; i < e; i += 32) {
+                const int d = (int)(val[i] >> 30) - 1;
+                if (d == 0) continue;
+                const uint32_t yk = (uint32_t)((key[i] >> L.bits_x) & ymask);
+                if (yk == (uint32_t)L.ny) z += d;
+                else if (yk == (uint32_t)(L.ny - 1)) inv += d;
+                else a += d;
+            }
+            a = __reduce_add_sync(0xFFFFFFFFu, a);
+            inv = __reduce_add_sync(0xFFFFFFFFu, inv);
+            z = __reduce_add_sync(0xFFFFFFFFu, z);
+            if (lane == 0 && (a | inv | z)) {
+                const int slot = atomicAdd(&ctr->n_band_entries, 1);
+                if (slot < XB_CAP) list[slot] = BandEntry{p, a, inv, z};
+            }
         }
     }
 }

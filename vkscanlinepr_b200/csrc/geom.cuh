@@ -223,11 +223,24 @@ struct BandCull {
     }
 };
 
+// (both band front ends also list the live paths — in ascending order inside a warp's 32 — for the segmented sort,
+// which then visits 1/n_bands of the paths instead of all of them)
 __global__ void __launch_bounds__(256) k_path_cull(const FrameParams *__restrict__ P, uint32_t n_paths,
-                                                   const float4 *__restrict__ path_obj_box, uint8_t *__restrict__ path_live) {
+                                                   const float4 *__restrict__ path_obj_box, uint8_t *__restrict__ path_live,
+                                                   uint32_t *__restrict__ live_paths, FrameCounters *__restrict__ ctr) {
     const BandCull cull(P);
-    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n_paths; p += gridDim.x * blockDim.x)
-        path_live[p] = cull.alive(path_obj_box[p]) ? 1 : 0;
+    const uint32_t n_round = (n_paths + 31u) & ~31u;
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n_round; p += gridDim.x * blockDim.x) {
+        const bool alive = p < n_paths && cull.alive(path_obj_box[p]);
+        if (p < n_paths) path_live[p] = alive ? 1 : 0;
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, alive);
+        if (m) {
+            uint32_t base = 0;
+            if (lane_id() == 0) base = (uint32_t)atomicAdd(&ctr->n_live_paths, __popc(m));
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (alive) live_paths[base + __popc(m & lanemask_lt())] = p;
+        }
+    }
 }
 
 // Band mode when the scene's points are grouped by path (they are whenever the scene comes from loadVG): cull,
@@ -241,7 +254,8 @@ __global__ void __launch_bounds__(256) k_band_paths(const FrameParams *__restric
                                                     const uint32_t *__restrict__ path_first_point,
                                                     const uint32_t *__restrict__ path_first_curve, const float2 *__restrict__ pos,
                                                     float2 *__restrict__ tpos, int *__restrict__ path_visible,
-                                                    uint32_t *__restrict__ list, FrameCounters *__restrict__ ctr) {
+                                                    uint32_t *__restrict__ list, FrameCounters *__restrict__ ctr,
+                                                    uint32_t *__restrict__ live_paths) {
     const BandCull cull(P);
     const PointXform xf(P);
     const uint32_t lane = lane_id();
@@ -258,6 +272,12 @@ __global__ void __launch_bounds__(256) k_band_paths(const FrameParams *__restric
         }
         uint32_t live_mask = __ballot_sync(0xFFFFFFFFu, alive);
         if (!live_mask) continue;
+        {   // the live paths, for the sort
+            uint32_t pbase = 0;
+            if (lane == 0) pbase = (uint32_t)atomicAdd(&ctr->n_live_paths, __popc(live_mask));
+            pbase = __shfl_sync(0xFFFFFFFFu, pbase, 0);
+            if (alive) live_paths[pbase + __popc(live_mask & lanemask_lt())] = p;
+        }
         // the warp's curves take one run of the list
         uint32_t incl = ncv;
 #pragma unroll

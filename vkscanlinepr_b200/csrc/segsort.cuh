@@ -19,6 +19,7 @@
 // the radix path (compact 64-bit key, 32-bit value), so everything downstream is unchanged.
 #pragma once
 #include "geom.cuh"
+#include "bands.cuh"
 
 namespace slpr {
 
@@ -143,52 +144,106 @@ struct SegIdxBits {
 // position, so (row|x, position) is the reference's (key, index) order. The value words are loaded together
 // with the keys (one exposure to HBM latency per path instead of two: the kernel waits on loads half of its
 // time) and parked in the warp's slice of shared memory, from where the sorted positions pick them.
-template <int R>
+// Two special row values sort after every real row of a path: the invalid key (row rank ny - 1: fragments outside the
+// frame, and in band mode the fragments of other bands) and row 0 (rank ny). Left as they are they stretch the path's
+// key range over the whole frame height and the path would need 64-bit words (twice the shuffles, and in band mode
+// EVERY path that straddles a band edge has them). So, when a path has any (warp-uniform test), they are folded in
+// right above its largest real key: rel = (mx - mn + 1) + (special rank << bits_x) + x — same order, small range —
+// and unfolded on the way out.
+struct SegGeo {
+    int bits_x, bits_y, ny;
+};
+
+// `sums` (band mode): the path's three winding sums are formed from the values while they pass through (bands.cuh).
+template <int R, bool BAND>
 __device__ __forceinline__ bool warp_sort_segment32(const uint64_t *__restrict__ key_in, const uint32_t *__restrict__ val_in,
                                                     uint64_t *__restrict__ key_out, uint32_t *__restrict__ val_out, int b, int n,
-                                                    int yx_bits, int lane, uint32_t *__restrict__ s_val) {
+                                                    int yx_bits, int lane, uint32_t *__restrict__ s_val, SegGeo geo, int (&sums)[3]) {
     constexpr int IB = SegIdxBits<R>::value;
     static_assert(R == 1 || R == 2 || R == 4 || R == 8 || R == 16, "R must be 1, 2, 4, 8 or 16");
     const uint64_t mask = (1ull << yx_bits) - 1;
+    const uint32_t special_from = (uint32_t)(geo.ny - 1) << geo.bits_x;  // keys at or above this are invalid / row 0
     uint32_t e[R];
     uint64_t path_bits = 0;
     uint32_t mn = 0xFFFFFFFFu, mx = 0u;
+    int a = 0, inv = 0, z = 0;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const int j = r * 32 + lane;
         e[r] = 0u;
         if (j < n) {
             const uint64_t k = key_in[b + j];
-            s_val[j] = val_in[b + j];
+            const uint32_t v = val_in[b + j];
+            s_val[j] = v;
             path_bits = k & ~mask;
             e[r] = (uint32_t)(k & mask);
             mn = min(mn, e[r]);
             mx = max(mx, e[r]);
+            if (BAND) {
+                const int d = (int)(v >> 30) - 1;
+                if (e[r] < special_from) a += d;
+                else if ((e[r] >> geo.bits_x) == (uint32_t)geo.ny) z += d;
+                else inv += d;
+            }
         }
     }
     mn = __reduce_min_sync(0xFFFFFFFFu, mn);
     mx = __reduce_max_sync(0xFFFFFFFFu, mx);  // (also orders the s_val stores before the reads below)
-    if (((mx - mn) >> (32 - IB)) != 0u) {  // the path spans too much of the frame for a 32-bit word
-        if constexpr (R > 8) return false;  // 32 registers of 64-bit words: left to the block kernel
-        else {
-            warp_sort_segment<R>(key_in, val_in, key_out, val_out, b, n, yx_bits, lane);
-            return true;
-        }
+    const bool special = BAND && mx >= special_from;  // warp-uniform. (Full frames: only paths at the frame border have such keys; they keep the 64-bit fall-back and the common path stays as lean as it was.)
+    uint32_t span = mx - mn + 1u;             // real keys map to [0, span)
+    if (special) {  // the real rows' range, and the special keys right above it
+        mn = 0xFFFFFFFFu; mx = 0u;
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if (r * 32 + lane < n && e[r] < special_from) { mn = min(mn, e[r]); mx = max(mx, e[r]); }
+        mn = __reduce_min_sync(0xFFFFFFFFu, mn);
+        mx = __reduce_max_sync(0xFFFFFFFFu, mx);
+        if (mn > mx) { mn = 0; mx = 0; }  // no real row at all
+        span = mx - mn + 1u;
+    }
+    const uint32_t range = special ? span + (2u << geo.bits_x) : span;
+    if (((range - 1u) >> (32 - IB)) != 0u) return false;  // too much of the frame for a 32-bit word: the caller's fall-back
+    if (BAND) {
+        sums[0] = __reduce_add_sync(0xFFFFFFFFu, a);
+        sums[1] = __reduce_add_sync(0xFFFFFFFFu, inv);
+        sums[2] = __reduce_add_sync(0xFFFFFFFFu, z);
     }
     path_bits = __shfl_sync(0xFFFFFFFFu, path_bits, 0);  // lane 0 always holds fragment 0
+    if (!special) {
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const int j = r * 32 + lane;
-        e[r] = (j < n) ? (((e[r] - mn) << IB) | (uint32_t)j) : 0xFFFFFFFFu;
+        for (int r = 0; r < R; ++r) {
+            const int j = r * 32 + lane;
+            e[r] = (j < n) ? (((e[r] - mn) << IB) | (uint32_t)j) : 0xFFFFFFFFu;
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int j = r * 32 + lane;
+            const uint32_t rel = (e[r] >= special_from) ? span + (e[r] - special_from) : e[r] - mn;
+            e[r] = (j < n) ? ((rel << IB) | (uint32_t)j) : 0xFFFFFFFFu;
+        }
     }
     warp_bitonic<R, uint32_t>(e, lane);
     __syncwarp();
+    if (!special) {
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const int j = r * 32 + lane;
-        if (j < n) {
-            key_out[b + j] = path_bits | (uint64_t)(mn + (e[r] >> IB));
-            val_out[b + j] = s_val[e[r] & ((1u << IB) - 1)];
+        for (int r = 0; r < R; ++r) {
+            const int j = r * 32 + lane;
+            if (j < n) {
+                key_out[b + j] = path_bits | (uint64_t)(mn + (e[r] >> IB));
+                val_out[b + j] = s_val[e[r] & ((1u << IB) - 1)];
+            }
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int j = r * 32 + lane;
+            if (j < n) {
+                const uint32_t rel = e[r] >> IB;
+                const uint32_t kk = (rel >= span) ? special_from + (rel - span) : mn + rel;
+                key_out[b + j] = path_bits | (uint64_t)kk;
+                val_out[b + j] = s_val[e[r] & ((1u << IB) - 1)];
+            }
         }
     }
     __syncwarp();  // the slice is rewritten by the warp's next path
@@ -228,35 +283,91 @@ __global__ void __launch_bounds__(256) k_path_segments(const uint32_t *__restric
 
 constexpr int SEG_CHUNK = 8;  // consecutive paths per warp trip (one contiguous run of fragments)
 
-__global__ void __launch_bounds__(256) k_segsort_warp(const int *__restrict__ seg, uint32_t n_paths,
+// Band mode (exact bands, device-side exchange): the kernel visits only the paths that can reach the band (the list the
+// band front end left) and, while it has a path's fragments in hand, forms the three winding sums the exchange needs
+// (normal rows | outside the frame | row 0; bands.cuh) — a separate pass over all paths cost as much as a third of
+// the sort itself (profiles/README.md, round 2).
+struct SegBand {
+    const uint32_t *live_paths;  // nullptr: every path (full frame)
+    BandEntry *sums;             // nullptr: no sums wanted
+    SegGeo geo;
+};
+
+template <bool BAND>
+__global__ void __launch_bounds__(256, BAND ? 3 : 4) k_segsort_warp(const int *__restrict__ seg, uint32_t n_paths,
                                                       const uint64_t *__restrict__ key_in, const uint32_t *__restrict__ val_in,
                                                       uint64_t *__restrict__ key_out, uint32_t *__restrict__ val_out,
                                                       FrameCounters *__restrict__ ctr, int capacity, int yx_bits,
-                                                      int *__restrict__ big_list) {
+                                                      int *__restrict__ big_list, SegBand band) {
     __shared__ uint32_t s_vals[256 / 32][SEG_WARP_MAX];  // values of the path a warp is sorting
     if (ctr->n_fragments > capacity) return;
     const int lane = threadIdx.x & 31;
     uint32_t *const s_val = s_vals[threadIdx.x >> 5];
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-    const uint32_t n_chunks = (n_paths + SEG_CHUNK - 1) / SEG_CHUNK;
+    const uint32_t n_items = (BAND && band.live_paths) ? (uint32_t)ctr->n_live_paths : n_paths;
+    const uint32_t n_chunks = (n_items + SEG_CHUNK - 1) / SEG_CHUNK;
     for (uint32_t ch = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ch < n_chunks; ch += warps) {
-        const uint32_t p0 = ch * SEG_CHUNK;
-        const int my_bound = seg[min(p0 + (uint32_t)lane, n_paths)];  // lanes 0..SEG_CHUNK hold the chunk's bounds
+        const uint32_t i0 = ch * SEG_CHUNK;
+        uint32_t my_path = 0;
+        int my_b = 0, my_e = 0;
+        if (BAND && band.live_paths) {  // lanes 0..SEG_CHUNK-1 hold the chunk's paths and their fragment ranges
+            if (lane < SEG_CHUNK && i0 + lane < n_items) {
+                my_path = band.live_paths[i0 + lane];
+                my_b = seg[my_path];
+                my_e = seg[my_path + 1];
+            }
+        } else {  // consecutive paths: lanes 0..SEG_CHUNK hold the chunk's bounds
+            my_b = seg[min(i0 + (uint32_t)lane, n_paths)];
+        }
 #pragma unroll 1
         for (int q = 0; q < SEG_CHUNK; ++q) {
-            const uint32_t p = p0 + q;
-            if (p >= n_paths) break;
-            const int b = __shfl_sync(0xFFFFFFFFu, my_bound, q), n = __shfl_sync(0xFFFFFFFFu, my_bound, q + 1) - b;
+            if (i0 + q >= n_items) break;
+            uint32_t p;
+            int b, n;
+            if (BAND && band.live_paths) {
+                p = __shfl_sync(0xFFFFFFFFu, my_path, q);
+                b = __shfl_sync(0xFFFFFFFFu, my_b, q);
+                n = __shfl_sync(0xFFFFFFFFu, my_e, q) - b;
+            } else {
+                p = i0 + q;
+                b = __shfl_sync(0xFFFFFFFFu, my_b, q);
+                n = __shfl_sync(0xFFFFFFFFu, my_b, q + 1) - b;
+            }
             if (n <= 0) continue;
-            bool done = true;
-            if (n == 1) {
-                if (lane == 0) { key_out[b] = key_in[b]; val_out[b] = val_in[b]; }
-            } else if (n <= 32) warp_sort_segment32<1>(key_in, val_in, key_out, val_out, b, n, yx_bits, lane, s_val);
-            else if (n <= 64) warp_sort_segment32<2>(key_in, val_in, key_out, val_out, b, n, yx_bits, lane, s_val);
-            else if (n <= 128) warp_sort_segment32<4>(key_in, val_in, key_out, val_out, b, n, yx_bits, lane, s_val);
-            else if (n <= 256) done = warp_sort_segment32<8>(key_in, val_in, key_out, val_out, b, n, yx_bits, lane, s_val);
-            else if (n <= SEG_WARP_MAX) done = warp_sort_segment32<16>(key_in, val_in, key_out, val_out, b, n, yx_bits, lane, s_val);
-            else done = false;
+            // 32-bit network by size; 0 = it did not fit (64-bit network up to 256 fragments, else the block kernel)
+            int sums[3] = {0, 0, 0};
+            bool fit = false, done = true;
+            if (n <= 32) fit = warp_sort_segment32<1, BAND>(key_in, val_in, key_out, val_out, b, n, yx_bits, lane, s_val, band.geo, sums);
+            else if (n <= 64) fit = warp_sort_segment32<2, BAND>(key_in, val_in, key_out, val_out, b, n, yx_bits, lane, s_val, band.geo, sums);
+            else if (n <= 128) fit = warp_sort_segment32<4, BAND>(key_in, val_in, key_out, val_out, b, n, yx_bits, lane, s_val, band.geo, sums);
+            else if (n <= 256) fit = warp_sort_segment32<8, BAND>(key_in, val_in, key_out, val_out, b, n, yx_bits, lane, s_val, band.geo, sums);
+            else if (n <= SEG_WARP_MAX) fit = warp_sort_segment32<16, BAND>(key_in, val_in, key_out, val_out, b, n, yx_bits, lane, s_val, band.geo, sums);
+            if (!fit) {
+                if (BAND && band.sums) {  // the path's winding sums from a pass of its own (rare)
+                    int a = 0, inv = 0, z = 0;
+                    for (int i = lane; i < n; i += 32) {
+                        const int d = (int)(val_in[b + i] >> 30) - 1;
+                        if (d != 0) {
+                            const uint32_t yk = (uint32_t)(key_in[b + i] >> band.geo.bits_x) & ((1u << band.geo.bits_y) - 1u);
+                            if (yk == (uint32_t)band.geo.ny) z += d;
+                            else if (yk == (uint32_t)(band.geo.ny - 1)) inv += d;
+                            else a += d;
+                        }
+                    }
+                    sums[0] = __reduce_add_sync(0xFFFFFFFFu, a);
+                    sums[1] = __reduce_add_sync(0xFFFFFFFFu, inv);
+                    sums[2] = __reduce_add_sync(0xFFFFFFFFu, z);
+                }
+                if (n <= 32) warp_sort_segment<1>(key_in, val_in, key_out, val_out, b, n, yx_bits, lane);
+                else if (n <= 64) warp_sort_segment<2>(key_in, val_in, key_out, val_out, b, n, yx_bits, lane);
+                else if (n <= 128) warp_sort_segment<4>(key_in, val_in, key_out, val_out, b, n, yx_bits, lane);
+                else if (n <= 256) warp_sort_segment<8>(key_in, val_in, key_out, val_out, b, n, yx_bits, lane);
+                else done = false;
+            }
+            if (BAND && band.sums && lane == 0 && (sums[0] | sums[1] | sums[2])) {
+                const int slot = atomicAdd(&ctr->n_band_entries, 1);
+                if (slot < XB_CAP) band.sums[slot] = BandEntry{p, sums[0], sums[1], sums[2]};
+            }
             if (!done && lane == 0) {
                 if (n > SEG_BLOCK_MAX) ctr->sort_fallback = 1;  // the host re-renders with the radix sort
                 else big_list[atomicAdd(&ctr->n_big_segments, 1)] = (int)p;

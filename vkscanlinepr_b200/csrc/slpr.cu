@@ -13,8 +13,13 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <sys/mman.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 
 #include <algorithm>
+#include <cctype>
+#include <utility>
 #include <string>
 #include <vector>
 
@@ -87,6 +92,7 @@ struct slpr_ctx {
     uint32_t *d_pfc = nullptr;   // [P+1] first curve whose path is >= p (static; [P] = n_curves)
     uint32_t *d_pfp = nullptr;   // [P+1] first point whose path is >= p, when the points are grouped by path (else null)
     uint8_t *d_plive = nullptr;  // [P] band mode: the path can reach the band (k_path_cull)
+    uint32_t *d_live_paths = nullptr;  // [P] band mode: the live paths, listed (k_band_paths / k_path_cull) for the sort
     float *d_cut = nullptr;
     int *d_count = nullptr, *d_offset = nullptr, *d_seg_tap = nullptr;  // d_seg_tap: [P+1] sort segment table (always built)
     int *d_big = nullptr;              // [P] paths queued for the block-level segmented sort
@@ -177,6 +183,7 @@ struct slpr_ctx {
     int *p_tab_cum = nullptr, *p_tab_n = nullptr, *p_tab_z = nullptr;
     std::vector<void *> ipc_mapped;   // peer allocations opened with slpr_ipc_import
     std::vector<void *> dev_allocs;   // slpr_alloc_device
+    std::vector<std::pair<void *, size_t>> host_allocs;  // slpr_host_alloc
     cudaEvent_t ev[SLPR_STAGE_COUNT + 1] = {};
     bool stage_times_valid = false;
     uint64_t launches = 0;
@@ -230,7 +237,7 @@ static void free_exchange(slpr_ctx *c) {
 static void free_scene(slpr_ctx *c) {
     free_exchange(c);
     cudaFree(c->d_pos); cudaFree(c->d_pos_path); cudaFree(c->d_cpm); cudaFree(c->d_ctype); cudaFree(c->d_cpath);
-    cudaFree(c->d_frule); cudaFree(c->d_finfo); cudaFree(c->d_tpos); cudaFree(c->d_pvis); cudaFree(c->d_pobj); cudaFree(c->d_pfc); cudaFree(c->d_pfp); cudaFree(c->d_plive); cudaFree(c->d_live); cudaFree(c->d_block_cnt); cudaFree(c->d_vhist); cudaFree(c->d_cut);
+    cudaFree(c->d_frule); cudaFree(c->d_finfo); cudaFree(c->d_tpos); cudaFree(c->d_pvis); cudaFree(c->d_pobj); cudaFree(c->d_pfc); cudaFree(c->d_pfp); cudaFree(c->d_plive); cudaFree(c->d_live_paths); c->d_live_paths = nullptr; cudaFree(c->d_live); cudaFree(c->d_block_cnt); cudaFree(c->d_vhist); cudaFree(c->d_cut);
     cudaFree(c->d_count); cudaFree(c->d_offset); cudaFree(c->d_seg_tap);
     cudaFree(c->d_big); c->d_big = nullptr;
     cudaFree(c->d_slots); cudaFree(c->d_pieces); cudaFree(c->d_boundary); cudaFree(c->d_fixlist);
@@ -288,6 +295,13 @@ static int alloc_capacity(slpr_ctx *c, int cap) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Device -> host copy of a frame: one linear copy when both sides are tightly packed (the usual case), else 2-D.
+static cudaError_t copy_frame_to_host(const slpr_ctx *c, uint8_t *dst, size_t dst_stride, const uint8_t *src, size_t src_stride, cudaStream_t s) {
+    const size_t row = (size_t)c->W * 4;
+    if (dst_stride == row && src_stride == row) return cudaMemcpyAsync(dst, src, row * c->H, cudaMemcpyDeviceToHost, s);
+    return cudaMemcpy2DAsync(dst, dst_stride, src, src_stride, row, c->H, cudaMemcpyDeviceToHost, s);
+}
+
 extern "C" slpr_ctx *slpr_create(int device, uint32_t width, uint32_t height, uint32_t flags) {
     if (width == 0 || height == 0 || width > 32766 || height > 32766) {
         fail(SLPR_ERR_INVALID, "slpr_create: width/height must be in [1, 32766] (16-bit key fields, SURVEY D.6)");
@@ -346,6 +360,7 @@ extern "C" void slpr_destroy(slpr_ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (void *p : c->ipc_mapped) cudaIpcCloseMemHandle(p);
     for (void *p : c->dev_allocs) cudaFree(p);
+    for (auto &h : c->host_allocs) { cudaHostUnregister(h.first); munmap(h.first, h.second); }
     cudaFree(c->p_box); cudaFree(c->p_list); cudaFree(c->p_tab_path); cudaFree(c->p_tab_cum); cudaFree(c->p_tab_n); cudaFree(c->p_tab_z);
     free_capacity(c);
     free_scene(c);
@@ -442,6 +457,7 @@ extern "C" int slpr_load_scene(slpr_ctx *c, const float *pos_xy, const uint32_t 
         CU(cudaMalloc(&c->d_pobj, box.size() * sizeof(float4)));
         CU(cudaMemcpy(c->d_pobj, box.data(), box.size() * sizeof(float4), cudaMemcpyHostToDevice));
         CU(cudaMalloc(&c->d_plive, std::max<size_t>(n_paths, 1)));
+        CU(cudaMalloc(&c->d_live_paths, std::max<size_t>(n_paths, 1) * 4));
     }
     CU(cudaMalloc(&c->d_live, std::max<size_t>(n_curves, 1) * 4));
     c->mono_blocks = (int)std::max<long long>(1, std::min<long long>(((long long)n_curves + 255) / 256, (long long)c->num_sms * 8));
@@ -527,14 +543,14 @@ static int enqueue_count_phase(slpr_ctx *c, cudaStream_t s, bool timed, int &lau
     if (band && c->d_pfp) {  // one pass over the paths: cull, transform the live ones, list their curves
         CU(cudaMemsetAsync(c->d_count, 0, (size_t)c->nc * 4, s));  // k_monotonize_count only writes the live curves
         k_band_paths<<<grid_for(c, c->P, 256, 8), 256, 0, s>>>(c->d_params, c->P, c->d_pobj, c->d_pfp, c->d_pfc, c->d_pos, c->d_tpos, c->d_pvis,
-                                                                c->d_live, c->d_ctr);
+                                                                c->d_live, c->d_ctr, c->d_live_paths);
         ++launches;
         if (timed) CU(cudaEventRecord(c->ev[1], s));
         live.list = c->d_live;
     } else {
         const uint8_t *plive = band ? c->d_plive : nullptr;
         if (plive) {
-            k_path_cull<<<grid_for(c, c->P, 256, 8), 256, 0, s>>>(c->d_params, c->P, c->d_pobj, c->d_plive);
+            k_path_cull<<<grid_for(c, c->P, 256, 8), 256, 0, s>>>(c->d_params, c->P, c->d_pobj, c->d_plive, c->d_live_paths, c->d_ctr);
             ++launches;
         }
         k_transform<<<grid_for(c, c->np, 256, 8), 256, 0, s>>>(c->d_params, c->np, c->d_pos, c->d_pos_path, c->d_tpos, c->d_pvis, plive);
@@ -585,11 +601,12 @@ static int enqueue_fragments(slpr_ctx *c, cudaStream_t s, bool timed, int &launc
         k_band_sums<<<grid_for(c, (long long)c->P * 32, 256, 8), 256, 0, s>>>(c->d_seg_tap, c->P, c->d_key[0], c->d_val[0], c->d_ctr,
                                                                              c->cap, c->L, c->x_sums);
         ++launches;
-    } else if (c->peers.n_bands > 0) {  // sparse: only the paths with a residue, stored straight into every band's mailbox
+    } else if (c->peers.n_bands > 0 && c->radix_mode) {
+        // sparse exchange, radix sort: the paths with a residue from a pass of its own (before the sort, which reuses
+        // buffer 0); with the segmented sort k_segsort_warp forms the sums while it has the path in hand
         k_band_sums_sparse<<<grid_for(c, (long long)c->P * 32, 256, 8), 256, 0, s>>>(c->d_seg_tap, c->P, c->d_key[0], c->d_val[0], c->d_ctr,
-                                                                                    c->cap, c->L, c->p_list);
-        k_band_publish<<<c->peers.n_bands, 256, 0, s>>>(c->d_params, c->d_ctr, c->cap, c->radix_mode ? 1 : 0, c->p_list, c->peers);
-        launches += 2;
+                                                                                    c->cap, c->L, c->p_list, c->hp.cull ? c->d_live_paths : nullptr);
+        ++launches;
     }
     CU(cudaGetLastError());
     return SLPR_OK;
@@ -600,8 +617,11 @@ static int enqueue_sort(slpr_ctx *c, cudaStream_t s, bool timed, int &launches) 
     if (!c->radix_mode) {  // every path sorted on chip, one read + one write of the pairs (segsort.cuh)
         if (timed) CU(cudaEventRecord(c->ev[6], s));
         const int yx_bits = c->L.bits_x + c->L.bits_y;
-        k_segsort_warp<<<grid_for(c, ((long long)c->P + SEG_CHUNK - 1) / SEG_CHUNK * 32, 256, 8), 256, 0, s>>>(
-            c->d_seg_tap, c->P, c->d_key[0], c->d_val[0], c->d_key[1], c->d_val[1], c->d_ctr, c->cap, yx_bits, c->d_big);
+        const bool peer_band = c->peers.n_bands > 0 && !c->x_sums;
+        SegBand sb{c->hp.cull ? c->d_live_paths : nullptr, peer_band ? c->p_list : nullptr, SegGeo{c->L.bits_x, c->L.bits_y, c->L.ny}};
+        auto segsort = (sb.live_paths || sb.sums) ? k_segsort_warp<true> : k_segsort_warp<false>;
+        segsort<<<grid_for(c, ((long long)c->P + SEG_CHUNK - 1) / SEG_CHUNK * 32, 256, 8), 256, 0, s>>>(
+            c->d_seg_tap, c->P, c->d_key[0], c->d_val[0], c->d_key[1], c->d_val[1], c->d_ctr, c->cap, yx_bits, c->d_big, sb);
         k_segsort_block<<<c->num_sms * 2, SEG_BLOCK_THREADS, 0, s>>>(c->d_seg_tap, c->d_key[0], c->d_val[0], c->d_key[1], c->d_val[1],
                                                                      c->d_ctr, c->cap, yx_bits, c->d_big);
         launches += 2;
@@ -621,6 +641,10 @@ static int enqueue_sort(slpr_ctx *c, cudaStream_t s, bool timed, int &launches) 
     }
     }
     c->sorted_buf = cur;
+    if (c->peers.n_bands > 0 && !c->x_sums) {  // the band's non-zero sums, stored straight into every band's mailbox
+        k_band_publish<<<c->peers.n_bands, 256, 0, s>>>(c->d_params, c->d_ctr, c->cap, c->radix_mode ? 1 : 0, c->p_list, c->peers);
+        ++launches;
+    }
     if (timed) CU(cudaEventRecord(c->ev[7], s));
     CU(cudaGetLastError());
     return SLPR_OK;
@@ -939,7 +963,7 @@ extern "C" int slpr_readback(slpr_ctx *c, uint8_t *rgba, size_t stride_bytes) {
     if (rc) return rc;
     const uint8_t *fb = c->target ? c->target : c->fb_cur;
     const size_t stride = c->target ? c->target_stride : c->fb_stride;
-    CU(cudaMemcpy2DAsync(rgba, stride_bytes, fb, stride, (size_t)c->W * 4, c->H, cudaMemcpyDeviceToHost, c->stream));
+    CU(copy_frame_to_host(c, rgba, stride_bytes, fb, stride, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return SLPR_OK;
 }
@@ -978,7 +1002,7 @@ static int pipe_recover(slpr_ctx *c, int first_slot) {
         if (!rc) rc = slpr_render(c);
         if (!rc) rc = finish_frame(c);  // grows the buffers / switches the sort until the frame is whole
         if (rc) { c->fb_cur = fb_keep; return rc; }
-        CU(cudaMemcpy2DAsync(p.rgba, p.stride, c->fb_cur, c->fb_stride, (size_t)c->W * 4, c->H, cudaMemcpyDeviceToHost, c->stream));
+        CU(copy_frame_to_host(c, p.rgba, p.stride, c->fb_cur, c->fb_stride, c->stream));
         CU(cudaStreamSynchronize(c->stream));
         ++c->pipe_redone;
     }
@@ -1026,7 +1050,7 @@ extern "C" int slpr_submit_to_host(slpr_ctx *c, const float rows[16], uint8_t *r
     CU(cudaMemcpyAsync(slot.h, c->d_ctr, sizeof(FrameCounters), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaEventRecord(c->ev_rendered[k], c->stream));
     CU(cudaStreamWaitEvent(c->copy_stream, c->ev_rendered[k], 0));
-    CU(cudaMemcpy2DAsync(rgba, stride_bytes, c->fb_cur, c->fb_stride, (size_t)c->W * 4, c->H, cudaMemcpyDeviceToHost, c->copy_stream));
+    CU(copy_frame_to_host(c, rgba, stride_bytes, c->fb_cur, c->fb_stride, c->copy_stream));
     CU(cudaEventRecord(c->ev_copied[k], c->copy_stream));
     c->copy_pending[k] = true;
     return SLPR_OK;
@@ -1354,6 +1378,60 @@ extern "C" int slpr_debug_diff_u32(slpr_ctx *c, const void *dev_a, const void *d
     if (e != cudaSuccess) return fail(SLPR_ERR_CUDA, "slpr_debug_diff_u32: %s", cudaGetErrorString(e));
     *n_diff = h;
     return SLPR_OK;
+}
+
+// ---- pinned host memory next to the GPU ---------------------------------------------------------------------
+// The end-to-end path moves a frame (33 MB at 4K) to host memory every ~1 ms per GPU; with eight ranks on a
+// two-socket host, buffers that all sit on one socket's memory put half of the GPUs' traffic on the inter-socket
+// link (e2e efficiency 0.41 at 8 GPUs). This allocator places the pages on the NUMA node the GPU
+// hangs off (sysfs numa_node of its PCI function; mbind(2), no libnuma needed) and pins them for DMA.
+static int gpu_numa_node(int device) {
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) return -1;
+    for (char *p = bus; *p; ++p) *p = (char)tolower(*p);
+    char path[128];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE *f = fopen(path, "r");
+    if (!f) return -1;
+    int node = -1;
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+    return node;
+}
+
+extern "C" int slpr_host_alloc(slpr_ctx *c, size_t bytes, void **host_ptr, int *numa_node_out) {
+    if (!c || !host_ptr || !bytes) return fail(SLPR_ERR_INVALID, "slpr_host_alloc: null argument");
+    CU(cudaSetDevice(c->device));
+    const size_t page = (size_t)sysconf(_SC_PAGESIZE);
+    const size_t len = align_up(bytes, page);
+    void *p = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (p == MAP_FAILED) return fail(SLPR_ERR_CUDA, "slpr_host_alloc: mmap of %zu bytes failed", len);
+    int node = gpu_numa_node(c->device), bound = -1;
+#ifdef SYS_mbind
+    if (node >= 0 && node < 64) {
+        unsigned long mask = 1ul << node;
+        if (syscall(SYS_mbind, p, len, 1 /* MPOL_PREFERRED */, &mask, 65ul, 0u) == 0) bound = node;
+    }
+#endif
+    memset(p, 0, len);  // fault the pages in under the policy
+    cudaError_t e = cudaHostRegister(p, len, cudaHostRegisterPortable);
+    if (e != cudaSuccess) { munmap(p, len); return fail(SLPR_ERR_CUDA, "slpr_host_alloc: cudaHostRegister failed: %s", cudaGetErrorString(e)); }
+    c->host_allocs.push_back({p, len});
+    *host_ptr = p;
+    if (numa_node_out) *numa_node_out = bound;
+    return SLPR_OK;
+}
+
+extern "C" int slpr_host_free(slpr_ctx *c, void *host_ptr) {
+    if (!c || !host_ptr) return fail(SLPR_ERR_INVALID, "slpr_host_free: null argument");
+    for (size_t i = 0; i < c->host_allocs.size(); ++i)
+        if (c->host_allocs[i].first == host_ptr) {
+            cudaHostUnregister(host_ptr);
+            munmap(host_ptr, c->host_allocs[i].second);
+            c->host_allocs.erase(c->host_allocs.begin() + (long)i);
+            return SLPR_OK;
+        }
+    return fail(SLPR_ERR_INVALID, "slpr_host_free: not a pointer from slpr_host_alloc");
 }
 
 extern "C" int slpr_sort_mode(slpr_ctx *c, int *mode) {
