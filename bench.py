@@ -247,26 +247,46 @@ class BandRunner:
         self.seq = 1
         self.retries = 0
         self.last_slot = 0
+        self.mode = "store"
+        y0, y1 = self.band_list[rank]
+        self.local = None
+        if rank != 0:  # gather by copy engine: the band is rendered into a local buffer (addressed like a full frame) and pushed
+            self.local = [self.r.alloc_device((y1 - y0) * W * 4) - (H - y1) * W * 4 for _ in range(2)]
+
+    def _set_mode(self, gather):
+        # "store": k_resolve writes into the root's peer-mapped frame and the graph ends with the arrival flag;
+        # "copy": the flag follows the copy-engine push (slpr_band_push), so the in-graph flag is switched off
+        want = "copy" if gather == "copy" else "store"
+        if want != self.mode:
+            self.r.set_band_peers(self.world, self.rank, -1 if want == "copy" else 0, self.peers["mailboxes"])
+            self.mode = want
 
     def _step(self, gather, first):
         r = self.r
-        if gather == "peer":
-            self.last_slot = self.seq & 1
-            r.set_target(self.peers["frames"][self.last_slot], self.W * 4)
+        slot = self.seq & 1
+        if gather == "store" or (gather == "copy" and self.rank == 0):
+            r.set_target(self.peers["frames"][slot], self.W * 4)
+        elif gather == "copy":
+            r.set_target(self.local[slot], self.W * 4)
         else:
             r.set_target(0, 0)
+        if gather != "none":
+            self.last_slot = slot
         r.setMVP(self.rows)
         r.render_band(self.seq)
-        if gather == "peer" and self.rank == 0 and not first:
+        if gather == "copy" and self.rank != 0:
+            r.band_push(self.seq, 0, self.peers["frames"][slot], self.W * 4)
+        if gather != "none" and self.rank == 0 and not first:
             r.band_wait_gather(self.seq - 1)
         self.seq += 1
 
     def _finish(self, gather):
-        if gather == "peer" and self.rank == 0:
+        if gather != "none" and self.rank == 0:
             self.r.band_wait_gather(self.seq - 1)
 
     def run(self, K, Wm, gather):
         import torch
+        self._set_mode(gather)
         for _ in range(max(Wm, 3)):  # waited for one by one: capacities and sort modes settle (a void frame is redone by all)
             for _ in range(4):
                 self._step(gather, True)
@@ -329,7 +349,11 @@ def bands_peer_report(V, PAR, sc, rows, W, H, rank, world, local_rank, dist, str
     """Resident and gathered exact bands + the 1-GPU full frame on rank 0: the north star's strong-scaling case."""
     br = BandRunner(V, PAR, sc, rows, W, H, rank, world, local_rank, dist, stream, rank0_share)
     resident = br.run(K, Wm, "none")
-    gathered = br.run(K, Wm, "peer") if gather else None
+    g_store = br.run(K, Wm, "store") if gather else None
+    g_copy = br.run(K, Wm, "copy") if gather else None
+    gathered = None
+    if gather:
+        gathered = g_copy if g_copy["ms_per_step"] <= g_store["ms_per_step"] else g_store
     rep = None
     ms1 = diff = nf1 = None
     if rank == 0:
@@ -341,9 +365,13 @@ def bands_peer_report(V, PAR, sc, rows, W, H, rank, world, local_rank, dist, str
                "ms_gathered": gathered["ms_per_step"] if gathered else None,
                "speedup_resident": (ms1 / resident["ms_per_step"]) if ms1 else None,
                "speedup_gathered": (ms1 / gathered["ms_per_step"]) if (ms1 and gathered) else None,
+               "ms_gathered_direct_stores": g_store["ms_per_step"] if g_store else None,
+               "ms_gathered_copy_engine": g_copy["ms_per_step"] if g_copy else None,
                "pixels_differing": diff, "pixels": W * H, "resident": resident, "gathered": gathered, "retried_warmup_frames": br.retries,
                "exchange": "sparse per-path winding sums stored into peer-mapped mailboxes (CUDA IPC over NVLink), no collective, no host sync",
-               "gather": "k_resolve stores each band straight into rank 0's peer-mapped frame buffer (two buffers, arrival of frame i awaited after frame i+1 is enqueued)",
+               "gather": "two ways, both into rank 0's peer-mapped frame buffers (two, alternating; the arrival of frame i is awaited after frame i+1 is enqueued): "
+                         "direct stores — k_resolve of every band writes straight into rank 0's HBM; copy engine — the band is rendered locally and pushed "
+                         "(slpr_band_push) on a second stream while the next frame renders. ms_gathered is the faster one; pixels_differing checks the last gathered frame",
                "timing": "CUDA events on each rank's stream around K back-to-back frames, max over ranks"}
     br.close()
     return rep

@@ -169,7 +169,7 @@ SLPR_API uint64_t slpr_pipeline_redone(slpr_ctx *ctx);
 
 /* Pinned host memory for the frames of slpr_submit_to_host / slpr_readback, placed on the NUMA node the context's
  * GPU is attached to (mbind; *numa_node receives the node, or -1 if the placement could not be applied — the
- * memory is pinned either way). With one rank per GPU on a two-socket host this keeps every GPU's device-to-host
+ * memory is pinned either way; -2: mbind was refused). With one rank per GPU on a two-socket host this keeps every GPU's device-to-host
  * traffic off the inter-socket link. Freed by slpr_host_free or with the context. */
 SLPR_API int slpr_host_alloc(slpr_ctx *ctx, size_t bytes, void **host_ptr, int *numa_node);
 SLPR_API int slpr_host_free(slpr_ctx *ctx, void *host_ptr);
@@ -233,6 +233,12 @@ SLPR_API int slpr_ipc_import(slpr_ctx *ctx, const unsigned char handle[64], void
 SLPR_API int slpr_set_band_peers(slpr_ctx *ctx, int n_bands, int band, int root, void *const *mailboxes);
 SLPR_API int slpr_render_band(slpr_ctx *ctx, uint32_t frame_seq);
 SLPR_API int slpr_band_wait_gather(slpr_ctx *ctx, uint32_t frame_seq);
+/* Gather by copy engine instead of direct stores (slpr_set_band_peers with root = -1 switches the in-graph
+ * "pixels are in place" flag off): the band just rendered into the current target travels to dst_frame — the
+ * root's peer-mapped frame buffer, addressed like a full frame — on a second stream, overlapping the next frame's
+ * kernels and using no SM (896 MB per 16K frame into one GPU's NVLink ingress take longer than a band's kernels);
+ * the flag for the root follows the copy. A later slpr_render_band into the same slot (frame_seq & 1) waits for it. */
+SLPR_API int slpr_band_push(slpr_ctx *ctx, uint32_t frame_seq, int root_band, void *dst_frame, size_t dst_stride);
 /* Number of differing 32-bit words (RGBA8 pixels) between two device buffers (checks an assembled frame against
  * the same frame rendered whole, on the device). Waits for the context's stream. */
 SLPR_API int slpr_debug_diff_u32(slpr_ctx *ctx, const void *dev_a, const void *dev_b, size_t n_words, uint64_t *n_diff);

@@ -284,6 +284,9 @@ class ScanlineRasterizer:
     def render_band(self, frame_seq):
         _check(lib().slpr_render_band(self._h, C.c_uint32(frame_seq & 0xFFFFFFFF)))
 
+    def band_push(self, frame_seq, root_band, dst_frame_ptr, dst_stride):
+        _check(lib().slpr_band_push(self._h, C.c_uint32(frame_seq & 0xFFFFFFFF), int(root_band), C.c_void_p(dst_frame_ptr), C.c_size_t(dst_stride)))
+
     def band_wait_gather(self, frame_seq):
         _check(lib().slpr_band_wait_gather(self._h, C.c_uint32(frame_seq & 0xFFFFFFFF)))
 

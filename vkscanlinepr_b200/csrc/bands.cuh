@@ -365,6 +365,12 @@ __global__ void k_band_done(const FrameParams *__restrict__ P, BandPeers peers) 
     st_release_sys_u64(&peers.box[peers.root]->done[(uint32_t)P->frame_seq & 1u][peers.me], (unsigned long long)(uint32_t)P->frame_seq + 1ull);
 }
 
+// The same after a copy-engine push of the band (slpr_band_push): the sequence number travels as an argument.
+__global__ void k_band_done_seq(uint32_t seq, int root, BandPeers peers) {
+    __threadfence_system();
+    st_release_sys_u64(&peers.box[root]->done[seq & 1u][peers.me], (unsigned long long)seq + 1ull);
+}
+
 // On the root: every band's pixels of frame seq have landed (bounded spin).
 __global__ void k_band_wait_done(uint32_t seq, BandPeers peers, FrameCounters *__restrict__ ctr) {
     const int r = threadIdx.x;

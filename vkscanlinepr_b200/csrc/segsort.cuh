@@ -254,10 +254,20 @@ __device__ __forceinline__ bool warp_sort_segment32(const uint64_t *__restrict__
 // seg[n_paths] = nf — read off the scanned curve offsets through the scene's static table of every path's first
 // curve (slpr_load_scene) — and, in the same pass, the path-size statistics for the host's choice between the two
 // sorts (slpr.cu: segmented_sort_pays).
+// Band mode: also the fragment ranges of the listed live paths, in list order (k_segsort_warp then reads its paths'
+// bounds with one coalesced load instead of two dependent scattered ones per path).
 __global__ void __launch_bounds__(256) k_path_segments(const uint32_t *__restrict__ path_first_curve, uint32_t n_paths,
                                                        const int *__restrict__ offsets, int *__restrict__ seg,
-                                                       FrameCounters *__restrict__ ctr, int capacity) {
+                                                       FrameCounters *__restrict__ ctr, int capacity,
+                                                       const uint32_t *__restrict__ live_paths, int2 *__restrict__ live_range) {
     if (ctr->n_fragments > capacity) return;
+    if (live_paths) {
+        const uint32_t n_live = (uint32_t)ctr->n_live_paths;
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_live; i += gridDim.x * blockDim.x) {
+            const uint32_t p = live_paths[i];
+            live_range[i] = make_int2(offsets[path_first_curve[p]], offsets[path_first_curve[p + 1]]);
+        }
+    }
     int mid = 0, big = 0, huge = 0;
     const uint32_t n_round = (n_paths + 1u + 31u) & ~31u;  // whole warps stay in the loop for the reductions
     for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n_round; p += gridDim.x * blockDim.x) {
@@ -288,13 +298,21 @@ constexpr int SEG_CHUNK = 8;  // consecutive paths per warp trip (one contiguous
 // (normal rows | outside the frame | row 0; bands.cuh) — a separate pass over all paths cost as much as a third of
 // the sort itself (profiles/README.md, round 2).
 struct SegBand {
+    int *ticket;                 // band mode: chunks are handed out dynamically (zeroed per frame)
     const uint32_t *live_paths;  // nullptr: every path (full frame)
+    const int2 *live_range;      // [n_live_paths] fragment range of each listed path
     BandEntry *sums;             // nullptr: no sums wanted
     SegGeo geo;
 };
 
+#ifndef SLPR_SEG_BAND_BLOCKS
+#define SLPR_SEG_BAND_BLOCKS 4
+#endif
+#ifndef SLPR_SEG_FUSE_SUMS
+#define SLPR_SEG_FUSE_SUMS 1 /* 0 (experiments): band sums from k_band_sums_sparse over the live paths instead */
+#endif
 template <bool BAND>
-__global__ void __launch_bounds__(256, BAND ? 3 : 4) k_segsort_warp(const int *__restrict__ seg, uint32_t n_paths,
+__global__ void __launch_bounds__(256, BAND ? SLPR_SEG_BAND_BLOCKS : 4) k_segsort_warp(const int *__restrict__ seg, uint32_t n_paths,
                                                       const uint64_t *__restrict__ key_in, const uint32_t *__restrict__ val_in,
                                                       uint64_t *__restrict__ key_out, uint32_t *__restrict__ val_out,
                                                       FrameCounters *__restrict__ ctr, int capacity, int yx_bits,
@@ -306,15 +324,25 @@ __global__ void __launch_bounds__(256, BAND ? 3 : 4) k_segsort_warp(const int *_
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
     const uint32_t n_items = (BAND && band.live_paths) ? (uint32_t)ctr->n_live_paths : n_paths;
     const uint32_t n_chunks = (n_items + SEG_CHUNK - 1) / SEG_CHUNK;
-    for (uint32_t ch = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ch < n_chunks; ch += warps) {
+    // Full frame: chunks strided over the warps (a hundred thousand chunks, a dozen per warp). Band mode: a band has an
+    // n-th of them — two per warp at 16K in eight bands — and a static deal leaves the last round half empty, so the
+    // warps take chunks from a ticket instead.
+    for (uint32_t ch = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;; ch += warps) {
+        if (BAND && band.live_paths) {
+            uint32_t t = 0;
+            if (lane == 0) t = (uint32_t)atomicAdd(band.ticket, 1);
+            ch = __shfl_sync(0xFFFFFFFFu, t, 0);
+        }
+        if (ch >= n_chunks) break;
         const uint32_t i0 = ch * SEG_CHUNK;
         uint32_t my_path = 0;
         int my_b = 0, my_e = 0;
         if (BAND && band.live_paths) {  // lanes 0..SEG_CHUNK-1 hold the chunk's paths and their fragment ranges
             if (lane < SEG_CHUNK && i0 + lane < n_items) {
                 my_path = band.live_paths[i0 + lane];
-                my_b = seg[my_path];
-                my_e = seg[my_path + 1];
+                const int2 r = band.live_range[i0 + lane];
+                my_b = r.x;
+                my_e = r.y;
             }
         } else {  // consecutive paths: lanes 0..SEG_CHUNK hold the chunk's bounds
             my_b = seg[min(i0 + (uint32_t)lane, n_paths)];

@@ -93,6 +93,7 @@ struct slpr_ctx {
     uint32_t *d_pfp = nullptr;   // [P+1] first point whose path is >= p, when the points are grouped by path (else null)
     uint8_t *d_plive = nullptr;  // [P] band mode: the path can reach the band (k_path_cull)
     uint32_t *d_live_paths = nullptr;  // [P] band mode: the live paths, listed (k_band_paths / k_path_cull) for the sort
+    int2 *d_live_range = nullptr;      // [P] band mode: fragment range of each listed path (k_path_segments)
     float *d_cut = nullptr;
     int *d_count = nullptr, *d_offset = nullptr, *d_seg_tap = nullptr;  // d_seg_tap: [P+1] sort segment table (always built)
     int *d_big = nullptr;              // [P] paths queued for the block-level segmented sort
@@ -181,6 +182,8 @@ struct slpr_ctx {
     BandEntry *p_list = nullptr;      // [XB_CAP] this band's non-zero per-path sums
     uint32_t *p_tab_path = nullptr;   // [XB_TOTAL] merged break-point table of the frame
     int *p_tab_cum = nullptr, *p_tab_n = nullptr, *p_tab_z = nullptr;
+    cudaEvent_t ev_band_rendered[2] = {}, ev_band_pushed[2] = {};  // slpr_band_push: per frame-buffer slot (frame_seq & 1)
+    bool band_push_pending[2] = {false, false};
     std::vector<void *> ipc_mapped;   // peer allocations opened with slpr_ipc_import
     std::vector<void *> dev_allocs;   // slpr_alloc_device
     std::vector<std::pair<void *, size_t>> host_allocs;  // slpr_host_alloc
@@ -237,7 +240,7 @@ static void free_exchange(slpr_ctx *c) {
 static void free_scene(slpr_ctx *c) {
     free_exchange(c);
     cudaFree(c->d_pos); cudaFree(c->d_pos_path); cudaFree(c->d_cpm); cudaFree(c->d_ctype); cudaFree(c->d_cpath);
-    cudaFree(c->d_frule); cudaFree(c->d_finfo); cudaFree(c->d_tpos); cudaFree(c->d_pvis); cudaFree(c->d_pobj); cudaFree(c->d_pfc); cudaFree(c->d_pfp); cudaFree(c->d_plive); cudaFree(c->d_live_paths); c->d_live_paths = nullptr; cudaFree(c->d_live); cudaFree(c->d_block_cnt); cudaFree(c->d_vhist); cudaFree(c->d_cut);
+    cudaFree(c->d_frule); cudaFree(c->d_finfo); cudaFree(c->d_tpos); cudaFree(c->d_pvis); cudaFree(c->d_pobj); cudaFree(c->d_pfc); cudaFree(c->d_pfp); cudaFree(c->d_plive); cudaFree(c->d_live_paths); c->d_live_paths = nullptr; cudaFree(c->d_live_range); c->d_live_range = nullptr; cudaFree(c->d_live); cudaFree(c->d_block_cnt); cudaFree(c->d_vhist); cudaFree(c->d_cut);
     cudaFree(c->d_count); cudaFree(c->d_offset); cudaFree(c->d_seg_tap);
     cudaFree(c->d_big); c->d_big = nullptr;
     cudaFree(c->d_slots); cudaFree(c->d_pieces); cudaFree(c->d_boundary); cudaFree(c->d_fixlist);
@@ -367,6 +370,7 @@ extern "C" void slpr_destroy(slpr_ctx *c) {
     cudaFree(c->d_params); cudaFreeHost(c->h_ctr); cudaFreeHost(c->pslot[0].h); cudaFreeHost(c->pslot[1].h); cudaFree(c->d_cells); cudaFree(c->d_fb); cudaFree(c->d_fb2); cudaFree(c->d_prim_temp);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     for (int i = 0; i < 2; ++i) { if (c->ev_rendered[i]) cudaEventDestroy(c->ev_rendered[i]); if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]); }
+    for (int i = 0; i < 2; ++i) { if (c->ev_band_rendered[i]) cudaEventDestroy(c->ev_band_rendered[i]); if (c->ev_band_pushed[i]) cudaEventDestroy(c->ev_band_pushed[i]); }
     for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
@@ -458,6 +462,7 @@ extern "C" int slpr_load_scene(slpr_ctx *c, const float *pos_xy, const uint32_t 
         CU(cudaMemcpy(c->d_pobj, box.data(), box.size() * sizeof(float4), cudaMemcpyHostToDevice));
         CU(cudaMalloc(&c->d_plive, std::max<size_t>(n_paths, 1)));
         CU(cudaMalloc(&c->d_live_paths, std::max<size_t>(n_paths, 1) * 4));
+        CU(cudaMalloc(&c->d_live_range, std::max<size_t>(n_paths, 1) * sizeof(int2)));
     }
     CU(cudaMalloc(&c->d_live, std::max<size_t>(n_curves, 1) * 4));
     c->mono_blocks = (int)std::max<long long>(1, std::min<long long>(((long long)n_curves + 255) / 256, (long long)c->num_sms * 8));
@@ -595,13 +600,14 @@ static int enqueue_fragments(slpr_ctx *c, cudaStream_t s, bool timed, int &launc
                                   c->d_fixlist, c->L, c->d_key[0], c->d_val[0], ft);
     launches += 3;
     if (timed) CU(cudaEventRecord(c->ev[5], s));
-    k_path_segments<<<grid_for(c, (long long)c->P + 1, 256, 4), 256, 0, s>>>(c->d_pfc, c->P, c->d_offset, c->d_seg_tap, c->d_ctr, c->cap);
+    k_path_segments<<<grid_for(c, (long long)c->P + 1, 256, 4), 256, 0, s>>>(c->d_pfc, c->P, c->d_offset, c->d_seg_tap, c->d_ctr, c->cap,
+                                                                             c->hp.cull ? c->d_live_paths : nullptr, c->d_live_range);
     ++launches;
     if (c->x_sums) {  // before the sort: the radix sort reuses buffer 0
         k_band_sums<<<grid_for(c, (long long)c->P * 32, 256, 8), 256, 0, s>>>(c->d_seg_tap, c->P, c->d_key[0], c->d_val[0], c->d_ctr,
                                                                              c->cap, c->L, c->x_sums);
         ++launches;
-    } else if (c->peers.n_bands > 0 && c->radix_mode) {
+    } else if (c->peers.n_bands > 0 && (c->radix_mode || !SLPR_SEG_FUSE_SUMS)) {
         // sparse exchange, radix sort: the paths with a residue from a pass of its own (before the sort, which reuses
         // buffer 0); with the segmented sort k_segsort_warp forms the sums while it has the path in hand
         k_band_sums_sparse<<<grid_for(c, (long long)c->P * 32, 256, 8), 256, 0, s>>>(c->d_seg_tap, c->P, c->d_key[0], c->d_val[0], c->d_ctr,
@@ -618,7 +624,7 @@ static int enqueue_sort(slpr_ctx *c, cudaStream_t s, bool timed, int &launches) 
         if (timed) CU(cudaEventRecord(c->ev[6], s));
         const int yx_bits = c->L.bits_x + c->L.bits_y;
         const bool peer_band = c->peers.n_bands > 0 && !c->x_sums;
-        SegBand sb{c->hp.cull ? c->d_live_paths : nullptr, peer_band ? c->p_list : nullptr, SegGeo{c->L.bits_x, c->L.bits_y, c->L.ny}};
+        SegBand sb{c->d_tickets + 3, c->hp.cull ? c->d_live_paths : nullptr, c->d_live_range, (peer_band && SLPR_SEG_FUSE_SUMS) ? c->p_list : nullptr, SegGeo{c->L.bits_x, c->L.bits_y, c->L.ny}};
         auto segsort = (sb.live_paths || sb.sums) ? k_segsort_warp<true> : k_segsort_warp<false>;
         segsort<<<grid_for(c, ((long long)c->P + SEG_CHUNK - 1) / SEG_CHUNK * 32, 256, 8), 256, 0, s>>>(
             c->d_seg_tap, c->P, c->d_key[0], c->d_val[0], c->d_key[1], c->d_val[1], c->d_ctr, c->cap, yx_bits, c->d_big, sb);
@@ -705,7 +711,7 @@ static int enqueue_back(slpr_ctx *c, cudaStream_t s, bool timed, int &launches) 
     else k_resolve<false><<<wide, 256, 0, s>>>(c->d_params, c->d_rec, c->d_finfo, c->d_cells, c->cw, fb, stride);
     ++launches;
     if (timed) CU(cudaEventRecord(c->ev[11], s));
-    if (!c->x_sums && c->peers.n_bands > 0 && c->peers.root != c->peers.me) {  // gather: tell the root this band's pixels are in place
+    if (!c->x_sums && c->peers.n_bands > 0 && c->peers.root >= 0 && c->peers.root != c->peers.me) {  // gather by direct stores: tell the root this band's pixels are in place
         k_band_done<<<1, 1, 0, s>>>(c->d_params, c->peers);
         ++launches;
     }
@@ -1325,8 +1331,8 @@ extern "C" int slpr_set_band_peers(slpr_ctx *c, int n_bands, int band, int root,
     if (n_bands == 0) { c->peers = BandPeers{}; return SLPR_OK; }
     if (!c->p_box) return fail(SLPR_ERR_STATE, "slpr_set_band_peers: call slpr_band_mailbox first");
     if (c->x_sums) return fail(SLPR_ERR_STATE, "slpr_set_band_peers: a host-driven exchange is configured (slpr_set_band_exchange)");
-    if (!mailboxes || n_bands < 1 || n_bands > XB_MAX_BANDS || band < 0 || band >= n_bands || root < 0 || root >= n_bands)
-        return fail(SLPR_ERR_INVALID, "slpr_set_band_peers: need 1 <= n_bands <= %d, 0 <= band, root < n_bands and the mailboxes", XB_MAX_BANDS);
+    if (!mailboxes || n_bands < 1 || n_bands > XB_MAX_BANDS || band < 0 || band >= n_bands || root < -1 || root >= n_bands)
+        return fail(SLPR_ERR_INVALID, "slpr_set_band_peers: need 1 <= n_bands <= %d, 0 <= band < n_bands, -1 <= root < n_bands and the mailboxes", XB_MAX_BANDS);
     if (mailboxes[band] != (void *)c->p_box) return fail(SLPR_ERR_INVALID, "slpr_set_band_peers: mailboxes[band] must be this context's own mailbox");
     BandPeers p{};
     for (int i = 0; i < n_bands; ++i) {
@@ -1342,12 +1348,52 @@ extern "C" int slpr_render_band(slpr_ctx *c, uint32_t frame_seq) {
     if (!c) return fail(SLPR_ERR_INVALID, "null context");
     if (c->peers.n_bands <= 0) return fail(SLPR_ERR_STATE, "slpr_render_band: call slpr_set_band_peers first");
     c->hp.frame_seq = (int)frame_seq;
+    const int slot = (int)(frame_seq & 1u);
+    if (c->band_push_pending[slot]) {  // the push that last read this slot's buffer must be over before it is rendered into again
+        CU(cudaSetDevice(c->device));
+        CU(cudaStreamWaitEvent(c->stream, c->ev_band_pushed[slot], 0));
+        c->band_push_pending[slot] = false;
+    }
     return slpr_render(c);
+}
+
+// Gather by copy engine: the band just rendered (into the current target, addressed like a full frame) travels to
+// `dst_frame` — the root's peer-mapped frame buffer — on a second stream, so that the transfer over NVLink overlaps
+// the next frame's kernels and uses no SM; the "pixels are in place" flag for the root follows the copy.
+extern "C" int slpr_band_push(slpr_ctx *c, uint32_t frame_seq, int root_band, void *dst_frame, size_t dst_stride) {
+    if (!c || !dst_frame) return fail(SLPR_ERR_INVALID, "slpr_band_push: null argument");
+    if (c->peers.n_bands <= 0 || root_band < 0 || root_band >= c->peers.n_bands) return fail(SLPR_ERR_STATE, "slpr_band_push: needs slpr_set_band_peers and a valid root band");
+    if (dst_stride < (size_t)c->W * 4) return fail(SLPR_ERR_INVALID, "slpr_band_push: stride smaller than a row");
+    CU(cudaSetDevice(c->device));
+    if (!c->copy_stream) CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    const int slot = (int)(frame_seq & 1u);
+    if (!c->ev_band_rendered[slot]) {
+        CU(cudaEventCreateWithFlags(&c->ev_band_rendered[slot], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c->ev_band_pushed[slot], cudaEventDisableTiming));
+    }
+    const uint8_t *src = c->target ? c->target : c->fb_cur;
+    const size_t src_stride = c->target ? c->target_stride : c->fb_stride;
+    const size_t row0 = (size_t)(c->H - (uint32_t)c->hp.band_y1);  // image rows [H - y1, H - y0) hold scanline rows [y0, y1)
+    const size_t rows = (size_t)(c->hp.band_y1 - c->hp.band_y0);
+    CU(cudaEventRecord(c->ev_band_rendered[slot], c->stream));
+    CU(cudaStreamWaitEvent(c->copy_stream, c->ev_band_rendered[slot], 0));
+    const size_t row_bytes = (size_t)c->W * 4;
+    if (src_stride == row_bytes && dst_stride == row_bytes)
+        CU(cudaMemcpyAsync(reinterpret_cast<uint8_t *>(dst_frame) + row0 * dst_stride, src + row0 * src_stride, rows * row_bytes, cudaMemcpyDeviceToDevice, c->copy_stream));
+    else
+        CU(cudaMemcpy2DAsync(reinterpret_cast<uint8_t *>(dst_frame) + row0 * dst_stride, dst_stride, src + row0 * src_stride, src_stride, row_bytes, rows,
+                             cudaMemcpyDeviceToDevice, c->copy_stream));
+    k_band_done_seq<<<1, 1, 0, c->copy_stream>>>(frame_seq, root_band, c->peers);
+    ++c->launches;
+    CU(cudaEventRecord(c->ev_band_pushed[slot], c->copy_stream));
+    c->band_push_pending[slot] = true;
+    CU(cudaGetLastError());
+    return SLPR_OK;
 }
 
 extern "C" int slpr_band_wait_gather(slpr_ctx *c, uint32_t frame_seq) {
     if (!c) return fail(SLPR_ERR_INVALID, "null context");
-    if (c->peers.n_bands <= 0 || c->peers.root != c->peers.me) return fail(SLPR_ERR_STATE, "slpr_band_wait_gather: only on the root band of a configured exchange");
+    if (c->peers.n_bands <= 0) return fail(SLPR_ERR_STATE, "slpr_band_wait_gather: needs a configured exchange (slpr_set_band_peers)");
     CU(cudaSetDevice(c->device));
     k_band_wait_done<<<1, 32, 0, c->stream>>>(frame_seq, c->peers, c->d_ctr);
     ++c->launches;
@@ -1406,11 +1452,11 @@ extern "C" int slpr_host_alloc(slpr_ctx *c, size_t bytes, void **host_ptr, int *
     const size_t len = align_up(bytes, page);
     void *p = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
     if (p == MAP_FAILED) return fail(SLPR_ERR_CUDA, "slpr_host_alloc: mmap of %zu bytes failed", len);
-    int node = gpu_numa_node(c->device), bound = -1;
+    int node = gpu_numa_node(c->device), bound = -1;  // -1: the GPU's node is unknown; -2: mbind refused
 #ifdef SYS_mbind
     if (node >= 0 && node < 64) {
         unsigned long mask = 1ul << node;
-        if (syscall(SYS_mbind, p, len, 1 /* MPOL_PREFERRED */, &mask, 65ul, 0u) == 0) bound = node;
+        bound = (syscall(SYS_mbind, p, len, 1 /* MPOL_PREFERRED */, &mask, 65ul, 0u) == 0) ? node : -2;
     }
 #endif
     memset(p, 0, len);  // fault the pages in under the policy

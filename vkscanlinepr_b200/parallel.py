@@ -101,7 +101,7 @@ def band_corrections(gathered, band):
 
 # --------------------------------------------------------------------------------------------------------------
 # Exact bands with the device-side sparse exchange (csrc/bands.cuh, second half; include/slpr.h)
-def connect_band_peers(rasterizer, dist, rank, world, root=0, frame_bytes=0, n_frames=2):
+def connect_band_peers(rasterizer, dist, rank, world, root=0, frame_bytes=0, n_frames=2, done_flags_in_graph=True):
     """Once per rasterizer: every rank allocates its mailbox, the 64-byte CUDA IPC handles are all-gathered over
     torch.distributed (host plumbing only), every rank maps the others' mailboxes (peer access over NVLink) and
     registers them (slpr_set_band_peers). With `frame_bytes`, the root also allocates `n_frames` frame buffers and
@@ -121,7 +121,9 @@ def connect_band_peers(rasterizer, dist, rank, world, root=0, frame_bytes=0, n_f
         everyone = [mine]
     boxes = [own if r == rank else rasterizer.ipc_import(everyone[r]["box"]) for r in range(world)]
     frames = frames_local if rank == root else [rasterizer.ipc_import(h) for h in everyone[root]["frames"]]
-    rasterizer.set_band_peers(world, rank, root, boxes)
+    # done_flags_in_graph: bands store their pixels straight into the root's frame (set_target(frames[i])) and the
+    # frame's graph ends with the "in place" flag; False: the caller moves bands with band_push (copy engine) instead
+    rasterizer.set_band_peers(world, rank, root if done_flags_in_graph else -1, boxes)
     return {"mailboxes": boxes, "frames": frames}
 
 
