@@ -63,7 +63,13 @@ enum {
     /* Keep the reference's draw records (output_buf, gen_merged_fragment_and_span.comp:77,102) readable through
      * slpr_debug_copy(SLPR_TAP_RECORDS). Without it a big frame never writes them: the span kernel marks the
      * coverage grid directly (16 B per record of HBM traffic saved). Implied by SLPR_FLAG_TAPS. */
-    SLPR_FLAG_RECORDS = 1u << 8
+    SLPR_FLAG_RECORDS = 1u << 8,
+    /* SURVEY section 8 f-1, beyond the reference: QUADRIC (3 points) and ARC (0x13: rational quadratic, 3 points + a weight per curve,
+     * slpr_set_curve_weights) curves get real arithmetic — monotonic cuts, bisection crossings, fragment end points — in
+     * place of the reference's `// TODO` arms (make_intersection_0.comp:141-144,273-276; make_intersection_1.comp:386-391;
+     * gen_fragment.comp:66-69). The arithmetic is defined in oracle/oracle.c (orc_set_full_rvg) and matched bit for bit.
+     * Scenes of lines and cubics render exactly as without the flag. Use with slpr_vg_load_rvg_full. */
+    SLPR_FLAG_FULL_RVG = 1u << 9
 };
 
 /* Buffers that slpr_debug_copy() can return. Layouts are the reference's:
@@ -125,6 +131,11 @@ SLPR_API int slpr_load_scene(slpr_ctx *ctx,
                              const uint32_t *curve_pos_map, const uint32_t *curve_type,
                              const uint32_t *curve_path, uint32_t n_curves,
                              const uint32_t *fill_rule, const uint32_t *fill_rgba8, uint32_t n_paths);
+
+/* SLPR_FLAG_FULL_RVG only: the weight of the middle control point of every ARC curve (rational quadratic with weights
+ * (1, w, 1), Euclidean control point; entries of other curves are ignored). float[n_curves], host pointer, copied.
+ * All weights are 1 until this is called. */
+SLPR_API int slpr_set_curve_weights(slpr_ctx *ctx, const float *curve_weight, uint32_t n_curves);
 
 /* Replaces ScanlineVGRasterizer::setMVP (scanline_rasterizer.cpp:191-197): rows m0..m3 of
  * TransPosIn (scanline/compute_ubo.h:9-13), i.e. x' = dot((x,y,0,1), m0) / dot((x,y,0,1), m3). */
@@ -280,9 +291,14 @@ typedef struct slpr_scene_view { /* pointers owned by the slpr_vg; valid until s
     const uint32_t *curve_pos_map, *curve_type, *curve_path; uint32_t n_curves;
     const uint32_t *fill_rule, *fill_rgba8; uint32_t n_paths;
     float viewport[4], window[4];
+    const float *curve_weight; /* float[n_curves] from slpr_vg_load_rvg_full (middle weight of ARC curves), else NULL */
 } slpr_scene_view;
 
 SLPR_API slpr_vg *slpr_vg_load_rvg(const char *path);
+/* a complete reader (rational arcs `A`, `Q`, `H`/`V`, relative commands, per-element transforms, every contour
+ * closed, gradient paints as their average colour) instead of the reference parser's behaviour. Its QUADRIC / ARC
+ * curves need a context created with SLPR_FLAG_FULL_RVG and slpr_set_curve_weights(view.curve_weight). */
+SLPR_API slpr_vg *slpr_vg_load_rvg_full(const char *path);
 /* Build a container from VGContainer-shaped arrays (vg_container.h:21-87). */
 SLPR_API slpr_vg *slpr_vg_from_arrays(const float *pos_xy, uint32_t n_points,
                                       const uint32_t *curve_pos, const uint32_t *curve_type, uint32_t n_curves,

@@ -101,11 +101,27 @@ public:
     void load(const std::string &filename) {
         slpr_vg *h = slpr_vg_load_rvg(filename.c_str());
         if (!h) throw std::runtime_error(slpr_last_error());
+        try { adopt(h); } catch (...) { slpr_vg_free(h); throw; }
+        slpr_vg_free(h);
+    }
+    std::shared_ptr<VGContainer> getVGContainer() { return _vgContainer; }
+    // SURVEY section 8 f-1, beyond the reference: the complete reader (rational arcs, quadratics, relative commands, per-element
+    // transforms, gradients as their average colour; slpr_vg_load_rvg_full). QUADRIC / ARC curves carry their three
+    // control points here (the reference's addCurve stores none for them) and getCurveWeights() has the arcs' weights:
+    // render with CudaVGRasterizer(device, SLPR_FLAG_FULL_RVG) and setCurveWeights().
+    void loadFull(const std::string &filename) {
+        slpr_vg *h = slpr_vg_load_rvg_full(filename.c_str());
+        if (!h) throw std::runtime_error(slpr_last_error());
+        try { adopt(h); } catch (...) { slpr_vg_free(h); throw; }
+        slpr_vg_free(h);
+    }
+    const std::vector<float> &getCurveWeights() const { return _curveWeights; }
+private:
+    void adopt(slpr_vg *h) {
         const float *pos, *col, *op; const uint32_t *cpos, *ctype, *pcur, *frule; uint32_t np, nc, npath;
         slpr_scene_view v;
-        if (slpr_vg_container(h, &pos, &np, &cpos, &ctype, &nc, &pcur, &frule, &col, &op, &npath) || slpr_vg_flatten(h, &v)) {
-            std::string e = slpr_last_error(); slpr_vg_free(h); throw std::runtime_error(e);
-        }
+        if (slpr_vg_container(h, &pos, &np, &cpos, &ctype, &nc, &pcur, &frule, &col, &op, &npath) || slpr_vg_flatten(h, &v))
+            throw std::runtime_error(slpr_last_error());
         auto vg = std::make_shared<VGContainer>();
         vg->vp = glm::vec4(v.viewport[0], v.viewport[1], v.viewport[2], v.viewport[3]);
         vg->win = glm::vec4(v.window[0], v.window[1], v.window[2], v.window[3]);
@@ -120,12 +136,11 @@ public:
             vg->pathData.fillOpacity.push_back(op[i]);
         }
         vg->pathData.pathIndex = (int)npath - 1;
-        slpr_vg_free(h);
+        _curveWeights.assign(v.curve_weight ? v.curve_weight : nullptr, v.curve_weight ? v.curve_weight + nc : nullptr);
         _vgContainer = vg;
     }
-    std::shared_ptr<VGContainer> getVGContainer() { return _vgContainer; }
-private:
     std::shared_ptr<VGContainer> _vgContainer;
+    std::vector<float> _curveWeights;
 };
 
 }  // namespace Galaxysailing
@@ -206,6 +221,8 @@ public:
     }
     void waitFrames() { need_ctx(); check(slpr_wait_host(_ctx)); }
     void setBand(uint32_t y_begin, uint32_t y_end) { need_ctx(); check(slpr_set_band(_ctx, y_begin, y_end)); }
+    // SLPR_FLAG_FULL_RVG (f-1): the middle weights of the scene's ARC curves, after loadVG
+    void setCurveWeights(const std::vector<float> &w) { need_ctx(); check(slpr_set_curve_weights(_ctx, w.data(), (uint32_t)w.size())); }
     void counts(uint32_t &n_fragments, uint32_t &n_out_fragments, uint32_t &n_spans) {
         need_ctx(); check(slpr_get_counts(_ctx, &n_fragments, &n_out_fragments, &n_spans));
     }

@@ -120,6 +120,34 @@ static void solve_quad(float a, float b, float c, float *r0, float *r1) {
     *r0 = tx; *r1 = ty;
 }
 
+/* ---- SURVEY section 8 f-1 (NOT in the reference: its QUADRIC / ARC arms are `// TODO`). With orc_set_full_rvg(1, w)
+ * the TODO arms get real arithmetic, defined HERE and mirrored operation for operation by the CUDA kernels
+ * (csrc/geom.cuh, SLPR_FLAG_FULL_RVG): QUADRIC by de Casteljau with the reference's LERP; ARC = rational quadratic
+ * with weights (1, w, 1), w per curve, control point Euclidean; monotonic cuts from the zero of the derivative's
+ * numerator w(p1-p0)u^2 + (p2-p0)ut + w(p2-p1)t^2 through the reference's own solveQuadEquation; crossings by
+ * the reference's 24-step bisection (MI1:392-436) with this evaluator. Default (off): reference behaviour. */
+static int g_full_rvg = 0;
+static const float *g_curve_weight = NULL;
+void orc_set_full_rvg(int on, const float *curve_weight) { g_full_rvg = on; g_curve_weight = on ? curve_weight : NULL; }
+
+static inline float eval_quadric(const float *p, float t) {
+    float q0 = lerpf(p[0], p[1], t), q1 = lerpf(p[1], p[2], t);
+    return lerpf(q0, q1, t);
+}
+static inline float eval_arc(const float *p, float t) { /* p[3] = weight of the middle control point */
+    float u = 1.0f - t;
+    float b0 = u * u, b2 = t * t;
+    float tt = 2.0f * t;
+    float tu = tt * u;
+    float b1 = tu * p[3];
+    float d01 = b0 + b1;
+    float D = d01 + b2;
+    float n0 = b0 * p[0], n1 = b1 * p[1], n2 = b2 * p[2];
+    float n01 = n0 + n1;
+    float N = n01 + n2;
+    return N / D;
+}
+
 /* MI0:131-165 (dflt = 1.0f) and MI1:81-148 (dflt = 0.0f) */
 static inline float interp_general(uint32_t type, float t, const float *p, float dflt) {
     if (type == T_LINE) return lerpf(p[0], p[1], t);
@@ -128,6 +156,8 @@ static inline float interp_general(uint32_t type, float t, const float *p, float
         float l0 = lerpf(q0, q1, t), l1 = lerpf(q1, q2, t);
         return lerpf(l0, l1, t);
     }
+    if (g_full_rvg && type == T_QUADRIC) return eval_quadric(p, t);
+    if (g_full_rvg && type == T_ARC) return eval_arc(p, t);
     return dflt; /* QUADRIC / ARC: TODO arms in the reference */
 }
 
@@ -169,10 +199,14 @@ static void update_cut_range(int w, int h, int *xb, int *xe, int *yb, int *ye, i
     }
 }
 
-static inline void load_points(uint32_t type, uint32_t po, const float *tpos, float *px, float *py) {
+static inline void load_points(uint32_t type, uint32_t po, const float *tpos, float *px, float *py, uint32_t curve) {
     for (uint32_t i = 0; i < 4; ++i) { /* MI0:251-257, MI1:237-243 */
         if (i < (type & 7u)) { px[i] = tpos[2 * (po + i)]; py[i] = tpos[2 * (po + i) + 1]; }
         else { px[i] = 0.f; py[i] = 0.f; } /* uninitialised shared memory in the reference; never consumed */
+    }
+    if (g_full_rvg && type == T_ARC) { /* f-1: the arc's weight rides in the unused fourth slot */
+        float w = g_curve_weight ? g_curve_weight[curve] : 1.0f;
+        px[3] = w; py[3] = w;
     }
 }
 
@@ -186,7 +220,7 @@ void orc_monotonize_count(uint32_t n_curves, const uint32_t *curve_type,
         uint32_t c = (uint32_t)ci;
         uint32_t type = curve_type[c];
         float px[4], py[4];
-        load_points(type, curve_pos_map[c], tpos, px, py);
+        load_points(type, curve_pos_map[c], tpos, px, py, c);
         uint32_t n_cuts = 0;
         int visible = !path_invisible(path_visible[curve_path[c]]); /* MI0:260-261 */
         float tq[5] = {0, 0, 0, 0, 0};
@@ -201,6 +235,19 @@ void orc_monotonize_count(uint32_t n_curves, const uint32_t *curve_type,
                     float b = 2.0f * ((x0 - x1) + (x2 - x1));
                     float cc = x1 - x0;
                     solve_quad(a, b, cc, &r0, &r1);
+                    if (r0 > 0.0f && r0 < 1.0f) tq[n_cuts++] = r0;
+                    if (r1 > 0.0f && r1 < 1.0f && r1 != r0) tq[n_cuts++] = r1;
+                } else if (g_full_rvg && (type == T_QUADRIC || type == T_ARC)) { /* f-1, see interp_general */
+                    const float *p = ax ? py : px;
+                    float w = (type == T_ARC) ? p[3] : 1.0f;
+                    float d10 = p[1] - p[0], d20 = p[2] - p[0], d21 = p[2] - p[1];
+                    float A = w * d10, B = d20, C = w * d21;
+                    float amb = A - B;
+                    float a = amb + C;
+                    float a2 = 2.0f * A;
+                    float b = B - a2;
+                    float r0 = 0.f, r1 = 0.f;
+                    solve_quad(a, b, A, &r0, &r1);
                     if (r0 > 0.0f && r0 < 1.0f) tq[n_cuts++] = r0;
                     if (r1 > 0.0f && r1 < 1.0f && r1 != r0) tq[n_cuts++] = r1;
                 }
@@ -276,7 +323,7 @@ void orc_intersect(uint32_t n_curves, const uint32_t *curve_type,
         uint32_t c = (uint32_t)ci;
         uint32_t type = curve_type[c];
         float P[10]; /* point_coords slots 0..3 = x, 4..7 = y, 8 = tx, 9 = ty */
-        load_points(type, curve_pos_map[c], tpos, P, P + 4);
+        load_points(type, curve_pos_map[c], tpos, P, P + 4, c);
         int visible = !path_invisible(path_visible[curve_path[c]]);
         float tq[5];
         tq[0] = cut_cache[5 * c + 0]; tq[1] = cut_cache[5 * c + 1];
@@ -344,7 +391,7 @@ void orc_intersect(uint32_t n_curves, const uint32_t *curve_type,
                         float v = (cst - cv[0]) * a;
                         v = (v < t_min) ? t_min : v;     /* GLSL max(x,y): y if x<y else x */
                         t_solve = (t1_ms < v) ? t1_ms : v; /* GLSL min(x,y): y if y<x else x */
-                    } else if (type == T_QUADRIC || type == T_ARC) {
+                    } else if (!g_full_rvg && (type == T_QUADRIC || type == T_ARC)) {
                         /* TODO arms: t_solve stays 0 */
                     } else { /* MI1:392-436 (every other type falls here; only CUBIC evaluates) */
                         float t0 = t_min, t1 = t1_ms;
@@ -379,6 +426,11 @@ static inline void curve_interp2(uint32_t type, float t, const float *cx, const 
         *oy = interp_general(T_CUBIC, t, cy, 0.f);
         return;
     }
+    if (g_full_rvg && (type == T_QUADRIC || type == T_ARC)) { /* f-1 */
+        *ox = interp_general(type, t, cx, 0.f);
+        *oy = interp_general(type, t, cy, 0.f);
+        return;
+    }
     *ox = cx[0]; *oy = cy[0];
 }
 
@@ -410,7 +462,9 @@ void orc_gen_fragment(int32_t nf, uint32_t n_paths, const int32_t *inter,
             uint32_t po = curve_pos_map[c0];
             float cx[4] = {0, 0, 0, 0}, cy[4] = {0, 0, 0, 0};
             uint32_t np = (type == T_LINE) ? 2 : (type == T_QUADRIC) ? 3 : (type == T_CUBIC) ? 4 : 0; /* GF:132-156 */
+            if (g_full_rvg && type == T_ARC) np = 3;
             for (uint32_t k = 0; k < np; ++k) { cx[k] = tpos[2 * (po + k)]; cy[k] = tpos[2 * (po + k) + 1]; }
+            if (g_full_rvg && type == T_ARC) cx[3] = cy[3] = g_curve_weight ? g_curve_weight[c0] : 1.0f;
             float pfx, pfy, plx, ply;
             curve_interp2(type, t0, cx, cy, &pfx, &pfy);
             curve_interp2(type, t1, cx, cy, &plx, &ply);

@@ -131,6 +131,11 @@ void orc_frame_free(orc_frame *f);
 /* Host flattening of SR.cpp:67-171 colour quantisation: rgba float[4], opacity -> RGBA8 word. */
 uint32_t orc_quantise_colour(const float *rgba, float opacity);
 
+/* SURVEY section 8 f-1, off by default: real QUADRIC / ARC arithmetic in place of the reference's TODO arms (definition in
+ * oracle.c next to interp_general). curve_weight: float[n_curves], the middle weight of ARC curves (others ignored);
+ * the pointer must stay valid while the mode is on. Process-wide. */
+void orc_set_full_rvg(int on, const float *curve_weight);
+
 int orc_num_threads(void);
 void orc_set_num_threads(int n);
 

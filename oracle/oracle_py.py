@@ -79,7 +79,7 @@ def _arr(ptr, n, dtype):
 STAGE_NAMES = ("transform", "monotonize", "scan1", "intersect", "gen_fragment", "sort", "spans", "fill")
 
 
-def render(scene, rows, width, height, do_fill=True, threads=None, keep=None):
+def render(scene, rows, width, height, do_fill=True, threads=None, keep=None, full=False):
     """Run the whole oracle frame. `scene` has the 7 flat loadVG arrays (see scene.Scene).
     Returns a dict of every intermediate buffer (numpy copies); `keep` (a set of names) limits the copies to
     those buffers — on frames of 10^8 fragments the full set is tens of gigabytes."""
@@ -88,10 +88,27 @@ def render(scene, rows, width, height, do_fill=True, threads=None, keep=None):
         L.orc_set_num_threads(int(threads))
     rows = np.ascontiguousarray(rows, dtype=np.float32).reshape(16)
     s = scene
-    fp = L.orc_render(C.c_uint32(s.n_points), _p(s.pos), _p(s.pos_path),
+    weights = None
+    if full:  # real QUADRIC / ARC arithmetic instead of the reference's TODO arms (oracle.c, orc_set_full_rvg)
+        w = getattr(s, "curve_weight", None)
+        weights = np.ascontiguousarray(w if w is not None else np.ones(s.n_curves), dtype=np.float32)
+        L.orc_set_full_rvg(C.c_int(1), _p(weights))
+    try:
+        fp = _call_render(L, s, rows, width, height, do_fill)
+    finally:
+        if full:
+            L.orc_set_full_rvg(C.c_int(0), None)
+    return _collect(L, fp, s, width, height, do_fill, keep)
+
+
+def _call_render(L, s, rows, width, height, do_fill):
+    return L.orc_render(C.c_uint32(s.n_points), _p(s.pos), _p(s.pos_path),
                       C.c_uint32(s.n_curves), _p(s.curve_pos_map), _p(s.curve_type), _p(s.curve_path),
                       C.c_uint32(s.n_paths), _p(s.fill_rule), _p(s.fill_info),
                       _p(rows), C.c_int(width), C.c_int(height), C.c_int(1 if do_fill else 0))
+
+
+def _collect(L, fp, s, width, height, do_fill, keep):
     f = fp.contents
     nf = f.n_fragments
     no = f.n_out_frag + f.n_span

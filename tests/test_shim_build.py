@@ -120,3 +120,24 @@ def test_reference_typed_driver_renders_like_the_oracle(tmp_path, name, size):
     ref = O.render(sc, S.fit_rows(vp, W, H), W, H)
     assert ref["n_fragments"] > 1000
     assert np.array_equal(img, ref["rgba"][:, :, :3])
+
+
+@pytest.mark.gpu
+def test_cpp_driver_full_rvg_mode(tmp_path):
+    """SURVEY section 8 f-1 through the C++ mirror: RVG::loadFull + CudaVGRasterizer(SLPR_FLAG_FULL_RVG) + setCurveWeights render a
+    file with quadratics, arcs at infinity, relative commands and an element transform like the oracle's full mode."""
+    from oracle import oracle_py as O
+    from vkscanlinepr_b200 import scene as S
+    import test_full_rvg
+    exe = _build(tmp_path)
+    rvg = tmp_path / "f.rvg"
+    rvg.write_text(test_full_rvg.RVG)
+    out = tmp_path / "o.ppm"
+    subprocess.check_call([exe, str(rvg), str(out), "400", "240", "full"])
+    raw = out.read_bytes()
+    hdr = b"P6\n400 240\n255\n"
+    img = np.frombuffer(raw[len(hdr):], np.uint8).reshape(240, 400, 3)
+    sc, vp, _ = V.load_rvg(str(rvg), full=True)
+    ref = O.render(sc, S.fit_rows(vp, 400, 240), 400, 240, full=True, keep={"rgba"})["rgba"]
+    assert (ref[..., :3] != 255).any(axis=2).mean() > 0.1
+    assert np.array_equal(img, ref[:, :, :3])

@@ -169,3 +169,103 @@ def write_rvg(container, path):
             col = ",".join(f"{float(v):.9g}" for v in c.fill_color[p])
             f.write(f"  1 element {rule} dyn_concrete 0,0 0,0 0,0: {' '.join(cmds)} dyn_identity dyn_paint "
                     f"{float(c.fill_opacity[p]) if float(c.fill_opacity[p]) > 0 else 1:.9g} solid rgba({col})\n")
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# SURVEY section 8 f-1 (full RVG: quadratics and rational arcs)
+def full_golden_scene(name):
+    """tests/golden/full_<name>.npz (tools/make_full_golden.py): a shipped scene through the complete RVG reader."""
+    z = np.load(os.path.join(GOLDEN, f"full_{name}.npz"))
+    sc = S.Scene(z["pos"], z["pos_path"], z["curve_pos_map"], z["curve_type"], z["curve_path"], z["fill_rule"], z["fill_info"], "full_" + name)
+    sc.curve_weight = z["curve_weight"].astype(np.float32)
+    return sc, z["vp"]
+
+
+def quad_arc_scene(n_paths=300, width=640, height=480, seed=5):
+    """Closed paths that mix all four curve types: line, quadratic, rational arc (weights 0.2 .. 3), cubic."""
+    rng = np.random.default_rng(seed)
+    pos, pos_path, cpm, ctype, cpath, wts = [], [], [], [], [], []
+    for p in range(n_paths):
+        cx, cy = rng.uniform(-20, width + 20), rng.uniform(-20, height + 20)
+        r = rng.uniform(8, 70)
+        k = int(rng.integers(3, 7))
+        ang = np.sort(rng.uniform(0, 2 * np.pi, k))
+        vert = [(cx + r * np.cos(a) * rng.uniform(0.6, 1.0), cy + r * np.sin(a) * rng.uniform(0.6, 1.0)) for a in ang]
+        for i in range(k):
+            a, b = vert[i], vert[(i + 1) % k]
+            mid = ((a[0] + b[0]) / 2, (a[1] + b[1]) / 2)
+            out = (mid[0] + (mid[0] - cx) * rng.uniform(-0.4, 1.2), mid[1] + (mid[1] - cy) * rng.uniform(-0.4, 1.2))
+            kind = int(rng.integers(0, 4))
+            cpm.append(len(pos)); cpath.append(p)
+            if kind == 0:
+                pts, t, w = [a, b], S.LINE, 1.0
+            elif kind == 1:
+                pts, t, w = [a, out, b], S.QUADRIC, 1.0
+            elif kind == 2:
+                pts, t, w = [a, out, b], S.ARC, float(rng.uniform(0.2, 3.0))
+            else:
+                o2 = (out[0] + rng.uniform(-r, r) * 0.5, out[1] + rng.uniform(-r, r) * 0.5)
+                pts, t, w = [a, out, o2, b], S.CUBIC, 1.0
+            ctype.append(t); wts.append(w)
+            for q in pts:
+                pos.append(q); pos_path.append(p)
+    col = (0xFF000000 | rng.integers(0, 1 << 24, n_paths)).astype(np.uint32)
+    sc = S.Scene(np.array(pos, np.float32), np.array(pos_path, np.uint32), np.array(cpm, np.uint32), np.array(ctype, np.uint32),
+                 np.array(cpath, np.uint32), (np.arange(n_paths) % 2).astype(np.uint32), col, "quad_arc")
+    sc.curve_weight = np.array(wts, np.float32)
+    return sc
+
+
+def point_sampled_fill(sc, rows, W, H, steps=48):
+    """An independent renderer for the full-RVG mode: every curve flattened in float64 (lines, quadratics, rational
+    arcs, cubics), affine `rows` applied, each path filled by its rule at PIXEL CENTRES with a plain scanline crossing
+    test, painted opaque in path order on white, image row = H-1-y like the pipeline. No 2x2 cells, no bisection."""
+    m = np.asarray(rows, np.float64)
+    img = np.full((H, W, 4), 255, np.uint8)
+    t = np.linspace(0.0, 1.0, steps + 1)[:, None]
+    w_all = sc.curve_weight if sc.curve_weight is not None else np.ones(sc.n_curves, np.float32)
+    first_curve = np.searchsorted(sc.curve_path, np.arange(sc.n_paths + 1))
+    yc = np.arange(H) + 0.5
+    for p in range(sc.n_paths):
+        segs = []
+        for c in range(first_curve[p], first_curve[p + 1]):
+            ty, po = int(sc.curve_type[c]), int(sc.curve_pos_map[c])
+            P = sc.pos[po:po + (ty & 7)].astype(np.float64)
+            if ty == S.LINE:
+                pts = P
+            elif ty == S.QUADRIC:
+                pts = (1 - t) ** 2 * P[0] + 2 * t * (1 - t) * P[1] + t ** 2 * P[2]
+            elif ty == S.ARC:
+                w = float(w_all[c])
+                b0, b1, b2 = (1 - t) ** 2, 2 * t * (1 - t) * w, t ** 2
+                pts = (b0 * P[0] + b1 * P[1] + b2 * P[2]) / (b0 + b1 + b2)
+            else:
+                pts = (1 - t) ** 3 * P[0] + 3 * t * (1 - t) ** 2 * P[1] + 3 * t ** 2 * (1 - t) * P[2] + t ** 3 * P[3]
+            x = m[0, 0] * pts[:, 0] + m[0, 1] * pts[:, 1] + m[0, 3]
+            y = m[1, 0] * pts[:, 0] + m[1, 1] * pts[:, 1] + m[1, 3]
+            segs.append(np.stack([x[:-1], y[:-1], x[1:], y[1:]], 1))
+        if not segs:
+            continue
+        e = np.concatenate(segs)
+        e = e[e[:, 1] != e[:, 3]]
+        if not len(e):
+            continue
+        lo, hi = int(max(0, np.floor(e[:, [1, 3]].min()))), int(min(H, np.ceil(e[:, [1, 3]].max())))
+        rgba = np.array([(int(sc.fill_info[p]) >> s) & 255 for s in (0, 8, 16, 24)], np.uint8)
+        for row in range(lo, hi):
+            y = yc[row]
+            hit = ((e[:, 1] <= y) & (y < e[:, 3])) | ((e[:, 3] <= y) & (y < e[:, 1]))
+            if not hit.any():
+                continue
+            h = e[hit]
+            xs = h[:, 0] + (y - h[:, 1]) * (h[:, 2] - h[:, 0]) / (h[:, 3] - h[:, 1])
+            d = np.where(h[:, 3] > h[:, 1], 1, -1)
+            o = np.argsort(xs)
+            xs, wn = xs[o], np.cumsum(d[o])
+            inside = (wn % 2 != 0) if sc.fill_rule[p] == 1 else (wn != 0)
+            for k in np.nonzero(inside[:-1])[0]:
+                a, b = int(np.ceil(xs[k] - 0.5)), int(np.ceil(xs[k + 1] - 0.5))
+                a, b = min(max(a, 0), W), min(max(b, 0), W)
+                if b > a:
+                    img[H - 1 - row, a:b] = rgba
+    return img

@@ -1,7 +1,7 @@
 // slpr_render.cpp — headless replacement of the reference's main.cpp + ScanlineVGApplication::run()
 // (VkScanlinePR/src/main.cpp:8-24, src/app/vg_app.cpp:146-165): same builder-style call sequence,
 // CudaVGRasterizer in place of ScanlineVGRasterizer, a PPM file in place of the GLFW window.
-//   slpr_render scene.rvg out.ppm [width height]
+//   slpr_render scene.rvg out.ppm [width height [full]]     (full: the complete RVG reader + SLPR_FLAG_FULL_RVG, f-1)
 // Build: g++ -std=c++17 -Iinclude tools/slpr_render.cpp -Lvkscanlinepr_b200 -lslpr -Wl,-rpath,$PWD/vkscanlinepr_b200
 #include <algorithm>
 #include <cstdio>
@@ -15,14 +15,21 @@ using namespace Galaxysailing;
 int main(int argc, char **argv) {
     if (argc < 3) { std::fprintf(stderr, "usage: %s scene.rvg out.ppm [width height]\n", argv[0]); return 2; }
     const uint32_t w = argc > 4 ? (uint32_t)std::atoi(argv[3]) : 1200, h = argc > 4 ? (uint32_t)std::atoi(argv[4]) : 1024;
+    const bool full = argc > 5 && std::string(argv[5]) == "full";
     try {
         RVG rvg;
+#if !defined(SLPR_WITH_REFERENCE_HEADERS)
+        if (full) rvg.loadFull(argv[1]); else
+#endif
         rvg.load(argv[1]);                               // app->loadPathFile(...)
         auto vg = rvg.getVGContainer();
         std::cout << "---------- vg load success ---------\n";
-        CudaVGRasterizer rast(0, 0);
+        CudaVGRasterizer rast(0, full ? SLPR_FLAG_FULL_RVG : 0);
         rast.initialize(nullptr, w, h);                  // _vgRasterizer->initialize(window, w, h)
         rast.loadVG(vg);                                 // _vgRasterizer->loadVG(_vgContainer)
+#if !defined(SLPR_WITH_REFERENCE_HEADERS)
+        if (full && !rvg.getCurveWeights().empty()) rast.setCurveWeights(rvg.getCurveWeights());
+#endif
         // camera: uniform fit of the file's viewport box, centred; the app passes transpose(camera.mv())
         const float sx = w / (vg->vp[2] - vg->vp[0]), sy = h / (vg->vp[3] - vg->vp[1]), s = std::min(sx, sy);
         glm::mat4 mv(1.0f);                              // identity (glm's default constructor leaves it unset); column-major affine: x' = s*x + tx

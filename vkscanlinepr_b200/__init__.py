@@ -22,7 +22,7 @@ LIB_PATH = os.environ.get("SLPR_LIB") or os.path.join(_HERE, "libslpr.so")  # SL
 _LIB = None
 
 FLAG_TAPS, FLAG_CONTRACT_FMA, FLAG_NO_GRAPH, FLAG_RADIX_SORT, FLAG_SEGMENTED_SORT = 1, 2, 4, 8, 16
-FLAG_FUSED_FILL, FLAG_SEPARATE_FILL, FLAG_WINDOWED_WALK, FLAG_RECORDS = 32, 64, 128, 256
+FLAG_FUSED_FILL, FLAG_SEPARATE_FILL, FLAG_WINDOWED_WALK, FLAG_RECORDS, FLAG_FULL_RVG = 32, 64, 128, 256, 512
 TAPS = dict(transformed_pos=0, path_visible=1, cut_cache=2, curve_count=3, curve_offset=4, intersection=5,
             key=6, path=7, winding=8, sorted_key=9, sorted_index=10, winding_scan=11, flags=12,
             flag_scan=13, records=14, segments=15)
@@ -76,6 +76,8 @@ def lib():
         L.slpr_pipeline_redone.argtypes = [C.c_void_p]
         L.slpr_vg_load_rvg.restype = C.c_void_p
         L.slpr_vg_load_rvg.argtypes = [C.c_char_p]
+        L.slpr_vg_load_rvg_full.restype = C.c_void_p
+        L.slpr_vg_load_rvg_full.argtypes = [C.c_char_p]
         L.slpr_vg_from_arrays.restype = C.c_void_p
         L.slpr_vg_free.argtypes = [C.c_void_p]
         _LIB = L
@@ -96,7 +98,7 @@ class _SceneView(C.Structure):
                 ("curve_pos_map", C.POINTER(C.c_uint32)), ("curve_type", C.POINTER(C.c_uint32)),
                 ("curve_path", C.POINTER(C.c_uint32)), ("n_curves", C.c_uint32),
                 ("fill_rule", C.POINTER(C.c_uint32)), ("fill_rgba8", C.POINTER(C.c_uint32)), ("n_paths", C.c_uint32),
-                ("viewport", C.c_float * 4), ("window", C.c_float * 4)]
+                ("viewport", C.c_float * 4), ("window", C.c_float * 4), ("curve_weight", C.POINTER(C.c_float))]
 
 
 def _np_from(ptr, n, dtype):
@@ -113,6 +115,7 @@ def _flatten_handle(h, name):
                _np_from(v.curve_pos_map, v.n_curves, np.uint32), _np_from(v.curve_type, v.n_curves, np.uint32),
                _np_from(v.curve_path, v.n_curves, np.uint32), _np_from(v.fill_rule, v.n_paths, np.uint32),
                _np_from(v.fill_rgba8, v.n_paths, np.uint32), name)
+    sc.curve_weight = _np_from(v.curve_weight, v.n_curves, np.float32) if v.curve_weight else None
     return sc, np.array(list(v.viewport), dtype=np.float32)
 
 
@@ -132,10 +135,12 @@ def container_from_handle(h):
                      _np_from(fop, n_path.value, np.float32))
 
 
-def load_rvg(path, name=None):
-    """RVG file -> (Scene, viewport, Container) through the library's parser (rvg.cpp:9-255 behaviour)."""
+def load_rvg(path, name=None, full=False):
+    """RVG file -> (Scene, viewport, Container) through the library's parser: the reference parser's behaviour
+    (rvg.cpp:9-255), or with full=True the complete reader (slpr_vg_load_rvg_full: arcs, quadratics, transforms;
+    the scene then carries curve_weight and needs FLAG_FULL_RVG)."""
     L = lib()
-    h = L.slpr_vg_load_rvg(os.fsencode(path))
+    h = (L.slpr_vg_load_rvg_full if full else L.slpr_vg_load_rvg)(os.fsencode(path))
     if not h:
         raise SlprError(L.slpr_last_error().decode())
     try:
@@ -196,6 +201,10 @@ class ScanlineRasterizer:
         _check(lib().slpr_load_scene(self._h, _p(sc.pos), _p(sc.pos_path), C.c_uint32(sc.n_points),
                                      _p(sc.curve_pos_map), _p(sc.curve_type), _p(sc.curve_path), C.c_uint32(sc.n_curves),
                                      _p(sc.fill_rule), _p(sc.fill_info), C.c_uint32(sc.n_paths)))
+        w = getattr(sc, "curve_weight", None)
+        if (self._flags & FLAG_FULL_RVG) and w is not None:
+            w = np.ascontiguousarray(w, dtype=np.float32)
+            _check(lib().slpr_set_curve_weights(self._h, _p(w), C.c_uint32(sc.n_curves)))
 
     def setMVP(self, rows):
         r = np.ascontiguousarray(rows, dtype=np.float32).reshape(16)

@@ -98,6 +98,30 @@ __device__ __forceinline__ float interp_general(uint32_t type, float t, float p0
     return dflt;
 }
 
+// ---- SURVEY section 8 f-1 (SLPR_FLAG_FULL_RVG; NOT in the reference, whose QUADRIC / ARC arms are `// TODO`): the arithmetic is
+// defined in oracle/oracle.c next to interp_general and mirrored here operation for operation.
+__device__ __forceinline__ float eval_quadric(float p0, float p1, float p2, float t) {
+    const float q0 = lerpf(p0, p1, t), q1 = lerpf(p1, p2, t);
+    return lerpf(q0, q1, t);
+}
+// rational quadratic with weights (1, w, 1), Euclidean control point
+__device__ __forceinline__ float eval_arc(float p0, float p1, float p2, float w, float t) {
+    const float u = __fsub_rn(1.0f, t);
+    const float b0 = __fmul_rn(u, u), b2 = __fmul_rn(t, t);
+    const float b1 = __fmul_rn(__fmul_rn(__fmul_rn(2.0f, t), u), w);
+    const float D = __fadd_rn(__fadd_rn(b0, b1), b2);
+    const float N = __fadd_rn(__fadd_rn(__fmul_rn(b0, p0), __fmul_rn(b1, p1)), __fmul_rn(b2, p2));
+    return __fdiv_rn(N, D);
+}
+// interp_general with the TODO arms filled in (p3 carries the weight of an ARC)
+__device__ __forceinline__ float interp_full(uint32_t type, float t, float p0, float p1, float p2, float p3, float dflt, bool full) {
+    if (type == T_LINE) return lerpf(p0, p1, t);
+    if (type == T_CUBIC) return cubic_eval(p0, p1, p2, p3, t);
+    if (full && type == T_QUADRIC) return eval_quadric(p0, p1, p2, t);
+    if (full && type == T_ARC) return eval_arc(p0, p1, p2, p3, t);
+    return dflt;
+}
+
 // streaming 128-bit accesses (bypass L1 allocation for data touched once; not .nc so that
 // in-place use is well defined)
 __device__ __forceinline__ int4 ld_stream(const int4 *p) {

@@ -131,6 +131,16 @@ __device__ __forceinline__ void load_points(uint32_t type, uint32_t po, const fl
     }
 }
 
+// f-1 (SLPR_FLAG_FULL_RVG): what the real QUADRIC / ARC arithmetic needs beyond the reference's inputs — the weight of
+// every ARC's middle control point (it rides in the unused fourth slot of the curve's points).
+struct FullRvg {
+    const float *curve_weight;  // nullptr: mode off (reference behaviour: the TODO arms)
+    __device__ __forceinline__ bool on() const { return curve_weight != nullptr; }
+    __device__ __forceinline__ void stash_weight(uint32_t type, uint32_t curve, CurvePts &c) const {
+        if (curve_weight && type == T_ARC) { const float w = curve_weight[curve]; c.x[3] = w; c.y[3] = w; }
+    }
+};
+
 // ------------------------------------------------------------------------------------------------
 // K2: make_intersection_0.comp:226-410. One thread per curve: monotonic cut parameters (<=4),
 // literal partial insertion sort (including the `float t2 = q3;` slip at MI0:340), and the number
@@ -353,7 +363,7 @@ __global__ void __launch_bounds__(256) k_monotonize_count(const FrameParams *__r
                                                           const int *__restrict__ path_visible,
                                                           float *__restrict__ cut_cache, int *__restrict__ count,
                                                           uint32_t *__restrict__ slots, uint32_t *__restrict__ block_cnt,
-                                                          LiveCurves live, PieceLayout lay) {
+                                                          LiveCurves live, PieceLayout lay, FullRvg full) {
     // Pieces are ranked inside (block, length bucket) with shared-memory atomics only; the block's 64 counts
     // go to block_cnt[bucket][block] at the end and k_bucket_scan turns them into positions. (One global
     // atomicAdd per block iteration and bucket on 64 addresses serialised in L2: 0.1 ms at 4 M curves.)
@@ -374,6 +384,7 @@ __global__ void __launch_bounds__(256) k_monotonize_count(const FrameParams *__r
         const uint32_t type = curve_type[c];
         CurvePts cp;
         load_points(type, curve_pos_map[c], tpos, cp);
+        full.stash_weight(type, c, cp);
         uint32_t n_cuts = 0;
         bool culled = false;  // band mode: a curve whose control-point box misses the band is skipped like an invisible one
         if (cull) {
@@ -397,6 +408,19 @@ __global__ void __launch_bounds__(256) k_monotonize_count(const FrameParams *__r
                     const float b = __fmul_rn(2.0f, __fadd_rn(__fsub_rn(x0, x1), __fsub_rn(x2, x1)));
                     const float cc = __fsub_rn(x1, x0);
                     solve_quad(a, b, cc, r0, r1);
+                    if (r0 > 0.0f && r0 < 1.0f) { tq[n_cuts] = r0; ++n_cuts; }
+                    if (r1 > 0.0f && r1 < 1.0f && r1 != r0) { tq[n_cuts] = r1; ++n_cuts; }
+                }
+            } else if (full.on() && (type == T_QUADRIC || type == T_ARC)) {  // f-1: zero of the derivative's numerator (oracle.c)
+#pragma unroll
+                for (int ax = 0; ax < 2; ++ax) {
+                    const float p0 = ax ? cp.y[0] : cp.x[0], p1 = ax ? cp.y[1] : cp.x[1], p2 = ax ? cp.y[2] : cp.x[2];
+                    const float w = (type == T_ARC) ? cp.x[3] : 1.0f;
+                    const float A = __fmul_rn(w, __fsub_rn(p1, p0)), B = __fsub_rn(p2, p0), C = __fmul_rn(w, __fsub_rn(p2, p1));
+                    const float a = __fadd_rn(__fsub_rn(A, B), C);
+                    const float b = __fsub_rn(B, __fmul_rn(2.0f, A));
+                    float r0 = 0.f, r1 = 0.f;
+                    solve_quad(a, b, A, r0, r1);
                     if (r0 > 0.0f && r0 < 1.0f) { tq[n_cuts] = r0; ++n_cuts; }
                     if (r1 > 0.0f && r1 < 1.0f && r1 != r0) { tq[n_cuts] = r1; ++n_cuts; }
                 }
@@ -429,8 +453,8 @@ __global__ void __launch_bounds__(256) k_monotonize_count(const FrameParams *__r
         int pcnt = 0;
         for (uint32_t i = 0; i < n_cuts; ++i) {  // MI0:383-408
             const float t1 = tq[i];
-            const float p1x = interp_general(type, t1, cp.x[0], cp.x[1], cp.x[2], cp.x[3], 1.0f);
-            const float p1y = interp_general(type, t1, cp.y[0], cp.y[1], cp.y[2], cp.y[3], 1.0f);
+            const float p1x = interp_full(type, t1, cp.x[0], cp.x[1], cp.x[2], cp.x[3], 1.0f, full.on());
+            const float p1y = interp_full(type, t1, cp.y[0], cp.y[1], cp.y[2], cp.y[3], 1.0f, full.on());
             // get_xy_begin_end, MI0:167-183 (floor)
             const float xlo = (p0x <= p1x) ? p0x : p1x, xhi = (p0x <= p1x) ? p1x : p0x;
             const float ylo = (p0y <= p1y) ? p0y : p1y, yhi = (p0y <= p1y) ? p1y : p0y;
@@ -586,8 +610,13 @@ __device__ __forceinline__ void emit_fragment(const FragEnv &P, const KeyLayout 
 }
 
 // curve_interpolate of gen_fragment.comp:59-87 (default result cv0; only LINE and CUBIC evaluate)
+template <bool FULL = false>
 __device__ __forceinline__ void eval_point(uint32_t type, const CurvePts &cp, float t, float &ox, float &oy) {
-    if (type == T_CUBIC) {
+    if (FULL && type == T_QUADRIC) {
+        ox = eval_quadric(cp.x[0], cp.x[1], cp.x[2], t); oy = eval_quadric(cp.y[0], cp.y[1], cp.y[2], t);
+    } else if (FULL && type == T_ARC) {
+        ox = eval_arc(cp.x[0], cp.x[1], cp.x[2], cp.x[3], t); oy = eval_arc(cp.y[0], cp.y[1], cp.y[2], cp.y[3], t);
+    } else if (type == T_CUBIC) {
         ox = cubic_eval(cp.x[0], cp.x[1], cp.x[2], cp.x[3], t);
         oy = cubic_eval(cp.y[0], cp.y[1], cp.y[2], cp.y[3], t);
     } else if (type == T_LINE) {

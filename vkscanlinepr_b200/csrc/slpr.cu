@@ -94,6 +94,7 @@ struct slpr_ctx {
     uint8_t *d_plive = nullptr;  // [P] band mode: the path can reach the band (k_path_cull)
     uint32_t *d_live_paths = nullptr;  // [P] band mode: the live paths, listed (k_band_paths / k_path_cull) for the sort
     int2 *d_live_range = nullptr;      // [P] band mode: fragment range of each listed path (k_path_segments)
+    float *d_cweight = nullptr;  // [nc] SLPR_FLAG_FULL_RVG: weight of every ARC's middle control point (1 until slpr_set_curve_weights)
     float *d_cut = nullptr;
     int *d_count = nullptr, *d_offset = nullptr, *d_seg_tap = nullptr;  // d_seg_tap: [P+1] sort segment table (always built)
     int *d_big = nullptr;              // [P] paths queued for the block-level segmented sort
@@ -240,7 +241,7 @@ static void free_exchange(slpr_ctx *c) {
 static void free_scene(slpr_ctx *c) {
     free_exchange(c);
     cudaFree(c->d_pos); cudaFree(c->d_pos_path); cudaFree(c->d_cpm); cudaFree(c->d_ctype); cudaFree(c->d_cpath);
-    cudaFree(c->d_frule); cudaFree(c->d_finfo); cudaFree(c->d_tpos); cudaFree(c->d_pvis); cudaFree(c->d_pobj); cudaFree(c->d_pfc); cudaFree(c->d_pfp); cudaFree(c->d_plive); cudaFree(c->d_live_paths); c->d_live_paths = nullptr; cudaFree(c->d_live_range); c->d_live_range = nullptr; cudaFree(c->d_live); cudaFree(c->d_block_cnt); cudaFree(c->d_vhist); cudaFree(c->d_cut);
+    cudaFree(c->d_frule); cudaFree(c->d_finfo); cudaFree(c->d_tpos); cudaFree(c->d_pvis); cudaFree(c->d_pobj); cudaFree(c->d_pfc); cudaFree(c->d_pfp); cudaFree(c->d_plive); cudaFree(c->d_live_paths); c->d_live_paths = nullptr; cudaFree(c->d_live_range); c->d_live_range = nullptr; cudaFree(c->d_live); cudaFree(c->d_block_cnt); cudaFree(c->d_vhist); cudaFree(c->d_cut); cudaFree(c->d_cweight); c->d_cweight = nullptr;
     cudaFree(c->d_count); cudaFree(c->d_offset); cudaFree(c->d_seg_tap);
     cudaFree(c->d_big); c->d_big = nullptr;
     cudaFree(c->d_slots); cudaFree(c->d_pieces); cudaFree(c->d_boundary); cudaFree(c->d_fixlist);
@@ -338,7 +339,8 @@ extern "C" slpr_ctx *slpr_create(int device, uint32_t width, uint32_t height, ui
     c->fb_cur = c->d_fb;
     for (auto &ev : c->ev) ok = ok && cudaEventCreate(&ev) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_onesweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM_BYTES) == cudaSuccess;
-    ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->walk_blocks_per_sm, k_walk, WALK_THREADS, 0) == cudaSuccess;
+    if (flags & SLPR_FLAG_FULL_RVG) ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->walk_blocks_per_sm, k_walk<true>, WALK_THREADS, 0) == cudaSuccess;
+    else ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->walk_blocks_per_sm, k_walk<false>, WALK_THREADS, 0) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_scan_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->scan_tma_blocks_per_sm, k_scan_tma, ST_THREADS, ST_SMEM_BYTES) == cudaSuccess;
     for (auto fn : {k_spans<false, true, false>, k_spans<true, true, false>, k_spans<true, false, false>, k_spans<false, true, true>, k_spans<true, true, true>})
@@ -476,6 +478,10 @@ extern "C" int slpr_load_scene(slpr_ctx *c, const float *pos_xy, const uint32_t 
     c->lay.blocks_per_window = (c->lay.n_blocks + c->lay.n_windows - 1) / c->lay.n_windows;
     CU(cudaMalloc(&c->d_vhist, (size_t)WALK_VBUCKETS_MAX * 4));
     CU(cudaMalloc(&c->d_cut, std::max<size_t>(n_curves, 1) * 5 * 4));
+    if (c->flags & SLPR_FLAG_FULL_RVG) {
+        std::vector<float> ones(std::max<size_t>(n_curves, 1), 1.0f);
+        if ((rc = upload(&c->d_cweight, ones.data(), ones.size()))) return rc;
+    }
     CU(cudaMalloc(&c->d_count, ((size_t)n_curves + 4) * 4));
     CU(cudaMalloc(&c->d_offset, ((size_t)n_curves + 4) * 4));
     CU(cudaMalloc(&c->d_slots, std::max<size_t>(n_curves, 1) * 5 * 4));
@@ -495,6 +501,16 @@ extern "C" int slpr_load_scene(slpr_ctx *c, const float *pos_xy, const uint32_t 
     c->passes = std::max(1, (c->key_bits + 7) / 8);
     c->scene_loaded = true;
     c->frame_done = c->frame_pending = false;
+    return SLPR_OK;
+}
+
+extern "C" int slpr_set_curve_weights(slpr_ctx *c, const float *curve_weight, uint32_t n_curves) {
+    if (!c || !curve_weight) return fail(SLPR_ERR_INVALID, "slpr_set_curve_weights: null argument");
+    if (!c->scene_loaded || n_curves != c->nc) return fail(SLPR_ERR_STATE, "slpr_set_curve_weights: load the scene first; n_curves must match it");
+    if (!(c->flags & SLPR_FLAG_FULL_RVG)) return fail(SLPR_ERR_STATE, "slpr_set_curve_weights: the context was not created with SLPR_FLAG_FULL_RVG");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    if (n_curves) CU(cudaMemcpy(c->d_cweight, curve_weight, (size_t)n_curves * 4, cudaMemcpyHostToDevice));
     return SLPR_OK;
 }
 
@@ -570,7 +586,7 @@ static int enqueue_count_phase(slpr_ctx *c, cudaStream_t s, bool timed, int &lau
     }
     k_monotonize_count<<<c->mono_blocks, 256, 0, s>>>(c->d_params, c->nc, c->d_ctype, c->d_cpm, c->d_cpath,
                                                                    c->d_tpos, c->d_pvis, c->d_cut, c->d_count, c->d_slots,
-                                                                   c->d_block_cnt, live, c->lay);
+                                                                   c->d_block_cnt, live, c->lay, FullRvg{c->d_cweight});
     k_bucket_scan<<<dim3(WALK_BUCKETS, c->lay.n_windows), c->lay.blocks_per_window > 256 ? 1024 : 128, 0, s>>>(c->d_block_cnt, c->lay, c->d_vhist);
     launches += 2;
     if (timed) CU(cudaEventRecord(c->ev[2], s));
@@ -591,13 +607,14 @@ static int enqueue_fragments(slpr_ctx *c, cudaStream_t s, bool timed, int &launc
     k_piece_emit<<<c->mono_blocks, 256, 0, s>>>(c->d_params, c->nc, c->d_ctype, c->d_cpm, c->d_cpath, c->d_frule, c->d_tpos, c->d_cut,
                                                              c->d_offset, c->d_slots, c->d_ctr, c->cap,
                                                              PieceRanks{c->d_block_cnt, c->d_vhist, c->lay},
-                                                             LiveCurves{c->hp.cull ? c->d_live : nullptr, c->d_ctr}, c->d_pieces);
+                                                             LiveCurves{c->hp.cull ? c->d_live : nullptr, c->d_ctr}, c->d_pieces, FullRvg{c->d_cweight});
     if (timed) CU(cudaEventRecord(c->ev[4], s));
-    k_walk<<<c->num_sms * std::max(1, c->walk_blocks_per_sm), WALK_THREADS, 0, s>>>(
+    auto walk = c->d_cweight ? k_walk<true> : k_walk<false>;
+    walk<<<c->num_sms * std::max(1, c->walk_blocks_per_sm), WALK_THREADS, 0, s>>>(
         c->d_params, c->d_pieces, c->d_ctr, c->cap, WalkTemp{c->d_tickets + 3 + RS_MAX_PASSES},
         c->L, c->d_key[0], c->d_val[0], ft, c->d_inter, c->d_boundary, c->d_fixlist);
     k_piece_fix<<<8, 256, 0, s>>>(c->d_params, c->d_ctype, c->d_cpm, c->d_cpath, c->d_frule, c->d_tpos, c->d_ctr, c->cap, c->d_boundary,
-                                  c->d_fixlist, c->L, c->d_key[0], c->d_val[0], ft);
+                                  c->d_fixlist, c->L, c->d_key[0], c->d_val[0], ft, FullRvg{c->d_cweight});
     launches += 3;
     if (timed) CU(cudaEventRecord(c->ev[5], s));
     k_path_segments<<<grid_for(c, (long long)c->P + 1, 256, 4), 256, 0, s>>>(c->d_pfc, c->P, c->d_offset, c->d_seg_tap, c->d_ctr, c->cap,

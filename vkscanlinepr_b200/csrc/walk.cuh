@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(256, SLPR_PE_MIN_BLOCKS) k_piece_emit(const Fr
                                                     const float2 *__restrict__ tpos, const float *__restrict__ cut_cache,
                                                     const int *__restrict__ offsets, const uint32_t *__restrict__ slots,
                                                     FrameCounters *__restrict__ ctr, int capacity, PieceRanks ranks,
-                                                    LiveCurves live, PieceRec *__restrict__ pieces) {
+                                                    LiveCurves live, PieceRec *__restrict__ pieces, FullRvg full) {
     __shared__ uint32_t s_vbase[WALK_VBUCKETS_MAX];
     __shared__ uint32_t s_pos[WALK_BUCKETS];
     __shared__ uint32_t s_total;
@@ -116,14 +116,15 @@ __global__ void __launch_bounds__(256, SLPR_PE_MIN_BLOCKS) k_piece_emit(const Fr
         const uint32_t path_rule = pidx | (fill_rule[pidx] == 1u ? 0x80000000u : 0u);
         CurvePts cp;
         load_points(type, curve_pos_map[c], tpos, cp);
+        full.stash_weight(type, c, cp);  // (an ARC's weight then travels in the piece record's fourth x slot)
         const float q0 = cut_cache[5 * c + 0], q1 = cut_cache[5 * c + 1], q2 = cut_cache[5 * c + 2], q3 = cut_cache[5 * c + 3];
         // count > 0 implies the path is visible (MI0:374-377), so MI1:257-260 appends t = 1
         const uint32_t n_cuts = f2u(cut_cache[5 * c + 4]) + 1u;  // MI1:255
         float t0_ms = 0.f, p0x = cp.x[0], p0y = cp.y[0];
         for (uint32_t piece = 0; piece < n_cuts; ++piece) {  // MI1:266-308
             float t1_ms = (piece + 1 == n_cuts) ? 1.f : (piece == 0) ? q0 : (piece == 1) ? q1 : (piece == 2) ? q2 : q3;
-            const float p1x = interp_general(type, t1_ms, cp.x[0], cp.x[1], cp.x[2], cp.x[3], 0.0f);
-            const float p1y = interp_general(type, t1_ms, cp.y[0], cp.y[1], cp.y[2], cp.y[3], 0.0f);
+            const float p1x = interp_full(type, t1_ms, cp.x[0], cp.x[1], cp.x[2], cp.x[3], 0.0f, full.on());
+            const float p1y = interp_full(type, t1_ms, cp.y[0], cp.y[1], cp.y[2], cp.y[3], 0.0f, full.on());
             // MI1:271-276: tag t1 in its two mantissa LSBs
             if (floorf(p1x) == p1x) t1_ms = u2f((f2u(t1_ms) & 0xFFFFFFFCu) | 2u);
             else t1_ms = u2f(f2u(t1_ms) | 3u);
@@ -224,6 +225,9 @@ constexpr int WALK_UNROLL = SLPR_WALK_UNROLL;  // bisection steps per loop trip
 #define SLPR_WALK_MIN_BLOCKS 1
 #endif
 
+// FULL (SLPR_FLAG_FULL_RVG, f-1): QUADRIC / ARC pieces are walked with the reference's bisection on their own evaluators
+// (common.cuh) instead of the reference's TODO arms; a separate instantiation, so the default kernel is untouched.
+template <bool FULL>
 __global__ void __launch_bounds__(WALK_THREADS, SLPR_WALK_MIN_BLOCKS) k_walk(const FrameParams *__restrict__ P,
                                                        const PieceRec *__restrict__ pieces,
                                                        FrameCounters *__restrict__ ctr, int capacity, WalkTemp tmp,
@@ -335,7 +339,7 @@ __global__ void __launch_bounds__(WALK_THREADS, SLPR_WALK_MIN_BLOCKS) k_walk(con
                 float tc = u2f(f2u(t_min) & 0xFFFFFFFCu);
                 tc = (tc < 0.0f) ? 0.0f : tc;
                 float ex, ey;
-                eval_point(type, cp, tc, ex, ey);
+                eval_point<FULL>(type, cp, tc, ex, ey);
                 if (have_prev) {
                     uint64_t k; uint32_t v;
                     make_fragment(env, L, pcnt - 1, pidx, rule_bit, prev_t, tc, prev_x, prev_y, ex, ey, k, v, taps);
@@ -392,6 +396,23 @@ __global__ void __launch_bounds__(WALK_THREADS, SLPR_WALK_MIN_BLOCKS) k_walk(con
                         float v = __fmul_rn(__fsub_rn(cst, c0), a);
                         v = (v < t_min) ? t_min : v;        // GLSL max(x,y) = x<y ? y : x
                         t_solve = (t1_ms < v) ? t1_ms : v;  // GLSL min(x,y) = y<x ? y : x
+                    } else if (FULL && (type == T_QUADRIC || type == T_ARC)) {  // f-1: the bisection of MI1:392-436 on this curve's evaluator
+                        const float c2 = side ? cp.y[2] : cp.x[2], w = cp.x[3];
+                        float t0 = t_min, t1 = t1_ms;
+                        float vt0 = (type == T_ARC) ? eval_arc(c0, c1, c2, w, t0) : eval_quadric(c0, c1, c2, t0);
+                        t_solve = t0;
+                        if (vt0 != cst) {
+                            const float raw_t0 = t0;
+                            float last_vtm = 0.f;
+                            for (int j = 0; j < CUBIC_ITERATION_NUMBER; ++j) {
+                                const float tm = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
+                                const float vtm = (type == T_ARC) ? eval_arc(c0, c1, c2, w, tm) : eval_quadric(c0, c1, c2, tm);
+                                t_solve = tm; last_vtm = vtm;
+                                if ((int)(f2u(__fsub_rn(vtm, cst)) ^ f2u(__fsub_rn(vt0, cst))) >= 0) { t0 = tm; vt0 = vtm; }
+                                else t1 = tm;
+                            }
+                            if (fabsf(__fsub_rn(last_vtm, cst)) > 1.f) t_solve = raw_t0;
+                        }
                     } else if (type == T_QUADRIC || type == T_ARC) {
                         t_solve = 0.0f;  // TODO arms in the reference: t_solve stays 0
                     } else {  // any other type value: interpolateGeneralCurve returns 0 (MI1:81-83,144)
@@ -423,7 +444,7 @@ __global__ void __launch_bounds__(WALK_THREADS, SLPR_WALK_MIN_BLOCKS) k_walk(con
             float tcl = u2f(f2u(t1_ms) & 0xFFFFFFFCu);
             tcl = (tcl < 0.0f) ? 0.0f : tcl;
             float ex, ey;
-            eval_point(type, cp, tcl, ex, ey);
+            eval_point<FULL>(type, cp, tcl, ex, ey);
             uint64_t k; uint32_t v;
             make_fragment(env, L, pcnt - 1, pidx, rule_bit, prev_t, tcl, prev_x, prev_y, ex, ey, k, v, taps);
             fs.put(pcnt - 1, k, v, key64, val);
@@ -450,7 +471,7 @@ __global__ void __launch_bounds__(256) k_piece_fix(const FrameParams *__restrict
                                                    const uint32_t *__restrict__ curve_path, const uint32_t *__restrict__ fill_rule,
                                                    const float2 *__restrict__ tpos, const FrameCounters *__restrict__ ctr, int capacity,
                                                    const float2 *__restrict__ boundary, const uint4 *__restrict__ fixlist, KeyLayout L,
-                                                   uint64_t *__restrict__ key64, uint32_t *__restrict__ val, FragTaps taps) {
+                                                   uint64_t *__restrict__ key64, uint32_t *__restrict__ val, FragTaps taps, FullRvg full) {
     if (ctr->n_fragments > capacity) return;
     const int n_fix = ctr->n_fix;
     if (n_fix == 0) return;  // the common case
@@ -463,6 +484,7 @@ __global__ void __launch_bounds__(256) k_piece_fix(const FrameParams *__restrict
         const uint32_t rule_bit = fill_rule[pidx] == 1u ? 1u : 0u;
         CurvePts cp;
         load_points(type, curve_pos_map[c], tpos, cp);
+        full.stash_weight(type, c, cp);
         const int f = (int)e.z - 1;  // last record of the piece before: a curve's records are consecutive
         // GF:99-104: t0 from that record, t1 from the next record of the curve
         float t0 = u2f(f2u(boundary[5 * c + piece - 1].y) & 0xFFFFFFFCu);
@@ -470,8 +492,8 @@ __global__ void __launch_bounds__(256) k_piece_fix(const FrameParams *__restrict
         t0 = (t0 < 0.0f) ? 0.0f : t0;
         t1 = (t1 < 0.0f) ? 0.0f : t1;
         float ax, ay, bx, by;
-        eval_point(type, cp, t0, ax, ay);
-        eval_point(type, cp, t1, bx, by);
+        if (full.on()) { eval_point<true>(type, cp, t0, ax, ay); eval_point<true>(type, cp, t1, bx, by); }
+        else { eval_point<false>(type, cp, t0, ax, ay); eval_point<false>(type, cp, t1, bx, by); }
         emit_fragment(env, L, f, pidx, rule_bit, t0, t1, ax, ay, bx, by, key64, val, taps);
     }
 }

@@ -26,6 +26,7 @@ class Scene:
     fill_rule: np.ndarray      # uint32  [n_paths] 0 = nonzero, 1 = even-odd
     fill_info: np.ndarray      # uint32  [n_paths] RGBA8, R in the low byte
     name: str = "scene"
+    curve_weight = None        # float32 [n_curves] or None: middle weight of ARC curves (full RVG loader)
 
     def __post_init__(self):
         self.pos = np.ascontiguousarray(self.pos, dtype=np.float32).reshape(-1, 2)
