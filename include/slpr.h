@@ -69,7 +69,13 @@ enum {
      * place of the reference's `// TODO` arms (make_intersection_0.comp:141-144,273-276; make_intersection_1.comp:386-391;
      * gen_fragment.comp:66-69). The arithmetic is defined in oracle/oracle.c (orc_set_full_rvg) and matched bit for bit.
      * Scenes of lines and cubics render exactly as without the flag. Use with slpr_vg_load_rvg_full. */
-    SLPR_FLAG_FULL_RVG = 1u << 9
+    SLPR_FLAG_FULL_RVG = 1u << 9,
+    /* SURVEY section 8 f-3, beyond the reference (which has no antialiasing: README.md:5, gen_fragment.comp:202): four coverage
+     * samples per pixel. The pipeline runs at four times the frame's size (the matrix rows are scaled by 4, exactly), so a
+     * pixel is 2 x 2 of its coverage cells; each cell holds the top-most path covering it (ordered, opaque compositing
+     * per sample, as the reference composites per 2 x 2 block) and the pixel is their box-filtered average. Same result
+     * as the reference path rendered at 4x and averaged over 4 x 4 blocks. Width and height at most 8191. */
+    SLPR_FLAG_AA4 = 1u << 10
 };
 
 /* Buffers that slpr_debug_copy() can return. Layouts are the reference's:

@@ -101,6 +101,25 @@ def render(scene, rows, width, height, do_fill=True, threads=None, keep=None, fu
     return _collect(L, fp, s, width, height, do_fill, keep)
 
 
+def box4(rgba_hi):
+    """(4H, 4W, 4) uint8 -> (H, W, 4): every pixel the rounded average of its 2 x 2 coverage cells (each cell is 2 x 2 equal
+    pixels of the 4x frame), (sum + 2) >> 2 per channel — the resolve of SLPR_FLAG_AA4."""
+    h, w = rgba_hi.shape[0] // 4, rgba_hi.shape[1] // 4
+    cells = rgba_hi[::2, ::2].astype(np.uint32).reshape(h, 2, w, 2, 4)
+    return ((cells.sum(axis=(1, 3)) + 2) >> 2).astype(np.uint8)
+
+
+def render_aa4(scene, rows, width, height, full=False):
+    """the definition of SLPR_FLAG_AA4 in terms of the reference path — the frame rendered at four times the
+    size (matrix rows 0 and 1 scaled by 4, exactly) and box-filtered. Returns the dict of the 4x frame plus "rgba_aa"."""
+    r4 = np.array(rows, dtype=np.float32).reshape(4, 4).copy()
+    r4[0] *= np.float32(4.0)
+    r4[1] *= np.float32(4.0)
+    out = render(scene, r4, 4 * width, 4 * height, full=full, keep={"rgba"})
+    out["rgba_aa"] = box4(out["rgba"])
+    return out
+
+
 def _call_render(L, s, rows, width, height, do_fill):
     return L.orc_render(C.c_uint32(s.n_points), _p(s.pos), _p(s.pos_path),
                       C.c_uint32(s.n_curves), _p(s.curve_pos_map), _p(s.curve_type), _p(s.curve_path),

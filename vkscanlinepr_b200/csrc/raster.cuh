@@ -100,4 +100,36 @@ __global__ void __launch_bounds__(256) k_resolve(const FrameParams *__restrict__
     }
 }
 
+// SLPR_FLAG_AA4 (beyond the reference, which has no antialiasing: README.md:5 "comb-like multisampling (TODO)"):
+// the pipeline ran at four times the frame's size, so every pixel of the frame is 2 x 2 coverage cells = four samples on
+// a regular grid, each holding the top-most path that covers it (ordered, opaque compositing per sample); the pixel is
+// their box-filtered average, (sum + 2) >> 2 per channel. One thread per pixel; the cells are re-zeroed.
+template <bool BY_PATH>
+__global__ void __launch_bounds__(256) k_resolve_aa4(const FrameParams *__restrict__ P, const int4 *__restrict__ records,
+                                                     const uint32_t *__restrict__ fill_info, uint32_t *__restrict__ cells, int cw,
+                                                     uint8_t *__restrict__ fb, size_t stride_bytes, int out_w, int out_h) {
+    const int y_lo = P->band_y0 >> 2, y_hi = (P->band_y1 + 3) >> 2;  // output scanline rows of the band
+    const long long total = (long long)out_w * (y_hi - y_lo);
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int y = y_lo + (int)(t / out_w), x = (int)(t % out_w);
+        if (y >= out_h) continue;
+        uint32_t sum[4] = {2u, 2u, 2u, 2u};
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy) {
+            uint2 *cp = reinterpret_cast<uint2 *>(cells + (size_t)(2 * y + dy) * cw + 2 * x);  // cw is even (4 x width / 2)
+            const uint2 v = *cp;
+            if (v.x | v.y) *cp = make_uint2(0u, 0u);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const uint32_t id = k ? v.y : v.x;
+                const uint32_t col = id ? (BY_PATH ? fill_info[id - 1] : (uint32_t)records[id - 1].z) : 0xFFFFFFFFu;
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) sum[ch] += (col >> (8 * ch)) & 0xFFu;
+            }
+        }
+        const uint32_t out = (sum[0] >> 2) | ((sum[1] >> 2) << 8) | ((sum[2] >> 2) << 16) | ((sum[3] >> 2) << 24);
+        *reinterpret_cast<uint32_t *>(fb + (size_t)(out_h - 1 - y) * stride_bytes + (size_t)x * 4) = out;
+    }
+}
+
 }  // namespace slpr

@@ -69,7 +69,8 @@ __global__ void k_set_params(FrameParams *dst, FrameParams src) { *dst = src; }
 // ------------------------------------------------------------------------------------------------
 struct slpr_ctx {
     int device = 0;
-    uint32_t W = 0, H = 0, flags = 0;
+    uint32_t W = 0, H = 0, flags = 0;  // W x H: the frame the caller sees
+    uint32_t ss = 1, iW = 0, iH = 0;   // the pipeline's own resolution: ss x (W, H); ss = 4 with SLPR_FLAG_AA4, else 1
     cudaStream_t own_stream = nullptr, stream = nullptr;
     int num_sms = NUM_SMS_B200;
     int walk_blocks_per_sm = 7, span_blocks_per_sm = 4;  // resident blocks of the persistent kernels (occupancy API)
@@ -311,6 +312,10 @@ extern "C" slpr_ctx *slpr_create(int device, uint32_t width, uint32_t height, ui
         fail(SLPR_ERR_INVALID, "slpr_create: width/height must be in [1, 32766] (16-bit key fields, SURVEY D.6)");
         return nullptr;
     }
+    if ((flags & SLPR_FLAG_AA4) && (width > 8191 || height > 8191)) {
+        fail(SLPR_ERR_INVALID, "slpr_create: with SLPR_FLAG_AA4 width/height must be at most 8191 (the pipeline runs at four times the size)");
+        return nullptr;
+    }
     if (flags & SLPR_FLAG_CONTRACT_FMA) {
         fail(SLPR_ERR_UNSUPPORTED, "slpr_create: SLPR_FLAG_CONTRACT_FMA is not built; the arithmetic policy is IEEE fp32 without contraction");
         return nullptr;
@@ -326,12 +331,14 @@ extern "C" slpr_ctx *slpr_create(int device, uint32_t width, uint32_t height, ui
     if (cudaSetDevice(device) != cudaSuccess) { fail(SLPR_ERR_CUDA, "cudaSetDevice(%d) failed", device); return nullptr; }
     slpr_ctx *c = new slpr_ctx();
     c->device = device; c->W = width; c->H = height; c->flags = flags;
+    c->ss = (flags & SLPR_FLAG_AA4) ? 4u : 1u;
+    c->iW = width * c->ss; c->iH = height * c->ss;
     cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device);
     bool ok = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) == cudaSuccess;
     c->stream = c->own_stream;
     ok = ok && cudaMalloc(&c->d_params, sizeof(FrameParams)) == cudaSuccess;
     ok = ok && cudaMallocHost(&c->h_ctr, sizeof(FrameCounters)) == cudaSuccess;
-    c->cw = (int)(width + 1) / 2; c->ch = (int)(height + 1) / 2;
+    c->cw = (int)(c->iW + 1) / 2; c->ch = (int)(c->iH + 1) / 2;
     ok = ok && cudaMalloc(&c->d_cells, (size_t)c->cw * c->ch * 4) == cudaSuccess;
     ok = ok && cudaMemset(c->d_cells, 0, (size_t)c->cw * c->ch * 4) == cudaSuccess;
     c->fb_stride = (size_t)width * 4;
@@ -354,8 +361,8 @@ extern "C" slpr_ctx *slpr_create(int device, uint32_t width, uint32_t height, ui
     memset(&c->hp, 0, sizeof c->hp);
     const float ident[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
     memcpy(c->hp.rows, ident, sizeof ident);
-    c->hp.width = (int)width; c->hp.height = (int)height;
-    c->hp.band_y0 = 0; c->hp.band_y1 = (int)height; c->hp.cull = 0;
+    c->hp.width = (int)c->iW; c->hp.height = (int)c->iH;
+    c->hp.band_y0 = 0; c->hp.band_y1 = (int)c->iH; c->hp.cull = 0;
     return c;
 }
 
@@ -492,8 +499,8 @@ extern "C" int slpr_load_scene(slpr_ctx *c, const float *pos_xy, const uint32_t 
     CU(cudaMalloc(&c->d_big, std::max<size_t>(n_paths, 1) * 4));
     c->radix_mode = (c->flags & SLPR_FLAG_RADIX_SORT) != 0;
     // compact key geometry: x cell in [0,(W'+4)/2], row rank in [0,ny], path in [0,P)
-    const int Wp = (int)(c->W & ~1u);
-    c->L.ny = (int)(c->H + 1) / 2;
+    const int Wp = (int)(c->iW & ~1u);
+    c->L.ny = (int)(c->iH + 1) / 2;
     c->L.bits_x = std::max(1, ceil_log2((uint64_t)(Wp + 4) / 2 + 1));
     c->L.bits_y = std::max(1, ceil_log2((uint64_t)c->L.ny + 1));
     c->L.bits_path = ceil_log2(std::max<uint64_t>(n_paths, 1));
@@ -517,6 +524,8 @@ extern "C" int slpr_set_curve_weights(slpr_ctx *c, const float *curve_weight, ui
 extern "C" int slpr_set_mvp(slpr_ctx *c, const float rows[16]) {
     if (!c || !rows) return fail(SLPR_ERR_INVALID, "slpr_set_mvp: null argument");
     memcpy(c->hp.rows, rows, 16 * sizeof(float));
+    if (c->ss != 1)  // supersampled: x and y rows scaled by a power of two — exact, so sample positions are ss x the plain frame's
+        for (int i = 0; i < 8; ++i) c->hp.rows[i] *= (float)c->ss;
     c->have_mvp = true;
     return SLPR_OK;
 }
@@ -527,7 +536,7 @@ extern "C" int slpr_set_band(slpr_ctx *c, uint32_t y0, uint32_t y1) {
         return fail(SLPR_ERR_INVALID, "slpr_set_band: need even 0 <= y_begin < y_end <= height (got %u,%u)", y0, y1);
     const int cull = (y0 != 0 || y1 != c->H) ? 1 : 0;
     if (cull != c->hp.cull) invalidate_graphs(c);  // the band-mode kernels take one more table (path row boxes)
-    c->hp.band_y0 = (int)y0; c->hp.band_y1 = (int)y1;
+    c->hp.band_y0 = (int)(y0 * c->ss); c->hp.band_y1 = (int)(y1 * c->ss);
     c->hp.cull = cull;
     return SLPR_OK;
 }
@@ -708,7 +717,7 @@ static int enqueue_back(slpr_ctx *c, cudaStream_t s, bool timed, int &launches) 
     const int span_grid = c->num_sms * std::max(1, c->span_blocks_per_sm);
     auto spans = taps ? (c->fill_fused ? k_spans<true, true, true> : k_spans<false, true, true>)
                       : !c->fill_fused ? k_spans<false, true, false> : (want_records(c) ? k_spans<true, true, false> : k_spans<true, false, false>);
-    spans<<<span_grid, SP_THREADS, SP_STAGE_BYTES, s>>>(c->d_key[cur], c->d_val[cur], c->d_finfo, c->d_rec, c->d_ctr, c->L, (int)c->W, (int)c->H,
+    spans<<<span_grid, SP_THREADS, SP_STAGE_BYTES, s>>>(c->d_key[cur], c->d_val[cur], c->d_finfo, c->d_rec, c->d_ctr, c->L, (int)c->iW, (int)c->iH,
                                                        c->cap, stp, stmp, corr, c->P, c->d_cells, c->cw, btab);
     ++launches;
     if (taps) {
@@ -724,7 +733,10 @@ static int enqueue_back(slpr_ctx *c, cudaStream_t s, bool timed, int &launches) 
         ++launches;
     }
     if (timed) CU(cudaEventRecord(c->ev[10], s));
-    if (c->fill_fused) k_resolve<true><<<wide, 256, 0, s>>>(c->d_params, c->d_rec, c->d_finfo, c->d_cells, c->cw, fb, stride);
+    if (c->ss == 4) {  // SLPR_FLAG_AA4: 2 x 2 cells of the 4x frame -> one pixel (box filter)
+        if (c->fill_fused) k_resolve_aa4<true><<<wide, 256, 0, s>>>(c->d_params, c->d_rec, c->d_finfo, c->d_cells, c->cw, fb, stride, (int)c->W, (int)c->H);
+        else k_resolve_aa4<false><<<wide, 256, 0, s>>>(c->d_params, c->d_rec, c->d_finfo, c->d_cells, c->cw, fb, stride, (int)c->W, (int)c->H);
+    } else if (c->fill_fused) k_resolve<true><<<wide, 256, 0, s>>>(c->d_params, c->d_rec, c->d_finfo, c->d_cells, c->cw, fb, stride);
     else k_resolve<false><<<wide, 256, 0, s>>>(c->d_params, c->d_rec, c->d_finfo, c->d_cells, c->cw, fb, stride);
     ++launches;
     if (timed) CU(cudaEventRecord(c->ev[11], s));
@@ -1390,8 +1402,8 @@ extern "C" int slpr_band_push(slpr_ctx *c, uint32_t frame_seq, int root_band, vo
     }
     const uint8_t *src = c->target ? c->target : c->fb_cur;
     const size_t src_stride = c->target ? c->target_stride : c->fb_stride;
-    const size_t row0 = (size_t)(c->H - (uint32_t)c->hp.band_y1);  // image rows [H - y1, H - y0) hold scanline rows [y0, y1)
-    const size_t rows = (size_t)(c->hp.band_y1 - c->hp.band_y0);
+    const size_t row0 = (size_t)(c->H - (uint32_t)c->hp.band_y1 / c->ss);  // image rows [H - y1, H - y0) hold scanline rows [y0, y1)
+    const size_t rows = (size_t)(c->hp.band_y1 - c->hp.band_y0) / c->ss;
     CU(cudaEventRecord(c->ev_band_rendered[slot], c->stream));
     CU(cudaStreamWaitEvent(c->copy_stream, c->ev_band_rendered[slot], 0));
     const size_t row_bytes = (size_t)c->W * 4;
