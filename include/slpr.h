@@ -75,7 +75,10 @@ enum {
      * pixel is 2 x 2 of its coverage cells; each cell holds the top-most path covering it (ordered, opaque compositing
      * per sample, as the reference composites per 2 x 2 block) and the pixel is their box-filtered average. Same result
      * as the reference path rendered at 4x and averaged over 4 x 4 blocks. Width and height at most 8191. */
-    SLPR_FLAG_AA4 = 1u << 10
+    SLPR_FLAG_AA4 = 1u << 10,
+    /* Never walk long monotone pieces chain by chain (csrc/walk.cuh, k_long_chains / k_long_emit; by default the context
+     * turns that on by itself when a frame has few pieces of 62 or more crossings). A scheduling choice: same results. */
+    SLPR_FLAG_NO_LONG_WALK = 1u << 11
 };
 
 /* Buffers that slpr_debug_copy() can return. Layouts are the reference's:
@@ -269,6 +272,9 @@ SLPR_API int slpr_sort_mode(slpr_ctx *ctx, int *mode);
  * (big frames), 0 = by a separate pass over the records (small frames). Chosen per scene and view from the
  * fragment count; the pixels are the same either way. */
 SLPR_API int slpr_fill_mode(slpr_ctx *ctx, int *fused);
+/* Long pieces (62 or more grid crossings) of the last frame, and whether the next frame walks them chain by chain
+ * (csrc/walk.cuh: k_long_chains / k_long_emit; chosen per scene and view from this count, SLPR_FLAG_NO_LONG_WALK). */
+SLPR_API int slpr_long_walk_info(slpr_ctx *ctx, int *mode_on, uint32_t *n_long_pieces);
 /* Monotone pieces walked by the last frame (64-byte piece records read by k_walk). */
 SLPR_API int slpr_walk_info(slpr_ctx *ctx, uint32_t *n_pieces);
 

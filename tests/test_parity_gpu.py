@@ -535,3 +535,44 @@ def test_exact_row_bands_device_side_exchange():
             assert np.array_equal(got, ref["rgba"]), f"{sc.name}: {int((got != ref['rgba']).any(axis=2).sum())} pixels differ ({G} bands)"
         for c in ctxs:
             c.close()
+
+
+def test_long_pieces_walked_chain_by_chain():
+    """Round 2 (csrc/walk.cuh): on frames with few long monotone pieces the context switches, after the first frame, to
+    walking them as two independent chains (x crossings, y crossings; lines all at once) merged by rank. Every tap of
+    the SECOND frame — intersection records with their tag bits, fragments, sorted order, draw records, pixels — must
+    still equal the oracle's: shipped scenes at large frames, cubics whose cuts are out of order, a deep zoom, and the
+    full-RVG arcs."""
+    tig, vp = util.golden_scene("tiger")
+    tst, tvp = util.golden_scene("test")
+    car, cvp = util.full_golden_scene("car")
+    zoom = S.fit_rows(vp, 1600, 1200)
+    zoom[0, 0] *= 6; zoom[1, 1] *= 6; zoom[0, 3] = -3000; zoom[1, 3] = -2500
+    cases = [(tig, S.fit_rows(vp, 2560, 1440), 2560, 1440, 0), (tst, S.fit_rows(tvp, 3840, 2160), 3840, 2160, 0),
+             (util.looping_cubics_scene(), S.identity_rows() * np.float32(4) + np.diag([0, 0, -3, -3]).astype(np.float32), 2048, 1536, 0),
+             (tig, zoom, 1600, 1200, 0), (car, S.fit_rows(cvp, 1800, 1200), 1800, 1200, V.FLAG_FULL_RVG),
+             (S.synth_scene(40, 2048, 2048, 300.0, 900.0, seed=0x5E650009), S.identity_rows(), 2048, 2048, 0)]
+    for sc, rows, W, H, extra in cases:
+        ref = O.render(sc, rows, W, H, full=bool(extra))
+        r = render_gpu(sc, rows, W, H, V.FLAG_TAPS | V.FLAG_NO_GRAPH | extra)
+        assert r.counts()["n_fragments"] == ref["n_fragments"]
+        on, n_long = r.long_walk_info()
+        assert on and n_long > 0, (sc.name, on, n_long)
+        r.render()  # this frame uses the long-piece walk
+        assert r.counts() == {k: ref[k] for k in ("n_fragments", "n_out_frag", "n_span")}
+        for t in INT_TAPS:
+            assert np.array_equal(r.tap(t), ref[ORACLE_NAME[t]]), f"{sc.name}: tap {t} differs"
+        key = r.tap("key")
+        assert np.array_equal(key[:-1], ref["key"])
+        assert np.array_equal(r.readback(), ref["rgba"])
+        r.close()
+        g = render_gpu(sc, rows, W, H, extra)          # graph replay: frames 2 and 3 in long mode
+        for _ in range(3):
+            assert np.array_equal(g.readback(), ref["rgba"])
+            g.render()
+        assert g.long_walk_info()[0]
+        g.close()
+        h = render_gpu(sc, rows, W, H, extra | V.FLAG_NO_LONG_WALK)
+        h.render()
+        assert np.array_equal(h.readback(), ref["rgba"]) and not h.long_walk_info()[0]
+        h.close()

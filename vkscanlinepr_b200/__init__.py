@@ -22,7 +22,7 @@ LIB_PATH = os.environ.get("SLPR_LIB") or os.path.join(_HERE, "libslpr.so")  # SL
 _LIB = None
 
 FLAG_TAPS, FLAG_CONTRACT_FMA, FLAG_NO_GRAPH, FLAG_RADIX_SORT, FLAG_SEGMENTED_SORT = 1, 2, 4, 8, 16
-FLAG_FUSED_FILL, FLAG_SEPARATE_FILL, FLAG_WINDOWED_WALK, FLAG_RECORDS, FLAG_FULL_RVG, FLAG_AA4 = 32, 64, 128, 256, 512, 1024
+FLAG_FUSED_FILL, FLAG_SEPARATE_FILL, FLAG_WINDOWED_WALK, FLAG_RECORDS, FLAG_FULL_RVG, FLAG_AA4, FLAG_NO_LONG_WALK = 32, 64, 128, 256, 512, 1024, 2048
 TAPS = dict(transformed_pos=0, path_visible=1, cut_cache=2, curve_count=3, curve_offset=4, intersection=5,
             key=6, path=7, winding=8, sorted_key=9, sorted_index=10, winding_scan=11, flags=12,
             flag_scan=13, records=14, segments=15)
@@ -344,6 +344,11 @@ class ScanlineRasterizer:
         n = C.c_uint32()
         _check(lib().slpr_walk_info(self._h, C.byref(n)))
         return int(n.value)
+
+    def long_walk_info(self):
+        on = C.c_int(); n = C.c_uint32()
+        _check(lib().slpr_long_walk_info(self._h, C.byref(on), C.byref(n)))
+        return bool(on.value), int(n.value)
 
     def stage_ms(self):
         ms = (C.c_float * len(STAGES))()

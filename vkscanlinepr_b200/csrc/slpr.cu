@@ -101,6 +101,7 @@ struct slpr_ctx {
     int *d_big = nullptr;              // [P] paths queued for the block-level segmented sort
     bool radix_mode = false;           // false: one-pass segmented sort; true: onesweep radix sort
     bool fill_fused = false;           // true: k_spans marks the cells itself (no k_fill_cells), see choose_fill_mode
+    bool long_mode = false;            // true: pieces of 62+ crossings are walked chain by chain (k_long_chains / k_long_emit)
     uint32_t *d_slots = nullptr;       // [5*nc] (length bucket << 26 | rank) of every monotone piece
     PieceRec *d_pieces = nullptr;      // [5*nc] piece records in length-sorted order
     float2 *d_boundary = nullptr;      // [5*nc] first / last emitted parameter of every piece
@@ -621,10 +622,25 @@ static int enqueue_fragments(slpr_ctx *c, cudaStream_t s, bool timed, int &launc
     auto walk = c->d_cweight ? k_walk<true> : k_walk<false>;
     walk<<<c->num_sms * std::max(1, c->walk_blocks_per_sm), WALK_THREADS, 0, s>>>(
         c->d_params, c->d_pieces, c->d_ctr, c->cap, WalkTemp{c->d_tickets + 3 + RS_MAX_PASSES},
-        c->L, c->d_key[0], c->d_val[0], ft, c->d_inter, c->d_boundary, c->d_fixlist);
+        c->L, c->d_key[0], c->d_val[0], ft, c->d_inter, c->d_boundary, c->d_fixlist, c->long_mode ? 1 : 0);
+    launches += 1;
+    if (c->long_mode) {  // few, long pieces (small scenes at large frames): two independent chains per piece, then a parallel emit
+        LongScratch ls{c->d_val[1], reinterpret_cast<uint32_t *>(c->d_key[1])};
+        const int lgrid = c->num_sms * 4;
+        if (c->d_cweight) {
+            k_long_chains<true><<<lgrid, 128, 0, s>>>(c->d_pieces, c->d_ctr, c->cap, ls);
+            k_long_emit<true><<<lgrid, 128, 0, s>>>(c->d_params, c->d_pieces, c->d_ctr, c->cap, ls, c->L, c->d_key[0], c->d_val[0], ft, c->d_inter,
+                                                   c->d_boundary, c->d_fixlist);
+        } else {
+            k_long_chains<false><<<lgrid, 128, 0, s>>>(c->d_pieces, c->d_ctr, c->cap, ls);
+            k_long_emit<false><<<lgrid, 128, 0, s>>>(c->d_params, c->d_pieces, c->d_ctr, c->cap, ls, c->L, c->d_key[0], c->d_val[0], ft, c->d_inter,
+                                                    c->d_boundary, c->d_fixlist);
+        }
+        launches += 2;
+    }
     k_piece_fix<<<8, 256, 0, s>>>(c->d_params, c->d_ctype, c->d_cpm, c->d_cpath, c->d_frule, c->d_tpos, c->d_ctr, c->cap, c->d_boundary,
                                   c->d_fixlist, c->L, c->d_key[0], c->d_val[0], ft, FullRvg{c->d_cweight});
-    launches += 3;
+    launches += 2;
     if (timed) CU(cudaEventRecord(c->ev[5], s));
     k_path_segments<<<grid_for(c, (long long)c->P + 1, 256, 4), 256, 0, s>>>(c->d_pfc, c->P, c->d_offset, c->d_seg_tap, c->d_ctr, c->cap,
                                                                              c->hp.cull ? c->d_live_paths : nullptr, c->d_live_range);
@@ -769,6 +785,15 @@ static bool choose_fill_mode(const slpr_ctx *c, long long n_fragments) {
     if (c->flags & SLPR_FLAG_FUSED_FILL) return true;
     if (c->flags & SLPR_FLAG_SEPARATE_FILL) return false;
     return c->fill_fused ? (n_fragments > (3ll << 19)) : (n_fragments > (1ll << 21));
+}
+
+// Long pieces chain by chain (walk.cuh)? Worth it when a frame has some but few of them: a warp per chain with one
+// lane walking a curve's bisections is the opposite of what a million-piece frame wants, where k_walk packs 32 pieces
+// of equal length into a warp. From the last frame's count, with hysteresis.
+static bool choose_long_mode(const slpr_ctx *c, const FrameCounters &k) {
+    if (c->flags & SLPR_FLAG_NO_LONG_WALK) return false;
+    const int hi = c->long_mode ? 12288 : 8192;
+    return k.n_long > 0 && k.n_long <= hi;
 }
 
 static int size_buffers_from_count(slpr_ctx *c) {
@@ -920,6 +945,10 @@ static int settle_modes(slpr_ctx *c, const FrameCounters &k) {
         c->fill_fused = !c->fill_fused;
         invalidate_graphs(c);
     }
+    if (choose_long_mode(c, k) != c->long_mode) {
+        c->long_mode = !c->long_mode;
+        invalidate_graphs(c);
+    }
     return SLPR_OK;
 }
 
@@ -946,6 +975,10 @@ static int finish_peer_frame(slpr_ctx *c) {
     if (k.fix_missed) return fail(SLPR_ERR_STATE, "internal: a piece started below its start parameter without ending below it");
     if (choose_fill_mode(c, k.n_fragments) != c->fill_fused) {  // (the sort mode of a band only ever moves to radix, above)
         c->fill_fused = !c->fill_fused;
+        invalidate_graphs(c);
+    }
+    if (choose_long_mode(c, k) != c->long_mode) {
+        c->long_mode = !c->long_mode;
         invalidate_graphs(c);
     }
     c->frame_done = true;
@@ -1526,6 +1559,15 @@ extern "C" int slpr_walk_info(slpr_ctx *c, uint32_t *n_pieces) {
     int rc = finish_frame(c);
     if (rc) return rc;
     *n_pieces = (uint32_t)c->h_ctr->n_pieces;
+    return SLPR_OK;
+}
+
+extern "C" int slpr_long_walk_info(slpr_ctx *c, int *mode_on, uint32_t *n_long_pieces) {
+    if (!c) return fail(SLPR_ERR_INVALID, "slpr_long_walk_info: null argument");
+    int rc = finish_frame(c);
+    if (rc) return rc;
+    if (mode_on) *mode_on = c->long_mode ? 1 : 0;  // what the NEXT frame will use
+    if (n_long_pieces) *n_long_pieces = (uint32_t)c->h_ctr->n_long;
     return SLPR_OK;
 }
 

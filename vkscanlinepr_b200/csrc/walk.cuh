@@ -92,7 +92,11 @@ __global__ void __launch_bounds__(256, SLPR_PE_MIN_BLOCKS) k_piece_emit(const Fr
     __shared__ uint32_t s_total;
     if (ctr->n_fragments > capacity) return;
     vbucket_bases(ranks, s_vbase, &s_total);
-    if (blockIdx.x == 0 && threadIdx.x == 0) ctr->n_pieces = (int)s_total;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        ctr->n_pieces = (int)s_total;
+        // the top length bucket (62 crossings or more) is laid out first: pieces [0, n_long) of the record array
+        ctr->n_long = (int)ranks.vhist[ranks.lay.n_windows * WALK_BUCKETS + (WALK_BUCKETS - 1)];
+    }
     // This block walks the work items the block of the same index ranked in k_monotonize_count (same launch
     // shape), so one 64-entry table — where this block's pieces of every length start — places all its pieces
     // without a global look-up per piece.
@@ -225,6 +229,88 @@ constexpr int WALK_UNROLL = SLPR_WALK_UNROLL;  // bisection steps per loop trip
 #define SLPR_WALK_MIN_BLOCKS 1
 #endif
 
+// One crossing of the piece with the grid line `cst` on axis `side` (0: x, 1: y), searched from t_min (the previous
+// crossing on this axis) up to the piece's end t1_ms: make_intersection_1.comp:377-437, shared by k_walk and the
+// long-piece chains (k_long_chains) so that both produce the same bits.
+template <bool FULL>
+__device__ __forceinline__ float solve_crossing(uint32_t type, const CurvePts &cp, int side, float t_min, float t1_ms, float cst) {
+    float t_solve = 0.0f;
+    const float c0 = side ? cp.y[0] : cp.x[0], c1 = side ? cp.y[1] : cp.x[1];
+    if (type == T_CUBIC) {  // MI1:392-436
+        const float c2 = side ? cp.y[2] : cp.x[2], c3 = side ? cp.y[3] : cp.x[3];
+        // LERP(a,b,t) = a + t*(b-a): the first-level differences do not depend on t
+        const float d01 = __fsub_rn(c1, c0), d12 = __fsub_rn(c2, c1), d23 = __fsub_rn(c3, c2);
+        float t0 = t_min, t1 = t1_ms;
+        float vt0;
+        {
+            const float a0 = __fadd_rn(c0, __fmul_rn(t0, d01)), a1 = __fadd_rn(c1, __fmul_rn(t0, d12)),
+                        a2 = __fadd_rn(c2, __fmul_rn(t0, d23));
+            const float b0 = lerpf(a0, a1, t0), b1 = lerpf(a1, a2, t0);
+            vt0 = lerpf(b0, b1, t0);
+        }
+        t_solve = t0;
+        if (vt0 != cst) {
+            const float raw_t0 = t0;
+            // the sign of (vt0 - c) never changes: t0 only moves to points of the same sign
+            const bool neg0 = (int)f2u(__fsub_rn(vt0, cst)) < 0;
+            uint32_t s_last = 0;
+#pragma unroll WALK_UNROLL
+            for (int j = 0; j < CUBIC_ITERATION_NUMBER; ++j) {
+                const float tm = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
+                const float a0 = __fadd_rn(c0, __fmul_rn(tm, d01)), a1 = __fadd_rn(c1, __fmul_rn(tm, d12)),
+                            a2 = __fadd_rn(c2, __fmul_rn(tm, d23));
+                const float b0 = lerpf(a0, a1, tm), b1 = lerpf(a1, a2, tm);
+                const float vtm = lerpf(b0, b1, tm);
+                t_solve = tm;
+                s_last = f2u(__fsub_rn(vtm, cst));
+                // same sign as at t0: t0 = tm (vt0 = vtm, MI1:421-424), else t1 = tm. One
+                // predicate instruction (sign test XOR the loop-invariant sign) + two selects.
+                asm("{\n\t.reg .pred p, q;\n\tsetp.ne.s32 q, %3, 0;\n\tsetp.lt.xor.s32 p, %2, 0, q;\n\t"
+                    "selp.f32 %0, %0, %4, p;\n\tselp.f32 %1, %4, %1, p;\n\t}"
+                    : "+f"(t0), "+f"(t1)
+                    : "r"(s_last), "r"((int)neg0), "f"(tm));
+            }
+            if (fabsf(u2f(s_last)) > 1.f) t_solve = raw_t0;  // MI1:430-433
+        }
+    } else if (type == T_LINE) {  // MI1:379-385
+        float a = __fsub_rn(c1, c0);
+        a = (a != 0.0f) ? __fdiv_rn(1.0f, a) : 0.0f;
+        float v = __fmul_rn(__fsub_rn(cst, c0), a);
+        v = (v < t_min) ? t_min : v;        // GLSL max(x,y) = x<y ? y : x
+        t_solve = (t1_ms < v) ? t1_ms : v;  // GLSL min(x,y) = y<x ? y : x
+    } else if (FULL && (type == T_QUADRIC || type == T_ARC)) {  // f-1: the bisection of MI1:392-436 on this curve's evaluator
+        const float c2 = side ? cp.y[2] : cp.x[2], w = cp.x[3];
+        float t0 = t_min, t1 = t1_ms;
+        float vt0 = (type == T_ARC) ? eval_arc(c0, c1, c2, w, t0) : eval_quadric(c0, c1, c2, t0);
+        t_solve = t0;
+        if (vt0 != cst) {
+            const float raw_t0 = t0;
+            float last_vtm = 0.f;
+            for (int j = 0; j < CUBIC_ITERATION_NUMBER; ++j) {
+                const float tm = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
+                const float vtm = (type == T_ARC) ? eval_arc(c0, c1, c2, w, tm) : eval_quadric(c0, c1, c2, tm);
+                t_solve = tm; last_vtm = vtm;
+                if ((int)(f2u(__fsub_rn(vtm, cst)) ^ f2u(__fsub_rn(vt0, cst))) >= 0) { t0 = tm; vt0 = vtm; }
+                else t1 = tm;
+            }
+            if (fabsf(__fsub_rn(last_vtm, cst)) > 1.f) t_solve = raw_t0;
+        }
+    } else if (type == T_QUADRIC || type == T_ARC) {
+        t_solve = 0.0f;  // TODO arms in the reference: t_solve stays 0
+    } else {  // any other type value: interpolateGeneralCurve returns 0 (MI1:81-83,144)
+        t_solve = t_min;
+        if (0.0f != cst) {
+            float t0 = t_min;
+            for (int j = 0; j < CUBIC_ITERATION_NUMBER; ++j) {  // vtm - c == vt0 - c: t0 always moves
+                const float tm = __fmul_rn(__fadd_rn(t0, t1_ms), 0.5f);
+                t_solve = tm; t0 = tm;
+            }
+            if (fabsf(__fsub_rn(0.0f, cst)) > 1.f) t_solve = t_min;
+        }
+    }
+    return t_solve;
+}
+
 // FULL (SLPR_FLAG_FULL_RVG, f-1): QUADRIC / ARC pieces are walked with the reference's bisection on their own evaluators
 // (common.cuh) instead of the reference's TODO arms; a separate instantiation, so the default kernel is untouched.
 template <bool FULL>
@@ -234,7 +320,7 @@ __global__ void __launch_bounds__(WALK_THREADS, SLPR_WALK_MIN_BLOCKS) k_walk(con
                                                        KeyLayout L, uint64_t *__restrict__ key64,
                                                        uint32_t *__restrict__ val, FragTaps taps,
                                                        int2 *__restrict__ inter, float2 *__restrict__ boundary,
-                                                       uint4 *__restrict__ fixlist) {
+                                                       uint4 *__restrict__ fixlist, int skip_long) {
     const int nf_total = ctr->n_fragments;
     if (nf_total > capacity) return;
     if (taps.key32 && blockIdx.x == 0 && threadIdx.x == 0 && nf_total > 0) taps.key32[nf_total] = -1;  // GF:240
@@ -242,6 +328,7 @@ __global__ void __launch_bounds__(WALK_THREADS, SLPR_WALK_MIN_BLOCKS) k_walk(con
     const uint32_t warp = threadIdx.x >> 5;
     __shared__ uint4 s_stage[WALK_THREADS / 32][2][128];  // per warp: two groups of 32 records (2 KB each)
     const uint32_t n_pieces = (uint32_t)ctr->n_pieces;  // k_piece_emit
+    const uint32_t n_long = skip_long ? (uint32_t)ctr->n_long : 0u;  // long pieces are walked by k_long_chains / k_long_emit
     const FragEnv env = load_frag_env(P);
     const uint32_t n_chunks = n_pieces * 4u;  // 16-byte chunks in the record array
     // group g's records -> stage st, one commit group per call (empty past the end)
@@ -273,7 +360,7 @@ __global__ void __launch_bounds__(WALK_THREADS, SLPR_WALK_MIN_BLOCKS) k_walk(con
         asm volatile("cp.async.wait_group 1;" ::: "memory");
         __syncwarp();
         const uint32_t idx = g_cur * 32u + lane;
-        const bool active = idx < n_pieces;
+        const bool active = idx < n_pieces && idx >= n_long;
 
         // ---- the piece, from the staged copy
         CurvePts cp;
@@ -352,81 +439,7 @@ __global__ void __launch_bounds__(WALK_THREADS, SLPR_WALK_MIN_BLOCKS) k_walk(con
             float t_solve = park ? 2.0f : 0.0f;
             const bool solve = live && !park;
             if (__any_sync(0xFFFFFFFFu, solve)) {
-                if (solve) {
-                    const float c0 = side ? cp.y[0] : cp.x[0], c1 = side ? cp.y[1] : cp.x[1];
-                    if (type == T_CUBIC) {  // MI1:392-436
-                        const float c2 = side ? cp.y[2] : cp.x[2], c3 = side ? cp.y[3] : cp.x[3];
-                        // LERP(a,b,t) = a + t*(b-a): the first-level differences do not depend on t
-                        const float d01 = __fsub_rn(c1, c0), d12 = __fsub_rn(c2, c1), d23 = __fsub_rn(c3, c2);
-                        float t0 = t_min, t1 = t1_ms;
-                        float vt0;
-                        {
-                            const float a0 = __fadd_rn(c0, __fmul_rn(t0, d01)), a1 = __fadd_rn(c1, __fmul_rn(t0, d12)),
-                                        a2 = __fadd_rn(c2, __fmul_rn(t0, d23));
-                            const float b0 = lerpf(a0, a1, t0), b1 = lerpf(a1, a2, t0);
-                            vt0 = lerpf(b0, b1, t0);
-                        }
-                        t_solve = t0;
-                        if (vt0 != cst) {
-                            const float raw_t0 = t0;
-                            // the sign of (vt0 - c) never changes: t0 only moves to points of the same sign
-                            const bool neg0 = (int)f2u(__fsub_rn(vt0, cst)) < 0;
-                            uint32_t s_last = 0;
-#pragma unroll WALK_UNROLL
-                            for (int j = 0; j < CUBIC_ITERATION_NUMBER; ++j) {
-                                const float tm = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
-                                const float a0 = __fadd_rn(c0, __fmul_rn(tm, d01)), a1 = __fadd_rn(c1, __fmul_rn(tm, d12)),
-                                            a2 = __fadd_rn(c2, __fmul_rn(tm, d23));
-                                const float b0 = lerpf(a0, a1, tm), b1 = lerpf(a1, a2, tm);
-                                const float vtm = lerpf(b0, b1, tm);
-                                t_solve = tm;
-                                s_last = f2u(__fsub_rn(vtm, cst));
-                                // same sign as at t0: t0 = tm (vt0 = vtm, MI1:421-424), else t1 = tm. One
-                                // predicate instruction (sign test XOR the loop-invariant sign) + two selects.
-                                asm("{\n\t.reg .pred p, q;\n\tsetp.ne.s32 q, %3, 0;\n\tsetp.lt.xor.s32 p, %2, 0, q;\n\t"
-                                    "selp.f32 %0, %0, %4, p;\n\tselp.f32 %1, %4, %1, p;\n\t}"
-                                    : "+f"(t0), "+f"(t1)
-                                    : "r"(s_last), "r"((int)neg0), "f"(tm));
-                            }
-                            if (fabsf(u2f(s_last)) > 1.f) t_solve = raw_t0;  // MI1:430-433
-                        }
-                    } else if (type == T_LINE) {  // MI1:379-385
-                        float a = __fsub_rn(c1, c0);
-                        a = (a != 0.0f) ? __fdiv_rn(1.0f, a) : 0.0f;
-                        float v = __fmul_rn(__fsub_rn(cst, c0), a);
-                        v = (v < t_min) ? t_min : v;        // GLSL max(x,y) = x<y ? y : x
-                        t_solve = (t1_ms < v) ? t1_ms : v;  // GLSL min(x,y) = y<x ? y : x
-                    } else if (FULL && (type == T_QUADRIC || type == T_ARC)) {  // f-1: the bisection of MI1:392-436 on this curve's evaluator
-                        const float c2 = side ? cp.y[2] : cp.x[2], w = cp.x[3];
-                        float t0 = t_min, t1 = t1_ms;
-                        float vt0 = (type == T_ARC) ? eval_arc(c0, c1, c2, w, t0) : eval_quadric(c0, c1, c2, t0);
-                        t_solve = t0;
-                        if (vt0 != cst) {
-                            const float raw_t0 = t0;
-                            float last_vtm = 0.f;
-                            for (int j = 0; j < CUBIC_ITERATION_NUMBER; ++j) {
-                                const float tm = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
-                                const float vtm = (type == T_ARC) ? eval_arc(c0, c1, c2, w, tm) : eval_quadric(c0, c1, c2, tm);
-                                t_solve = tm; last_vtm = vtm;
-                                if ((int)(f2u(__fsub_rn(vtm, cst)) ^ f2u(__fsub_rn(vt0, cst))) >= 0) { t0 = tm; vt0 = vtm; }
-                                else t1 = tm;
-                            }
-                            if (fabsf(__fsub_rn(last_vtm, cst)) > 1.f) t_solve = raw_t0;
-                        }
-                    } else if (type == T_QUADRIC || type == T_ARC) {
-                        t_solve = 0.0f;  // TODO arms in the reference: t_solve stays 0
-                    } else {  // any other type value: interpolateGeneralCurve returns 0 (MI1:81-83,144)
-                        t_solve = t_min;
-                        if (0.0f != cst) {
-                            float t0 = t_min;
-                            for (int j = 0; j < CUBIC_ITERATION_NUMBER; ++j) {  // vtm - c == vt0 - c: t0 always moves
-                                const float tm = __fmul_rn(__fadd_rn(t0, t1_ms), 0.5f);
-                                t_solve = tm; t0 = tm;
-                            }
-                            if (fabsf(__fsub_rn(0.0f, cst)) > 1.f) t_solve = t_min;
-                        }
-                    }
-                }
+                if (solve) t_solve = solve_crossing<FULL>(type, cp, side, t_min, t1_ms, cst);
             }
             if (live) {  // MI1:440
                 const float tagged = u2f((f2u(t_solve) & 0xFFFFFFFCu) | (uint32_t)side);
@@ -457,6 +470,194 @@ __global__ void __launch_bounds__(WALK_THREADS, SLPR_WALK_MIN_BLOCKS) k_walk(con
             if (piece > 0 && (first_bits & 0xFFFFFFFCu) != (f2u(t0_ms) & 0xFFFFFFFCu)) {  // rare: a few dozen per million curves
                 if (unordered) fixlist[atomicAdd(&ctr->n_fix, 1)] = make_uint4(c, piece, (uint32_t)fs.f_first, 0u);
                 else ctr->fix_missed = 1;  // cannot happen (see above); the host refuses the frame if it does
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Long pieces (round 2). A piece's crossings with the x grid lines form one chain — every bisection bracket starts
+// at the previous x crossing (MI1:392-436) — and its crossings with the y grid lines another; only the order in
+// which the reference EMITS them couples the two (MI1:321-359: repeatedly the smaller of the two chain heads, x on
+// ties). k_walk gives a piece to one lane, which is right for a million short pieces but leaves a frame of a few
+// thousand curves waiting for the one lane that walks its longest piece: the shipped scenes at 4K spend 85-95 % of
+// the frame in k_walk (tiger: 1.28 of 1.42 ms, one cubic of ~2000 crossings; test.rvg: a full-height line). With
+// long_mode on (few long pieces; chosen by the host from the last frame's count), pieces of 62 or more crossings are
+// instead walked in three steps, bit-identical to the sequential walk:
+//   k_long_chains  one warp per (piece, axis): a LINE's crossings are closed-form and independent but for a clamp
+//                  against the previous one — all lanes evaluate them at once and check that no clamp was active
+//                  (else lane 0 redoes the chain in order); a curve's chain is walked by lane 0 (solve_crossing);
+//   k_long_emit    one warp per piece: the merged emission order by rank (binary search; valid when both chains
+//                  ascend, which is checked — else lane 0 merges head by head), then all lanes form the fragments
+//                  between consecutive records exactly as k_walk does (make_fragment), plus the boundary fragment
+//                  and the rare boundary-repair bookkeeping.
+// Scratch: two 32-bit words per record, in the sort's output buffers (free until the sort).
+// ------------------------------------------------------------------------------------------------
+struct LongScratch {
+    uint32_t *chain;   // [capacity] tagged crossing parameters: x chain at [first record, +n_x), y chain behind it
+    uint32_t *merged;  // [capacity] the emitted record parameters in order
+};
+
+struct LongPiece {
+    CurvePts cp;
+    float t0_ms, t1_ms, x0, y0, dx, dy;
+    int n_x, n_y, pcnt;
+    uint32_t c, type, piece, pidx, rule_bit, keep_last;
+};
+__device__ __forceinline__ LongPiece load_long_piece(const PieceRec *__restrict__ pieces, uint32_t idx) {
+    const uint4 *r = reinterpret_cast<const uint4 *>(pieces + idx);
+    const uint4 a = r[0], b = r[1], t = r[2], m = r[3];
+    LongPiece p;
+    p.cp.x[0] = u2f(a.x); p.cp.x[1] = u2f(a.y); p.cp.x[2] = u2f(a.z); p.cp.x[3] = u2f(a.w);
+    p.cp.y[0] = u2f(b.x); p.cp.y[1] = u2f(b.y); p.cp.y[2] = u2f(b.z); p.cp.y[3] = u2f(b.w);
+    p.t0_ms = u2f(t.x); p.t1_ms = u2f(t.y);
+    p.x0 = (float)(t.z & 0xFFFFu); p.y0 = (float)(t.z >> 16);
+    p.pidx = t.w & 0x7FFFFFFFu; p.rule_bit = t.w >> 31;
+    p.n_x = (int)(m.x & 0x7FFFu); p.n_y = (int)((m.x >> 15) & 0x7FFFu);
+    p.dx = (m.x & (1u << 30)) ? -2.f : 2.f; p.dy = (m.x & (1u << 31)) ? -2.f : 2.f;
+    p.c = m.y; p.pcnt = (int)m.z;
+    p.type = (m.w & 0x80u) ? 0xFFFFu : (m.w & 0x7Fu);
+    p.piece = (m.w >> 8) & 0xFFu;
+    p.keep_last = (m.w >> 16) & 1u;
+    return p;
+}
+
+template <bool FULL>
+__global__ void __launch_bounds__(128) k_long_chains(const PieceRec *__restrict__ pieces, const FrameCounters *__restrict__ ctr,
+                                                     int capacity, LongScratch sc) {
+    if (ctr->n_fragments > capacity) return;
+    const uint32_t n_items = 2u * (uint32_t)ctr->n_long;
+    const uint32_t lane = lane_id();
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < n_items; item += n_warps) {
+        const int side = (int)(item & 1u);
+        const LongPiece p = load_long_piece(pieces, item >> 1);
+        const int n = side ? p.n_y : p.n_x;
+        if (n == 0) continue;
+        const float g0 = side ? p.y0 : p.x0, d = side ? p.dy : p.dx;
+        uint32_t *out = sc.chain + p.pcnt + (side ? p.n_x : 0);
+        bool done = false;
+        if (p.type == T_LINE) {  // MI1:379-385, all crossings at once
+            const float c0 = side ? p.cp.y[0] : p.cp.x[0], c1 = side ? p.cp.y[1] : p.cp.x[1];
+            float a = __fsub_rn(c1, c0);
+            a = (a != 0.0f) ? __fdiv_rn(1.0f, a) : 0.0f;
+            bool ok = true;
+            for (int k0 = 0; k0 < n; k0 += 32) {
+                const int k = k0 + (int)lane;
+                if (k < n) {
+                    // grid lines are small integers: g0 + k * d is exact, like the reference's repeated additions
+                    const float v = __fmul_rn(__fsub_rn(__fadd_rn(g0, __fmul_rn((float)k, d)), c0), a);
+                    float t_before = p.t0_ms;  // what the sequential walk would have clamped against
+                    if (k > 0) {
+                        const float vp = __fmul_rn(__fsub_rn(__fadd_rn(g0, __fmul_rn((float)(k - 1), d)), c0), a);
+                        const float tp = (p.t1_ms < vp) ? p.t1_ms : vp;
+                        t_before = u2f((f2u(tp) & 0xFFFFFFFCu) | (uint32_t)side);
+                    }
+                    if (v < t_before) ok = false;  // the clamp max(v, t_min) would have been active: order matters
+                    const float t = (p.t1_ms < v) ? p.t1_ms : v;
+                    out[k] = (f2u(t) & 0xFFFFFFFCu) | (uint32_t)side;
+                }
+            }
+            done = __all_sync(0xFFFFFFFFu, ok);
+        }
+        if (!done && lane == 0) {  // in order (curves always; lines when a clamp was active)
+            float t_prev = p.t0_ms, g = g0;
+            for (int k = 0; k < n; ++k) {
+                const float cst = g;
+                g = __fadd_rn(g, d);
+                const float ts = solve_crossing<FULL>(p.type, p.cp, side, t_prev, p.t1_ms, cst);
+                const uint32_t tg = (f2u(ts) & 0xFFFFFFFCu) | (uint32_t)side;
+                out[k] = tg;
+                t_prev = u2f(tg);
+            }
+        }
+    }
+}
+
+template <bool FULL>
+__global__ void __launch_bounds__(128) k_long_emit(const FrameParams *__restrict__ P, const PieceRec *__restrict__ pieces,
+                                                   FrameCounters *__restrict__ ctr, int capacity, LongScratch sc, KeyLayout L,
+                                                   uint64_t *__restrict__ key64, uint32_t *__restrict__ val, FragTaps taps,
+                                                   int2 *__restrict__ inter, float2 *__restrict__ boundary, uint4 *__restrict__ fixlist) {
+    if (ctr->n_fragments > capacity) return;
+    const uint32_t n_long = (uint32_t)ctr->n_long;
+    const uint32_t lane = lane_id();
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    const FragEnv env = load_frag_env(P);
+    for (uint32_t idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; idx < n_long; idx += n_warps) {
+        const LongPiece p = load_long_piece(pieces, idx);
+        const int n_loop = p.n_x + p.n_y + 1;
+        // the two chains as the reference's merge sees them: the piece's start record leads the y chain, or the x chain
+        // when there is no y crossing (MI1:321-333); an exhausted chain reads 2.0 tagged with its side (MI1:340-359)
+        const bool x_leads = p.n_x > 0 && p.n_y == 0;
+        const int len_x = p.n_x + (x_leads ? 1 : 0), len_y = p.n_y + (x_leads ? 0 : 1);
+        const uint32_t *cx = sc.chain + p.pcnt, *cy = sc.chain + p.pcnt + p.n_x;
+        const uint32_t t0_bits = f2u(p.t0_ms);
+        auto get_x = [&](int i) { return x_leads ? (i == 0 ? t0_bits : cx[i - 1]) : cx[i]; };
+        auto get_y = [&](int j) { return x_leads ? cy[j] : (j == 0 ? t0_bits : cy[j - 1]); };
+        uint32_t *mg = sc.merged + p.pcnt;
+        bool mono = true;
+        for (int i = (int)lane + 1; i < len_x; i += 32) mono = mono && !(u2f(get_x(i)) < u2f(get_x(i - 1)));
+        for (int j = (int)lane + 1; j < len_y; j += 32) mono = mono && !(u2f(get_y(j)) < u2f(get_y(j - 1)));
+        if (__all_sync(0xFFFFFFFFu, mono)) {  // both ascend: a record's place is its index plus its rank in the other chain
+            for (int i = (int)lane; i < len_x; i += 32) {
+                const uint32_t vb = get_x(i);
+                const float v = u2f(vb);
+                int lo = 0, hi = len_y;  // y records strictly before v (x goes first on ties: `tx <= ty`)
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (u2f(get_y(mid)) < v) lo = mid + 1; else hi = mid; }
+                mg[i + lo] = vb;
+            }
+            for (int j = (int)lane; j < len_y; j += 32) {
+                const uint32_t vb = get_y(j);
+                const float v = u2f(vb);
+                int lo = 0, hi = len_x;  // x records at or before v
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (u2f(get_x(mid)) <= v) lo = mid + 1; else hi = mid; }
+                mg[j + lo] = vb;
+            }
+        } else if (lane == 0) {  // head by head, as the reference does
+            int i = 0, j = 0;
+            for (int k = 0; k < n_loop; ++k) {
+                const uint32_t hx = i < len_x ? get_x(i) : (f2u(2.0f) | 0u), hy = j < len_y ? get_y(j) : (f2u(2.0f) | 1u);
+                if (u2f(hx) <= u2f(hy)) { mg[k] = hx; ++i; } else { mg[k] = hy; ++j; }
+            }
+        }
+        __syncwarp();
+        if (inter && lane == 0) {  // debug tap (MI1:361-375): the records with their tag bits merged across equal parameters
+            int i_inte_last = (int)f2u(-1.0f);
+            for (int k = 0; k < n_loop; ++k) {
+                int i_out = (int)mg[k];
+                if ((mg[k] & 0xFFFFFFFCu) == ((uint32_t)i_inte_last & 0xFFFFFFFCu)) {
+                    i_out |= i_inte_last;
+                    inter[p.pcnt + k - 1] = make_int2((int)p.c, i_out);
+                }
+                inter[p.pcnt + k] = make_int2((int)p.c, i_out);
+                i_inte_last = i_out;
+            }
+        }
+        // ---- fragments: record k closes the fragment that record k - 1 opened (gen_fragment fused, as in k_walk)
+        for (int k0 = 1; k0 <= n_loop; k0 += 32) {
+            const int k = k0 + (int)lane;
+            if (k <= n_loop) {
+                float ta = u2f(mg[k - 1] & 0xFFFFFFFCu);
+                ta = (ta < 0.0f) ? 0.0f : ta;
+                float tb = u2f((k < n_loop ? mg[k] : f2u(p.t1_ms)) & 0xFFFFFFFCu);  // k == n_loop: the fragment across the piece boundary
+                tb = (tb < 0.0f) ? 0.0f : tb;
+                float ax, ay, bx, by;
+                eval_point<FULL>(p.type, p.cp, ta, ax, ay);
+                eval_point<FULL>(p.type, p.cp, tb, bx, by);
+                uint64_t kk; uint32_t vv;
+                make_fragment(env, L, p.pcnt + k - 1, p.pidx, p.rule_bit, ta, tb, ax, ay, bx, by, kk, vv, taps);
+                key64[p.pcnt + k - 1] = kk;
+                val[p.pcnt + k - 1] = vv;
+            }
+        }
+        if (lane == 0) {  // the boundary-repair bookkeeping of k_walk
+            const uint32_t first_bits = mg[0], last_bits = mg[n_loop - 1];
+            const bool unordered = p.piece > 0 && (f2u(p.t1_ms) & 0xFFFFFFFCu) <= (f2u(p.t0_ms) | 3u);
+            if (unordered || p.keep_last) boundary[5 * p.c + p.piece] = make_float2(u2f(first_bits), u2f(last_bits));
+            if (p.piece > 0 && (first_bits & 0xFFFFFFFCu) != (f2u(p.t0_ms) & 0xFFFFFFFCu)) {
+                if (unordered) fixlist[atomicAdd(&ctr->n_fix, 1)] = make_uint4(p.c, p.piece, (uint32_t)p.pcnt, 0u);
+                else ctr->fix_missed = 1;
             }
         }
     }
