@@ -153,8 +153,12 @@ __global__ void __launch_bounds__(SP_THREADS, SP_BLOCKS) k_spans(const uint64_t 
     const long long ntiles = (n == 0) ? 1 : (n + SP_TILE - 1) / SP_TILE;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nbp = btab.count ? *btab.count : 0;  // exact bands, sparse exchange: break points of this frame (usually 0)
+    constexpr bool CHAIN = REC || TAPS;  // record indices wanted: the flag-count look-back chain across tiles
+    int acc_frag = 0, acc_span = 0;      // !CHAIN: this warp's counts over all the block's tiles (lane 31)
 
     while (true) {
+        // tiles in ticket order: with the look-back chain a tile's predecessors are then always running; without it
+        // (independent tiles) the ticket still balances the load better than a static deal (measured 0.256 vs 0.270 ms)
         if (tid == 0) s_tile = (long long)atomicAdd(tmp.ticket, 1);
         __syncthreads();
         const long long tile = s_tile;
@@ -239,7 +243,7 @@ __global__ void __launch_bounds__(SP_THREADS, SP_BLOCKS) k_spans(const uint64_t 
         }
         __syncthreads();
         int wn = (int)(uint32_t)s_prefix + (int)s_warp[warp] + (wincl - dsum);  // winding left of element i0
-        __syncthreads();  // s_warp is reused by chain F
+        if (CHAIN) __syncthreads();  // s_warp is reused by chain F (without it, only after the next ticket barrier)
 
         // ---- flags (MARK:38-93) from the keys and the winding prefix
         uint32_t fmask = 0, smask = 0;
@@ -285,7 +289,11 @@ __global__ void __launch_bounds__(SP_THREADS, SP_BLOCKS) k_spans(const uint64_t 
             }
         }
 
-        // ---- chain F: exclusive prefix of (frag count | span count << 16) inside the tile, 2x31 bits across tiles
+        // ---- chain F: exclusive prefix of (frag count | span count << 16) inside the tile, 2x31 bits across tiles.
+        //      Only the record indices need it. When no records are written (the default big-frame path: the cells carry
+        //      the path, REC and TAPS off) a tile depends on NO other tile: the chain — one look-back window per ~1.4 us
+        //      poll, 135 hops for 4321 tiles, the longest serial path of the kernel — is dropped and the two counts are
+        //      summed per warp over the block's tiles and added to the frame counters once, at the end.
         const uint32_t cnt = (uint32_t)__popc(fmask) | ((uint32_t)__popc(smask) << 16);
         uint32_t cincl = cnt;
 #pragma unroll
@@ -293,6 +301,8 @@ __global__ void __launch_bounds__(SP_THREADS, SP_BLOCKS) k_spans(const uint64_t 
             const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, cincl, d);
             if (lane >= d) cincl += o;
         }
+        int frag_before = 0, span_before = 0;
+        if (CHAIN) {
         if (lane == 31) s_warp[warp] = cincl;
         __syncthreads();
         if (warp == 0) {
@@ -322,15 +332,19 @@ __global__ void __launch_bounds__(SP_THREADS, SP_BLOCKS) k_spans(const uint64_t 
         __syncthreads();
         const unsigned long long tp = s_prefix;
         const uint32_t local = s_warp[warp] + (cincl - cnt);
-        int frag_before = (int)(tp & 0x7FFFFFFFu) + (int)(local & 0xFFFFu);
-        int span_before = (int)((tp >> 31) & 0x7FFFFFFFu) + (int)(local >> 16);
+        frag_before = (int)(tp & 0x7FFFFFFFu) + (int)(local & 0xFFFFu);
+        span_before = (int)((tp >> 31) & 0x7FFFFFFFu) + (int)(local >> 16);
+        } else if (lane == 31) {
+            acc_frag += (int)(cincl & 0xFFFFu);
+            acc_span += (int)(cincl >> 16);
+        }
 
         // ---- emit the draw records (GEN:42-102). A thread's records are consecutive in the output
         //      and so are the threads of a warp, so the warp first lays its records out in shared memory
         //      (three 32-bit planes: position, width | fragment ordinal, colour) and then writes them as
         //      full 512-byte rows: 16-byte stores scattered at 128-byte strides cost the kernel a third
         //      of its time (measured with SLPR_SP_NOSTORE).
-        if (SLPR_SP_FAKE) { frag_before = (int)(tile * SP_TILE) + (int)(local & 0xFFFFu); span_before = (int)(local >> 16); }
+
 #if SLPR_SP_STAGE
         uint32_t *const wp = s_stage + warp * (3 * SP_WARP_RECORDS);
         const uint32_t wexcl = cincl - cnt;                           // packed counts of the lanes before this one
@@ -429,6 +443,11 @@ __global__ void __launch_bounds__(SP_THREADS, SP_BLOCKS) k_spans(const uint64_t 
         __syncwarp();
 #endif
         // the __syncthreads after the next ticket fetch orders the reuse of s_warp / s_prefix
+    }
+    if (!CHAIN && lane == 31 && (acc_frag | acc_span)) {  // SR.cpp:578-580, as sums
+        atomicAdd(&ctr->n_out_frag, acc_frag);
+        atomicAdd(&ctr->n_span, acc_span);
+        atomicAdd(&ctr->n_records, acc_frag + acc_span);
     }
 }
 
