@@ -30,4 +30,54 @@ for sc in scenes:
     # independent bands (no winding-sum exchange) equal the full frame only on scenes without a winding residue; all
     # three scenes here have one, so this line is information, not a check (the parity tests cover exact bands)
     print(sc.name, "independent bands equal full frame:", bool(np.array_equal(full, imgs[sc.name])))
+# round 2: exact bands with the device-side exchange (mailboxes, merge table, fused sums in the band sort, copy-engine
+# push), the long-piece walk, the full-RVG arithmetic, the 4x supersampled resolve, the long-path fall-back on default
+# flags, and the stand-alone primitives (ticketed scan, TMA-pipelined scan, radix sort)
+import torch
+from vkscanlinepr_b200 import parallel as PAR
+sc = util.looping_cubics_scene(120, W, H)
+G = 3
+frame = torch.zeros((H, W, 4), dtype=torch.uint8, device="cuda")
+ctxs = []
+for g, (y0, y1) in enumerate(PAR.band_rows(H, G)):
+    c = V.ScanlineRasterizer(0, 0).initialize(None, W, H)
+    c.loadVG(sc); c.setMVP(S.identity_rows()); c.set_band(y0, y1); c.set_target(frame.data_ptr(), W * 4)
+    ctxs.append(c)
+boxes = [c.band_mailbox()[0] for c in ctxs]
+for g, c in enumerate(ctxs):
+    c.set_band_peers(G, g, 0, boxes)
+seq = 1
+for _ in range(3):
+    for c in ctxs:
+        c.prepare()
+    for c in ctxs:
+        c.render_band(seq)
+    ctxs[0].band_wait_gather(seq)
+    for c in ctxs:
+        try:
+            c.synchronize()
+        except V.SlprRetry:
+            pass
+    seq += 1
+assert np.array_equal(frame.cpu().numpy(), imgs[sc.name]), "exact bands"
+for c in ctxs:
+    c.close()
+big = S.synth_scene(12, 1024, 768, 200.0, 380.0, seed=3)   # long pieces; the second frame walks them chain by chain
+for flags in (0, V.FLAG_TAPS | V.FLAG_NO_GRAPH):
+    r = V.ScanlineRasterizer(0, flags).initialize(None, 1024, 768)
+    r.loadVG(big); r.setMVP(S.identity_rows()); r.render(); a = r.readback(); r.render(); b = r.readback()
+    assert r.long_walk_info()[0] and np.array_equal(a, b)
+    r.close()
+qa = util.quad_arc_scene(80, W, H)
+for flags in (V.FLAG_FULL_RVG, V.FLAG_FULL_RVG | V.FLAG_AA4, V.FLAG_AA4 | V.FLAG_SEPARATE_FILL):
+    r = V.ScanlineRasterizer(0, flags).initialize(None, W, H)
+    r.loadVG(qa); r.setMVP(S.identity_rows()); r.render(); r.render(); r.readback(); r.close()
+r = V.ScanlineRasterizer(0, 0).initialize(None, 64, 64)
+for n in (5, 100_003, (1 << 22) + 8192 * 3 + 5):
+    a = torch.randint(0, 4, (n,), dtype=torch.int32, device="cuda"); o = torch.empty(n + 1, dtype=torch.int32, device="cuda")
+    r.scan_i32(a.data_ptr(), o.data_ptr(), n); r.synchronize()
+    assert int(o[-1]) == int(a.sum())
+k = torch.randint(0, 1 << 40, (200_003,), dtype=torch.int64, device="cuda"); v = torch.arange(200_003, dtype=torch.int32, device="cuda")
+k2, v2 = torch.empty_like(k), torch.empty_like(v)
+r.sort_pairs(k.data_ptr(), v.data_ptr(), k2.data_ptr(), v2.data_ptr(), 200_003, 40); r.synchronize(); r.close()
 print("done")

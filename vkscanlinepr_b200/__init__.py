@@ -181,6 +181,7 @@ class ScanlineRasterizer:
         self._h = None
         self._device = device
         self._flags = flags
+        self._stream_ptr = 0  # 0: the context's own stream
         self.width = self.height = 0
 
     # -- VGRasterizer ------------------------------------------------------------------------
@@ -245,6 +246,7 @@ class ScanlineRasterizer:
 
     def set_stream(self, cuda_stream_ptr):
         _check(lib().slpr_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+        self._stream_ptr = int(cuda_stream_ptr or 0)
 
     def set_target(self, dev_ptr, stride_bytes):
         _check(lib().slpr_set_target(self._h, C.c_void_p(dev_ptr), C.c_size_t(stride_bytes)))

@@ -77,6 +77,11 @@ def render_bands_exact(rasterizer, sums, gathered, dist, comm_stream=None):
     stream (torch's current stream); the collective is issued from `comm_stream` so that it overlaps the
     sort, and the current stream waits for it before the second half."""
     import torch
+    if gathered.is_cuda and getattr(rasterizer, "_stream_ptr", 0) != torch.cuda.current_stream().cuda_stream:
+        # slpr_render_band_end reads `gathered` on the rasterizer's stream; the collective is ordered against torch's
+        # CURRENT stream only — they must be the same stream, or the corrections are read while NCCL still writes them
+        raise RuntimeError("render_bands_exact: bind the rasterizer to torch's current stream first "
+                           "(rasterizer.set_stream(torch.cuda.current_stream().cuda_stream))")
     rasterizer.render_band_begin()
     if comm_stream is not None and gathered.is_cuda:
         with torch.cuda.stream(comm_stream):
