@@ -656,7 +656,12 @@ def main():
                                  "what": "slpr_render_to_host (set_mvp + render + readback, synchronous per frame)"},
                "frames_rendered_twice": int(e2e_redone),
                "host_buffers": {"allocator": host_alloc, "numa_node": host_nodes[0], "torch_sees_pinned": bool(hosts[0].is_pinned())},
-               "d2h_probe": {"torch_pinned": d2h_probe(W, H, stream, dist, None), "gpu_numa_node": d2h_probe(W, H, stream, dist, hosts[0])}}
+               "d2h_probe": {"torch_pinned": d2h_probe(W, H, stream, dist, None), "gpu_numa_node": d2h_probe(W, H, stream, dist, hosts[0]),
+                             "what": "every rank copies one RGBA8 frame device -> pinned host, 20 times back to back, all ranks at once, nothing rendered: "
+                                     "the host-side ceiling of the end-to-end path (max-over-ranks timing follows the slowest rank)"}}
+        floor = W * H * 4 / (e2e["d2h_probe"]["gpu_numa_node"]["per_rank_gbs_min"] * 1e9) * 1e3
+        e2e["d2h_floor_ms_per_step"] = floor  # a frame cannot reach host memory faster than the slowest rank's copy
+        e2e["of_d2h_floor"] = floor / e2e["ms_per_step"]
     else:
         e2e = None
 
@@ -762,7 +767,7 @@ def main():
                "sample": f"{len(ts)} full frame(s) of {args.workload}, best; all {cores} OpenMP threads",
                "ms_per_frame": min(ts) * 1e3, "gpu_frame_matches_oracle": ok}
 
-    sort_now, fused_now = r.sort_mode(), r.fill_fused()
+    sort_now, fused_now, long_now = r.sort_mode(), r.fill_fused(), r.long_walk_info()
     bands16k = None
     if world > 1 and args.mode == "frames" and not args.no_bands16k:
         # The north star's multi-GPU case in the driver-run line: BASELINE cfg4, one 16384 x 16384 frame
@@ -780,7 +785,7 @@ def main():
             "vs_baseline": None, "dtype": "f32+i32", "data": "synthetic",
             "config": {"workload": args.workload, "width": W, "height": H, "curves": sc.n_curves, "paths": sc.n_paths,
                        "points": sc.n_points, "fragments": cnt["n_fragments"], "records": cnt["n_out_frag"] + cnt["n_span"],
-                       "scene_sha256": sc.sha256()[:16], "sort": sort_now, "fill": "fused into k_spans" if fused_now else "k_fill_cells", "sort_key_bits": info["key_bits"],
+                       "scene_sha256": sc.sha256()[:16], "sort": sort_now, "fill": "fused into k_spans" if fused_now else "k_fill_cells", "long_piece_walk": long_now[0], "long_pieces": long_now[1], "sort_key_bits": info["key_bits"],
                        "radix_passes_if_radix": info["passes"],
                        "parallelism": (("bands%d" % world) + ("+independent" if args.independent_bands else "+nccl-allgather-of-winding-sums")
                                         + ("+no-gather" if args.no_gather else "+pipelined-nccl-gather")

@@ -626,7 +626,7 @@ static int enqueue_fragments(slpr_ctx *c, cudaStream_t s, bool timed, int &launc
     launches += 1;
     if (c->long_mode) {  // few, long pieces (small scenes at large frames): two independent chains per piece, then a parallel emit
         LongScratch ls{c->d_val[1], reinterpret_cast<uint32_t *>(c->d_key[1])};
-        const int lgrid = c->num_sms * 4;
+        const int lgrid = c->num_sms * 8;
         if (c->d_cweight) {
             k_long_chains<true><<<lgrid, 128, 0, s>>>(c->d_pieces, c->d_ctr, c->cap, ls);
             k_long_emit<true><<<lgrid, 128, 0, s>>>(c->d_params, c->d_pieces, c->d_ctr, c->cap, ls, c->L, c->d_key[0], c->d_val[0], ft, c->d_inter,
@@ -790,10 +790,12 @@ static bool choose_fill_mode(const slpr_ctx *c, long long n_fragments) {
 // Long pieces chain by chain (walk.cuh)? Worth it when a frame has some but few of them: a warp per chain with one
 // lane walking a curve's bisections is the opposite of what a million-piece frame wants, where k_walk packs 32 pieces
 // of equal length into a warp. From the last frame's count, with hysteresis.
+// Measured (profiles/README.md): shipped scenes at 4K 1.4-3.4x faster with it; the 16K frame (9 M pieces, thousands of
+// them long) 4 % slower — there the walk is bound by throughput, not by its longest piece. Hence both limits.
 static bool choose_long_mode(const slpr_ctx *c, const FrameCounters &k) {
     if (c->flags & SLPR_FLAG_NO_LONG_WALK) return false;
-    const int hi = c->long_mode ? 12288 : 8192;
-    return k.n_long > 0 && k.n_long <= hi;
+    const int hi_long = c->long_mode ? 6144 : 4096, hi_pieces = c->long_mode ? 600000 : 400000;
+    return k.n_long > 0 && k.n_long <= hi_long && k.n_pieces <= hi_pieces;
 }
 
 static int size_buffers_from_count(slpr_ctx *c) {
