@@ -33,7 +33,7 @@ enum {
     SLPR_ERR_INVALID = 1,     /* bad argument */
     SLPR_ERR_CUDA = 2,        /* CUDA runtime error (message has the CUDA string) */
     SLPR_ERR_STATE = 3,       /* call order violated (e.g. render before load_scene) */
-    SLPR_ERR_UNSUPPORTED = 4, /* feature not built (e.g. SLPR_FLAG_CONTRACT_FMA) */
+    SLPR_ERR_UNSUPPORTED = 4, /* feature not built */
     SLPR_ERR_IO = 5,          /* file / parse error (host scene helpers) */
     SLPR_ERR_RETRY = 6        /* exact bands: the frame is void on some band; render it again on EVERY band (new frame_seq) */
 };
@@ -42,7 +42,11 @@ enum {
     /* Keep every reference-format intermediate buffer (fragment_data planes etc.) so that
      * slpr_debug_copy() can return them for parity checks. Costs extra HBM traffic. */
     SLPR_FLAG_TAPS = 1u << 0,
-    /* Evaluate LERP/dot with FMA contraction, as a Vulkan driver may. Not built. */
+    /* Evaluate LERP / dot / the cubic's coefficients with fused multiply-adds, as a Vulkan driver's compiler may (GLSL
+     * allows contraction unless `precise`). The policy — which a*b + c shapes are fused — is defined in
+     * oracle/oracle.c (orc_set_contract_fma) and matched bit for bit; the default (off) is the reading the executed
+     * SPIR-V fixtures pin. Results differ from the default by rounding only; the bisection issues 14 instead of 21
+     * instructions per step. */
     SLPR_FLAG_CONTRACT_FMA = 1u << 1,
     /* Launch kernels directly instead of replaying the captured CUDA graph of the frame. */
     SLPR_FLAG_NO_GRAPH = 1u << 2,

@@ -33,8 +33,22 @@ static inline int f2i(float x) {
 }
 
 /* MI0:10, MI1:12, GF:10: LERP(a,b,t) = a + t*(b-a), three separately rounded fp32 ops. */
+/* SLPR_FLAG_CONTRACT_FMA / orc_set_contract_fma (NOT pinned by the reference: no driver here): the
+ * other legitimate reading of the shaders, in which the compiler contracts a*b + c into one fused multiply-add. The
+ * policy, mirrored by csrc/common.cuh: (1) LERP(a,b,t) = fma(t, b - a, a); (2) dot(vec4(x,y,0,1), m) accumulated left to
+ * right, x*m.x then one fma per further term; (3) MI0's a = fma(3, x1 - x2, x3 - x0) and the discriminant
+ * fma(B, B, -(A*C)); (4) the f-1 arc evaluator's numerator as an fma chain. Nothing else has the a*b + c shape. */
+static int g_contract_fma = 0;
+void orc_set_contract_fma(int on) { g_contract_fma = on; }
+static inline float madd(float a, float b, float c) { /* a * b + c under the current policy */
+    if (g_contract_fma) return fmaf(a, b, c);
+    float m = a * b;
+    return m + c;
+}
+
 static inline float lerpf(float a, float b, float t) {
     float d = b - a;
+    if (g_contract_fma) return fmaf(t, d, a);
     float m = t * d;
     return a + m;
 }
@@ -63,13 +77,21 @@ void orc_transform(uint32_t n_points, const float *pos, const uint32_t *pos_path
         float op[4];
         for (int r = 0; r < 4; ++r) { /* TP:41-46; dot evaluated left to right */
             const float *m = rows + 4 * r;
-            float a = x * m[0];
-            float b = y * m[1];
-            float c = 0.0f * m[2];
-            float d = 1.0f * m[3];
-            float s = a + b;
-            s = s + c;
-            s = s + d;
+            float s;
+            if (g_contract_fma) {
+                s = x * m[0];
+                s = fmaf(y, m[1], s);
+                s = fmaf(0.0f, m[2], s);
+                s = fmaf(1.0f, m[3], s);
+            } else {
+                float a = x * m[0];
+                float b = y * m[1];
+                float c = 0.0f * m[2];
+                float d = 1.0f * m[3];
+                s = a + b;
+                s = s + c;
+                s = s + d;
+            }
             op[r] = s;
         }
         op[0] = op[0] / op[3]; /* TP:53-55 */
@@ -106,7 +128,7 @@ static void solve_quad(float a, float b, float c, float *r0, float *r1) {
     float A = a, B = b * 0.5f, C = c;
     float tx = 0.f, ty = 0.f;
     float bb = B * B, ac = A * C;
-    float R = bb - ac;
+    float R = g_contract_fma ? fmaf(B, B, -ac) : bb - ac;
     if (R > 0.0f) {
         float SR = sqrtf(R);
         if (B > 0.0f) {
@@ -142,9 +164,9 @@ static inline float eval_arc(const float *p, float t) { /* p[3] = weight of the 
     float b1 = tu * p[3];
     float d01 = b0 + b1;
     float D = d01 + b2;
-    float n0 = b0 * p[0], n1 = b1 * p[1], n2 = b2 * p[2];
-    float n01 = n0 + n1;
-    float N = n01 + n2;
+    float n0 = b0 * p[0];
+    float n01 = madd(b1, p[1], n0);
+    float N = madd(b2, p[2], n01);
     return N / D;
 }
 
@@ -231,7 +253,7 @@ void orc_monotonize_count(uint32_t n_curves, const uint32_t *curve_type,
                     const float *p = ax ? py : px;
                     float x0 = p[0], x1 = p[1], x2 = p[2], x3 = p[3];
                     float r0 = 0.f, r1 = 0.f;
-                    float a = 3.0f * (x1 - x2) + (x3 - x0);
+                    float a = madd(3.0f, x1 - x2, x3 - x0);
                     float b = 2.0f * ((x0 - x1) + (x2 - x1));
                     float cc = x1 - x0;
                     solve_quad(a, b, cc, &r0, &r1);

@@ -136,6 +136,10 @@ uint32_t orc_quantise_colour(const float *rgba, float opacity);
  * the pointer must stay valid while the mode is on. Process-wide. */
 void orc_set_full_rvg(int on, const float *curve_weight);
 
+/* SURVEY App. D.1, off by default: evaluate the shaders with a*b + c contracted into fused multiply-adds (policy in oracle.c
+ * next to lerpf). NOT pinned by anything of the reference's: no Vulkan driver here to say what it contracts. Process-wide. */
+void orc_set_contract_fma(int on);
+
 int orc_num_threads(void);
 void orc_set_num_threads(int n);
 

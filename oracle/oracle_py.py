@@ -79,7 +79,7 @@ def _arr(ptr, n, dtype):
 STAGE_NAMES = ("transform", "monotonize", "scan1", "intersect", "gen_fragment", "sort", "spans", "fill")
 
 
-def render(scene, rows, width, height, do_fill=True, threads=None, keep=None, full=False):
+def render(scene, rows, width, height, do_fill=True, threads=None, keep=None, full=False, fma=False):
     """Run the whole oracle frame. `scene` has the 7 flat loadVG arrays (see scene.Scene).
     Returns a dict of every intermediate buffer (numpy copies); `keep` (a set of names) limits the copies to
     those buffers — on frames of 10^8 fragments the full set is tens of gigabytes."""
@@ -93,11 +93,15 @@ def render(scene, rows, width, height, do_fill=True, threads=None, keep=None, fu
         w = getattr(s, "curve_weight", None)
         weights = np.ascontiguousarray(w if w is not None else np.ones(s.n_curves), dtype=np.float32)
         L.orc_set_full_rvg(C.c_int(1), _p(weights))
+    if fma:  # the contracted reading of the shaders (oracle.c, orc_set_contract_fma)
+        L.orc_set_contract_fma(C.c_int(1))
     try:
         fp = _call_render(L, s, rows, width, height, do_fill)
     finally:
         if full:
             L.orc_set_full_rvg(C.c_int(0), None)
+        if fma:
+            L.orc_set_contract_fma(C.c_int(0))
     return _collect(L, fp, s, width, height, do_fill, keep)
 
 

@@ -316,8 +316,6 @@ def test_error_paths():
         r.loadVG(bad)                   # path index out of range
     r.close()
     with pytest.raises(V.SlprError):
-        V.ScanlineRasterizer(0, V.FLAG_CONTRACT_FMA).initialize(None, 64, 64)
-    with pytest.raises(V.SlprError):
         V.ScanlineRasterizer(0, 0).initialize(None, 40000, 64)
 
 
@@ -576,3 +574,33 @@ def test_long_pieces_walked_chain_by_chain():
         h.render()
         assert np.array_equal(h.readback(), ref["rgba"]) and not h.long_walk_info()[0]
         h.close()
+
+
+def test_contracted_fma_mode():
+    """SURVEY App. D.1 / SLPR_FLAG_CONTRACT_FMA: the other legitimate reading of the shaders (a*b + c fused, as a Vulkan
+    driver's compiler may). Nothing of the reference's pins it; the policy is defined in the oracle
+    (orc_set_contract_fma) and the CUDA path must reproduce it bit for bit, tap by tap — and differ from the default
+    reading only by rounding (a handful of fragments, no visible change)."""
+    tig, vp = util.golden_scene("tiger")
+    cases = [(tig, S.fit_rows(vp, 1024, 768), 1024, 768, False), (S.synth_scene(4096, 1024, 768, 6.0, 30.0), S.identity_rows(), 1024, 768, False),
+             (util.looping_cubics_scene(), S.anim_rows(29, 512, 384), 512, 384, False), (util.quad_arc_scene(300, 640, 480), S.identity_rows(), 640, 480, True)]
+    for sc, rows, W, H, full in cases:
+        ref = O.render(sc, rows, W, H, full=full, fma=True)
+        extra = V.FLAG_CONTRACT_FMA | (V.FLAG_FULL_RVG if full else 0)
+        r = render_gpu(sc, rows, W, H, V.FLAG_TAPS | V.FLAG_NO_GRAPH | extra)
+        assert r.counts() == {k: ref[k] for k in ("n_fragments", "n_out_frag", "n_span")}
+        assert np.array_equal(r.tap("transformed_pos").view(np.uint32), ref["tpos"].view(np.uint32))
+        assert np.array_equal(r.tap("cut_cache").view(np.uint32), ref["cut_cache"].view(np.uint32))
+        for t in INT_TAPS:
+            assert np.array_equal(r.tap(t), ref[ORACLE_NAME[t]]), f"{sc.name}: tap {t} differs"
+        assert np.array_equal(r.readback(), ref["rgba"])
+        r.render()   # second frame: long-piece walk where the scene has long pieces
+        for t in ("intersection", "records"):
+            assert np.array_equal(r.tap(t), ref[ORACLE_NAME[t]]), f"{sc.name}: tap {t} differs (frame 2)"
+        r.close()
+        f = render_gpu(sc, rows, W, H, extra)
+        f.render()
+        assert np.array_equal(f.readback(), ref["rgba"])
+        f.close()
+        plain = O.render(sc, rows, W, H, full=full, keep={"rgba", "tpos"})
+        assert (plain["rgba"] != ref["rgba"]).any(axis=2).mean() < 0.002

@@ -74,6 +74,22 @@ __device__ __forceinline__ float lerpf(float a, float b, float t) {
     return __fadd_rn(a, __fmul_rn(t, __fsub_rn(b, a)));
 }
 
+// ---- SLPR_FLAG_CONTRACT_FMA: the other legitimate reading of the shaders. GLSL lets a compiler
+// contract a*b + c into one fused multiply-add unless the expression is `precise`; whether a given Vulkan driver does
+// is not pinned by anything in the reference. Policy of the contracted mode, defined in oracle/oracle.c
+// (orc_set_contract_fma) and mirrored here: (1) LERP(a,b,t) = fma(t, b - a, a); (2) dot(vec4(x,y,0,1), m) accumulated
+// left to right, x*m.x then one fma per further term; (3) make_intersection_0's a = fma(3, x1 - x2, x3 - x0) and the
+// discriminant fma(B, B, -(A*C)); (4) the f-1 arc evaluator's numerator as an fma chain. Nothing else has the a*b + c
+// shape. FMA = false is the default, pinned by the executed SPIR-V fixtures.
+template <bool FMA>
+__device__ __forceinline__ float madd_t(float a, float b, float c) {  // a * b + c
+    return FMA ? __fmaf_rn(a, b, c) : __fadd_rn(__fmul_rn(a, b), c);
+}
+template <bool FMA>
+__device__ __forceinline__ float lerp_t(float a, float b, float t) {
+    return FMA ? __fmaf_rn(t, __fsub_rn(b, a), a) : __fadd_rn(a, __fmul_rn(t, __fsub_rn(b, a)));
+}
+
 // make_intersection_1.comp:76-79, gen_fragment.comp:54-57
 __device__ __forceinline__ int float2int_rd(float x) { return x >= 0.0f ? f2i(x) : f2i(__fsub_rn(x, 1.0f)); }
 
@@ -84,41 +100,45 @@ __device__ __forceinline__ bool path_invisible(int mask) {
            ((m & 0x11010110u) == 0);
 }
 
+template <bool FMA = false>
 __device__ __forceinline__ float cubic_eval(float p0, float p1, float p2, float p3, float t) {
-    float q0 = lerpf(p0, p1, t), q1 = lerpf(p1, p2, t), q2 = lerpf(p2, p3, t);
-    float l0 = lerpf(q0, q1, t), l1 = lerpf(q1, q2, t);
-    return lerpf(l0, l1, t);
+    float q0 = lerp_t<FMA>(p0, p1, t), q1 = lerp_t<FMA>(p1, p2, t), q2 = lerp_t<FMA>(p2, p3, t);
+    float l0 = lerp_t<FMA>(q0, q1, t), l1 = lerp_t<FMA>(q1, q2, t);
+    return lerp_t<FMA>(l0, l1, t);
 }
 
 // interpolateGeneralCurve: make_intersection_0.comp:131-165 (dflt 1.0f), make_intersection_1.comp:81-148 (dflt 0.0f)
 __device__ __forceinline__ float interp_general(uint32_t type, float t, float p0, float p1, float p2, float p3,
                                                 float dflt) {
     if (type == T_LINE) return lerpf(p0, p1, t);
-    if (type == T_CUBIC) return cubic_eval(p0, p1, p2, p3, t);
+    if (type == T_CUBIC) return cubic_eval<false>(p0, p1, p2, p3, t);
     return dflt;
 }
 
 // ---- SURVEY section 8 f-1 (SLPR_FLAG_FULL_RVG; NOT in the reference, whose QUADRIC / ARC arms are `// TODO`): the arithmetic is
 // defined in oracle/oracle.c next to interp_general and mirrored here operation for operation.
+template <bool FMA = false>
 __device__ __forceinline__ float eval_quadric(float p0, float p1, float p2, float t) {
-    const float q0 = lerpf(p0, p1, t), q1 = lerpf(p1, p2, t);
-    return lerpf(q0, q1, t);
+    const float q0 = lerp_t<FMA>(p0, p1, t), q1 = lerp_t<FMA>(p1, p2, t);
+    return lerp_t<FMA>(q0, q1, t);
 }
 // rational quadratic with weights (1, w, 1), Euclidean control point
+template <bool FMA = false>
 __device__ __forceinline__ float eval_arc(float p0, float p1, float p2, float w, float t) {
     const float u = __fsub_rn(1.0f, t);
     const float b0 = __fmul_rn(u, u), b2 = __fmul_rn(t, t);
     const float b1 = __fmul_rn(__fmul_rn(__fmul_rn(2.0f, t), u), w);
     const float D = __fadd_rn(__fadd_rn(b0, b1), b2);
-    const float N = __fadd_rn(__fadd_rn(__fmul_rn(b0, p0), __fmul_rn(b1, p1)), __fmul_rn(b2, p2));
+    const float N = madd_t<FMA>(b2, p2, madd_t<FMA>(b1, p1, __fmul_rn(b0, p0)));
     return __fdiv_rn(N, D);
 }
 // interp_general with the TODO arms filled in (p3 carries the weight of an ARC)
+template <bool FMA = false>
 __device__ __forceinline__ float interp_full(uint32_t type, float t, float p0, float p1, float p2, float p3, float dflt, bool full) {
-    if (type == T_LINE) return lerpf(p0, p1, t);
-    if (type == T_CUBIC) return cubic_eval(p0, p1, p2, p3, t);
-    if (full && type == T_QUADRIC) return eval_quadric(p0, p1, p2, t);
-    if (full && type == T_ARC) return eval_arc(p0, p1, p2, p3, t);
+    if (type == T_LINE) return lerp_t<FMA>(p0, p1, t);
+    if (type == T_CUBIC) return cubic_eval<FMA>(p0, p1, p2, p3, t);
+    if (full && type == T_QUADRIC) return eval_quadric<FMA>(p0, p1, p2, t);
+    if (full && type == T_ARC) return eval_arc<FMA>(p0, p1, p2, p3, t);
     return dflt;
 }
 

@@ -26,11 +26,12 @@ struct PointXform {
         : m0x(P->rows[0]), m0y(P->rows[1]), m0z(P->rows[2]), m0w(P->rows[3]), m1x(P->rows[4]), m1y(P->rows[5]), m1z(P->rows[6]),
           m1w(P->rows[7]), m3x(P->rows[12]), m3y(P->rows[13]), m3z(P->rows[14]), m3w(P->rows[15]),
           w((float)P->width), h((float)P->height) {}  // TP:8 (floats), SR.cpp:1153-1154
+    template <bool FMA = false>
     __device__ __forceinline__ uint32_t apply(float2 p, float2 &out) const {
         // dot(vec4(x,y,0,1), m) evaluated left to right (TP:41-46)
-        float ox = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(p.x, m0x), __fmul_rn(p.y, m0y)), __fmul_rn(0.0f, m0z)), __fmul_rn(1.0f, m0w));
-        float oy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(p.x, m1x), __fmul_rn(p.y, m1y)), __fmul_rn(0.0f, m1z)), __fmul_rn(1.0f, m1w));
-        const float ow = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(p.x, m3x), __fmul_rn(p.y, m3y)), __fmul_rn(0.0f, m3z)), __fmul_rn(1.0f, m3w));
+        float ox = madd_t<FMA>(1.0f, m0w, madd_t<FMA>(0.0f, m0z, madd_t<FMA>(p.y, m0y, __fmul_rn(p.x, m0x))));
+        float oy = madd_t<FMA>(1.0f, m1w, madd_t<FMA>(0.0f, m1z, madd_t<FMA>(p.y, m1y, __fmul_rn(p.x, m1x))));
+        const float ow = madd_t<FMA>(1.0f, m3w, madd_t<FMA>(0.0f, m3z, madd_t<FMA>(p.y, m3y, __fmul_rn(p.x, m3x))));
         ox = __fdiv_rn(ox, ow);  // TP:53-54
         oy = __fdiv_rn(oy, ow);
         out = make_float2(ox, oy);
@@ -51,6 +52,7 @@ struct PointXform {
     }
 };
 
+template <bool FMA>
 __global__ void __launch_bounds__(256) k_transform(const FrameParams *__restrict__ P, uint32_t n_points,
                                                    const float2 *__restrict__ pos,
                                                    const uint32_t *__restrict__ pos_path,
@@ -69,7 +71,7 @@ __global__ void __launch_bounds__(256) k_transform(const FrameParams *__restrict
         }
         if (live) {
             float2 o;
-            flag = xf.apply(pos[i], o);
+            flag = xf.apply<FMA>(pos[i], o);
             pidx = pos_path[i];
             tpos[i] = o;
         }
@@ -86,6 +88,7 @@ __global__ void __launch_bounds__(256) k_transform(const FrameParams *__restrict
 // helpers shared by K2 and K4
 // ------------------------------------------------------------------------------------------------
 // make_intersection_0.comp:76-129
+template <bool FMA = false>
 __device__ __forceinline__ void solve_quad(float a, float b, float c, float &r0, float &r1) {
     if (a == 0) {
         const float x = __fdiv_rn(-c, b);
@@ -94,7 +97,7 @@ __device__ __forceinline__ void solve_quad(float a, float b, float c, float &r0,
     }
     const float A = a, B = __fmul_rn(b, 0.5f), C = c;
     float tx = 0.f, ty = 0.f;
-    const float R = __fsub_rn(__fmul_rn(B, B), __fmul_rn(A, C));
+    const float R = FMA ? __fmaf_rn(B, B, -__fmul_rn(A, C)) : __fsub_rn(__fmul_rn(B, B), __fmul_rn(A, C));
     if (R > 0.0f) {
         const float SR = __fsqrt_rn(R);
         if (B > 0.0f) {
@@ -259,6 +262,7 @@ __global__ void __launch_bounds__(256) k_path_cull(const FrameParams *__restrict
 // more than the band's own points and curves (0.16 of 1.55 ms per band at 16K). One thread tests one path; the
 // warp then takes its live paths one after the other: transforms the path's points (k_transform's arithmetic),
 // stores the path's visibility mask (the warp is its only writer) and appends its curves to the live list.
+template <bool FMA>
 __global__ void __launch_bounds__(256) k_band_paths(const FrameParams *__restrict__ P, uint32_t n_paths,
                                                     const float4 *__restrict__ path_obj_box,
                                                     const uint32_t *__restrict__ path_first_point,
@@ -310,7 +314,7 @@ __global__ void __launch_bounds__(256) k_band_paths(const FrameParams *__restric
             uint32_t flags = 0;
             for (uint32_t i = lane; i < s_npt; i += 32) {
                 float2 o;
-                flags |= xf.apply(pos[s_pt0 + i], o);
+                flags |= xf.apply<FMA>(pos[s_pt0 + i], o);
                 tpos[s_pt0 + i] = o;
             }
             flags = __reduce_or_sync(0xFFFFFFFFu, flags);
@@ -355,6 +359,7 @@ __global__ void __launch_bounds__(256) k_band_live(uint32_t n_curves, const uint
     }
 }
 
+template <bool FMA>
 __global__ void __launch_bounds__(256) k_monotonize_count(const FrameParams *__restrict__ P, uint32_t n_curves,
                                                           const uint32_t *__restrict__ curve_type,
                                                           const uint32_t *__restrict__ curve_pos_map,
@@ -404,10 +409,10 @@ __global__ void __launch_bounds__(256) k_monotonize_count(const FrameParams *__r
                     const float x0 = ax ? cp.y[0] : cp.x[0], x1 = ax ? cp.y[1] : cp.x[1];
                     const float x2 = ax ? cp.y[2] : cp.x[2], x3 = ax ? cp.y[3] : cp.x[3];
                     float r0 = 0.f, r1 = 0.f;
-                    const float a = __fadd_rn(__fmul_rn(3.0f, __fsub_rn(x1, x2)), __fsub_rn(x3, x0));
+                    const float a = madd_t<FMA>(3.0f, __fsub_rn(x1, x2), __fsub_rn(x3, x0));
                     const float b = __fmul_rn(2.0f, __fadd_rn(__fsub_rn(x0, x1), __fsub_rn(x2, x1)));
                     const float cc = __fsub_rn(x1, x0);
-                    solve_quad(a, b, cc, r0, r1);
+                    solve_quad<FMA>(a, b, cc, r0, r1);
                     if (r0 > 0.0f && r0 < 1.0f) { tq[n_cuts] = r0; ++n_cuts; }
                     if (r1 > 0.0f && r1 < 1.0f && r1 != r0) { tq[n_cuts] = r1; ++n_cuts; }
                 }
@@ -420,7 +425,7 @@ __global__ void __launch_bounds__(256) k_monotonize_count(const FrameParams *__r
                     const float a = __fadd_rn(__fsub_rn(A, B), C);
                     const float b = __fsub_rn(B, __fmul_rn(2.0f, A));
                     float r0 = 0.f, r1 = 0.f;
-                    solve_quad(a, b, A, r0, r1);
+                    solve_quad<FMA>(a, b, A, r0, r1);
                     if (r0 > 0.0f && r0 < 1.0f) { tq[n_cuts] = r0; ++n_cuts; }
                     if (r1 > 0.0f && r1 < 1.0f && r1 != r0) { tq[n_cuts] = r1; ++n_cuts; }
                 }
@@ -453,8 +458,8 @@ __global__ void __launch_bounds__(256) k_monotonize_count(const FrameParams *__r
         int pcnt = 0;
         for (uint32_t i = 0; i < n_cuts; ++i) {  // MI0:383-408
             const float t1 = tq[i];
-            const float p1x = interp_full(type, t1, cp.x[0], cp.x[1], cp.x[2], cp.x[3], 1.0f, full.on());
-            const float p1y = interp_full(type, t1, cp.y[0], cp.y[1], cp.y[2], cp.y[3], 1.0f, full.on());
+            const float p1x = interp_full<FMA>(type, t1, cp.x[0], cp.x[1], cp.x[2], cp.x[3], 1.0f, full.on());
+            const float p1y = interp_full<FMA>(type, t1, cp.y[0], cp.y[1], cp.y[2], cp.y[3], 1.0f, full.on());
             // get_xy_begin_end, MI0:167-183 (floor)
             const float xlo = (p0x <= p1x) ? p0x : p1x, xhi = (p0x <= p1x) ? p1x : p0x;
             const float ylo = (p0y <= p1y) ? p0y : p1y, yhi = (p0y <= p1y) ? p1y : p0y;
@@ -610,17 +615,17 @@ __device__ __forceinline__ void emit_fragment(const FragEnv &P, const KeyLayout 
 }
 
 // curve_interpolate of gen_fragment.comp:59-87 (default result cv0; only LINE and CUBIC evaluate)
-template <bool FULL = false>
+template <bool FULL = false, bool FMA = false>
 __device__ __forceinline__ void eval_point(uint32_t type, const CurvePts &cp, float t, float &ox, float &oy) {
     if (FULL && type == T_QUADRIC) {
-        ox = eval_quadric(cp.x[0], cp.x[1], cp.x[2], t); oy = eval_quadric(cp.y[0], cp.y[1], cp.y[2], t);
+        ox = eval_quadric<FMA>(cp.x[0], cp.x[1], cp.x[2], t); oy = eval_quadric<FMA>(cp.y[0], cp.y[1], cp.y[2], t);
     } else if (FULL && type == T_ARC) {
-        ox = eval_arc(cp.x[0], cp.x[1], cp.x[2], cp.x[3], t); oy = eval_arc(cp.y[0], cp.y[1], cp.y[2], cp.y[3], t);
+        ox = eval_arc<FMA>(cp.x[0], cp.x[1], cp.x[2], cp.x[3], t); oy = eval_arc<FMA>(cp.y[0], cp.y[1], cp.y[2], cp.y[3], t);
     } else if (type == T_CUBIC) {
-        ox = cubic_eval(cp.x[0], cp.x[1], cp.x[2], cp.x[3], t);
-        oy = cubic_eval(cp.y[0], cp.y[1], cp.y[2], cp.y[3], t);
+        ox = cubic_eval<FMA>(cp.x[0], cp.x[1], cp.x[2], cp.x[3], t);
+        oy = cubic_eval<FMA>(cp.y[0], cp.y[1], cp.y[2], cp.y[3], t);
     } else if (type == T_LINE) {
-        ox = lerpf(cp.x[0], cp.x[1], t); oy = lerpf(cp.y[0], cp.y[1], t);
+        ox = lerp_t<FMA>(cp.x[0], cp.x[1], t); oy = lerp_t<FMA>(cp.y[0], cp.y[1], t);
     } else if (type == T_QUADRIC) {
         ox = cp.x[0]; oy = cp.y[0];
     } else {

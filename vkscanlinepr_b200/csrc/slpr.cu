@@ -317,10 +317,6 @@ extern "C" slpr_ctx *slpr_create(int device, uint32_t width, uint32_t height, ui
         fail(SLPR_ERR_INVALID, "slpr_create: with SLPR_FLAG_AA4 width/height must be at most 8191 (the pipeline runs at four times the size)");
         return nullptr;
     }
-    if (flags & SLPR_FLAG_CONTRACT_FMA) {
-        fail(SLPR_ERR_UNSUPPORTED, "slpr_create: SLPR_FLAG_CONTRACT_FMA is not built; the arithmetic policy is IEEE fp32 without contraction");
-        return nullptr;
-    }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) {
@@ -347,8 +343,11 @@ extern "C" slpr_ctx *slpr_create(int device, uint32_t width, uint32_t height, ui
     c->fb_cur = c->d_fb;
     for (auto &ev : c->ev) ok = ok && cudaEventCreate(&ev) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_onesweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM_BYTES) == cudaSuccess;
-    if (flags & SLPR_FLAG_FULL_RVG) ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->walk_blocks_per_sm, k_walk<true>, WALK_THREADS, 0) == cudaSuccess;
-    else ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->walk_blocks_per_sm, k_walk<false>, WALK_THREADS, 0) == cudaSuccess;
+    {
+        const bool full = (flags & SLPR_FLAG_FULL_RVG) != 0, fma = (flags & SLPR_FLAG_CONTRACT_FMA) != 0;
+        auto walk = full ? (fma ? k_walk<true, true> : k_walk<true, false>) : (fma ? k_walk<false, true> : k_walk<false, false>);
+        ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->walk_blocks_per_sm, walk, WALK_THREADS, 0) == cudaSuccess;
+    }
     ok = ok && cudaFuncSetAttribute(k_scan_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->scan_tma_blocks_per_sm, k_scan_tma, ST_THREADS, ST_SMEM_BYTES) == cudaSuccess;
     for (auto fn : {k_spans<false, true, false>, k_spans<true, true, false>, k_spans<true, false, false>, k_spans<false, true, true>, k_spans<true, true, true>})
@@ -570,10 +569,11 @@ static int enqueue_count_phase(slpr_ctx *c, cudaStream_t s, bool timed, int &lau
     CU(cudaMemsetAsync(c->d_pvis, 0, std::max<size_t>(c->P, 1) * 4, s));
     if (timed) CU(cudaEventRecord(c->ev[0], s));
     const bool band = c->hp.cull != 0;
+    const bool fma = (c->flags & SLPR_FLAG_CONTRACT_FMA) != 0;
     LiveCurves live{nullptr, c->d_ctr};
     if (band && c->d_pfp) {  // one pass over the paths: cull, transform the live ones, list their curves
         CU(cudaMemsetAsync(c->d_count, 0, (size_t)c->nc * 4, s));  // k_monotonize_count only writes the live curves
-        k_band_paths<<<grid_for(c, c->P, 256, 8), 256, 0, s>>>(c->d_params, c->P, c->d_pobj, c->d_pfp, c->d_pfc, c->d_pos, c->d_tpos, c->d_pvis,
+        (fma ? k_band_paths<true> : k_band_paths<false>)<<<grid_for(c, c->P, 256, 8), 256, 0, s>>>(c->d_params, c->P, c->d_pobj, c->d_pfp, c->d_pfc, c->d_pos, c->d_tpos, c->d_pvis,
                                                                 c->d_live, c->d_ctr, c->d_live_paths);
         ++launches;
         if (timed) CU(cudaEventRecord(c->ev[1], s));
@@ -584,7 +584,7 @@ static int enqueue_count_phase(slpr_ctx *c, cudaStream_t s, bool timed, int &lau
             k_path_cull<<<grid_for(c, c->P, 256, 8), 256, 0, s>>>(c->d_params, c->P, c->d_pobj, c->d_plive, c->d_live_paths, c->d_ctr);
             ++launches;
         }
-        k_transform<<<grid_for(c, c->np, 256, 8), 256, 0, s>>>(c->d_params, c->np, c->d_pos, c->d_pos_path, c->d_tpos, c->d_pvis, plive);
+        (fma ? k_transform<true> : k_transform<false>)<<<grid_for(c, c->np, 256, 8), 256, 0, s>>>(c->d_params, c->np, c->d_pos, c->d_pos_path, c->d_tpos, c->d_pvis, plive);
         ++launches;
         if (timed) CU(cudaEventRecord(c->ev[1], s));
         if (plive) {
@@ -594,7 +594,7 @@ static int enqueue_count_phase(slpr_ctx *c, cudaStream_t s, bool timed, int &lau
             live.list = c->d_live;
         }
     }
-    k_monotonize_count<<<c->mono_blocks, 256, 0, s>>>(c->d_params, c->nc, c->d_ctype, c->d_cpm, c->d_cpath,
+    (fma ? k_monotonize_count<true> : k_monotonize_count<false>)<<<c->mono_blocks, 256, 0, s>>>(c->d_params, c->nc, c->d_ctype, c->d_cpm, c->d_cpath,
                                                                    c->d_tpos, c->d_pvis, c->d_cut, c->d_count, c->d_slots,
                                                                    c->d_block_cnt, live, c->lay, FullRvg{c->d_cweight});
     k_bucket_scan<<<dim3(WALK_BUCKETS, c->lay.n_windows), c->lay.blocks_per_window > 256 ? 1024 : 128, 0, s>>>(c->d_block_cnt, c->lay, c->d_vhist);
@@ -614,12 +614,13 @@ static int enqueue_fragments(slpr_ctx *c, cudaStream_t s, bool timed, int &launc
     int rc = enqueue_count_phase(c, s, timed, launches);
     if (rc) return rc;
     FragTaps ft{c->t_key32, c->t_path, c->t_wind};
-    k_piece_emit<<<c->mono_blocks, 256, 0, s>>>(c->d_params, c->nc, c->d_ctype, c->d_cpm, c->d_cpath, c->d_frule, c->d_tpos, c->d_cut,
+    const bool fma = (c->flags & SLPR_FLAG_CONTRACT_FMA) != 0, full = c->d_cweight != nullptr;
+    (fma ? k_piece_emit<true> : k_piece_emit<false>)<<<c->mono_blocks, 256, 0, s>>>(c->d_params, c->nc, c->d_ctype, c->d_cpm, c->d_cpath, c->d_frule, c->d_tpos, c->d_cut,
                                                              c->d_offset, c->d_slots, c->d_ctr, c->cap,
                                                              PieceRanks{c->d_block_cnt, c->d_vhist, c->lay},
                                                              LiveCurves{c->hp.cull ? c->d_live : nullptr, c->d_ctr}, c->d_pieces, FullRvg{c->d_cweight});
     if (timed) CU(cudaEventRecord(c->ev[4], s));
-    auto walk = c->d_cweight ? k_walk<true> : k_walk<false>;
+    auto walk = full ? (fma ? k_walk<true, true> : k_walk<true, false>) : (fma ? k_walk<false, true> : k_walk<false, false>);
     walk<<<c->num_sms * std::max(1, c->walk_blocks_per_sm), WALK_THREADS, 0, s>>>(
         c->d_params, c->d_pieces, c->d_ctr, c->cap, WalkTemp{c->d_tickets + 3 + RS_MAX_PASSES},
         c->L, c->d_key[0], c->d_val[0], ft, c->d_inter, c->d_boundary, c->d_fixlist, c->long_mode ? 1 : 0);
@@ -627,18 +628,13 @@ static int enqueue_fragments(slpr_ctx *c, cudaStream_t s, bool timed, int &launc
     if (c->long_mode) {  // few, long pieces (small scenes at large frames): two independent chains per piece, then a parallel emit
         LongScratch ls{c->d_val[1], reinterpret_cast<uint32_t *>(c->d_key[1])};
         const int lgrid = c->num_sms * 8;
-        if (c->d_cweight) {
-            k_long_chains<true><<<lgrid, 128, 0, s>>>(c->d_pieces, c->d_ctr, c->cap, ls);
-            k_long_emit<true><<<lgrid, 128, 0, s>>>(c->d_params, c->d_pieces, c->d_ctr, c->cap, ls, c->L, c->d_key[0], c->d_val[0], ft, c->d_inter,
-                                                   c->d_boundary, c->d_fixlist);
-        } else {
-            k_long_chains<false><<<lgrid, 128, 0, s>>>(c->d_pieces, c->d_ctr, c->cap, ls);
-            k_long_emit<false><<<lgrid, 128, 0, s>>>(c->d_params, c->d_pieces, c->d_ctr, c->cap, ls, c->L, c->d_key[0], c->d_val[0], ft, c->d_inter,
-                                                    c->d_boundary, c->d_fixlist);
-        }
+        auto chains = full ? (fma ? k_long_chains<true, true> : k_long_chains<true, false>) : (fma ? k_long_chains<false, true> : k_long_chains<false, false>);
+        auto emit = full ? (fma ? k_long_emit<true, true> : k_long_emit<true, false>) : (fma ? k_long_emit<false, true> : k_long_emit<false, false>);
+        chains<<<lgrid, 128, 0, s>>>(c->d_pieces, c->d_ctr, c->cap, ls);
+        emit<<<lgrid, 128, 0, s>>>(c->d_params, c->d_pieces, c->d_ctr, c->cap, ls, c->L, c->d_key[0], c->d_val[0], ft, c->d_inter, c->d_boundary, c->d_fixlist);
         launches += 2;
     }
-    k_piece_fix<<<8, 256, 0, s>>>(c->d_params, c->d_ctype, c->d_cpm, c->d_cpath, c->d_frule, c->d_tpos, c->d_ctr, c->cap, c->d_boundary,
+    (fma ? k_piece_fix<true> : k_piece_fix<false>)<<<8, 256, 0, s>>>(c->d_params, c->d_ctype, c->d_cpm, c->d_cpath, c->d_frule, c->d_tpos, c->d_ctr, c->cap, c->d_boundary,
                                   c->d_fixlist, c->L, c->d_key[0], c->d_val[0], ft, FullRvg{c->d_cweight});
     launches += 2;
     if (timed) CU(cudaEventRecord(c->ev[5], s));

@@ -78,6 +78,7 @@ __device__ __forceinline__ void vbucket_bases(const PieceRanks &pr, uint32_t *s_
 #ifndef SLPR_PE_MIN_BLOCKS
 #define SLPR_PE_MIN_BLOCKS 1
 #endif
+template <bool FMA>
 __global__ void __launch_bounds__(256, SLPR_PE_MIN_BLOCKS) k_piece_emit(const FrameParams *__restrict__ P, uint32_t n_curves,
                                                     const uint32_t *__restrict__ curve_type,
                                                     const uint32_t *__restrict__ curve_pos_map,
@@ -127,8 +128,8 @@ __global__ void __launch_bounds__(256, SLPR_PE_MIN_BLOCKS) k_piece_emit(const Fr
         float t0_ms = 0.f, p0x = cp.x[0], p0y = cp.y[0];
         for (uint32_t piece = 0; piece < n_cuts; ++piece) {  // MI1:266-308
             float t1_ms = (piece + 1 == n_cuts) ? 1.f : (piece == 0) ? q0 : (piece == 1) ? q1 : (piece == 2) ? q2 : q3;
-            const float p1x = interp_full(type, t1_ms, cp.x[0], cp.x[1], cp.x[2], cp.x[3], 0.0f, full.on());
-            const float p1y = interp_full(type, t1_ms, cp.y[0], cp.y[1], cp.y[2], cp.y[3], 0.0f, full.on());
+            const float p1x = interp_full<FMA>(type, t1_ms, cp.x[0], cp.x[1], cp.x[2], cp.x[3], 0.0f, full.on());
+            const float p1y = interp_full<FMA>(type, t1_ms, cp.y[0], cp.y[1], cp.y[2], cp.y[3], 0.0f, full.on());
             // MI1:271-276: tag t1 in its two mantissa LSBs
             if (floorf(p1x) == p1x) t1_ms = u2f((f2u(t1_ms) & 0xFFFFFFFCu) | 2u);
             else t1_ms = u2f(f2u(t1_ms) | 3u);
@@ -232,7 +233,7 @@ constexpr int WALK_UNROLL = SLPR_WALK_UNROLL;  // bisection steps per loop trip
 // One crossing of the piece with the grid line `cst` on axis `side` (0: x, 1: y), searched from t_min (the previous
 // crossing on this axis) up to the piece's end t1_ms: make_intersection_1.comp:377-437, shared by k_walk and the
 // long-piece chains (k_long_chains) so that both produce the same bits.
-template <bool FULL>
+template <bool FULL, bool FMA = false>
 __device__ __forceinline__ float solve_crossing(uint32_t type, const CurvePts &cp, int side, float t_min, float t1_ms, float cst) {
     float t_solve = 0.0f;
     const float c0 = side ? cp.y[0] : cp.x[0], c1 = side ? cp.y[1] : cp.x[1];
@@ -243,10 +244,9 @@ __device__ __forceinline__ float solve_crossing(uint32_t type, const CurvePts &c
         float t0 = t_min, t1 = t1_ms;
         float vt0;
         {
-            const float a0 = __fadd_rn(c0, __fmul_rn(t0, d01)), a1 = __fadd_rn(c1, __fmul_rn(t0, d12)),
-                        a2 = __fadd_rn(c2, __fmul_rn(t0, d23));
-            const float b0 = lerpf(a0, a1, t0), b1 = lerpf(a1, a2, t0);
-            vt0 = lerpf(b0, b1, t0);
+            const float a0 = madd_t<FMA>(t0, d01, c0), a1 = madd_t<FMA>(t0, d12, c1), a2 = madd_t<FMA>(t0, d23, c2);
+            const float b0 = lerp_t<FMA>(a0, a1, t0), b1 = lerp_t<FMA>(a1, a2, t0);
+            vt0 = lerp_t<FMA>(b0, b1, t0);
         }
         t_solve = t0;
         if (vt0 != cst) {
@@ -257,10 +257,9 @@ __device__ __forceinline__ float solve_crossing(uint32_t type, const CurvePts &c
 #pragma unroll WALK_UNROLL
             for (int j = 0; j < CUBIC_ITERATION_NUMBER; ++j) {
                 const float tm = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
-                const float a0 = __fadd_rn(c0, __fmul_rn(tm, d01)), a1 = __fadd_rn(c1, __fmul_rn(tm, d12)),
-                            a2 = __fadd_rn(c2, __fmul_rn(tm, d23));
-                const float b0 = lerpf(a0, a1, tm), b1 = lerpf(a1, a2, tm);
-                const float vtm = lerpf(b0, b1, tm);
+                const float a0 = madd_t<FMA>(tm, d01, c0), a1 = madd_t<FMA>(tm, d12, c1), a2 = madd_t<FMA>(tm, d23, c2);
+                const float b0 = lerp_t<FMA>(a0, a1, tm), b1 = lerp_t<FMA>(a1, a2, tm);
+                const float vtm = lerp_t<FMA>(b0, b1, tm);
                 t_solve = tm;
                 s_last = f2u(__fsub_rn(vtm, cst));
                 // same sign as at t0: t0 = tm (vt0 = vtm, MI1:421-424), else t1 = tm. One
@@ -281,14 +280,14 @@ __device__ __forceinline__ float solve_crossing(uint32_t type, const CurvePts &c
     } else if (FULL && (type == T_QUADRIC || type == T_ARC)) {  // f-1: the bisection of MI1:392-436 on this curve's evaluator
         const float c2 = side ? cp.y[2] : cp.x[2], w = cp.x[3];
         float t0 = t_min, t1 = t1_ms;
-        float vt0 = (type == T_ARC) ? eval_arc(c0, c1, c2, w, t0) : eval_quadric(c0, c1, c2, t0);
+        float vt0 = (type == T_ARC) ? eval_arc<FMA>(c0, c1, c2, w, t0) : eval_quadric<FMA>(c0, c1, c2, t0);
         t_solve = t0;
         if (vt0 != cst) {
             const float raw_t0 = t0;
             float last_vtm = 0.f;
             for (int j = 0; j < CUBIC_ITERATION_NUMBER; ++j) {
                 const float tm = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
-                const float vtm = (type == T_ARC) ? eval_arc(c0, c1, c2, w, tm) : eval_quadric(c0, c1, c2, tm);
+                const float vtm = (type == T_ARC) ? eval_arc<FMA>(c0, c1, c2, w, tm) : eval_quadric<FMA>(c0, c1, c2, tm);
                 t_solve = tm; last_vtm = vtm;
                 if ((int)(f2u(__fsub_rn(vtm, cst)) ^ f2u(__fsub_rn(vt0, cst))) >= 0) { t0 = tm; vt0 = vtm; }
                 else t1 = tm;
@@ -313,7 +312,7 @@ __device__ __forceinline__ float solve_crossing(uint32_t type, const CurvePts &c
 
 // FULL (SLPR_FLAG_FULL_RVG, f-1): QUADRIC / ARC pieces are walked with the reference's bisection on their own evaluators
 // (common.cuh) instead of the reference's TODO arms; a separate instantiation, so the default kernel is untouched.
-template <bool FULL>
+template <bool FULL, bool FMA>
 __global__ void __launch_bounds__(WALK_THREADS, SLPR_WALK_MIN_BLOCKS) k_walk(const FrameParams *__restrict__ P,
                                                        const PieceRec *__restrict__ pieces,
                                                        FrameCounters *__restrict__ ctr, int capacity, WalkTemp tmp,
@@ -426,7 +425,7 @@ __global__ void __launch_bounds__(WALK_THREADS, SLPR_WALK_MIN_BLOCKS) k_walk(con
                 float tc = u2f(f2u(t_min) & 0xFFFFFFFCu);
                 tc = (tc < 0.0f) ? 0.0f : tc;
                 float ex, ey;
-                eval_point<FULL>(type, cp, tc, ex, ey);
+                eval_point<FULL, FMA>(type, cp, tc, ex, ey);
                 if (have_prev) {
                     uint64_t k; uint32_t v;
                     make_fragment(env, L, pcnt - 1, pidx, rule_bit, prev_t, tc, prev_x, prev_y, ex, ey, k, v, taps);
@@ -439,7 +438,7 @@ __global__ void __launch_bounds__(WALK_THREADS, SLPR_WALK_MIN_BLOCKS) k_walk(con
             float t_solve = park ? 2.0f : 0.0f;
             const bool solve = live && !park;
             if (__any_sync(0xFFFFFFFFu, solve)) {
-                if (solve) t_solve = solve_crossing<FULL>(type, cp, side, t_min, t1_ms, cst);
+                if (solve) t_solve = solve_crossing<FULL, FMA>(type, cp, side, t_min, t1_ms, cst);
             }
             if (live) {  // MI1:440
                 const float tagged = u2f((f2u(t_solve) & 0xFFFFFFFCu) | (uint32_t)side);
@@ -457,7 +456,7 @@ __global__ void __launch_bounds__(WALK_THREADS, SLPR_WALK_MIN_BLOCKS) k_walk(con
             float tcl = u2f(f2u(t1_ms) & 0xFFFFFFFCu);
             tcl = (tcl < 0.0f) ? 0.0f : tcl;
             float ex, ey;
-            eval_point<FULL>(type, cp, tcl, ex, ey);
+            eval_point<FULL, FMA>(type, cp, tcl, ex, ey);
             uint64_t k; uint32_t v;
             make_fragment(env, L, pcnt - 1, pidx, rule_bit, prev_t, tcl, prev_x, prev_y, ex, ey, k, v, taps);
             fs.put(pcnt - 1, k, v, key64, val);
@@ -522,7 +521,7 @@ __device__ __forceinline__ LongPiece load_long_piece(const PieceRec *__restrict_
     return p;
 }
 
-template <bool FULL>
+template <bool FULL, bool FMA>
 __global__ void __launch_bounds__(128) k_long_chains(const PieceRec *__restrict__ pieces, const FrameCounters *__restrict__ ctr,
                                                      int capacity, LongScratch sc) {
     if (ctr->n_fragments > capacity) return;
@@ -565,7 +564,7 @@ __global__ void __launch_bounds__(128) k_long_chains(const PieceRec *__restrict_
             for (int k = 0; k < n; ++k) {
                 const float cst = g;
                 g = __fadd_rn(g, d);
-                const float ts = solve_crossing<FULL>(p.type, p.cp, side, t_prev, p.t1_ms, cst);
+                const float ts = solve_crossing<FULL, FMA>(p.type, p.cp, side, t_prev, p.t1_ms, cst);
                 const uint32_t tg = (f2u(ts) & 0xFFFFFFFCu) | (uint32_t)side;
                 out[k] = tg;
                 t_prev = u2f(tg);
@@ -574,7 +573,7 @@ __global__ void __launch_bounds__(128) k_long_chains(const PieceRec *__restrict_
     }
 }
 
-template <bool FULL>
+template <bool FULL, bool FMA>
 __global__ void __launch_bounds__(128) k_long_emit(const FrameParams *__restrict__ P, const PieceRec *__restrict__ pieces,
                                                    FrameCounters *__restrict__ ctr, int capacity, LongScratch sc, KeyLayout L,
                                                    uint64_t *__restrict__ key64, uint32_t *__restrict__ val, FragTaps taps,
@@ -643,8 +642,8 @@ __global__ void __launch_bounds__(128) k_long_emit(const FrameParams *__restrict
                 float tb = u2f((k < n_loop ? mg[k] : f2u(p.t1_ms)) & 0xFFFFFFFCu);  // k == n_loop: the fragment across the piece boundary
                 tb = (tb < 0.0f) ? 0.0f : tb;
                 float ax, ay, bx, by;
-                eval_point<FULL>(p.type, p.cp, ta, ax, ay);
-                eval_point<FULL>(p.type, p.cp, tb, bx, by);
+                eval_point<FULL, FMA>(p.type, p.cp, ta, ax, ay);
+                eval_point<FULL, FMA>(p.type, p.cp, tb, bx, by);
                 uint64_t kk; uint32_t vv;
                 make_fragment(env, L, p.pcnt + k - 1, p.pidx, p.rule_bit, ta, tb, ax, ay, bx, by, kk, vv, taps);
                 key64[p.pcnt + k - 1] = kk;
@@ -667,6 +666,7 @@ __global__ void __launch_bounds__(128) k_long_emit(const FrameParams *__restrict
 // One thread per listed piece (curve, piece >= 1, its first record): the fragment between the last
 // record of the piece before it and its own first record, from the parameters both pieces recorded. Runs after
 // k_walk, when every piece of the frame has left its boundary parameters.
+template <bool FMA>
 __global__ void __launch_bounds__(256) k_piece_fix(const FrameParams *__restrict__ P, const uint32_t *__restrict__ curve_type,
                                                    const uint32_t *__restrict__ curve_pos_map,
                                                    const uint32_t *__restrict__ curve_path, const uint32_t *__restrict__ fill_rule,
@@ -693,8 +693,8 @@ __global__ void __launch_bounds__(256) k_piece_fix(const FrameParams *__restrict
         t0 = (t0 < 0.0f) ? 0.0f : t0;
         t1 = (t1 < 0.0f) ? 0.0f : t1;
         float ax, ay, bx, by;
-        if (full.on()) { eval_point<true>(type, cp, t0, ax, ay); eval_point<true>(type, cp, t1, bx, by); }
-        else { eval_point<false>(type, cp, t0, ax, ay); eval_point<false>(type, cp, t1, bx, by); }
+        if (full.on()) { eval_point<true, FMA>(type, cp, t0, ax, ay); eval_point<true, FMA>(type, cp, t1, bx, by); }
+        else { eval_point<false, FMA>(type, cp, t0, ax, ay); eval_point<false, FMA>(type, cp, t1, bx, by); }
         emit_fragment(env, L, f, pidx, rule_bit, t0, t1, ax, ay, bx, by, key64, val, taps);
     }
 }
