@@ -775,9 +775,12 @@ def main():
         from vkscanlinepr_b200 import scene as S16
         r.close()
         r = None
-        sc16 = S16.synth_16k()
-        bands16k = bands_peer_report(V, PAR, sc16, S16.identity_rows(), 16384, 16384, rank, world, local_rank, dist, stream,
-                                     min(K, 20), 3, "synth_16k")
+        try:
+            sc16 = S16.synth_16k()
+            bands16k = bands_peer_report(V, PAR, sc16, S16.identity_rows(), 16384, 16384, rank, world, local_rank, dist, stream,
+                                         min(K, 20), 3, "synth_16k")
+        except Exception as e:  # the frame-batch line above stands on its own; say what happened instead of losing it
+            bands16k = {"workload": "synth_16k", "error": repr(e)[:500]}
     if rank == 0:
         out = {
             "metric": "Mpixel/s", "value": mpix, "unit": "Mpixel/s", "n_gpus": world, "steps": K, "warmup": Wm,
