@@ -82,7 +82,15 @@ enum {
     SLPR_FLAG_AA4 = 1u << 10,
     /* Never walk long monotone pieces chain by chain (csrc/walk.cuh, k_long_chains / k_long_emit; by default the context
      * turns that on by itself when a frame has few pieces of 62 or more crossings). A scheduling choice: same results. */
-    SLPR_FLAG_NO_LONG_WALK = 1u << 11
+    SLPR_FLAG_NO_LONG_WALK = 1u << 11,
+    /* SURVEY section 8 f-3, beyond the reference (which composites opaque: blendEnable = VK_FALSE, scanline_rasterizer.cpp:893-895,
+     * so a fill's alpha byte only lands in the framebuffer): fills with 0 < alpha < 255 are composited "source over" in
+     * path order onto the white clear colour, per coverage cell — with SLPR_FLAG_AA4 per sample, then averaged. Each
+     * channel is (src * a + dst * (255 - a) + 127) / 255 in integers; alpha 255 overwrites, alpha 0 leaves the pixel
+     * alone; the frame's alpha stays 255. Checked bit for bit against the oracle's orc_set_blend(1). Opaque paths keep the
+     * atomicMax coverage marks; translucent ones append per-cell list nodes from a pool that grows when a frame needs
+     * more (the frame is then rendered again, like a fragment overflow; with band peers: SLPR_ERR_RETRY). */
+    SLPR_FLAG_BLEND = 1u << 12
 };
 
 /* Buffers that slpr_debug_copy() can return. Layouts are the reference's:

@@ -637,8 +637,46 @@ void orc_emit(int32_t nf, const int32_t *key, const int32_t *path, const int32_t
 }
 
 /* ------------------------------------------------------------------ stage 5 */
+/* SURVEY section 8 f-3 (NOT in the reference, which composites opaque: blendEnable = VK_FALSE, SR:893-895): with orc_set_blend(1)
+ * the records are composited "source over" in their order — which is path order — onto the white clear colour:
+ * alpha 255 overwrites (as the reference does), alpha 0 leaves the pixel alone, anything between blends each colour
+ * channel as (src * a + dst * (255 - a) + 127) / 255 in integers; the frame stays opaque (alpha 255). Mirrored bit for
+ * bit by SLPR_FLAG_BLEND (csrc/raster.cuh). Off by default. */
+static int g_blend = 0;
+void orc_set_blend(int on) { g_blend = on; }
+static inline uint32_t blend_over(uint32_t dst, uint32_t src) {
+    uint32_t a = src >> 24;
+    if (a == 255u) return src;
+    if (a == 0u) return dst;
+    uint32_t out = 0xFF000000u;
+    for (int ch = 0; ch < 3; ++ch) {
+        uint32_t s = (src >> (8 * ch)) & 0xFFu, d = (dst >> (8 * ch)) & 0xFFu;
+        out |= ((s * a + d * (255u - a) + 127u) / 255u) << (8 * ch);
+    }
+    return out;
+}
+
 void orc_fill(int64_t n_records, const int32_t *rec, int width, int height, uint8_t *rgba) {
     memset(rgba, 0xFF, (size_t)width * (size_t)height * 4); /* SR:622 clear white */
+    if (g_blend) {
+        for (int64_t r = 0; r < n_records; ++r) {
+            int32_t yx = rec[4 * r], w = rec[4 * r + 1];
+            uint32_t col = (uint32_t)rec[4 * r + 2];
+            int X = yx & 0xFFFF, Y = yx >> 16;
+            int xa = imax(X, 0), xb = imin(X + w, width);
+            for (int row = Y; row <= Y + 1; ++row) {
+                if (row < 0 || row >= height) continue;
+                uint8_t *dst = rgba + ((size_t)(height - 1 - row) * (size_t)width) * 4;
+                for (int x = xa; x < xb; ++x) {
+                    uint32_t d;
+                    memcpy(&d, dst + 4 * (size_t)x, 4);
+                    d = blend_over(d, col);
+                    memcpy(dst + 4 * (size_t)x, &d, 4);
+                }
+            }
+        }
+        return;
+    }
     for (int64_t r = 0; r < n_records; ++r) {
         int32_t yx = rec[4 * r], w = rec[4 * r + 1];
         uint32_t col = (uint32_t)rec[4 * r + 2];

@@ -140,6 +140,10 @@ void orc_set_full_rvg(int on, const float *curve_weight);
  * next to lerpf). NOT pinned by anything of the reference's: no Vulkan driver here to say what it contracts. Process-wide. */
 void orc_set_contract_fma(int on);
 
+/* SURVEY section 8 f-3, off by default: stage 5 composites the records "source over" in path order (integer arithmetic defined in
+ * oracle.c next to orc_fill) instead of the reference's opaque overwrite. Process-wide. */
+void orc_set_blend(int on);
+
 int orc_num_threads(void);
 void orc_set_num_threads(int n);
 

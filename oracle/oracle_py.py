@@ -79,7 +79,7 @@ def _arr(ptr, n, dtype):
 STAGE_NAMES = ("transform", "monotonize", "scan1", "intersect", "gen_fragment", "sort", "spans", "fill")
 
 
-def render(scene, rows, width, height, do_fill=True, threads=None, keep=None, full=False, fma=False):
+def render(scene, rows, width, height, do_fill=True, threads=None, keep=None, full=False, fma=False, blend=False):
     """Run the whole oracle frame. `scene` has the 7 flat loadVG arrays (see scene.Scene).
     Returns a dict of every intermediate buffer (numpy copies); `keep` (a set of names) limits the copies to
     those buffers — on frames of 10^8 fragments the full set is tens of gigabytes."""
@@ -95,6 +95,8 @@ def render(scene, rows, width, height, do_fill=True, threads=None, keep=None, fu
         L.orc_set_full_rvg(C.c_int(1), _p(weights))
     if fma:  # the contracted reading of the shaders (oracle.c, orc_set_contract_fma)
         L.orc_set_contract_fma(C.c_int(1))
+    if blend:  # source-over compositing of translucent fills in path order (oracle.c, orc_set_blend)
+        L.orc_set_blend(C.c_int(1))
     try:
         fp = _call_render(L, s, rows, width, height, do_fill)
     finally:
@@ -102,6 +104,8 @@ def render(scene, rows, width, height, do_fill=True, threads=None, keep=None, fu
             L.orc_set_full_rvg(C.c_int(0), None)
         if fma:
             L.orc_set_contract_fma(C.c_int(0))
+        if blend:
+            L.orc_set_blend(C.c_int(0))
     return _collect(L, fp, s, width, height, do_fill, keep)
 
 
@@ -113,13 +117,13 @@ def box4(rgba_hi):
     return ((cells.sum(axis=(1, 3)) + 2) >> 2).astype(np.uint8)
 
 
-def render_aa4(scene, rows, width, height, full=False):
+def render_aa4(scene, rows, width, height, full=False, blend=False):
     """the definition of SLPR_FLAG_AA4 in terms of the reference path — the frame rendered at four times the
     size (matrix rows 0 and 1 scaled by 4, exactly) and box-filtered. Returns the dict of the 4x frame plus "rgba_aa"."""
     r4 = np.array(rows, dtype=np.float32).reshape(4, 4).copy()
     r4[0] *= np.float32(4.0)
     r4[1] *= np.float32(4.0)
-    out = render(scene, r4, 4 * width, 4 * height, full=full, keep={"rgba"})
+    out = render(scene, r4, 4 * width, 4 * height, full=full, blend=blend, keep={"rgba"})
     out["rgba_aa"] = box4(out["rgba"])
     return out
 
@@ -160,11 +164,17 @@ def _collect(L, fp, s, width, height, do_fill, keep):
     return out
 
 
-def fill(records, width, height):
+def fill(records, width, height, blend=False):
     L = lib()
     rec = np.ascontiguousarray(records, dtype=np.int32).reshape(-1, 4)
     rgba = np.empty((height, width, 4), dtype=np.uint8)
-    L.orc_fill(C.c_int64(rec.shape[0]), _p(rec), C.c_int(width), C.c_int(height), _p(rgba))
+    if blend:
+        L.orc_set_blend(C.c_int(1))
+    try:
+        L.orc_fill(C.c_int64(rec.shape[0]), _p(rec), C.c_int(width), C.c_int(height), _p(rgba))
+    finally:
+        if blend:
+            L.orc_set_blend(C.c_int(0))
     return rgba
 
 

@@ -23,6 +23,7 @@ _LIB = None
 
 FLAG_TAPS, FLAG_CONTRACT_FMA, FLAG_NO_GRAPH, FLAG_RADIX_SORT, FLAG_SEGMENTED_SORT = 1, 2, 4, 8, 16
 FLAG_FUSED_FILL, FLAG_SEPARATE_FILL, FLAG_WINDOWED_WALK, FLAG_RECORDS, FLAG_FULL_RVG, FLAG_AA4, FLAG_NO_LONG_WALK = 32, 64, 128, 256, 512, 1024, 2048
+FLAG_BLEND = 1 << 12          # f-3: translucent fills composited source-over in path order (integer arithmetic of the oracle)
 TAPS = dict(transformed_pos=0, path_visible=1, cut_cache=2, curve_count=3, curve_offset=4, intersection=5,
             key=6, path=7, winding=8, sorted_key=9, sorted_index=10, winding_scan=11, flags=12,
             flag_scan=13, records=14, segments=15)

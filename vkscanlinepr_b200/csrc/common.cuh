@@ -48,7 +48,40 @@ struct FrameCounters {
     int n_live_paths;    // band mode: paths that can reach the band (k_band_paths / k_path_cull), listed for the sort
     int band_void;       // exact bands: 1 = another band's frame was void, 2 = a band never published (timeout),
                          //              3 = more entries than the merge table holds; the frame must be rendered again
+    int n_blend_nodes;   // SLPR_FLAG_BLEND: (cell, translucent path) pairs asked for this frame; more than the node buffer
+                         //              holds = the frame lacks some and is rendered again with a bigger buffer
 };
+
+// SLPR_FLAG_BLEND (beyond the reference, which overwrites: blendEnable = VK_FALSE, SR.cpp:893-895): fills with
+// 0 < alpha < 255 are composited "source over" in path order. Opaque paths keep marking the coverage grid with
+// atomicMax (the top-most opaque path hides everything below it); a translucent path appends one node (its priority,
+// next) to the cell's list; the resolve kernel composites, in ascending priority, the nodes above the opaque top.
+struct BlendList {
+    uint32_t *heads;  // per coverage cell: 0 or node index + 1
+    uint2 *nodes;     // (priority = path + 1 or record index + 1, next)
+    uint32_t cap;
+};
+
+__device__ __forceinline__ void blend_append(const BlendList &bl, size_t cell, uint32_t node, uint32_t prio) {
+    if (node < bl.cap) {
+        const uint32_t prev = atomicExch(bl.heads + cell, node + 1u);
+        bl.nodes[node] = make_uint2(prio, prev);
+    }
+}
+
+// dst, src: R,G,B,A bytes (low to high). The integer arithmetic of oracle/oracle.c blend_over(); the frame stays opaque.
+__device__ __forceinline__ uint32_t blend_over(uint32_t dst, uint32_t src) {
+    const uint32_t a = src >> 24;
+    if (a == 255u) return src;
+    if (a == 0u) return dst;
+    uint32_t out = 0xFF000000u;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        const uint32_t s = (src >> (8 * ch)) & 0xFFu, d = (dst >> (8 * ch)) & 0xFFu;
+        out |= ((s * a + d * (255u - a) + 127u) / 255u) << (8 * ch);
+    }
+    return out;
+}
 
 // The back half of a frame (winding prefix, spans, coverage) must not touch the sorted buffers of a frame the
 // host is going to render again: one whose fragments outgrew the buffers (overflow; nothing was generated) or one

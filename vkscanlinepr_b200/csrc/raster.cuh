@@ -18,10 +18,64 @@ namespace slpr {
 #define SLPR_FILL_NARROW 8 /* records up to this many cells are filled by their own thread (measured: 4 -> 0.162, 8 -> 0.147, 16 -> 0.199 ms) */
 #endif
 
+// The coverage marks of 32 records, one per lane (ncell cells from cell (cx0, cy), priority prio; alpha = the
+// record's alpha byte, looked at only when BLEND): opaque records atomicMax their priority into the cells, narrow
+// ones by their own lane, wide ones by the whole warp. BLEND: translucent records append list nodes instead; the
+// warp allocates the nodes of its narrow records with one atomicAdd, those of a wide span with another.
+template <bool BLEND>
+__device__ __forceinline__ void mark_cells32(uint32_t *__restrict__ cells, int cw, int cx0, int ncell, int cy, uint32_t prio,
+                                             uint32_t alpha, const BlendList &bl, FrameCounters *ctr, uint32_t lane) {
+    bool soft = false;  // translucent
+    if (BLEND) {
+        if (alpha == 0u) ncell = 0;  // fully transparent: leaves no trace
+        soft = ncell > 0 && alpha != 255u;
+    }
+    if (ncell > 0 && ncell <= SLPR_FILL_NARROW && !soft) {
+        uint32_t *row = cells + (size_t)cy * cw + cx0;
+        for (int c = 0; c < ncell; ++c) atomicMax(row + c, prio);
+    }
+    if (BLEND && __any_sync(0xFFFFFFFFu, soft && ncell <= SLPR_FILL_NARROW)) {
+        const int need = (soft && ncell <= SLPR_FILL_NARROW) ? ncell : 0;
+        int incl = need;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if ((int)lane >= d) incl += o;
+        }
+        uint32_t base = 0;
+        if (lane == 31) base = (uint32_t)atomicAdd(&ctr->n_blend_nodes, incl);
+        base = __shfl_sync(0xFFFFFFFFu, base, 31) + (uint32_t)(incl - need);
+        const size_t cell0 = (size_t)cy * cw + cx0;
+        for (int c = 0; c < need; ++c) blend_append(bl, cell0 + c, base + (uint32_t)c, prio);
+    }
+    // wide spans: the whole warp fills them, one after the other
+    uint32_t wide = __ballot_sync(0xFFFFFFFFu, ncell > SLPR_FILL_NARROW);
+    const uint32_t wide_soft = BLEND ? __ballot_sync(0xFFFFFFFFu, soft) : 0u;
+    while (wide) {
+        const int src = __ffs(wide) - 1;
+        wide &= wide - 1;
+        const int s_cx0 = __shfl_sync(0xFFFFFFFFu, cx0, src);
+        const int s_n = __shfl_sync(0xFFFFFFFFu, ncell, src);
+        const int s_cy = __shfl_sync(0xFFFFFFFFu, cy, src);
+        const uint32_t s_prio = __shfl_sync(0xFFFFFFFFu, prio, src);
+        if (BLEND && ((wide_soft >> src) & 1u)) {
+            uint32_t base = 0;
+            if (lane == 0) base = (uint32_t)atomicAdd(&ctr->n_blend_nodes, s_n);
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            const size_t cell0 = (size_t)s_cy * cw + s_cx0;
+            for (int c = (int)lane; c < s_n; c += 32) blend_append(bl, cell0 + c, base + (uint32_t)c, s_prio);
+            continue;
+        }
+        uint32_t *row = cells + (size_t)s_cy * cw + s_cx0;
+        for (int c = (int)lane; c < s_n; c += 32) atomicMax(row + c, s_prio);
+    }
+}
+
+template <bool BLEND>
 __global__ void __launch_bounds__(256) k_fill_cells(const FrameParams *__restrict__ P,
-                                                    const FrameCounters *__restrict__ ctr, int capacity,
+                                                    FrameCounters *__restrict__ ctr, int capacity,
                                                     const int4 *__restrict__ records, uint32_t *__restrict__ cells,
-                                                    int cw) {
+                                                    int cw, BlendList bl) {
     if (frame_void(ctr, capacity)) return;
     const int nrec = ctr->n_records;
     const int nround = (nrec + 31) & ~31;
@@ -29,8 +83,10 @@ __global__ void __launch_bounds__(256) k_fill_cells(const FrameParams *__restric
     const uint32_t lane = lane_id();
     for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nround; r += gridDim.x * blockDim.x) {
         int cx0 = 0, ncell = 0, cy = 0;
+        uint32_t alpha = 255u;
         if (r < nrec) {
             const int4 rec = records[r];
+            if (BLEND) alpha = (uint32_t)rec.z >> 24;
             const int X = rec.x & 0xFFFF, Y = rec.x >> 16;  // VERT:27
             if (Y >= 0 && Y < height) {
                 cx0 = X >> 1;
@@ -38,34 +94,40 @@ __global__ void __launch_bounds__(256) k_fill_cells(const FrameParams *__restric
                 cy = Y >> 1;
             }
         }
-        const uint32_t prio = (uint32_t)r + 1u;
-        if (ncell > 0 && ncell <= SLPR_FILL_NARROW) {
-            uint32_t *row = cells + (size_t)cy * cw + cx0;
-            for (int c = 0; c < ncell; ++c) atomicMax(row + c, prio);
-        }
-        // wide spans: the whole warp fills them, one after the other
-        uint32_t wide = __ballot_sync(0xFFFFFFFFu, ncell > SLPR_FILL_NARROW);
-        while (wide) {
-            const int src = __ffs(wide) - 1;
-            wide &= wide - 1;
-            const int s_cx0 = __shfl_sync(0xFFFFFFFFu, cx0, src);
-            const int s_n = __shfl_sync(0xFFFFFFFFu, ncell, src);
-            const int s_cy = __shfl_sync(0xFFFFFFFFu, cy, src);
-            const uint32_t s_prio = __shfl_sync(0xFFFFFFFFu, prio, src);
-            uint32_t *row = cells + (size_t)s_cy * cw + s_cx0;
-            for (int c = (int)lane; c < s_n; c += 32) atomicMax(row + c, s_prio);
-        }
+        mark_cells32<BLEND>(cells, cw, cx0, ncell, cy, (uint32_t)r + 1u, alpha, bl, ctr, lane);
     }
 }
 
 // One thread resolves two horizontally adjacent cells = 4 pixels on 2 image rows. A cell holds 0 (empty) or, + 1,
 // the index of the last record that covers it (BY_PATH false: marked by k_fill_cells) or the highest path that
 // covers it (BY_PATH true: marked by k_spans<true, .>); its colour is that record's / that path's.
+// SLPR_FLAG_BLEND: the colour of one cell = white, or its top-most opaque record / path, with the translucent ones above
+// it composited in ascending priority (blend_over). The list is unordered (atomicExch pushes); it is walked once per
+// entry composited, each walk picking the smallest priority not yet done — lists are a handful of nodes long.
 template <bool BY_PATH>
+__device__ __forceinline__ uint32_t composite_cell(uint32_t top, uint32_t head, const uint2 *__restrict__ nodes,
+                                                   const int4 *__restrict__ records, const uint32_t *__restrict__ fill_info) {
+    uint32_t dst = top ? (BY_PATH ? fill_info[top - 1] : (uint32_t)records[top - 1].z) : 0xFFFFFFFFu;
+    uint32_t last = top;
+    while (head) {
+        uint32_t best = 0xFFFFFFFFu;
+        for (uint32_t n = head; n; ) {
+            const uint2 nd = nodes[n - 1];
+            if (nd.x > last && nd.x < best) best = nd.x;
+            n = nd.y;
+        }
+        if (best == 0xFFFFFFFFu) break;
+        dst = blend_over(dst, BY_PATH ? fill_info[best - 1] : (uint32_t)records[best - 1].z);
+        last = best;
+    }
+    return dst;
+}
+
+template <bool BY_PATH, bool BLEND>
 __global__ void __launch_bounds__(256) k_resolve(const FrameParams *__restrict__ P, const int4 *__restrict__ records,
                                                  const uint32_t *__restrict__ fill_info,
                                                  uint32_t *__restrict__ cells, int cw, uint8_t *__restrict__ fb,
-                                                 size_t stride_bytes) {
+                                                 size_t stride_bytes, BlendList bl) {
     const int width = P->width, height = P->height;
     const int cy0 = P->band_y0 >> 1, cy1 = (P->band_y1 + 1) >> 1;
     const int pairs = (cw + 1) >> 1;
@@ -80,7 +142,13 @@ __global__ void __launch_bounds__(256) k_resolve(const FrameParams *__restrict__
             col[k] = 0xFFFFFFFFu;  // clear colour (1,1,1,1), SR.cpp:622
             if (cx + k < cw) {
                 const uint32_t v = cp[k];
-                if (v) { col[k] = BY_PATH ? fill_info[v - 1] : (uint32_t)records[v - 1].z; cp[k] = 0; }  // colour bytes R,G,B,A = fill_info (VERT:8-10)
+                if (BLEND) {
+                    uint32_t *hp = bl.heads + (size_t)cy * cw + cx + k;
+                    const uint32_t head = *hp;
+                    if (head) *hp = 0;
+                    if (v) cp[k] = 0;
+                    col[k] = composite_cell<BY_PATH>(v, head, bl.nodes, records, fill_info);
+                } else if (v) { col[k] = BY_PATH ? fill_info[v - 1] : (uint32_t)records[v - 1].z; cp[k] = 0; }  // colour bytes R,G,B,A = fill_info (VERT:8-10)
             }
         }
         const int px = cx * 2;
@@ -104,10 +172,10 @@ __global__ void __launch_bounds__(256) k_resolve(const FrameParams *__restrict__
 // the pipeline ran at four times the frame's size, so every pixel of the frame is 2 x 2 coverage cells = four samples on
 // a regular grid, each holding the top-most path that covers it (ordered, opaque compositing per sample); the pixel is
 // their box-filtered average, (sum + 2) >> 2 per channel. One thread per pixel; the cells are re-zeroed.
-template <bool BY_PATH>
+template <bool BY_PATH, bool BLEND>
 __global__ void __launch_bounds__(256) k_resolve_aa4(const FrameParams *__restrict__ P, const int4 *__restrict__ records,
                                                      const uint32_t *__restrict__ fill_info, uint32_t *__restrict__ cells, int cw,
-                                                     uint8_t *__restrict__ fb, size_t stride_bytes, int out_w, int out_h) {
+                                                     uint8_t *__restrict__ fb, size_t stride_bytes, int out_w, int out_h, BlendList bl) {
     const int y_lo = P->band_y0 >> 2, y_hi = (P->band_y1 + 3) >> 2;  // output scanline rows of the band
     const long long total = (long long)out_w * (y_hi - y_lo);
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
@@ -119,10 +187,17 @@ __global__ void __launch_bounds__(256) k_resolve_aa4(const FrameParams *__restri
             uint2 *cp = reinterpret_cast<uint2 *>(cells + (size_t)(2 * y + dy) * cw + 2 * x);  // cw is even (4 x width / 2)
             const uint2 v = *cp;
             if (v.x | v.y) *cp = make_uint2(0u, 0u);
+            uint2 hd = make_uint2(0u, 0u);
+            if (BLEND) {
+                uint2 *hp = reinterpret_cast<uint2 *>(bl.heads + (size_t)(2 * y + dy) * cw + 2 * x);
+                hd = *hp;
+                if (hd.x | hd.y) *hp = make_uint2(0u, 0u);
+            }
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 const uint32_t id = k ? v.y : v.x;
-                const uint32_t col = id ? (BY_PATH ? fill_info[id - 1] : (uint32_t)records[id - 1].z) : 0xFFFFFFFFu;
+                const uint32_t col = BLEND ? composite_cell<BY_PATH>(id, k ? hd.y : hd.x, bl.nodes, records, fill_info)
+                                           : id ? (BY_PATH ? fill_info[id - 1] : (uint32_t)records[id - 1].z) : 0xFFFFFFFFu;
 #pragma unroll
                 for (int ch = 0; ch < 4; ++ch) sum[ch] += (col >> (8 * ch)) & 0xFFu;
             }

@@ -140,6 +140,9 @@ struct slpr_ctx {
 
     uint32_t *d_cells = nullptr;
     int cw = 0, ch = 0;
+    uint32_t *d_heads = nullptr;       // SLPR_FLAG_BLEND: per-cell list heads, the node pool and its size (grown on demand)
+    uint2 *d_nodes = nullptr;
+    uint32_t node_cap = 0;
     uint8_t *d_fb = nullptr;
     uint8_t *d_fb2 = nullptr;          // second framebuffer of the pipelined host path (lazy)
     uint8_t *fb_cur = nullptr;         // framebuffer the next frame renders into (d_fb unless pipelining)
@@ -154,6 +157,7 @@ struct slpr_ctx {
         uint8_t *rgba = nullptr;
         size_t stride = 0;
         bool in_flight = false, was_radix = false;
+        uint32_t node_cap = 0;       // SLPR_FLAG_BLEND: the node pool this frame was rendered with
         FrameCounters *h = nullptr;  // pinned: this frame's counters, copied right behind its kernels
     } pslot[2];
     uint64_t pipe_redone = 0;          // frames the pipelined path had to render twice
@@ -338,6 +342,12 @@ extern "C" slpr_ctx *slpr_create(int device, uint32_t width, uint32_t height, ui
     c->cw = (int)(c->iW + 1) / 2; c->ch = (int)(c->iH + 1) / 2;
     ok = ok && cudaMalloc(&c->d_cells, (size_t)c->cw * c->ch * 4) == cudaSuccess;
     ok = ok && cudaMemset(c->d_cells, 0, (size_t)c->cw * c->ch * 4) == cudaSuccess;
+    if (flags & SLPR_FLAG_BLEND) {
+        c->node_cap = (uint32_t)std::max<size_t>((size_t)1 << 20, (size_t)c->cw * c->ch);
+        ok = ok && cudaMalloc(&c->d_heads, (size_t)c->cw * c->ch * 4) == cudaSuccess;
+        ok = ok && cudaMemset(c->d_heads, 0, (size_t)c->cw * c->ch * 4) == cudaSuccess;
+        ok = ok && cudaMalloc(&c->d_nodes, (size_t)c->node_cap * sizeof(uint2)) == cudaSuccess;
+    }
     c->fb_stride = (size_t)width * 4;
     ok = ok && cudaMalloc(&c->d_fb, c->fb_stride * height) == cudaSuccess;
     c->fb_cur = c->d_fb;
@@ -350,7 +360,8 @@ extern "C" slpr_ctx *slpr_create(int device, uint32_t width, uint32_t height, ui
     }
     ok = ok && cudaFuncSetAttribute(k_scan_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->scan_tma_blocks_per_sm, k_scan_tma, ST_THREADS, ST_SMEM_BYTES) == cudaSuccess;
-    for (auto fn : {k_spans<false, true, false>, k_spans<true, true, false>, k_spans<true, false, false>, k_spans<false, true, true>, k_spans<true, true, true>})
+    for (auto fn : {k_spans<false, true, false>, k_spans<true, true, false>, k_spans<true, false, false>, k_spans<false, true, true>, k_spans<true, true, true>,
+                    k_spans<true, true, false, true>, k_spans<true, false, false, true>, k_spans<true, true, true, true>})
         ok = ok && cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_STAGE_BYTES) == cudaSuccess;
     ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->span_blocks_per_sm, k_spans<true, false, false>, SP_THREADS, SP_STAGE_BYTES) == cudaSuccess;
     if (!ok) {
@@ -376,7 +387,7 @@ extern "C" void slpr_destroy(slpr_ctx *c) {
     cudaFree(c->p_box); cudaFree(c->p_list); cudaFree(c->p_tab_path); cudaFree(c->p_tab_cum); cudaFree(c->p_tab_n); cudaFree(c->p_tab_z);
     free_capacity(c);
     free_scene(c);
-    cudaFree(c->d_params); cudaFreeHost(c->h_ctr); cudaFreeHost(c->pslot[0].h); cudaFreeHost(c->pslot[1].h); cudaFree(c->d_cells); cudaFree(c->d_fb); cudaFree(c->d_fb2); cudaFree(c->d_prim_temp);
+    cudaFree(c->d_params); cudaFreeHost(c->h_ctr); cudaFreeHost(c->pslot[0].h); cudaFreeHost(c->pslot[1].h); cudaFree(c->d_cells); cudaFree(c->d_heads); cudaFree(c->d_nodes); cudaFree(c->d_fb); cudaFree(c->d_fb2); cudaFree(c->d_prim_temp);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     for (int i = 0; i < 2; ++i) { if (c->ev_rendered[i]) cudaEventDestroy(c->ev_rendered[i]); if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]); }
     for (int i = 0; i < 2; ++i) { if (c->ev_band_rendered[i]) cudaEventDestroy(c->ev_band_rendered[i]); if (c->ev_band_pushed[i]) cudaEventDestroy(c->ev_band_pushed[i]); }
@@ -727,10 +738,14 @@ static int enqueue_back(slpr_ctx *c, cudaStream_t s, bool timed, int &launches) 
 #endif
     if (timed) CU(cudaEventRecord(c->ev[8], s));
     const int span_grid = c->num_sms * std::max(1, c->span_blocks_per_sm);
+    const bool blend = (c->flags & SLPR_FLAG_BLEND) != 0;
+    const BlendList bl{c->d_heads, c->d_nodes, c->node_cap};
     auto spans = taps ? (c->fill_fused ? k_spans<true, true, true> : k_spans<false, true, true>)
                       : !c->fill_fused ? k_spans<false, true, false> : (want_records(c) ? k_spans<true, true, false> : k_spans<true, false, false>);
+    if (blend && c->fill_fused)
+        spans = taps ? k_spans<true, true, true, true> : (want_records(c) ? k_spans<true, true, false, true> : k_spans<true, false, false, true>);
     spans<<<span_grid, SP_THREADS, SP_STAGE_BYTES, s>>>(c->d_key[cur], c->d_val[cur], c->d_finfo, c->d_rec, c->d_ctr, c->L, (int)c->iW, (int)c->iH,
-                                                       c->cap, stp, stmp, corr, c->P, c->d_cells, c->cw, btab);
+                                                       c->cap, stp, stmp, corr, c->P, c->d_cells, c->cw, btab, bl);
     ++launches;
     if (taps) {
         k_scan3_fixup<<<wide, 256, 0, s>>>(c->d_ctr, c->cap, c->t_scan3);
@@ -741,15 +756,20 @@ static int enqueue_back(slpr_ctx *c, cudaStream_t s, bool timed, int &launches) 
     uint8_t *fb = c->target ? c->target : c->fb_cur;
     const size_t stride = c->target ? c->target_stride : c->fb_stride;
     if (!c->fill_fused) {  // small frames: a grid-wide pass over the records spreads the few wide spans better
-        k_fill_cells<<<wide, 256, 0, s>>>(c->d_params, c->d_ctr, c->cap, c->d_rec, c->d_cells, c->cw);
+        if (blend) k_fill_cells<true><<<wide, 256, 0, s>>>(c->d_params, c->d_ctr, c->cap, c->d_rec, c->d_cells, c->cw, bl);
+        else k_fill_cells<false><<<wide, 256, 0, s>>>(c->d_params, c->d_ctr, c->cap, c->d_rec, c->d_cells, c->cw, bl);
         ++launches;
     }
     if (timed) CU(cudaEventRecord(c->ev[10], s));
     if (c->ss == 4) {  // SLPR_FLAG_AA4: 2 x 2 cells of the 4x frame -> one pixel (box filter)
-        if (c->fill_fused) k_resolve_aa4<true><<<wide, 256, 0, s>>>(c->d_params, c->d_rec, c->d_finfo, c->d_cells, c->cw, fb, stride, (int)c->W, (int)c->H);
-        else k_resolve_aa4<false><<<wide, 256, 0, s>>>(c->d_params, c->d_rec, c->d_finfo, c->d_cells, c->cw, fb, stride, (int)c->W, (int)c->H);
-    } else if (c->fill_fused) k_resolve<true><<<wide, 256, 0, s>>>(c->d_params, c->d_rec, c->d_finfo, c->d_cells, c->cw, fb, stride);
-    else k_resolve<false><<<wide, 256, 0, s>>>(c->d_params, c->d_rec, c->d_finfo, c->d_cells, c->cw, fb, stride);
+        auto resolve = c->fill_fused ? (blend ? k_resolve_aa4<true, true> : k_resolve_aa4<true, false>)
+                                     : (blend ? k_resolve_aa4<false, true> : k_resolve_aa4<false, false>);
+        resolve<<<wide, 256, 0, s>>>(c->d_params, c->d_rec, c->d_finfo, c->d_cells, c->cw, fb, stride, (int)c->W, (int)c->H, bl);
+    } else {
+        auto resolve = c->fill_fused ? (blend ? k_resolve<true, true> : k_resolve<true, false>)
+                                     : (blend ? k_resolve<false, true> : k_resolve<false, false>);
+        resolve<<<wide, 256, 0, s>>>(c->d_params, c->d_rec, c->d_finfo, c->d_cells, c->cw, fb, stride, bl);
+    }
     ++launches;
     if (timed) CU(cudaEventRecord(c->ev[11], s));
     if (!c->x_sums && c->peers.n_bands > 0 && c->peers.root >= 0 && c->peers.root != c->peers.me) {  // gather by direct stores: tell the root this band's pixels are in place
@@ -950,6 +970,23 @@ static int settle_modes(slpr_ctx *c, const FrameCounters &k) {
     return SLPR_OK;
 }
 
+// SLPR_FLAG_BLEND: did the frame ask for more list nodes than the pool holds? Then it lacks some translucent
+// coverage and must be rendered again; grow_nodes() makes the pool fit that frame (plus a quarter).
+static bool nodes_short(const slpr_ctx *c, const FrameCounters &k, uint32_t pool) {
+    return (c->flags & SLPR_FLAG_BLEND) && (k.n_blend_nodes < 0 || (uint32_t)k.n_blend_nodes > pool);
+}
+
+static int grow_nodes(slpr_ctx *c, const FrameCounters &k) {
+    const long long need = k.n_blend_nodes;
+    if (need < 0 || need >= (1ll << 30)) return fail(SLPR_ERR_INVALID, "frame needs %lld blend nodes; limit is 2^30", need);
+    CU(cudaStreamSynchronize(c->stream));
+    cudaFree(c->d_nodes); c->d_nodes = nullptr;
+    c->node_cap = (uint32_t)std::min<long long>(need + need / 4 + 65536, (1ll << 30));
+    CU(cudaMalloc(&c->d_nodes, (size_t)c->node_cap * sizeof(uint2)));
+    invalidate_graphs(c);
+    return SLPR_OK;
+}
+
 // Exact bands with the device-side exchange: a band cannot redo a frame on its own (the other bands have consumed
 // what it published), so a void frame is reported and the caller renders it again on every band with a new seq.
 static int finish_peer_frame(slpr_ctx *c) {
@@ -967,6 +1004,11 @@ static int finish_peer_frame(slpr_ctx *c) {
         c->radix_mode = true;
         invalidate_graphs(c);
         return fail(SLPR_ERR_RETRY, "band %d has a path too long for the segmented sort (now radix): render the frame again on every band", c->peers.me);
+    }
+    if (nodes_short(c, k, c->node_cap)) {
+        int rc = grow_nodes(c, k);
+        if (rc) return rc;
+        return fail(SLPR_ERR_RETRY, "band %d outgrew its blend node pool (now %u): render the frame again on every band", c->peers.me, c->node_cap);
     }
     if (k.band_void == 2) return fail(SLPR_ERR_STATE, "band %d: another band did not publish its winding sums within the time-out", c->peers.me);
     if (k.band_void) return fail(SLPR_ERR_RETRY, "band %d: the frame was void on another band (%d): render it again on every band", c->peers.me, k.band_void);
@@ -995,6 +1037,12 @@ static int finish_frame(slpr_ctx *c) {
             c->radix_mode = true;
             invalidate_graphs(c);
             int rc2 = slpr_render(c);
+            if (rc2) return rc2;
+            continue;
+        }
+        if (!c->h_ctr->overflow && nodes_short(c, *c->h_ctr, c->node_cap)) {
+            int rc2 = grow_nodes(c, *c->h_ctr);
+            if (!rc2) rc2 = slpr_render(c);
             if (rc2) return rc2;
             continue;
         }
@@ -1048,8 +1096,8 @@ extern "C" int slpr_render_to_host(slpr_ctx *c, const float rows[16], uint8_t *r
 // or one of its paths outgrew the segmented sort — both common in an animation that zooms in). Its counters
 // are copied into the slot right behind its kernels; they are looked at when the slot comes round again and in
 // slpr_wait_host, and an invalid frame is then rendered again, synchronously, into the caller's buffer.
-static bool slot_invalid(const slpr_ctx::PipeSlot &p) {
-    return p.in_flight && (p.h->overflow || (p.h->sort_fallback && !p.was_radix));
+static bool slot_invalid(const slpr_ctx *c, const slpr_ctx::PipeSlot &p) {
+    return p.in_flight && (p.h->overflow || (p.h->sort_fallback && !p.was_radix) || nodes_short(c, *p.h, p.node_cap));
 }
 
 static int pipe_recover(slpr_ctx *c, int first_slot) {
@@ -1060,7 +1108,7 @@ static int pipe_recover(slpr_ctx *c, int first_slot) {
     uint8_t *const fb_keep = c->fb_cur;
     for (int i = 0; i < 2; ++i) {  // older frame first
         slpr_ctx::PipeSlot &p = c->pslot[(first_slot + i) & 1];
-        const bool bad = slot_invalid(p);
+        const bool bad = slot_invalid(c, p);
         p.in_flight = false;
         if (!bad) continue;
         c->fb_cur = ((first_slot + i) & 1) ? c->d_fb2 : c->d_fb;
@@ -1094,7 +1142,7 @@ extern "C" int slpr_submit_to_host(slpr_ctx *c, const float rows[16], uint8_t *r
     slpr_ctx::PipeSlot &slot = c->pslot[k];
     if (slot.in_flight) {  // the frame submitted two calls ago: finished long since; was it whole?
         CU(cudaEventSynchronize(c->ev_rendered[k]));
-        if (slot_invalid(slot)) {
+        if (slot_invalid(c, slot)) {
             int rc = pipe_recover(c, k);
             if (rc) return rc;
         } else if (slot.was_radix == c->radix_mode) {  // (not while a mode change is still working its way through the pipeline)
@@ -1112,7 +1160,7 @@ extern "C" int slpr_submit_to_host(slpr_ctx *c, const float rows[16], uint8_t *r
     if (!rc) rc = slpr_render(c);
     if (rc) return rc;
     memcpy(slot.rows, rows, sizeof slot.rows);
-    slot.rgba = rgba; slot.stride = stride_bytes; slot.was_radix = c->radix_mode; slot.in_flight = true;
+    slot.rgba = rgba; slot.stride = stride_bytes; slot.was_radix = c->radix_mode; slot.node_cap = c->node_cap; slot.in_flight = true;
     CU(cudaMemcpyAsync(slot.h, c->d_ctr, sizeof(FrameCounters), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaEventRecord(c->ev_rendered[k], c->stream));
     CU(cudaStreamWaitEvent(c->copy_stream, c->ev_rendered[k], 0));

@@ -133,14 +133,15 @@ __device__ __forceinline__ KeyFields decode_key(const KeyLayout &L, uint64_t k) 
 //       wins" (opaque overwrite in primitive order, SR.cpp:893-895) is "the highest path wins", and k_resolve
 //       finds the colour in fill_info[path]. Nobody then reads the 16-byte draw records, so they are
 // REC:  only written when asked for (SLPR_FLAG_RECORDS / taps), or for the separate coverage pass (!FILL).
-template <bool FILL, bool REC, bool TAPS>
+// BLEND (with FILL): translucent paths append list nodes instead (SLPR_FLAG_BLEND, raster.cuh mark_cells32).
+template <bool FILL, bool REC, bool TAPS, bool BLEND = false>
 __global__ void __launch_bounds__(SP_THREADS, SP_BLOCKS) k_spans(const uint64_t *__restrict__ skey,
                                                          const uint32_t *__restrict__ sval,
                                                          const uint32_t *__restrict__ fill_info,
                                                          int4 *__restrict__ records, FrameCounters *__restrict__ ctr,
                                                          KeyLayout L, int width, int height, int capacity, SpanTaps taps,
                                                          SpanTemp tmp, const int *__restrict__ band_corr, uint32_t n_paths,
-                                                         uint32_t *__restrict__ cells, int cw, BandTable btab) {
+                                                         uint32_t *__restrict__ cells, int cw, BandTable btab, BlendList bl) {
     __shared__ uint32_t s_warp[SP_THREADS / 32];
     __shared__ unsigned long long s_prefix;
     __shared__ long long s_tile;
@@ -405,7 +406,7 @@ __global__ void __launch_bounds__(SP_THREADS, SP_BLOCKS) k_spans(const uint64_t 
             for (uint32_t q0 = 0; q0 < wtot; q0 += 32) {
                 const uint32_t q = q0 + (uint32_t)lane;
                 int cx0 = 0, ncell = 0, cy = 0;
-                uint32_t prio = 0;
+                uint32_t prio = 0, alpha = 255u;
                 if (q < wtot) {
                     const uint32_t pos = wp[q], w1 = wp[SP_WARP_RECORDS + q], ord = w1 >> 16, path = wp[2 * SP_WARP_RECORDS + q];
                     if (REC)
@@ -419,25 +420,10 @@ __global__ void __launch_bounds__(SP_THREADS, SP_BLOCKS) k_spans(const uint64_t 
                             cy = Y >> 1;
                         }
                         prio = path + 1u;
+                        if (BLEND && ncell > 0) alpha = fill_info[path] >> 24;
                     }
                 }
-                if (FILL) {
-                    if (ncell > 0 && ncell <= SLPR_FILL_NARROW) {
-                        uint32_t *row = cells + (size_t)cy * cw + cx0;
-                        for (int c = 0; c < ncell; ++c) atomicMax(row + c, prio);
-                    }
-                    uint32_t wide = __ballot_sync(0xFFFFFFFFu, ncell > SLPR_FILL_NARROW);
-                    while (wide) {
-                        const int src = __ffs(wide) - 1;
-                        wide &= wide - 1;
-                        const int s_cx0 = __shfl_sync(0xFFFFFFFFu, cx0, src);
-                        const int s_n = __shfl_sync(0xFFFFFFFFu, ncell, src);
-                        const int s_cy = __shfl_sync(0xFFFFFFFFu, cy, src);
-                        const uint32_t s_prio = __shfl_sync(0xFFFFFFFFu, prio, src);
-                        uint32_t *row = cells + (size_t)s_cy * cw + s_cx0;
-                        for (int c = lane; c < s_n; c += 32) atomicMax(row + c, s_prio);
-                    }
-                }
+                if (FILL) mark_cells32<BLEND>(cells, cw, cx0, ncell, cy, prio, alpha, bl, ctr, (uint32_t)lane);
             }
         }
         __syncwarp();
