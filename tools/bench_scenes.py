@@ -42,7 +42,8 @@ for name in scenes:
 # the shipped scenes only the complete RVG reader can load (SLPR_FLAG_FULL_RVG), and f-3: 4 samples per pixel
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import util  # noqa: E402
-for name, extra, label in (("car", V.FLAG_FULL_RVG, "full-RVG"), ("chord", V.FLAG_FULL_RVG, "full-RVG"), ("car", V.FLAG_FULL_RVG | V.FLAG_AA4, "full-RVG + AA4")):
+for name, extra, label in (("car", V.FLAG_FULL_RVG, "full-RVG"), ("chord", V.FLAG_FULL_RVG, "full-RVG"), ("car", V.FLAG_FULL_RVG | V.FLAG_AA4, "full-RVG + AA4"),
+                           ("car", V.FLAG_FULL_RVG | V.FLAG_BLEND, "full-RVG + blend"), ("car", V.FLAG_FULL_RVG | V.FLAG_BLEND | V.FLAG_AA4, "full-RVG + blend + AA4")):
     sc, vp = util.full_golden_scene(name)
     for W, H in sizes[1:]:
         if (extra & V.FLAG_AA4) and W > 1920:
@@ -59,7 +60,8 @@ for name, extra, label in (("car", V.FLAG_FULL_RVG, "full-RVG"), ("chord", V.FLA
         ms = e0.elapsed_time(e1) / frames
         img = r.readback(); cnt = r.counts()
         t = time.perf_counter()
-        ref = O.render_aa4(sc, rows, W, H, full=True) if extra & V.FLAG_AA4 else O.render(sc, rows, W, H, full=True, keep={"rgba"})
+        bl = bool(extra & V.FLAG_BLEND)
+        ref = O.render_aa4(sc, rows, W, H, full=True, blend=bl) if extra & V.FLAG_AA4 else O.render(sc, rows, W, H, full=True, blend=bl, keep={"rgba"})
         tor = (time.perf_counter() - t) * 1e3
         same = np.array_equal(img, ref["rgba_aa"] if extra & V.FLAG_AA4 else ref["rgba"]) and cnt["n_fragments"] == ref["n_fragments"]
         print(f"| {name} ({label}) | {W}x{H} | {sc.n_curves} | {cnt['n_fragments']} | {cnt['n_out_frag'] + cnt['n_span']} | {ms:.3f} | {W*H/ms/1e3:.0f} | "

@@ -31,7 +31,7 @@ for sc in scenes:
     # three scenes here have one, so this line is information, not a check (the parity tests cover exact bands)
     print(sc.name, "independent bands equal full frame:", bool(np.array_equal(full, imgs[sc.name])))
 # round 2: exact bands with the device-side exchange (mailboxes, merge table, fused sums in the band sort, copy-engine
-# push), the long-piece walk, the full-RVG arithmetic, the 4x supersampled resolve, the long-path fall-back on default
+# push), the long-piece walk, the full-RVG arithmetic, the 4x supersampled resolve, the blend lists, the long-path fall-back on default
 # flags, and the stand-alone primitives (ticketed scan, TMA-pipelined scan, radix sort)
 import torch
 from vkscanlinepr_b200 import parallel as PAR
@@ -72,6 +72,11 @@ qa = util.quad_arc_scene(80, W, H)
 for flags in (V.FLAG_FULL_RVG, V.FLAG_FULL_RVG | V.FLAG_AA4, V.FLAG_AA4 | V.FLAG_SEPARATE_FILL):
     r = V.ScanlineRasterizer(0, flags).initialize(None, W, H)
     r.loadVG(qa); r.setMVP(S.identity_rows()); r.render(); r.render(); r.readback(); r.close()
+import dataclasses
+qb = dataclasses.replace(qa, fill_info=(qa.fill_info & np.uint32(0x00FFFFFF)) | ((np.arange(len(qa.fill_info), dtype=np.uint32) * np.uint32(37) % np.uint32(256)) << np.uint32(24)))
+for flags in (V.FLAG_BLEND, V.FLAG_BLEND | V.FLAG_SEPARATE_FILL, V.FLAG_BLEND | V.FLAG_AA4):   # translucent fills: node lists
+    r = V.ScanlineRasterizer(0, flags | V.FLAG_FULL_RVG).initialize(None, W, H)
+    r.loadVG(qb); r.setMVP(S.identity_rows()); r.render(); r.render(); r.readback(); r.close()
 r = V.ScanlineRasterizer(0, 0).initialize(None, 64, 64)
 for n in (5, 100_003, (1 << 22) + 8192 * 3 + 5):
     a = torch.randint(0, 4, (n,), dtype=torch.int32, device="cuda"); o = torch.empty(n + 1, dtype=torch.int32, device="cuda")

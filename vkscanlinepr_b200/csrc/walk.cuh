@@ -474,6 +474,102 @@ __global__ void __launch_bounds__(WALK_THREADS, SLPR_WALK_MIN_BLOCKS) k_walk(con
     }
 }
 
+// One crossing, solved by a whole warp: the bisection of MI1:392-436 is a chain of 24 dependent evaluations (about 57
+// cycles each on one lane — what a frame of few, long curves waits for). A warp runs it five steps at a time: lane L
+// in 1..31 is node L of the binary tree of possible outcomes of the next five steps (depth d = floor(log2 L); the bits
+// of L below the leading one are the decisions taken on the way down, 1 = "t0 moves"), derives that node's bracket with
+// the same (t0 + t1) * 0.5 roundings the sequential loop would perform along that path, and evaluates the curve at
+// its midpoint. One ballot collects the 31 sign tests; the leaf whose ancestors all decided the way its index says
+// holds the bracket after the five steps and hands it to the warp. Every value is produced by the same operations, in
+// the same order, as in solve_crossing — only the evaluations that the sequential loop would not have reached are
+// thrown away. 24 steps = 4 rounds of five and one of four: ~1.7 x faster than one lane (profiles/README.md).
+// ev(t) must be solve_crossing's evaluator for the curve type; returns the parameter for all lanes.
+#ifndef SLPR_LONG_WARP
+#define SLPR_LONG_WARP 1
+#endif
+#ifndef SLPR_TREE_BCAST
+#define SLPR_TREE_BCAST 1
+#endif
+// What a lane needs to know about its node, computed once per kernel; selections by lane-constant conditions are
+// bitwise (one LOP3 on a mask register) so that no predicate has to be kept or recomputed inside the rounds.
+__device__ __forceinline__ float bsel(uint32_t m, float a, float b) { return u2f((f2u(a) & m) | (f2u(b) & ~m)); }
+struct TreeLane {
+    uint32_t right[4];  // all ones: the path to this node goes right (t0 moves) at level k; 0: left, or below the node
+    uint32_t at[5];     // all ones at this node's depth (lane 0 evaluates the root a second time, unused)
+    uint32_t amask, aexp;  // the ballot bits of this node's ancestors, and what they must read for the bisection to come here
+    bool leaf5, leaf4;     // last level of a five-step / four-step round
+    __device__ __forceinline__ explicit TreeLane(uint32_t lane) {
+        const int d = lane ? 31 - __clz((int)lane) : 0;
+        amask = aexp = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const bool r = lane && k < d && ((lane >> (d - 1 - k)) & 1u);
+            right[k] = r ? 0xFFFFFFFFu : 0u;
+            if (lane && k < d) { amask |= 1u << (lane >> (d - k)); if (r) aexp |= 1u << (lane >> (d - k)); }
+        }
+#pragma unroll
+        for (int k = 0; k < 5; ++k) at[k] = (k == d) ? 0xFFFFFFFFu : 0u;
+        leaf5 = lane && d == 4; leaf4 = lane && d == 3;
+    }
+};
+
+template <class Eval>
+__device__ __forceinline__ float warp_bisect(Eval ev, float t_min, float t1_ms, float cst, const TreeLane &tl, volatile float *bc) {
+    float t0 = t_min, t1 = t1_ms;
+    const float vt0 = ev(t0);
+    if (vt0 == cst) return t0;
+    const uint32_t s0 = f2u(__fsub_rn(vt0, cst));  // its sign never changes: t0 only moves to points of the same sign
+    uint32_t t_last = 0, s_last = 0;
+#pragma unroll
+    for (int done = 0; done < CUBIC_ITERATION_NUMBER; done += 5) {
+        const bool five = done + 5 <= CUBIC_ITERATION_NUMBER;  // else the last, four-step round
+        // Four levels down this lane's path (lanes of shallower nodes just go on to the left; they keep what they
+        // passed). A level's midpoint is (previous midpoint + the end that stayed) * 0.5 — the sum the sequential
+        // loop forms, fp addition commutes — so the dependent chain is one add and one multiply per level.
+        float lo = t0, hi = t1, tm = __fmul_rn(__fadd_rn(lo, hi), 0.5f);
+        float my_tm = tm, lo3 = lo, hi3 = hi;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float other = bsel(tl.right[k], hi, lo);
+            lo = bsel(tl.right[k], tm, lo);
+            hi = bsel(tl.right[k], hi, tm);
+            tm = __fmul_rn(__fadd_rn(tm, other), 0.5f);
+            my_tm = bsel(tl.at[k + 1], tm, my_tm);
+            if (k == 2) { lo3 = lo; hi3 = hi; }
+        }
+        const uint32_t sb = f2u(__fsub_rn(ev(my_tm), cst));
+        const bool same = (int)(sb ^ s0) >= 0;  // same sign as at t0: t0 = tm (MI1:421-424), else t1 = tm
+        const uint32_t mask = __ballot_sync(0xFFFFFFFFu, same);
+        // exactly one leaf of the round's last level has all its ancestors deciding the way that leads to it: it holds
+        // the bracket after the round, and an OR across the warp (everyone else contributes 0) hands it out
+        const bool on = (five ? tl.leaf5 : tl.leaf4) && (mask & tl.amask) == tl.aexp;
+        const float nlo = five ? lo : lo3, nhi = five ? hi : hi3;
+#if SLPR_TREE_BCAST == 0
+        t0 = u2f(__reduce_or_sync(0xFFFFFFFFu, on ? f2u(same ? my_tm : nlo) : 0u));
+        t1 = u2f(__reduce_or_sync(0xFFFFFFFFu, on ? f2u(same ? nhi : my_tm) : 0u));
+        if (!five) {
+            t_last = __reduce_or_sync(0xFFFFFFFFu, on ? f2u(my_tm) : 0u);
+            s_last = __reduce_or_sync(0xFFFFFFFFu, on ? sb : 0u);
+        }
+#elif SLPR_TREE_BCAST == 1
+        const int src = 31 - __clz((int)__ballot_sync(0xFFFFFFFFu, on));
+        t0 = __shfl_sync(0xFFFFFFFFu, same ? my_tm : nlo, src);
+        t1 = __shfl_sync(0xFFFFFFFFu, same ? nhi : my_tm, src);
+        if (!five) {
+            t_last = f2u(__shfl_sync(0xFFFFFFFFu, my_tm, src));
+            s_last = __shfl_sync(0xFFFFFFFFu, sb, src);
+        }
+#else
+        if (on) { bc[0] = same ? my_tm : nlo; bc[1] = same ? nhi : my_tm; bc[2] = my_tm; bc[3] = u2f(sb); }
+        __syncwarp();
+        t0 = bc[0]; t1 = bc[1];
+        if (!five) { t_last = f2u(bc[2]); s_last = f2u(bc[3]); }
+        __syncwarp();
+#endif
+    }
+    return (fabsf(u2f(s_last)) > 1.f) ? t_min : u2f(t_last);  // MI1:430-433
+}
+
 // ------------------------------------------------------------------------------------------------
 // Long pieces (round 2). A piece's crossings with the x grid lines form one chain — every bisection bracket starts
 // at the previous x crossing (MI1:392-436) — and its crossings with the y grid lines another; only the order in
@@ -496,6 +592,9 @@ struct LongScratch {
     uint32_t *chain;   // [capacity] tagged crossing parameters: x chain at [first record, +n_x), y chain behind it
     uint32_t *merged;  // [capacity] the emitted record parameters in order
 };
+
+constexpr int LONG_EMIT_WARPS = 2;       // k_long_emit: warps per block
+constexpr int LONG_STAGE_WORDS = 5632;  // and the words of shared memory in which each stages its piece's two chains (22 KB)
 
 struct LongPiece {
     CurvePts cp;
@@ -525,8 +624,10 @@ template <bool FULL, bool FMA>
 __global__ void __launch_bounds__(128) k_long_chains(const PieceRec *__restrict__ pieces, const FrameCounters *__restrict__ ctr,
                                                      int capacity, LongScratch sc) {
     if (ctr->n_fragments > capacity) return;
+    __shared__ float s_bc[4][4];
     const uint32_t n_items = 2u * (uint32_t)ctr->n_long;
     const uint32_t lane = lane_id();
+    const TreeLane tl(lane);
     const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < n_items; item += n_warps) {
         const int side = (int)(item & 1u);
@@ -559,7 +660,33 @@ __global__ void __launch_bounds__(128) k_long_chains(const PieceRec *__restrict_
             }
             done = __all_sync(0xFFFFFFFFu, ok);
         }
-        if (!done && lane == 0) {  // in order (curves always; lines when a clamp was active)
+        if (SLPR_LONG_WARP && !done && (p.type == T_CUBIC || (FULL && (p.type == T_QUADRIC || p.type == T_ARC)))) {
+            // in order, each crossing by the whole warp (warp_bisect): the evaluators are solve_crossing's
+            const float c0 = side ? p.cp.y[0] : p.cp.x[0], c1 = side ? p.cp.y[1] : p.cp.x[1], c2 = side ? p.cp.y[2] : p.cp.x[2];
+            const float c3 = side ? p.cp.y[3] : p.cp.x[3], w = p.cp.x[3];
+            const float d01 = __fsub_rn(c1, c0), d12 = __fsub_rn(c2, c1), d23 = __fsub_rn(c3, c2);
+            auto cubic = [&](float t) {
+                const float a0 = madd_t<FMA>(t, d01, c0), a1 = madd_t<FMA>(t, d12, c1), a2 = madd_t<FMA>(t, d23, c2);
+                const float b0 = lerp_t<FMA>(a0, a1, t), b1 = lerp_t<FMA>(a1, a2, t);
+                return lerp_t<FMA>(b0, b1, t);
+            };
+            auto quadric = [&](float t) { return eval_quadric<FMA>(c0, c1, c2, t); };
+            auto arc = [&](float t) { return eval_arc<FMA>(c0, c1, c2, w, t); };
+            float t_prev = p.t0_ms, g = g0;
+            for (int k = 0; k < n; ++k) {
+                const float cst = g;
+                g = __fadd_rn(g, d);
+                float ts;
+                if (FULL && p.type == T_ARC) ts = warp_bisect(arc, t_prev, p.t1_ms, cst, tl, s_bc[threadIdx.x >> 5]);
+                else if (FULL && p.type == T_QUADRIC) ts = warp_bisect(quadric, t_prev, p.t1_ms, cst, tl, s_bc[threadIdx.x >> 5]);
+                else ts = warp_bisect(cubic, t_prev, p.t1_ms, cst, tl, s_bc[threadIdx.x >> 5]);
+                const uint32_t tg = (f2u(ts) & 0xFFFFFFFCu) | (uint32_t)side;
+                if (lane == 0) out[k] = tg;
+                t_prev = u2f(tg);
+            }
+            done = true;
+        }
+        if (!done && lane == 0) {  // in order by one lane (lines when a clamp was active; other types)
             float t_prev = p.t0_ms, g = g0;
             for (int k = 0; k < n; ++k) {
                 const float cst = g;
@@ -574,10 +701,11 @@ __global__ void __launch_bounds__(128) k_long_chains(const PieceRec *__restrict_
 }
 
 template <bool FULL, bool FMA>
-__global__ void __launch_bounds__(128) k_long_emit(const FrameParams *__restrict__ P, const PieceRec *__restrict__ pieces,
+__global__ void __launch_bounds__(LONG_EMIT_WARPS * 32) k_long_emit(const FrameParams *__restrict__ P, const PieceRec *__restrict__ pieces,
                                                    FrameCounters *__restrict__ ctr, int capacity, LongScratch sc, KeyLayout L,
                                                    uint64_t *__restrict__ key64, uint32_t *__restrict__ val, FragTaps taps,
                                                    int2 *__restrict__ inter, float2 *__restrict__ boundary, uint4 *__restrict__ fixlist) {
+    __shared__ uint32_t s_chain[LONG_EMIT_WARPS][LONG_STAGE_WORDS];
     if (ctr->n_fragments > capacity) return;
     const uint32_t n_long = (uint32_t)ctr->n_long;
     const uint32_t lane = lane_id();
@@ -591,6 +719,15 @@ __global__ void __launch_bounds__(128) k_long_emit(const FrameParams *__restrict
         const bool x_leads = p.n_x > 0 && p.n_y == 0;
         const int len_x = p.n_x + (x_leads ? 1 : 0), len_y = p.n_y + (x_leads ? 0 : 1);
         const uint32_t *cx = sc.chain + p.pcnt, *cy = sc.chain + p.pcnt + p.n_x;
+        // the ranks below are binary searches, one per record: from shared memory when the piece fits (any piece of a
+        // 4K frame does), at a thirtieth of the latency of the global copy
+        __syncwarp();
+        if (p.n_x + p.n_y <= LONG_STAGE_WORDS) {
+            uint32_t *st = s_chain[threadIdx.x >> 5];
+            for (int i = (int)lane; i < p.n_x + p.n_y; i += 32) st[i] = cx[i];
+            __syncwarp();
+            cx = st; cy = st + p.n_x;
+        }
         const uint32_t t0_bits = f2u(p.t0_ms);
         auto get_x = [&](int i) { return x_leads ? (i == 0 ? t0_bits : cx[i - 1]) : cx[i]; };
         auto get_y = [&](int j) { return x_leads ? cy[j] : (j == 0 ? t0_bits : cy[j - 1]); };
