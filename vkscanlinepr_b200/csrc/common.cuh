@@ -44,7 +44,7 @@ struct FrameCounters {
     int fix_missed;    // invariant check of k_walk's conditional boundary stores (always 0)
     int n_band_entries;  // exact bands: paths of this band with a non-zero winding sum (k_band_sums_sparse)
     int n_band_bp;       // exact bands: break points in the merged correction table (k_band_merge)
-    int n_long;          // monotone pieces of 62 or more crossings (k_piece_emit): walked chain by chain when long_mode is on
+    int n_long;          // the longest monotone pieces, laid out first (k_piece_emit: 62 records or more, and shorter ones while few): walked chain by chain when long_mode is on
     int n_live_paths;    // band mode: paths that can reach the band (k_band_paths / k_path_cull), listed for the sort
     int band_void;       // exact bands: 1 = another band's frame was void, 2 = a band never published (timeout),
                          //              3 = more entries than the merge table holds; the frame must be rendered again

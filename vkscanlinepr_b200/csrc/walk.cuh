@@ -74,6 +74,12 @@ __device__ __forceinline__ void vbucket_bases(const PieceRanks &pr, uint32_t *s_
     __syncthreads();
 }
 
+#ifndef SLPR_LONG_MIN_RECORDS
+#define SLPR_LONG_MIN_RECORDS 20
+#endif
+constexpr uint32_t LONG_MIN_RECORDS = SLPR_LONG_MIN_RECORDS;  // (> WALK_LONG, so that these buckets are never windowed)
+constexpr uint32_t LONG_PIECES_MAX = 4096;
+
 // ------------------------------------------------------------------------------------------------
 #ifndef SLPR_PE_MIN_BLOCKS
 #define SLPR_PE_MIN_BLOCKS 1
@@ -95,8 +101,17 @@ __global__ void __launch_bounds__(256, SLPR_PE_MIN_BLOCKS) k_piece_emit(const Fr
     vbucket_bases(ranks, s_vbase, &s_total);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         ctr->n_pieces = (int)s_total;
-        // the top length bucket (62 crossings or more) is laid out first: pieces [0, n_long) of the record array
-        ctr->n_long = (int)ranks.vhist[ranks.lay.n_windows * WALK_BUCKETS + (WALK_BUCKETS - 1)];
+        // The longest pieces are laid out first: [0, n_long) of the record array are the ones the long-piece kernels
+        // walk when long_mode is on — the top length bucket (62 records or more) and as many of the next buckets,
+        // down to LONG_MIN_RECORDS, as keep the count within LONG_PIECES_MAX (few pieces: a lane of k_walk then
+        // never walks more than a couple of dozen crossings on its own; many pieces: nothing changes).
+        const uint32_t *top = ranks.vhist + ranks.lay.n_windows * WALK_BUCKETS;
+        uint32_t n_long = top[WALK_BUCKETS - 1];
+        for (uint32_t b = WALK_BUCKETS - 2; b >= LONG_MIN_RECORDS && b > ranks.lay.long_min; --b) {
+            if (n_long + top[b] > LONG_PIECES_MAX) break;
+            n_long += top[b];
+        }
+        ctr->n_long = (int)n_long;
     }
     // This block walks the work items the block of the same index ranked in k_monotonize_count (same launch
     // shape), so one 64-entry table — where this block's pieces of every length start — places all its pieces
