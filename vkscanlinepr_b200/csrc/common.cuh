@@ -48,6 +48,7 @@ struct FrameCounters {
     int n_live_paths;    // band mode: paths that can reach the band (k_band_paths / k_path_cull), listed for the sort
     int band_void;       // exact bands: 1 = another band's frame was void, 2 = a band never published (timeout),
                          //              3 = more entries than the merge table holds; the frame must be rendered again
+    int n_top;           // pieces in the top length bucket (62 records or more): the first n_top of the record array
     int n_blend_nodes;   // SLPR_FLAG_BLEND: (cell, translucent path) pairs asked for this frame; more than the node buffer
                          //              holds = the frame lacks some and is rendered again with a bigger buffer
 };

@@ -642,7 +642,7 @@ static int enqueue_fragments(slpr_ctx *c, cudaStream_t s, bool timed, int &launc
         auto chains = full ? (fma ? k_long_chains<true, true> : k_long_chains<true, false>) : (fma ? k_long_chains<false, true> : k_long_chains<false, false>);
         auto emit = full ? (fma ? k_long_emit<true, true> : k_long_emit<true, false>) : (fma ? k_long_emit<false, true> : k_long_emit<false, false>);
         chains<<<lgrid, 128, 0, s>>>(c->d_pieces, c->d_ctr, c->cap, ls);
-        emit<<<lgrid * (4 / LONG_EMIT_WARPS), LONG_EMIT_WARPS * 32, 0, s>>>(c->d_params, c->d_pieces, c->d_ctr, c->cap, ls, c->L, c->d_key[0], c->d_val[0], ft, c->d_inter, c->d_boundary, c->d_fixlist);
+        emit<<<c->num_sms * 4, LONG_EMIT_THREADS, 0, s>>>(c->d_params, c->d_pieces, c->d_ctr, c->cap, ls, c->L, c->d_key[0], c->d_val[0], ft, c->d_inter, c->d_boundary, c->d_fixlist);
         launches += 2;
     }
     (fma ? k_piece_fix<true> : k_piece_fix<false>)<<<8, 256, 0, s>>>(c->d_params, c->d_ctype, c->d_cpm, c->d_cpath, c->d_frule, c->d_tpos, c->d_ctr, c->cap, c->d_boundary,

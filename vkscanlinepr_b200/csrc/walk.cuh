@@ -112,6 +112,7 @@ __global__ void __launch_bounds__(256, SLPR_PE_MIN_BLOCKS) k_piece_emit(const Fr
             n_long += top[b];
         }
         ctr->n_long = (int)n_long;
+        ctr->n_top = (int)top[WALK_BUCKETS - 1];
     }
     // This block walks the work items the block of the same index ranked in k_monotonize_count (same launch
     // shape), so one 64-entry table — where this block's pieces of every length start — places all its pieces
@@ -502,9 +503,6 @@ __global__ void __launch_bounds__(WALK_THREADS, SLPR_WALK_MIN_BLOCKS) k_walk(con
 #ifndef SLPR_LONG_WARP
 #define SLPR_LONG_WARP 1
 #endif
-#ifndef SLPR_TREE_BCAST
-#define SLPR_TREE_BCAST 1
-#endif
 // What a lane needs to know about its node, computed once per kernel; selections by lane-constant conditions are
 // bitwise (one LOP3 on a mask register) so that no predicate has to be kept or recomputed inside the rounds.
 __device__ __forceinline__ float bsel(uint32_t m, float a, float b) { return u2f((f2u(a) & m) | (f2u(b) & ~m)); }
@@ -529,12 +527,11 @@ struct TreeLane {
 };
 
 template <class Eval>
-__device__ __forceinline__ float warp_bisect(Eval ev, float t_min, float t1_ms, float cst, const TreeLane &tl, volatile float *bc) {
+__device__ __forceinline__ float warp_bisect(Eval ev, float t_min, float t1_ms, float cst, const TreeLane &tl, uint32_t lane) {
     float t0 = t_min, t1 = t1_ms;
-    const float vt0 = ev(t0);
-    if (vt0 == cst) return t0;
-    const uint32_t s0 = f2u(__fsub_rn(vt0, cst));  // its sign never changes: t0 only moves to points of the same sign
-    uint32_t t_last = 0, s_last = 0;
+    uint32_t flip = 0;  // all ones when v(t0) - cst is negative: the ballots of the sign bits, flipped, read "same sign as at t0"
+    float t_last = 0.f;
+    uint32_t s_last = 0;
 #pragma unroll
     for (int done = 0; done < CUBIC_ITERATION_NUMBER; done += 5) {
         const bool five = done + 5 <= CUBIC_ITERATION_NUMBER;  // else the last, four-step round
@@ -552,37 +549,29 @@ __device__ __forceinline__ float warp_bisect(Eval ev, float t_min, float t1_ms, 
             my_tm = bsel(tl.at[k + 1], tm, my_tm);
             if (k == 2) { lo3 = lo; hi3 = hi; }
         }
-        const uint32_t sb = f2u(__fsub_rn(ev(my_tm), cst));
-        const bool same = (int)(sb ^ s0) >= 0;  // same sign as at t0: t0 = tm (MI1:421-424), else t1 = tm
-        const uint32_t mask = __ballot_sync(0xFFFFFFFFu, same);
+        if (done == 0 && lane == 0) my_tm = t0;  // the first round's spare lane evaluates v(t0) (MI1:396-404) alongside
+        const float v = ev(my_tm);
+        const uint32_t sb = f2u(__fsub_rn(v, cst));
+        uint32_t mask = __ballot_sync(0xFFFFFFFFu, (int)sb < 0);
+        if (done == 0) {
+            if (__any_sync(0xFFFFFFFFu, lane == 0 && v == cst)) return t0;  // the curve is on the grid line at t0
+            flip = (mask & 1u) ? 0u : 0xFFFFFFFFu;  // the sign at t0 never changes: t0 only moves to points of the same sign
+        }
+        mask ^= flip;  // bit L: node L has the sign of t0, so t0 = tm there (MI1:421-424), else t1 = tm
+        const bool same = ((mask >> lane) & 1u) != 0u;
         // exactly one leaf of the round's last level has all its ancestors deciding the way that leads to it: it holds
-        // the bracket after the round, and an OR across the warp (everyone else contributes 0) hands it out
+        // the bracket after the round and hands it to the warp
         const bool on = (five ? tl.leaf5 : tl.leaf4) && (mask & tl.amask) == tl.aexp;
         const float nlo = five ? lo : lo3, nhi = five ? hi : hi3;
-#if SLPR_TREE_BCAST == 0
-        t0 = u2f(__reduce_or_sync(0xFFFFFFFFu, on ? f2u(same ? my_tm : nlo) : 0u));
-        t1 = u2f(__reduce_or_sync(0xFFFFFFFFu, on ? f2u(same ? nhi : my_tm) : 0u));
-        if (!five) {
-            t_last = __reduce_or_sync(0xFFFFFFFFu, on ? f2u(my_tm) : 0u);
-            s_last = __reduce_or_sync(0xFFFFFFFFu, on ? sb : 0u);
-        }
-#elif SLPR_TREE_BCAST == 1
         const int src = 31 - __clz((int)__ballot_sync(0xFFFFFFFFu, on));
         t0 = __shfl_sync(0xFFFFFFFFu, same ? my_tm : nlo, src);
         t1 = __shfl_sync(0xFFFFFFFFu, same ? nhi : my_tm, src);
         if (!five) {
-            t_last = f2u(__shfl_sync(0xFFFFFFFFu, my_tm, src));
+            t_last = __shfl_sync(0xFFFFFFFFu, my_tm, src);
             s_last = __shfl_sync(0xFFFFFFFFu, sb, src);
         }
-#else
-        if (on) { bc[0] = same ? my_tm : nlo; bc[1] = same ? nhi : my_tm; bc[2] = my_tm; bc[3] = u2f(sb); }
-        __syncwarp();
-        t0 = bc[0]; t1 = bc[1];
-        if (!five) { t_last = f2u(bc[2]); s_last = f2u(bc[3]); }
-        __syncwarp();
-#endif
     }
-    return (fabsf(u2f(s_last)) > 1.f) ? t_min : u2f(t_last);  // MI1:430-433
+    return (fabsf(u2f(s_last)) > 1.f) ? t_min : t_last;  // MI1:430-433
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -596,8 +585,9 @@ __device__ __forceinline__ float warp_bisect(Eval ev, float t_min, float t1_ms, 
 // instead walked in three steps, bit-identical to the sequential walk:
 //   k_long_chains  one warp per (piece, axis): a LINE's crossings are closed-form and independent but for a clamp
 //                  against the previous one — all lanes evaluate them at once and check that no clamp was active
-//                  (else lane 0 redoes the chain in order); a curve's chain is walked by lane 0 (solve_crossing);
-//   k_long_emit    one warp per piece: the merged emission order by rank (binary search; valid when both chains
+//                  (else lane 0 redoes the chain in order); a curve's chain is walked crossing by crossing, each
+//                  crossing by the whole warp (warp_bisect: five bisection steps per round);
+//   k_long_emit    one block per piece: the merged emission order by rank (binary search; valid when both chains
 //                  ascend, which is checked — else lane 0 merges head by head), then all lanes form the fragments
 //                  between consecutive records exactly as k_walk does (make_fragment), plus the boundary fragment
 //                  and the rare boundary-repair bookkeeping.
@@ -608,8 +598,9 @@ struct LongScratch {
     uint32_t *merged;  // [capacity] the emitted record parameters in order
 };
 
-constexpr int LONG_EMIT_WARPS = 2;       // k_long_emit: warps per block
-constexpr int LONG_STAGE_WORDS = 5632;  // and the words of shared memory in which each stages its piece's two chains (22 KB)
+constexpr int LONG_EMIT_THREADS = 128;   // k_long_emit
+constexpr int LONG_WARP_RECORDS = 256;   // pieces of up to this many records are emitted by one warp, longer ones by a block
+constexpr int LONG_STAGE_WORDS = 5632;   // records of a piece whose chains and merged order it keeps in shared memory (2 x 22 KB)
 
 struct LongPiece {
     CurvePts cp;
@@ -639,7 +630,6 @@ template <bool FULL, bool FMA>
 __global__ void __launch_bounds__(128) k_long_chains(const PieceRec *__restrict__ pieces, const FrameCounters *__restrict__ ctr,
                                                      int capacity, LongScratch sc) {
     if (ctr->n_fragments > capacity) return;
-    __shared__ float s_bc[4][4];
     const uint32_t n_items = 2u * (uint32_t)ctr->n_long;
     const uint32_t lane = lane_id();
     const TreeLane tl(lane);
@@ -692,9 +682,9 @@ __global__ void __launch_bounds__(128) k_long_chains(const PieceRec *__restrict_
                 const float cst = g;
                 g = __fadd_rn(g, d);
                 float ts;
-                if (FULL && p.type == T_ARC) ts = warp_bisect(arc, t_prev, p.t1_ms, cst, tl, s_bc[threadIdx.x >> 5]);
-                else if (FULL && p.type == T_QUADRIC) ts = warp_bisect(quadric, t_prev, p.t1_ms, cst, tl, s_bc[threadIdx.x >> 5]);
-                else ts = warp_bisect(cubic, t_prev, p.t1_ms, cst, tl, s_bc[threadIdx.x >> 5]);
+                if (FULL && p.type == T_ARC) ts = warp_bisect(arc, t_prev, p.t1_ms, cst, tl, lane);
+                else if (FULL && p.type == T_QUADRIC) ts = warp_bisect(quadric, t_prev, p.t1_ms, cst, tl, lane);
+                else ts = warp_bisect(cubic, t_prev, p.t1_ms, cst, tl, lane);
                 const uint32_t tg = (f2u(ts) & 0xFFFFFFFCu) | (uint32_t)side;
                 if (lane == 0) out[k] = tg;
                 t_prev = u2f(tg);
@@ -715,102 +705,131 @@ __global__ void __launch_bounds__(128) k_long_chains(const PieceRec *__restrict_
     }
 }
 
+// One piece, by a warp (BLOCKWIDE false; `tid` = lane) or by a whole block (true; `tid` = thread): merged order, then fragments.
+template <bool FULL, bool FMA, bool BLOCKWIDE>
+__device__ __forceinline__ void emit_long_piece(const LongPiece &p, int tid, uint32_t *st_chain, uint32_t *st_merged, int stage_words,
+                                                const FragEnv &env, FrameCounters *__restrict__ ctr, const LongScratch &sc, const KeyLayout &L,
+                                                uint64_t *__restrict__ key64, uint32_t *__restrict__ val, const FragTaps &taps,
+                                                int2 *__restrict__ inter, float2 *__restrict__ boundary, uint4 *__restrict__ fixlist) {
+    constexpr int G = BLOCKWIDE ? LONG_EMIT_THREADS : 32;
+    auto group_sync = [] { if (BLOCKWIDE) __syncthreads(); else __syncwarp(); };
+    const int n_loop = p.n_x + p.n_y + 1;
+    // the two chains as the reference's merge sees them: the piece's start record leads the y chain, or the x chain
+    // when there is no y crossing (MI1:321-333); an exhausted chain reads 2.0 tagged with its side (MI1:340-359)
+    const bool x_leads = p.n_x > 0 && p.n_y == 0;
+    const int len_x = p.n_x + (x_leads ? 1 : 0), len_y = p.n_y + (x_leads ? 0 : 1);
+    const uint32_t *cx = sc.chain + p.pcnt, *cy = sc.chain + p.pcnt + p.n_x;
+    uint32_t *mg = sc.merged + p.pcnt;
+    // The ranks below are binary searches, one per record, and every record is read twice more when the fragments
+    // are formed: chains and merged order live in shared memory when the piece fits (any piece of a 4K frame does).
+    group_sync();  // the previous piece is done with the stage
+    if (n_loop <= stage_words) {
+        for (int i = tid; i < p.n_x + p.n_y; i += G) st_chain[i] = cx[i];
+        cx = st_chain; cy = st_chain + p.n_x; mg = st_merged;
+    }
+    group_sync();
+    const uint32_t t0_bits = f2u(p.t0_ms);
+    auto get_x = [&](int i) { return x_leads ? (i == 0 ? t0_bits : cx[i - 1]) : cx[i]; };
+    auto get_y = [&](int j) { return x_leads ? cy[j] : (j == 0 ? t0_bits : cy[j - 1]); };
+    // Head by head (MI1:321-359), an element is emitted once its predecessors in its chain are out and it is the smaller
+    // head: that is a merge by the running maximum of each chain. The chains ascend — every bracket starts at the previous
+    // crossing — except that the first crossing of the leading chain can read below the piece's start record by its tag
+    // bits (a piece that starts on a grid line: the tiger's full-height line at 4K), so the leading chain is ranked by
+    // max(element, start record). Anything else out of order (not observed) goes the sequential way below.
+    const float head = u2f(t0_bits);
+    auto eff_x = [&](int i) { const float v = u2f(get_x(i)); return (x_leads && v < head) ? head : v; };
+    auto eff_y = [&](int j) { const float v = u2f(get_y(j)); return (!x_leads && v < head) ? head : v; };
+    bool mono = true;
+    for (int i = tid + 1; i < len_x; i += G) mono = mono && !(eff_x(i) < eff_x(i - 1));
+    for (int j = tid + 1; j < len_y; j += G) mono = mono && !(eff_y(j) < eff_y(j - 1));
+    if (BLOCKWIDE ? __syncthreads_and(mono) : __all_sync(0xFFFFFFFFu, mono)) {  // a record's place is its index plus its rank in the other chain
+        for (int i = tid; i < len_x; i += G) {
+            const float v = eff_x(i);
+            int lo = 0, hi = len_y;  // y records strictly before v (x goes first on ties: `tx <= ty`)
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (eff_y(mid) < v) lo = mid + 1; else hi = mid; }
+            mg[i + lo] = get_x(i);
+        }
+        for (int j = tid; j < len_y; j += G) {
+            const float v = eff_y(j);
+            int lo = 0, hi = len_x;  // x records at or before v
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (eff_x(mid) <= v) lo = mid + 1; else hi = mid; }
+            mg[j + lo] = get_y(j);
+        }
+    } else if (tid == 0) {  // head by head, as the reference does
+#ifdef SLPR_DEBUG_MONO
+        printf("non-monotone piece: n_x %d n_y %d blockwide %d\n", p.n_x, p.n_y, (int)BLOCKWIDE);
+#endif
+        int i = 0, j = 0;
+        for (int k = 0; k < n_loop; ++k) {
+            const uint32_t hx = i < len_x ? get_x(i) : (f2u(2.0f) | 0u), hy = j < len_y ? get_y(j) : (f2u(2.0f) | 1u);
+            if (u2f(hx) <= u2f(hy)) { mg[k] = hx; ++i; } else { mg[k] = hy; ++j; }
+        }
+    }
+    group_sync();
+    if (inter && tid == 0) {  // debug tap (MI1:361-375): the records with their tag bits merged across equal parameters
+        int i_inte_last = (int)f2u(-1.0f);
+        for (int k = 0; k < n_loop; ++k) {
+            int i_out = (int)mg[k];
+            if ((mg[k] & 0xFFFFFFFCu) == ((uint32_t)i_inte_last & 0xFFFFFFFCu)) {
+                i_out |= i_inte_last;
+                inter[p.pcnt + k - 1] = make_int2((int)p.c, i_out);
+            }
+            inter[p.pcnt + k] = make_int2((int)p.c, i_out);
+            i_inte_last = i_out;
+        }
+    }
+    // ---- fragments: record k closes the fragment that record k - 1 opened (gen_fragment fused, as in k_walk)
+    for (int k = 1 + tid; k <= n_loop; k += G) {
+        {
+            float ta = u2f(mg[k - 1] & 0xFFFFFFFCu);
+            ta = (ta < 0.0f) ? 0.0f : ta;
+            float tb = u2f((k < n_loop ? mg[k] : f2u(p.t1_ms)) & 0xFFFFFFFCu);  // k == n_loop: the fragment across the piece boundary
+            tb = (tb < 0.0f) ? 0.0f : tb;
+            float ax, ay, bx, by;
+            eval_point<FULL, FMA>(p.type, p.cp, ta, ax, ay);
+            eval_point<FULL, FMA>(p.type, p.cp, tb, bx, by);
+            uint64_t kk; uint32_t vv;
+            make_fragment(env, L, p.pcnt + k - 1, p.pidx, p.rule_bit, ta, tb, ax, ay, bx, by, kk, vv, taps);
+            key64[p.pcnt + k - 1] = kk;
+            val[p.pcnt + k - 1] = vv;
+        }
+    }
+    if (tid == 0) {  // the boundary-repair bookkeeping of k_walk
+        const uint32_t first_bits = mg[0], last_bits = mg[n_loop - 1];
+        const bool unordered = p.piece > 0 && (f2u(p.t1_ms) & 0xFFFFFFFCu) <= (f2u(p.t0_ms) | 3u);
+        if (unordered || p.keep_last) boundary[5 * p.c + p.piece] = make_float2(u2f(first_bits), u2f(last_bits));
+        if (p.piece > 0 && (first_bits & 0xFFFFFFFCu) != (f2u(p.t0_ms) & 0xFFFFFFFCu)) {
+            if (unordered) fixlist[atomicAdd(&ctr->n_fix, 1)] = make_uint4(p.c, p.piece, (uint32_t)p.pcnt, 0u);
+            else ctr->fix_missed = 1;
+        }
+    }
+}
+
+// Pieces of more than LONG_WARP_RECORDS records — all in the top length bucket, the first n_top pieces — are emitted by
+// a whole block each; the others by a warp each (a block would idle on their 20 to 250 records and its barriers would
+// only add latency: tiger at 4K has ~4000 of them).
 template <bool FULL, bool FMA>
-__global__ void __launch_bounds__(LONG_EMIT_WARPS * 32) k_long_emit(const FrameParams *__restrict__ P, const PieceRec *__restrict__ pieces,
+__global__ void __launch_bounds__(LONG_EMIT_THREADS) k_long_emit(const FrameParams *__restrict__ P, const PieceRec *__restrict__ pieces,
                                                    FrameCounters *__restrict__ ctr, int capacity, LongScratch sc, KeyLayout L,
                                                    uint64_t *__restrict__ key64, uint32_t *__restrict__ val, FragTaps taps,
                                                    int2 *__restrict__ inter, float2 *__restrict__ boundary, uint4 *__restrict__ fixlist) {
-    __shared__ uint32_t s_chain[LONG_EMIT_WARPS][LONG_STAGE_WORDS];
+    __shared__ uint32_t s_chain[LONG_STAGE_WORDS], s_merged[LONG_STAGE_WORDS];
     if (ctr->n_fragments > capacity) return;
-    const uint32_t n_long = (uint32_t)ctr->n_long;
-    const uint32_t lane = lane_id();
-    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t n_long = (uint32_t)ctr->n_long, n_top = (uint32_t)ctr->n_top;
     const FragEnv env = load_frag_env(P);
-    for (uint32_t idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; idx < n_long; idx += n_warps) {
+    for (uint32_t idx = blockIdx.x; idx < n_top; idx += gridDim.x) {
         const LongPiece p = load_long_piece(pieces, idx);
-        const int n_loop = p.n_x + p.n_y + 1;
-        // the two chains as the reference's merge sees them: the piece's start record leads the y chain, or the x chain
-        // when there is no y crossing (MI1:321-333); an exhausted chain reads 2.0 tagged with its side (MI1:340-359)
-        const bool x_leads = p.n_x > 0 && p.n_y == 0;
-        const int len_x = p.n_x + (x_leads ? 1 : 0), len_y = p.n_y + (x_leads ? 0 : 1);
-        const uint32_t *cx = sc.chain + p.pcnt, *cy = sc.chain + p.pcnt + p.n_x;
-        // the ranks below are binary searches, one per record: from shared memory when the piece fits (any piece of a
-        // 4K frame does), at a thirtieth of the latency of the global copy
-        __syncwarp();
-        if (p.n_x + p.n_y <= LONG_STAGE_WORDS) {
-            uint32_t *st = s_chain[threadIdx.x >> 5];
-            for (int i = (int)lane; i < p.n_x + p.n_y; i += 32) st[i] = cx[i];
-            __syncwarp();
-            cx = st; cy = st + p.n_x;
-        }
-        const uint32_t t0_bits = f2u(p.t0_ms);
-        auto get_x = [&](int i) { return x_leads ? (i == 0 ? t0_bits : cx[i - 1]) : cx[i]; };
-        auto get_y = [&](int j) { return x_leads ? cy[j] : (j == 0 ? t0_bits : cy[j - 1]); };
-        uint32_t *mg = sc.merged + p.pcnt;
-        bool mono = true;
-        for (int i = (int)lane + 1; i < len_x; i += 32) mono = mono && !(u2f(get_x(i)) < u2f(get_x(i - 1)));
-        for (int j = (int)lane + 1; j < len_y; j += 32) mono = mono && !(u2f(get_y(j)) < u2f(get_y(j - 1)));
-        if (__all_sync(0xFFFFFFFFu, mono)) {  // both ascend: a record's place is its index plus its rank in the other chain
-            for (int i = (int)lane; i < len_x; i += 32) {
-                const uint32_t vb = get_x(i);
-                const float v = u2f(vb);
-                int lo = 0, hi = len_y;  // y records strictly before v (x goes first on ties: `tx <= ty`)
-                while (lo < hi) { const int mid = (lo + hi) >> 1; if (u2f(get_y(mid)) < v) lo = mid + 1; else hi = mid; }
-                mg[i + lo] = vb;
-            }
-            for (int j = (int)lane; j < len_y; j += 32) {
-                const uint32_t vb = get_y(j);
-                const float v = u2f(vb);
-                int lo = 0, hi = len_x;  // x records at or before v
-                while (lo < hi) { const int mid = (lo + hi) >> 1; if (u2f(get_x(mid)) <= v) lo = mid + 1; else hi = mid; }
-                mg[j + lo] = vb;
-            }
-        } else if (lane == 0) {  // head by head, as the reference does
-            int i = 0, j = 0;
-            for (int k = 0; k < n_loop; ++k) {
-                const uint32_t hx = i < len_x ? get_x(i) : (f2u(2.0f) | 0u), hy = j < len_y ? get_y(j) : (f2u(2.0f) | 1u);
-                if (u2f(hx) <= u2f(hy)) { mg[k] = hx; ++i; } else { mg[k] = hy; ++j; }
-            }
-        }
-        __syncwarp();
-        if (inter && lane == 0) {  // debug tap (MI1:361-375): the records with their tag bits merged across equal parameters
-            int i_inte_last = (int)f2u(-1.0f);
-            for (int k = 0; k < n_loop; ++k) {
-                int i_out = (int)mg[k];
-                if ((mg[k] & 0xFFFFFFFCu) == ((uint32_t)i_inte_last & 0xFFFFFFFCu)) {
-                    i_out |= i_inte_last;
-                    inter[p.pcnt + k - 1] = make_int2((int)p.c, i_out);
-                }
-                inter[p.pcnt + k] = make_int2((int)p.c, i_out);
-                i_inte_last = i_out;
-            }
-        }
-        // ---- fragments: record k closes the fragment that record k - 1 opened (gen_fragment fused, as in k_walk)
-        for (int k0 = 1; k0 <= n_loop; k0 += 32) {
-            const int k = k0 + (int)lane;
-            if (k <= n_loop) {
-                float ta = u2f(mg[k - 1] & 0xFFFFFFFCu);
-                ta = (ta < 0.0f) ? 0.0f : ta;
-                float tb = u2f((k < n_loop ? mg[k] : f2u(p.t1_ms)) & 0xFFFFFFFCu);  // k == n_loop: the fragment across the piece boundary
-                tb = (tb < 0.0f) ? 0.0f : tb;
-                float ax, ay, bx, by;
-                eval_point<FULL, FMA>(p.type, p.cp, ta, ax, ay);
-                eval_point<FULL, FMA>(p.type, p.cp, tb, bx, by);
-                uint64_t kk; uint32_t vv;
-                make_fragment(env, L, p.pcnt + k - 1, p.pidx, p.rule_bit, ta, tb, ax, ay, bx, by, kk, vv, taps);
-                key64[p.pcnt + k - 1] = kk;
-                val[p.pcnt + k - 1] = vv;
-            }
-        }
-        if (lane == 0) {  // the boundary-repair bookkeeping of k_walk
-            const uint32_t first_bits = mg[0], last_bits = mg[n_loop - 1];
-            const bool unordered = p.piece > 0 && (f2u(p.t1_ms) & 0xFFFFFFFCu) <= (f2u(p.t0_ms) | 3u);
-            if (unordered || p.keep_last) boundary[5 * p.c + p.piece] = make_float2(u2f(first_bits), u2f(last_bits));
-            if (p.piece > 0 && (first_bits & 0xFFFFFFFCu) != (f2u(p.t0_ms) & 0xFFFFFFFCu)) {
-                if (unordered) fixlist[atomicAdd(&ctr->n_fix, 1)] = make_uint4(p.c, p.piece, (uint32_t)p.pcnt, 0u);
-                else ctr->fix_missed = 1;
-            }
-        }
+        if (p.n_x + p.n_y + 1 <= LONG_WARP_RECORDS) continue;  // (block-uniform)
+        emit_long_piece<FULL, FMA, true>(p, (int)threadIdx.x, s_chain, s_merged, LONG_STAGE_WORDS, env, ctr, sc, L, key64, val, taps, inter, boundary, fixlist);
+    }
+    __syncthreads();
+    constexpr int WARPS = LONG_EMIT_THREADS / 32, SLICE = LONG_STAGE_WORDS / WARPS;
+    static_assert(SLICE >= LONG_WARP_RECORDS, "a warp's slice of the stage holds its piece");
+    const uint32_t warp = threadIdx.x >> 5, n_warps = gridDim.x * WARPS;
+    for (uint32_t idx = blockIdx.x * WARPS + warp; idx < n_long; idx += n_warps) {
+        const LongPiece p = load_long_piece(pieces, idx);
+        if (idx < n_top && p.n_x + p.n_y + 1 > LONG_WARP_RECORDS) continue;
+        emit_long_piece<FULL, FMA, false>(p, (int)lane_id(), s_chain + warp * SLICE, s_merged + warp * SLICE, SLICE, env, ctr, sc, L, key64, val, taps, inter, boundary, fixlist);
     }
 }
 
