@@ -20,7 +20,7 @@ def test_fuzz_scenes_are_deterministic_and_in_the_loader_domain():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("first", [1000, 1012, 1024])
+@pytest.mark.parametrize("first", [0, 120, 1000, 1012])  # (seeds 0 and 124: a curve type without a shader arm is drawn at the origin, far from its control points — exact bands must not cull it)
 def test_gpu_fuzz_against_the_oracle(first):
     for seed in range(first, first + 12):
         F.check(seed, False)

@@ -89,6 +89,32 @@ def random_scene(seed, nonfinite=False, full=False):
     return sc, rows.astype(np.float32), W, H
 
 
+def check_bands(sc, rows, W, H, ref, flags):
+    """Exact row bands with the device-side exchange of winding sums: three bands into one frame buffer, two frames."""
+    import torch
+    from vkscanlinepr_b200 import parallel as PAR
+    frame = torch.zeros((H, W, 4), dtype=torch.uint8, device="cuda")
+    ctxs = []
+    for y0, y1 in PAR.band_rows(H, 3):
+        c = V.ScanlineRasterizer(0, flags).initialize(None, W, H)
+        c.loadVG(sc); c.setMVP(rows); c.set_band(y0, y1); c.set_target(frame.data_ptr(), W * 4)
+        ctxs.append(c)
+    boxes = [c.band_mailbox()[0] for c in ctxs]
+    for g, c in enumerate(ctxs):
+        c.set_band_peers(3, g, 0, boxes)
+    for seq in (1, 2):
+        for c in ctxs:
+            c.prepare()
+        for c in ctxs:
+            c.render_band(seq)
+        ctxs[0].band_wait_gather(seq)
+        for c in ctxs:
+            c.synchronize()
+        assert np.array_equal(frame.cpu().numpy(), ref), "exact bands"
+    for c in ctxs:
+        c.close()
+
+
 def check(seed, nonfinite):
     import test_parity_gpu as T
     sc, rows, W, H = random_scene(seed, nonfinite)
@@ -108,6 +134,8 @@ def check(seed, nonfinite):
         r.loadVG(sc); r.setMVP(rows); r.render(); r.render()
         assert np.array_equal(r.readback(), ref2), f"{kw}"
         r.close()
+    if seed % 4 == 0 and H >= 6:
+        check_bands(sc, rows, W, H, ref, 0)
     # the full-RVG arithmetic on a scene of its own (quadratics and rational arcs with odd weights)
     sc, rows, W, H = random_scene(seed, nonfinite, full=True)
     ref3 = O.render(sc, rows, W, H, full=True)
@@ -119,6 +147,8 @@ def check(seed, nonfinite):
         assert np.array_equal(r.tap("intersection"), ref3["inter"]), "full: intersection tap"
         assert np.array_equal(r.readback(), ref3["rgba"]), "full: frame"
     r.close()
+    if seed % 4 == 1 and H >= 6:
+        check_bands(sc, rows, W, H, ref3["rgba"], V.FLAG_FULL_RVG)
 
 
 def survive(seed):

@@ -392,7 +392,10 @@ __global__ void __launch_bounds__(256) k_monotonize_count(const FrameParams *__r
         full.stash_weight(type, c, cp);
         uint32_t n_cuts = 0;
         bool culled = false;  // band mode: a curve whose control-point box misses the band is skipped like an invisible one
-        if (cull) {
+        // (only for curves that stay inside their control points' box: a type without a shader arm — and ARC without the
+        // full-RVG arithmetic — is evaluated as the point (0, 0), a rational arc with a weight <= 0 leaves the hull)
+        const bool boxed = type == T_LINE || type == T_CUBIC || type == T_QUADRIC || (full.on() && type == T_ARC && cp.x[3] > 0.0f);
+        if (cull && boxed) {
             const uint32_t np = type & 7u;
             float ymin = cp.y[0], ymax = cp.y[0];
             for (uint32_t i = 1; i < 4; ++i)

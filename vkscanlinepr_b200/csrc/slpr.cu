@@ -93,6 +93,8 @@ struct slpr_ctx {
     PieceLayout lay{};
     uint32_t *d_live = nullptr;  // [nc] band mode: curves whose path comes near the band (k_band_live)
     float4 *d_pobj = nullptr;    // [P] object-space box of each path's control points (static)
+    std::vector<float4> h_pobj;  // its host copy, and the curves' types and paths: slpr_set_curve_weights may have to open a box
+    std::vector<uint32_t> h_ctype, h_cpath;
     uint32_t *d_pfc = nullptr;   // [P+1] first curve whose path is >= p (static; [P] = n_curves)
     uint32_t *d_pfp = nullptr;   // [P+1] first point whose path is >= p, when the points are grouped by path (else null)
     uint8_t *d_plive = nullptr;  // [P] band mode: the path can reach the band (k_path_cull)
@@ -466,6 +468,18 @@ extern "C" int slpr_load_scene(slpr_ctx *c, const float *pos_xy, const uint32_t 
             if (!(x == x) || !(y == y)) { b = make_float4(-3.0e38f, -3.0e38f, 3.0e38f, 3.0e38f); continue; }  // NaN: never culled
             b.x = std::min(b.x, x); b.y = std::min(b.y, y); b.z = std::max(b.z, x); b.w = std::max(b.w, y);
         }
+        // A curve type the shaders have no arm for is evaluated as the point (0, 0) whatever its control points are
+        // (gen_fragment.comp:132-156 loads nothing; ARC too without SLPR_FLAG_FULL_RVG), so its fragments are not where its
+        // box is: such a path is never culled (found by tools/fuzz_parity.py: the fragment at the origin went missing).
+        const bool full_rvg = (c->flags & SLPR_FLAG_FULL_RVG) != 0;
+        for (uint32_t i = 0; i < n_curves; ++i) {
+            const uint32_t t = curve_type[i];
+            if (!(t == T_LINE || t == T_CUBIC || t == T_QUADRIC || (full_rvg && t == T_ARC)))
+                box[curve_path[i]] = make_float4(-3.0e38f, -3.0e38f, 3.0e38f, 3.0e38f);
+        }
+        c->h_pobj = box;
+        c->h_ctype.assign(curve_type, curve_type + n_curves);
+        c->h_cpath.assign(curve_path, curve_path + n_curves);
         // first curve of every path (curve_path is non-decreasing): the per-frame segment table is offsets[] read through it
         std::vector<uint32_t> pfc((size_t)n_paths + 1);
         uint32_t cur = 0;
@@ -538,6 +552,15 @@ extern "C" int slpr_set_curve_weights(slpr_ctx *c, const float *curve_weight, ui
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
     if (n_curves) CU(cudaMemcpy(c->d_cweight, curve_weight, (size_t)n_curves * 4, cudaMemcpyHostToDevice));
+    // a rational arc stays inside its control points' hull only with a non-negative weight: otherwise the band front
+    // end must not cull its path by the box (geom.cuh does the same per curve)
+    bool opened = false;
+    for (uint32_t i = 0; i < n_curves; ++i)
+        if (c->h_ctype[i] == T_ARC && !(curve_weight[i] > 0.0f)) {
+            c->h_pobj[c->h_cpath[i]] = make_float4(-3.0e38f, -3.0e38f, 3.0e38f, 3.0e38f);
+            opened = true;
+        }
+    if (opened) CU(cudaMemcpy(c->d_pobj, c->h_pobj.data(), c->h_pobj.size() * sizeof(float4), cudaMemcpyHostToDevice));
     return SLPR_OK;
 }
 
