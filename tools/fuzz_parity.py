@@ -34,11 +34,14 @@ def coord(rng, W, H, nonfinite):
     return float(rng.uniform(-2.0, span + 2.0))
 
 
-def random_scene(seed, nonfinite=False, full=False):
+def random_scene(seed, nonfinite=False, full=False, big=False):
     rng = np.random.default_rng(seed)
     W = int(rng.choice([1, 2, 3, 16, 33, 64, 97, 128, 200, 320]))
     H = int(rng.choice([1, 2, 5, 16, 31, 48, 81, 128, 150, 240]))
     n_paths = int(rng.integers(1, 24))
+    if big:  # few curves on a big frame: pieces of hundreds of crossings (the long-piece kernels, warp-wide bisection)
+        W, H = [(1024, 768), (1920, 1080), (2049, 1537), (3840, 2160)][int(rng.integers(0, 4))]
+        n_paths = int(rng.integers(1, 5))
     pos, pos_path, cpm, ctype, cpath = [], [], [], [], []
     weights = []
     for p in range(n_paths):
@@ -149,6 +152,32 @@ def check(seed, nonfinite):
     r.close()
     if seed % 4 == 1 and H >= 6:
         check_bands(sc, rows, W, H, ref3["rgba"], V.FLAG_FULL_RVG)
+    if seed % 4 == 2:  # four samples per pixel, with and without blending (defined through the reference path at 4x)
+        sc, rows, W, H = random_scene(seed, nonfinite)
+        for blend in (False, True):
+            ref4 = O.render_aa4(sc, rows, W, H, blend=blend)["rgba_aa"]
+            r = V.ScanlineRasterizer(0, V.FLAG_AA4 | (V.FLAG_BLEND if blend else 0)).initialize(None, W, H)
+            r.loadVG(sc); r.setMVP(rows); r.render(); r.render()
+            assert np.array_equal(r.readback(), ref4), f"aa4 blend={blend}"
+            r.close()
+    if seed % 4 == 3:  # a big frame with few, long curves: every tap, then the frames on which the long-piece walk is on
+        for full in (False, True):
+            sc, rows, W, H = random_scene(seed, nonfinite, full=full, big=True)
+            refb = O.render(sc, rows, W, H, full=full)
+            r = V.ScanlineRasterizer(0, V.FLAG_TAPS | V.FLAG_NO_GRAPH | (V.FLAG_FULL_RVG if full else 0)).initialize(None, W, H)
+            r.loadVG(sc); r.setMVP(rows)
+            for _ in range(2):
+                r.render()
+                assert np.array_equal(r.tap("intersection"), refb["inter"]), f"big full={full}: intersection tap"
+                assert np.array_equal(r.tap("sorted_key"), refb["skey"]), f"big full={full}: sorted keys"
+                assert np.array_equal(r.readback(), refb["rgba"]), f"big full={full}: frame"
+            r.close()
+            g = V.ScanlineRasterizer(0, V.FLAG_FULL_RVG if full else 0).initialize(None, W, H)
+            g.loadVG(sc); g.setMVP(rows)
+            for _ in range(3):
+                g.render()
+                assert np.array_equal(g.readback(), refb["rgba"]), f"big full={full}: graph frames"
+            g.close()
 
 
 def survive(seed):
