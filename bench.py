@@ -393,6 +393,7 @@ def main():
     ap.add_argument("--no-radix-leg", action="store_true", help="skip timing the radix sort beside the segmented sort")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="bands mode: device-side sparse exchange over peer-mapped mailboxes (default) or the host-driven NCCL all-gather of dense sums")
     ap.add_argument("--no-bands16k", action="store_true", help="N > 1, frames mode: skip the cfg4 row-band leg (bands16k in the JSON line)")
+    ap.add_argument("--no-scenes", action="store_true", help="N = 1, frames mode: skip the shipped-scene leg (scenes_4k in the JSON line)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -768,6 +769,33 @@ def main():
                "ms_per_frame": min(ts) * 1e3, "gpu_frame_matches_oracle": ok}
 
     sort_now, fused_now, long_now = r.sort_mode(), r.fill_fused(), r.long_walk_info()
+    scenes_4k = None
+    if world == 1 and args.mode == "frames" and args.workload == "synth_1m_4k" and not args.no_scenes:
+        # BASELINE cfg2 in the driver-run line: the reference's shipped scenes at 3840 x 2160 — few, long
+        # curves, the opposite regime of the headline — device time per frame (graph replay) and the frame against the oracle.
+        scenes_4k = {}
+        try:
+            from oracle import oracle_py as O2
+            for name in ("test", "tiger", "reschart", "drops", "embrace"):
+                s2, rows2, W2, H2 = load_workload(name + "@3840x2160")
+                r2 = V.ScanlineRasterizer(local_rank, 0).initialize(None, W2, H2)
+                r2.set_stream(stream.cuda_stream); r2.loadVG(s2); r2.setMVP(rows2)
+                for _ in range(5):
+                    r2.render()
+                r2.synchronize()
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record(stream)
+                for _ in range(20):
+                    r2.render()
+                a1.record(stream); torch.cuda.synchronize()
+                entry = {"ms_per_frame": a0.elapsed_time(a1) / 20, "curves": s2.n_curves, "fragments": r2.counts()["n_fragments"],
+                         "long_pieces": r2.long_walk_info()[1], "sort": r2.sort_mode()}
+                if not args.no_cpu_baseline:
+                    entry["identical_to_oracle"] = bool(np.array_equal(r2.readback(), O2.render(s2, rows2, W2, H2, keep={"rgba"})["rgba"]))
+                scenes_4k[name] = entry
+                r2.close()
+        except Exception as e:  # the headline line stands on its own
+            scenes_4k["error"] = repr(e)[:300]
     bands16k = None
     if world > 1 and args.mode == "frames" and not args.no_bands16k:
         # The north star's multi-GPU case in the driver-run line: BASELINE cfg4, one 16384 x 16384 frame
@@ -803,6 +831,8 @@ def main():
             out["bands_vs_full_frame"] = band_check
         if bands16k is not None:
             out["bands16k"] = bands16k
+        if scenes_4k is not None:
+            out["scenes_4k"] = scenes_4k
         if anim_info is not None:
             out["anim"] = anim_info
         print(json.dumps(out))
