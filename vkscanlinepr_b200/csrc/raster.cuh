@@ -15,9 +15,15 @@
 namespace slpr {
 
 #ifndef SLPR_FILL_NARROW
-#define SLPR_FILL_NARROW 8 /* records up to this many cells are filled by their own thread (measured: 4 -> 0.162, 8 -> 0.147, 16 -> 0.199 ms) */
+#define SLPR_FILL_NARROW 2 /* records up to this many cells are filled by their own thread (round 1, whole-warp spans: 4 -> 0.162, 8 -> 0.147, 16 -> 0.199 ms; with spans by groups of 8 lanes, k_spans: 1 -> 0.2283, 2 -> 0.2296, 4 -> 0.2308, 8 -> 0.2334) */
 #endif
 
+#ifndef SLPR_FILL_WARP
+#define SLPR_FILL_WARP 64 /* spans of more cells than this are filled by the whole warp (the big shapes of small scenes: test.rvg at 4K 0.141 -> 0.131 ms) */
+#endif
+#ifndef SLPR_FILL_GROUP
+#define SLPR_FILL_GROUP 8 /* lanes that fill one wide span together (measured on the 1 M-curve 4K frame, k_spans, narrow = 8: 32 -> 0.2555, 16 -> 0.2357, 8 -> 0.2334, 4 -> 0.2506 ms) */
+#endif
 // The coverage marks of 32 records, one per lane (ncell cells from cell (cx0, cy), priority prio; alpha = the
 // record's alpha byte, looked at only when BLEND): opaque records atomicMax their priority into the cells, narrow
 // ones by their own lane, wide ones by the whole warp. BLEND: translucent records append list nodes instead; the
@@ -48,9 +54,44 @@ __device__ __forceinline__ void mark_cells32(uint32_t *__restrict__ cells, int c
         const size_t cell0 = (size_t)cy * cw + cx0;
         for (int c = 0; c < need; ++c) blend_append(bl, cell0 + c, base + (uint32_t)c, prio);
     }
-    // wide spans: the whole warp fills them, one after the other
+    // wide spans: groups of lanes fill them, 32 / SLPR_FILL_GROUP at a time (with blending: the whole warp, one after the other).
+    // ncu had the one-span-per-warp loop at 26 % of k_spans' instructions: 25 per span, most lanes idle on a 9-cell span.
     uint32_t wide = __ballot_sync(0xFFFFFFFFu, ncell > SLPR_FILL_NARROW);
     const uint32_t wide_soft = BLEND ? __ballot_sync(0xFFFFFFFFu, soft) : 0u;
+    if constexpr (!BLEND) {
+        // SLPR_FILL_GROUP lanes per span, 32 / SLPR_FILL_GROUP spans at a time (a group without a span of its own
+        // repeats the first one: harmless); spans of more than SLPR_FILL_WARP cells by the whole warp
+        constexpr int GROUPS = 32 / SLPR_FILL_GROUP;
+        const int grp = (int)lane / SLPR_FILL_GROUP;
+        uint32_t huge = __ballot_sync(0xFFFFFFFFu, ncell > SLPR_FILL_WARP);
+        wide &= ~huge;
+        while (huge) {
+            const int src = __ffs(huge) - 1;
+            huge &= huge - 1;
+            const int s_cx0 = __shfl_sync(0xFFFFFFFFu, cx0, src);
+            const int s_n = __shfl_sync(0xFFFFFFFFu, ncell, src);
+            const int s_cy = __shfl_sync(0xFFFFFFFFu, cy, src);
+            const uint32_t s_prio = __shfl_sync(0xFFFFFFFFu, prio, src);
+            uint32_t *row = cells + (size_t)s_cy * cw + s_cx0;
+            for (int c = (int)lane; c < s_n; c += 32) atomicMax(row + c, s_prio);
+        }
+        while (wide) {
+            int src = __ffs(wide) - 1;
+#pragma unroll
+            for (int g = 0; g < GROUPS; ++g) {
+                const int s = wide ? __ffs(wide) - 1 : src;
+                wide &= wide - 1;
+                if (g == grp) src = s;
+            }
+            const int s_cx0 = __shfl_sync(0xFFFFFFFFu, cx0, src);
+            const int s_n = __shfl_sync(0xFFFFFFFFu, ncell, src);
+            const int s_cy = __shfl_sync(0xFFFFFFFFu, cy, src);
+            const uint32_t s_prio = __shfl_sync(0xFFFFFFFFu, prio, src);
+            uint32_t *row = cells + (size_t)s_cy * cw + s_cx0;
+            for (int c = (int)lane % SLPR_FILL_GROUP; c < s_n; c += SLPR_FILL_GROUP) atomicMax(row + c, s_prio);
+        }
+        return;
+    }
     while (wide) {
         const int src = __ffs(wide) - 1;
         wide &= wide - 1;
