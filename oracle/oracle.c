@@ -22,6 +22,12 @@
 
 static inline uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 static inline float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+/* A NaN that an arithmetic instruction PRODUCES has an implementation-defined bit pattern: x86 SSE writes the negative
+ * default NaN 0xFFC00000, NVIDIA GPUs — the reference's target and ours — the positive 0x7FFFFFFF, and pass it on
+ * unchanged. Wherever the path looks at the BITS of a computed float (the sign tests of the bisection, MI1:421; the
+ * parameters, cuts and transformed points it stores) the restatement therefore pins the GPU's pattern. Found by
+ * tools/fuzz_parity.py: a line whose y extent is a denormal has 1/a = inf and (c - c0) * a = 0 * inf. */
+static inline float canon(float x) { return (x != x) ? u2f(0x7FFFFFFFu) : x; }
 
 /* GLSL int(x): round toward zero. Out-of-range is undefined in GLSL; we pin it to the
  * saturating behaviour of the GPU conversion instruction (NaN -> 0) so both sides agree. */
@@ -112,8 +118,8 @@ void orc_transform(uint32_t n_points, const float *pos, const uint32_t *pos_path
         default: break;
         }
         path_visible[pos_path[i]] = (int32_t)((uint32_t)path_visible[pos_path[i]] | flag);
-        tpos_out[2 * i] = op[0];
-        tpos_out[2 * i + 1] = op[1];
+        tpos_out[2 * i] = canon(op[0]);
+        tpos_out[2 * i + 1] = canon(op[1]);
     }
 }
 
@@ -304,10 +310,10 @@ void orc_monotonize_count(uint32_t n_curves, const uint32_t *curve_type,
             }
         }
         tq[0] = q0; tq[1] = q1; tq[2] = q2; tq[3] = q3; /* MI0:363-366 */
-        cut_cache_out[5 * c + 0] = q0; /* MI0:368-372 */
-        cut_cache_out[5 * c + 1] = q1;
-        cut_cache_out[5 * c + 2] = q2;
-        cut_cache_out[5 * c + 3] = q3;
+        cut_cache_out[5 * c + 0] = canon(q0); /* MI0:368-372 */
+        cut_cache_out[5 * c + 1] = canon(q1);
+        cut_cache_out[5 * c + 2] = canon(q2);
+        cut_cache_out[5 * c + 3] = canon(q3);
         cut_cache_out[5 * c + 4] = u2f(n_cuts);
         if (visible) { tq[n_cuts] = 1.f; ++n_cuts; } /* MI0:374-377 */
 
@@ -425,14 +431,14 @@ void orc_intersect(uint32_t n_curves, const uint32_t *curve_type,
                                 float tm = (t0 + t1) * 0.5f;
                                 float vtm = interp_general(type, tm, cv, 0.0f);
                                 t_solve = tm; last_vtm = vtm;
-                                if ((int32_t)(f2u(vtm - cst) ^ f2u(vt0 - cst)) >= 0) { t0 = tm; vt0 = vtm; }
+                                if ((int32_t)(f2u(canon(vtm - cst)) ^ f2u(canon(vt0 - cst))) >= 0) { t0 = tm; vt0 = vtm; }
                                 else t1 = tm;
                             }
                             if (fabsf(last_vtm - cst) > 1.f) t_solve = raw_t0;
                         }
                     }
                 }
-                P[8 + side] = u2f((f2u(t_solve) & 0xFFFFFFFCu) | (uint32_t)side); /* MI1:440 */
+                P[8 + side] = u2f((f2u(canon(t_solve)) & 0xFFFFFFFCu) | (uint32_t)side); /* MI1:440 */
             }
             t0_ms = t1_ms; p0x = p1x; p0y = p1y; /* MI1:442-443 */
         }
