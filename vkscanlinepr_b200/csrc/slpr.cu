@@ -288,7 +288,8 @@ static int alloc_capacity(slpr_ctx *c, int cap) {
         CU(cudaMalloc(&c->t_scan3, (2 * n + 1) * 4));
     }
     // per-frame zeroed temp block
-    const size_t scan_tiles[3] = {(size_t)c->nc / SCAN_TILE_MIN + 2, n / SCAN_TILE_MIN + 2, n / SCAN_TILE_MIN + 2};
+    constexpr size_t frag_tile = SCAN_TILE_MIN < SP_TILE ? SCAN_TILE_MIN : SP_TILE;  // status arrays 1 and 2 also serve k_spans' tiles
+    const size_t scan_tiles[3] = {(size_t)c->nc / SCAN_TILE_MIN + 2, n / frag_tile + 2, n / frag_tile + 2};
     c->sort_tiles_cap = (int)(n / RS_TILE + 2);
     size_t off = 0;
     const size_t o_ctr = off; off += align_up(sizeof(FrameCounters), 256);
@@ -770,7 +771,7 @@ static int enqueue_back(slpr_ctx *c, cudaStream_t s, bool timed, int &launches) 
     SpanTaps stp{c->d_wn, c->t_sidx, c->t_skey32, c->t_flags, c->t_scan3};
     SpanTemp stmp{c->d_wsum, c->d_status[1], c->d_status[2], c->d_tickets + 1};
 #if SLPR_SP_WPRE
-    k_wsum<<<c->num_sms * 4, SP_THREADS, 0, s>>>(c->d_val[cur], c->d_ctr, c->cap, c->d_wsum);
+    k_wsum<<<c->num_sms * 8, WSUM_THREADS, 0, s>>>(c->d_val[cur], c->d_ctr, c->cap, c->d_wsum);
     k_wscan<<<1, 1024, 0, s>>>(c->d_ctr, c->cap, c->d_wsum, c->d_wn);
     launches += 2;
 #endif

@@ -18,11 +18,15 @@
 
 namespace slpr {
 
+// Tile = SLPR_SP_THREADS x SLPR_SP_ITEMS fragments. Without the look-back chain the tiles are independent and small blocks
+// win (their barriers cost less and the ticket balances finer): k_spans on the 1 M-curve 4K frame, threads x blocks/SM:
+// 512 x 2: 0.231 ms, 256 x 4: 0.221, 192 x 5: 0.219, 128 x 8: 0.208, 64 x 16: 0.204 but the winding prefix over four times the
+// tiles costs what is saved (k_wsum + k_wscan 0.026 -> 0.032 -> 0.072); 128 x 8 is the best frame (1.024 -> 1.011 ms).
 #ifndef SLPR_SP_THREADS
-#define SLPR_SP_THREADS 512
+#define SLPR_SP_THREADS 128
 #endif
 #ifndef SLPR_SP_BLOCKS
-#define SLPR_SP_BLOCKS 2
+#define SLPR_SP_BLOCKS 8
 #endif
 #ifndef SLPR_SP_LOOK
 #define SLPR_SP_LOOK 1
@@ -443,41 +447,39 @@ __global__ void __launch_bounds__(SP_THREADS, SP_BLOCKS) k_spans(const uint64_t 
 // every tile with its global winding prefix known and needs a single look-back chain (the flag
 // counts), whose aggregate no longer waits for another chain to resolve.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SP_THREADS) k_wsum(const uint32_t *__restrict__ sval, const FrameCounters *__restrict__ ctr,
-                                                     int capacity, int *__restrict__ wsum) {
-    __shared__ int s_w[SP_THREADS / 32];
+constexpr int WSUM_THREADS = 256;
+__global__ void __launch_bounds__(WSUM_THREADS) k_wsum(const uint32_t *__restrict__ sval, const FrameCounters *__restrict__ ctr,
+                                                       int capacity, int *__restrict__ wsum) {
     const int nf = ctr->n_fragments;
     if (frame_void(ctr, capacity)) return;
     const long long n = nf;
     const long long ntiles = (n == 0) ? 1 : (n + SP_TILE - 1) / SP_TILE;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const long long i0 = tile * SP_TILE + (long long)tid * SP_ITEMS;
+    const int lane = threadIdx.x & 31;
+    const long long warps = (long long)gridDim.x * (WSUM_THREADS / 32);
+    // a warp per span tile (the tile size is k_spans' business; this kernel's launch shape is its own)
+    for (long long tile = (long long)blockIdx.x * (WSUM_THREADS / 32) + (threadIdx.x >> 5); tile < ntiles; tile += warps) {
+        const long long t0 = tile * SP_TILE;
         int dsum = 0;
-        if (i0 + SP_ITEMS <= n) {
-#pragma unroll
-            for (int j = 0; j < SP_ITEMS; j += 4) {
-                const int4 q = ld_stream(reinterpret_cast<const int4 *>(sval + i0 + j));
+        if (t0 + SP_TILE <= n) {
+#pragma unroll 4
+            for (int k = lane; k < SP_TILE / 4; k += 32) {
+                const int4 q = ld_stream(reinterpret_cast<const int4 *>(sval + t0) + k);
                 dsum += (int)((uint32_t)q.x >> 30) + (int)((uint32_t)q.y >> 30) + (int)((uint32_t)q.z >> 30) + (int)((uint32_t)q.w >> 30) - 4;
             }
         } else {
-            for (int j = 0; j < SP_ITEMS; ++j)
-                if (i0 + j < n) dsum += (int)(sval[i0 + j] >> 30) - 1;
+            for (long long i = t0 + lane; i < n; i += 32) dsum += (int)(sval[i] >> 30) - 1;
         }
         dsum = __reduce_add_sync(0xFFFFFFFFu, dsum);
-        if (lane == 0) s_w[warp] = dsum;
-        __syncthreads();
-        if (warp == 0) {
-            int v = (lane < SP_THREADS / 32) ? s_w[lane] : 0;
-            v = __reduce_add_sync(0xFFFFFFFFu, v);
-            if (lane == 0) wsum[tile] = v;
-        }
-        __syncthreads();
+        if (lane == 0) wsum[tile] = dsum;
     }
 }
 
+// One block scans the tile sums in chunks of 8192 that pass through shared memory: global accesses coalesced, every
+// thread scans eight neighbours, one block-wide scan of the 1024 partial sums per chunk.
 __global__ void __launch_bounds__(1024) k_wscan(FrameCounters *__restrict__ ctr, int capacity, int *__restrict__ wsum,
                                                 int *__restrict__ wn_tap) {
+    constexpr int PER = 8, CHUNK = 1024 * PER;
+    __shared__ int s_v[CHUNK + CHUNK / 32];  // (one pad word per 32: a thread's eight neighbours start on different banks)
     __shared__ int s_w[32];
     __shared__ int s_carry;
     const int nf = ctr->n_fragments;
@@ -486,10 +488,20 @@ __global__ void __launch_bounds__(1024) k_wscan(FrameCounters *__restrict__ ctr,
     const int ntiles = (int)((n == 0) ? 1 : (n + SP_TILE - 1) / SP_TILE);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_carry = 0;
-    __syncthreads();
-    for (int base = 0; base < ntiles; base += 1024) {
-        const int i = base + tid;
-        const int v = (i < ntiles) ? wsum[i] : 0;
+    for (int base = 0; base < ntiles; base += CHUNK) {
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const int j = tid + 1024 * k;
+            s_v[j + (j >> 5)] = (base + j < ntiles) ? wsum[base + j] : 0;
+        }
+        __syncthreads();
+        int t[PER], v = 0;
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const int j = tid * PER + k;
+            t[k] = s_v[j + (j >> 5)];
+            v += t[k];
+        }
         int incl = v;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -499,7 +511,7 @@ __global__ void __launch_bounds__(1024) k_wscan(FrameCounters *__restrict__ ctr,
         if (lane == 31) s_w[warp] = incl;
         __syncthreads();
         if (warp == 0) {
-            int w = s_w[lane];
+            const int w = s_w[lane];
             int wi = w;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
@@ -510,10 +522,20 @@ __global__ void __launch_bounds__(1024) k_wscan(FrameCounters *__restrict__ ctr,
         }
         __syncthreads();
         const int carry = s_carry;
-        const int excl = carry + s_w[warp] + incl - v;
-        if (i < ntiles) wsum[i] = excl;  // exclusive winding prefix of tile i
+        int run = carry + s_w[warp] + incl - v;  // exclusive winding prefix of this thread's first tile
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const int j = tid * PER + k;
+            s_v[j + (j >> 5)] = run;
+            run += t[k];
+        }
         __syncthreads();
-        if (tid == 1023) s_carry = excl + v;
+        if (tid == 1023) s_carry = run;
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const int j = tid + 1024 * k;
+            if (base + j < ntiles) wsum[base + j] = s_v[j + (j >> 5)];
+        }
         __syncthreads();
     }
     if (tid == 0) {
