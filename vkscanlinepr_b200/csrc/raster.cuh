@@ -15,7 +15,7 @@
 namespace slpr {
 
 #ifndef SLPR_FILL_NARROW
-#define SLPR_FILL_NARROW 2 /* records up to this many cells are filled by their own thread (round 1, whole-warp spans: 4 -> 0.162, 8 -> 0.147, 16 -> 0.199 ms; with spans by groups of 8 lanes, k_spans: 1 -> 0.2283, 2 -> 0.2296, 4 -> 0.2308, 8 -> 0.2334) */
+#define SLPR_FILL_NARROW 1 /* records up to this many cells are filled by their own thread (round 1, whole-warp spans: 4 -> 0.162, 8 -> 0.147, 16 -> 0.199 ms; with spans by groups of 8 lanes, k_spans at 512-thread tiles: 1 -> 0.2283, 2 -> 0.2296, 4 -> 0.2308, 8 -> 0.2334; at 128-thread tiles: 1 -> 0.2058, 2 -> 0.2091) */
 #endif
 
 #ifndef SLPR_FILL_WARP
