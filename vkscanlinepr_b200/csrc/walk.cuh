@@ -194,7 +194,7 @@ __device__ __forceinline__ uint32_t take_ticket(int *counter) {
 // pair (one 16-byte store instead of two 8-byte ones) and values until it has an aligned quad: the
 // scattered stores of the walk are its second cost after the bisection.
 #ifndef SLPR_WALK_PAIR
-#define SLPR_WALK_PAIR 1
+#define SLPR_WALK_PAIR 2 /* 1: held-back pairs / quads with one arm per f mod 4 (divergent); 2: sliding window, predicated stores: walk 0.4604 -> 0.4510 ms */
 #endif
 struct FragStore {
     uint64_t pk;
@@ -207,6 +207,24 @@ struct FragStore {
             key64[f] = k; val[f] = v;
             return;
         }
+#if SLPR_WALK_PAIR == 2
+        // Without divergent arms (the lanes of a warp are at different f mod 4): the held-back key is simply the last
+        // one, the held-back values a sliding window (pv0, pv1, pv2 = values of f-3, f-2, f-1); the stores are predicated.
+        if (f & 1) {
+            if (f > f_first) *reinterpret_cast<ulonglong2 *>(key64 + f - 1) = make_ulonglong2(pk, k);
+            else key64[f] = k;
+        }
+        pk = k;
+        if ((f & 3) == 3) {
+            if (f - 3 >= f_first) *reinterpret_cast<uint4 *>(val + f - 3) = make_uint4(pv0, pv1, pv2, v);
+            else {
+                if (f - 2 >= f_first) val[f - 2] = pv1;
+                if (f - 1 >= f_first) val[f - 1] = pv2;
+                val[f] = v;
+            }
+        }
+        pv0 = pv1; pv1 = pv2; pv2 = v;
+#else
         if (f & 1) {
             if (f > f_first) *reinterpret_cast<ulonglong2 *>(key64 + f - 1) = make_ulonglong2(pk, k);
             else key64[f] = k;
@@ -223,17 +241,26 @@ struct FragStore {
         } else if (q == 0) pv0 = v;
         else if (q == 1) pv1 = v;
         else pv2 = v;
+#endif
     }
     // after the piece's last fragment
     __device__ __forceinline__ void flush(int f_last, uint64_t *__restrict__ key64, uint32_t *__restrict__ val) {
         if (!SLPR_WALK_PAIR || direct) return;
         if (!(f_last & 1)) key64[f_last] = pk;
         const int q = f_last & 3, base = f_last - q;
+#if SLPR_WALK_PAIR == 2
+        if (q != 3) {  // window: pv2 = value of f_last, pv1 of f_last - 1, pv0 of f_last - 2
+            val[f_last] = pv2;
+            if (q >= 1 && f_last - 1 >= f_first) val[f_last - 1] = pv1;
+            if (q >= 2 && base >= f_first) val[base] = pv0;
+        }
+#else
         if (q != 3) {
             if (base >= f_first) val[base] = pv0;
             if (q >= 1 && base + 1 >= f_first) val[base + 1] = pv1;
             if (q >= 2) val[base + 2] = pv2;
         }
+#endif
     }
 };
 
