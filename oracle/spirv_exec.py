@@ -23,10 +23,10 @@ import numpy as np
 
 # ---- opcodes (SPIR-V 1.0 unified spec) ---------------------------------------------------------
 OP = dict(Name=5, MemberName=6, ExtInstImport=11, ExtInst=12, EntryPoint=15, ExecutionMode=16, TypeVoid=19, TypeBool=20,
-          TypeInt=21, TypeFloat=22, TypeVector=23, TypeArray=28, TypeRuntimeArray=29, TypeStruct=30, TypePointer=32,
+          TypeInt=21, TypeFloat=22, TypeVector=23, TypeImage=25, TypeSampledImage=27, TypeArray=28, TypeRuntimeArray=29, TypeStruct=30, TypePointer=32,
           TypeFunction=33, ConstantTrue=41, ConstantFalse=42, Constant=43, ConstantComposite=44, Function=54,
           FunctionParameter=55, FunctionEnd=56, FunctionCall=57, Variable=59, Load=61, Store=62, AccessChain=65,
-          Decorate=71, MemberDecorate=72, VectorShuffle=79, CompositeConstruct=80, CompositeExtract=81, ConvertFToU=109,
+          Decorate=71, MemberDecorate=72, VectorShuffle=79, CompositeConstruct=80, CompositeExtract=81, ImageFetch=95, Image=100, ConvertFToU=109,
           ConvertFToS=110, ConvertSToF=111, ConvertUToF=112, Bitcast=124, SNegate=126, FNegate=127, IAdd=128, FAdd=129,
           ISub=130, FSub=131, IMul=132, FMul=133, UDiv=134, SDiv=135, FDiv=136, VectorTimesScalar=142, Dot=148,
           LogicalOr=166, LogicalAnd=167, LogicalNot=168, Select=169, IEqual=170, INotEqual=171, UGreaterThan=172,
@@ -38,7 +38,8 @@ OP = dict(Name=5, MemberName=6, ExtInstImport=11, ExtInst=12, EntryPoint=15, Exe
           BranchConditional=250, Switch=251, Return=253, ReturnValue=254)
 O = type("O", (), OP)
 DEC_ARRAY_STRIDE, DEC_BUILTIN, DEC_BINDING, DEC_OFFSET = 6, 11, 33, 35
-SC_INPUT, SC_UNIFORM, SC_WORKGROUP, SC_PRIVATE, SC_FUNCTION, SC_PUSH, SC_STORAGE = 1, 2, 4, 6, 7, 9, 12
+SC_UNIFORM_CONSTANT, SC_INPUT, SC_UNIFORM, SC_OUTPUT, SC_WORKGROUP, SC_PRIVATE, SC_FUNCTION, SC_PUSH, SC_STORAGE = 0, 1, 2, 3, 4, 6, 7, 9, 12
+DEC_LOCATION = 30
 BI_NUM_WG, BI_WG_ID, BI_LOCAL_ID, BI_GLOBAL_ID, BI_LOCAL_INDEX = 24, 26, 27, 28, 29
 M32 = 0xFFFFFFFF
 F32 = np.float32
@@ -118,6 +119,10 @@ class Module:
                 self.types[a[0]] = Type("float", width=a[1], id=a[0])
             elif op == O.TypeVector:
                 self.types[a[0]] = Type("vector", elem=a[1], count=a[2], id=a[0])
+            elif op == O.TypeImage:
+                self.types[a[0]] = Type("image", elem=a[1], id=a[0])
+            elif op == O.TypeSampledImage:
+                self.types[a[0]] = Type("image", elem=a[1], id=a[0])
             elif op == O.TypeArray:
                 self.types[a[0]] = Type("array", elem=a[1], count=("const", a[2]), id=a[0])
             elif op == O.TypeRuntimeArray:
@@ -227,6 +232,10 @@ class Runner:
                 self.global_ptr[vid] = (arr, off, module.types[ptid].elem)
             elif sc == SC_PUSH:
                 self.global_ptr[vid] = (push, 0, module.types[ptid].elem)
+            elif sc == SC_UNIFORM_CONSTANT:  # a texel buffer (isamplerBuffer): bindings[b] = (int32 texels, 4 words each; 0)
+                b = module.decor.get(vid, {}).get(DEC_BINDING)
+                arr, off = bindings[b[0]]
+                self.global_ptr[vid] = (arr, off, module.types[ptid].elem)
 
     # value <-> memory ---------------------------------------------------------------------------
     def load(self, ptr):
@@ -244,6 +253,8 @@ class Runner:
             return tuple(int(mem[off + i]) & M32 for i in range(t.count))
         if k == "bool":
             return bool(mem[off])
+        if k == "image":
+            return ("image", mem, off)
         raise ValueError("load of " + k)
 
     def store(self, ptr, val):
@@ -306,6 +317,49 @@ class Runner:
                             except StopIteration:
                                 pass
                         live = nxt
+
+    # one vertex / fragment invocation -----------------------------------------------------------
+    def run_stage(self, builtins=None, locations=None):
+        """Run the entry point once as a graphics-stage invocation (scanlinepr.vert / .frag: no barriers, no
+        derivatives). Input variables are fed from `builtins` {BuiltIn number: tuple} (42 = VertexIndex, 15 =
+        FragCoord) and `locations` {location: tuple} (floats as numpy.float32, integers as ints); returns
+        ({BuiltIn: value}, {location: value}) read back from the Output variables (a gl_PerVertex block is reported
+        member by member under its members' BuiltIn numbers, 0 = Position)."""
+        m = self.m
+        env = dict(self.global_ptr)
+        outs = []
+        for vid, (ptid, sc) in m.globals.items():
+            if sc not in (SC_INPUT, SC_OUTPUT, SC_PRIVATE):
+                continue
+            et = m.types[ptid].elem
+            mem = [0] * m.size_words(et)
+            env[vid] = (mem, 0, et)
+            dec = m.decor.get(vid, {})
+            if sc == SC_INPUT:
+                src = builtins.get(dec[DEC_BUILTIN][0]) if DEC_BUILTIN in dec else (locations or {}).get(dec.get(DEC_LOCATION, [None])[0])
+                if src is not None:
+                    self.store(env[vid], src if m.types[et].kind == "vector" else src[0])
+            elif sc == SC_OUTPUT:
+                outs.append((vid, et, dec))
+        for _ in self.call(m.entry, [], env):
+            raise RuntimeError("barrier in a graphics stage")
+        out_b, out_l = {}, {}
+        for vid, et, dec in outs:
+            t = m.types[et]
+            if t.kind == "struct":  # gl_PerVertex
+                for k, mt in enumerate(t.members):
+                    bi = m.mdecor.get((et, k), {}).get(DEC_BUILTIN)
+                    if bi is not None and m.types[mt].kind in ("vector", "float", "int"):
+                        o, _ = m.step(et, k)
+                        out_b[bi[0]] = self.load((env[vid][0], o, mt))
+            elif t.kind == "array":  # gl_SampleMask[]
+                if DEC_BUILTIN in dec:
+                    out_b[dec[DEC_BUILTIN][0]] = tuple(int(x) & M32 for x in env[vid][0])
+            elif DEC_BUILTIN in dec:
+                out_b[dec[DEC_BUILTIN][0]] = self.load(env[vid])
+            elif DEC_LOCATION in dec:
+                out_l[dec[DEC_LOCATION][0]] = self.load(env[vid])
+        return out_b, out_l
 
     # interpreter --------------------------------------------------------------------------------
     def call(self, fid, args, genv):
@@ -449,7 +503,8 @@ class Runner:
                     c, x, y = val(a[2]), val(a[3]), val(a[4])
                     v[a[1]] = tuple(p if k else q for k, p, q in zip(c, x, y)) if isinstance(c, tuple) else (x if c else y)
                 elif op == O.ConvertFToS:
-                    v[a[1]] = f2i_sat(val(a[2])) & M32
+                    x = val(a[2])
+                    v[a[1]] = tuple(f2i_sat(p) & M32 for p in x) if isinstance(x, tuple) else (f2i_sat(x) & M32)
                 elif op == O.ConvertSToF:
                     v[a[1]] = F32(s32(val(a[2])))
                 elif op == O.ConvertUToF:
@@ -476,6 +531,12 @@ class Runner:
                     for ix in a[3:]:
                         x = x[ix]
                     v[a[1]] = x
+                elif op == O.Image:
+                    v[a[1]] = val(a[2])
+                elif op == O.ImageFetch:  # texelFetch on a buffer texture of 4-component 32-bit integer texels
+                    _, mem, off = val(a[2])
+                    i = s32(val(a[3]))
+                    v[a[1]] = tuple(int(mem[off + 4 * i + k]) & M32 for k in range(4))
                 elif op == O.VectorShuffle:
                     x, y = val(a[2]), val(a[3])
                     both = tuple(x) + tuple(y)
