@@ -206,6 +206,14 @@ SLPR_API uint64_t slpr_pipeline_redone(slpr_ctx *ctx);
 SLPR_API int slpr_host_alloc(slpr_ctx *ctx, size_t bytes, void **host_ptr, int *numa_node);
 SLPR_API int slpr_host_free(slpr_ctx *ctx, void *host_ptr);
 
+/* Stage 5 alone — the reference's draw call over output_buf (scanline_rasterizer.cpp:611-656; scanlinepr.vert:19-46,
+ * scanlinepr.frag): clears the frame to white and draws `n_records` draw records given in the reference's own format,
+ * four int32 each (yx = y << 16 | x, width, fill_info, frag_index — the rows of workdir/test_data*.csv), later records
+ * over earlier ones. Blocking; the frame is then read with slpr_readback / slpr_framebuffer. Records must lie on the
+ * 2 x 2 fragment grid (x, y, width even — true of every record the path emits). Needs no scene. Not with SLPR_FLAG_AA4,
+ * SLPR_FLAG_BLEND or a band. New entry point: lets the reference's record dumps be drawn and compared directly. */
+SLPR_API int slpr_draw_records(slpr_ctx *ctx, const int32_t *records, uint64_t n_records);
+
 /* Device pointer of the last rendered frame (RGBA8) and its row stride. Does not synchronise. */
 SLPR_API int slpr_framebuffer(slpr_ctx *ctx, void **dev_rgba, size_t *stride_bytes);
 

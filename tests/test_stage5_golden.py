@@ -137,3 +137,45 @@ def test_interpreter_still_reproduces_the_stage5_fixture():
     out = M5.run_records(sub, log=lambda *a: None)
     assert np.array_equal(out["position"].view(np.float32).reshape(-1, 4), np.concatenate([pos[:80], pos[-80:]]))
     assert np.array_equal(out["color"].view(np.float32).reshape(-1, 4), np.concatenate([col[:40], col[-40:]]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["1", "3"])
+def test_cuda_stage5_equals_the_executed_shaders_rasterized(tag):
+    """The CUDA stage 5 (k_fill_cells + k_resolve through slpr_draw_records) draws the reference's own record dumps into
+    the frame the reference's own shaders + the fixed-function rules give."""
+    import vkscanlinepr_b200 as V
+    rec, pos, col, _, _ = load(tag)
+    want = rasterize(rec, pos, col)
+    r = V.ScanlineRasterizer(0, 0).initialize(None, W, H)
+    try:
+        r.draw_records(rec)
+        got = r.readback().view(np.uint32).reshape(H, W)
+        assert np.array_equal(got, want)
+        r.draw_records(rec[:0])  # an empty list clears the frame
+        assert np.all(r.readback().view(np.uint32) == 0xFFFFFFFF)
+        with pytest.raises(V.SlprError):
+            r.draw_records(np.array([[3, 2, -1, 0]], np.int32))  # x = 3: off the 2 x 2 fragment grid
+    finally:
+        r.close()
+
+
+@pytest.mark.gpu
+def test_cuda_draw_records_between_rendered_frames():
+    """slpr_draw_records leaves a context with a scene as it was: the next rendered frame is the scene's."""
+    import vkscanlinepr_b200 as V
+    from vkscanlinepr_b200 import scene as S
+    sc, rows = S.synth_scene(300, 512, 512), S.identity_rows()
+    r = V.ScanlineRasterizer(0, 0).initialize(None, 512, 512)
+    try:
+        r.loadVG(sc)
+        r.setMVP(rows)
+        r.render()
+        a = r.readback().copy()
+        r.draw_records(np.array([[(10 << 16) | 4, 20, 0x7F112233, 0]], np.int32))
+        b = r.readback().view(np.uint32).reshape(512, 512)
+        assert np.count_nonzero(b != 0xFFFFFFFF) == 40 and np.all(b[512 - 1 - 11:512 - 1 - 9, 4:24] == 0x7F112233)
+        r.render()
+        assert np.array_equal(r.readback(), a)
+    finally:
+        r.close()

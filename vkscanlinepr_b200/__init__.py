@@ -225,6 +225,11 @@ class ScanlineRasterizer:
         _check(lib().slpr_readback(self._h, _p(out), C.c_size_t(out.strides[0])))
         return out
 
+    def draw_records(self, records):
+        """Stage 5 alone (slpr_draw_records): draw int32 [n, 4] records in the reference's output_buf format."""
+        r = np.ascontiguousarray(records, dtype=np.int32).reshape(-1, 4)
+        _check(lib().slpr_draw_records(self._h, _p(r), C.c_uint64(r.shape[0])))
+
     def render_to_host(self, rows, out):
         r = np.ascontiguousarray(rows, dtype=np.float32).reshape(16)
         _check(lib().slpr_render_to_host(self._h, _p(r), _p(out), C.c_size_t(out.strides[0])))

@@ -1068,6 +1068,10 @@ static int finish_frame(slpr_ctx *c) {
     if (!c->frame_pending && !c->frame_done) return fail(SLPR_ERR_STATE, "no frame has been rendered");
     CU(cudaSetDevice(c->device));
     if (c->peers.n_bands > 0 && !c->x_sums && c->frame_pending) return finish_peer_frame(c);
+    if (!c->frame_pending) {  // finished before (a second read-back, or slpr_draw_records): its counters were dealt with then
+        CU(cudaStreamSynchronize(c->stream));
+        return SLPR_OK;
+    }
     for (int attempt = 0; attempt < 4; ++attempt) {
         CU(cudaStreamSynchronize(c->stream));
         c->frame_pending = false;
@@ -1118,6 +1122,56 @@ extern "C" int slpr_readback(slpr_ctx *c, uint8_t *rgba, size_t stride_bytes) {
     const size_t stride = c->target ? c->target_stride : c->fb_stride;
     CU(copy_frame_to_host(c, rgba, stride_bytes, fb, stride, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    return SLPR_OK;
+}
+
+// Stage 5 alone: the reference's draw call (scanline_rasterizer.cpp:611-656: clear to white, LINE_LIST over output_buf
+// through scanlinepr.vert / .frag) over a caller-supplied list of draw records in the reference's own format
+// (yx, width, fill_info, frag_index) — what workdir/test_data*.csv hold. The frame is then read with slpr_readback /
+// slpr_framebuffer like a rendered one. Records must lie on the 2 x 2 fragment grid (x, y and width even), as every
+// record the path emits does: the coverage grid works in those cells.
+extern "C" int slpr_draw_records(slpr_ctx *c, const int32_t *records, uint64_t n_records) {
+    if (!c || (!records && n_records)) return fail(SLPR_ERR_INVALID, "slpr_draw_records: null argument");
+    if (n_records >= (1ull << 30)) return fail(SLPR_ERR_INVALID, "slpr_draw_records: too many records");
+    if (c->ss != 1 || (c->flags & SLPR_FLAG_BLEND)) return fail(SLPR_ERR_STATE, "slpr_draw_records: not with SLPR_FLAG_AA4 / SLPR_FLAG_BLEND");
+    if (c->hp.cull || c->peers.n_bands > 0) return fail(SLPR_ERR_STATE, "slpr_draw_records: not in band mode");
+    for (uint64_t i = 0; i < n_records; ++i) {
+        const int32_t yx = records[4 * i], w = records[4 * i + 1];
+        if (((yx & 0xFFFF) | (yx >> 16) | w) & 1 || w < 0)
+            return fail(SLPR_ERR_INVALID, "slpr_draw_records: record %llu is off the 2 x 2 fragment grid", (unsigned long long)i);
+    }
+    CU(cudaSetDevice(c->device));
+    if (c->frame_pending) {
+        int rc = finish_frame(c);
+        if (rc) return rc;
+    }
+    if (!c->d_temp) {
+        int rc = alloc_capacity(c, 1 << 14);
+        if (rc) return rc;
+    }
+    int4 *d_rec = nullptr;
+    CU(cudaMalloc(&d_rec, std::max<size_t>(n_records, 1) * sizeof(int4)));
+    cudaStream_t s = c->stream;
+    const int n = (int)n_records;
+    const BlendList bl{c->d_heads, c->d_nodes, c->node_cap};
+    uint8_t *fb = c->target ? c->target : c->fb_cur;
+    const size_t stride = c->target ? c->target_stride : c->fb_stride;
+    const int wide = c->num_sms * 8;
+    cudaError_t e = cudaMemcpyAsync(d_rec, records, n_records * sizeof(int4), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(c->d_temp, 0, c->temp_bytes, s);  // the frame's counters: nothing void
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&c->d_ctr->n_records, &n, sizeof(int), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) {
+        k_set_params<<<1, 1, 0, s>>>(c->d_params, c->hp);
+        k_fill_cells<false><<<wide, 256, 0, s>>>(c->d_params, c->d_ctr, c->cap, d_rec, c->d_cells, c->cw, bl);
+        k_resolve<false, false><<<wide, 256, 0, s>>>(c->d_params, d_rec, c->d_finfo, c->d_cells, c->cw, fb, stride, bl);
+        c->launches += 3;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(d_rec);
+    if (e != cudaSuccess) return fail(SLPR_ERR_CUDA, "slpr_draw_records: %s", cudaGetErrorString(e));
+    c->frame_pending = false;
+    c->frame_done = true;
     return SLPR_OK;
 }
 
