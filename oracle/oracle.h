@@ -15,7 +15,9 @@
  * (tests/test_spirv_golden.py: 5 scenes incl. a 4-cut cubic, QUADRIC-typed curves, clipping on
  * all edges, a tiger subset with a winding residue). Caveats: the interpreter evaluates fp32
  * without FMA contraction and sums OpDot left to right (a real driver may differ),
- * and the fixed-function line raster of stage 5 is restated from the Vulkan rules, not executed.
+ * and the fixed-function line raster of stage 5 is restated from the Vulkan rules, not executed —
+ * its vertex and fragment shaders ARE executed (tools/make_stage5_golden.py, on the reference's own
+ * record dumps; tests/test_stage5_golden.py: orc_fill equals their output rasterized by those rules).
  * Also pinned: (1) scene flattening (loadVG + RVG parser) against the reference's own parser
  * compiled from its sources (oracle/_ref, see oracle/Makefile); (2) the output record format /
  * ordering invariants against workdir/test_data.csv and test_data3.csv.

@@ -1,4 +1,5 @@
-"""spirv_exec.py — a small SPIR-V 1.0 interpreter for the reference's compute shaders.
+"""spirv_exec.py — a small SPIR-V 1.0 interpreter for the reference's shaders: the nine compute shaders of the path
+and (Runner.run_stage) the vertex / fragment pair of its stage 5.
 
 TEST INFRASTRUCTURE ONLY (see oracle/oracle.h). Purpose: execute the reference's own shipped
 binaries — workdir/shaders/**/spv/*.comp.spv — on the CPU, because no Vulkan loader/ICD exists
@@ -7,7 +8,11 @@ ScanlineVGRasterizer::drawFrame (scanline_rasterizer.cpp:282-608) on small scene
 every buffer as a golden fixture; tests/test_spirv_golden.py then pins the C oracle (and, on a
 GPU, the CUDA path) to those buffers bit for bit.
 
-Semantics implemented: the 84 opcodes glslang emitted for these nine shaders (logical addressing,
+tools/make_stage5_golden.py runs workdir/shaders/scanline/surface/spv/scanlinepr.{vert,frag}.spv per vertex / per
+record over the reference's own output_buf dumps (tests/golden/stage5_*.npz, tests/test_stage5_golden.py).
+
+Semantics implemented: the 84 opcodes glslang emitted for the nine compute shaders (+ OpImage / OpImageFetch on an integer
+texel buffer, Input / Output variables and gl_PerVertex for the two graphics shaders) (logical addressing,
 GLSL450 memory model), GLSL.std.450 {Floor, Sqrt, FAbs, FMin, FMax, SMin, SMax, SClamp}, std140 /
 std430 buffer layouts from the Offset / ArrayStride decorations, Workgroup storage, barriers
 (every invocation of a workgroup is a Python generator that yields at OpControlBarrier), and
