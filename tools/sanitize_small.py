@@ -85,4 +85,7 @@ for n in (5, 100_003, (1 << 22) + 8192 * 3 + 5):
 k = torch.randint(0, 1 << 40, (200_003,), dtype=torch.int64, device="cuda"); v = torch.arange(200_003, dtype=torch.int32, device="cuda")
 k2, v2 = torch.empty_like(k), torch.empty_like(v)
 r.sort_pairs(k.data_ptr(), v.data_ptr(), k2.data_ptr(), v2.data_ptr(), 200_003, 40); r.synchronize(); r.close()
+r = V.ScanlineRasterizer(0, 0).initialize(None, 200, 120)   # stage 5 alone over a caller's records, without a scene
+rec = np.array([[(10 << 16) | 4, 20, 0x7F112233, 0], [(118 << 16) | 0, 200, -1, 1], [(0 << 16) | 198, 2, 5, 2], [(4 << 16) | 190, 64, 7, 0]], np.int32)
+r.draw_records(rec); r.readback(); r.draw_records(rec[:0]); r.readback(); r.close()
 print("done")
