@@ -52,6 +52,9 @@ struct PointXform {
     }
 };
 
+#ifndef SLPR_XF_PREFETCH
+#define SLPR_XF_PREFETCH 1
+#endif
 template <bool FMA>
 __global__ void __launch_bounds__(256) k_transform(const FrameParams *__restrict__ P, uint32_t n_points,
                                                    const float2 *__restrict__ pos,
@@ -61,6 +64,31 @@ __global__ void __launch_bounds__(256) k_transform(const FrameParams *__restrict
     const PointXform xf(P);
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t n_round = (n_points + 31u) & ~31u;  // keep whole warps in the loop for the shuffles
+#if SLPR_XF_PREFETCH
+    // The point and its path index are fetched together, one trip ahead: the kernel used to wait twice per point —
+    // for the point, and again, behind the divisions, for the path index the match needs (ncu: 2 x 30 % of its stalls).
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    float2 p_nx = make_float2(0.f, 0.f);
+    uint32_t pid_nx = 0xFFFFFFFFu;
+    if (i < n_points) { pid_nx = pos_path[i]; p_nx = pos[i]; }
+    for (; i < n_round; i += stride) {
+        const float2 p = p_nx;
+        uint32_t pidx = pid_nx;
+        bool live = i < n_points;
+        const uint32_t i_nx = i + stride;
+        pid_nx = 0xFFFFFFFFu;
+        if (i_nx < n_points) { pid_nx = pos_path[i_nx]; p_nx = pos[i_nx]; }
+        uint32_t flag = 0;
+        if (live && path_live) {  // band mode: the points of a path that cannot reach the band are not needed
+            live = path_live[pidx] != 0;
+            if (!live) pidx = 0xFFFFFFFFu;
+        }
+        if (live) {
+            float2 o;
+            flag = xf.apply<FMA>(p, o);
+            tpos[i] = o;
+        }
+#else
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
         bool live = i < n_points;
         uint32_t flag = 0, pidx = 0xFFFFFFFFu;
@@ -75,6 +103,7 @@ __global__ void __launch_bounds__(256) k_transform(const FrameParams *__restrict
             pidx = pos_path[i];
             tpos[i] = o;
         }
+#endif
         const uint32_t peers = __match_any_sync(0xFFFFFFFFu, pidx);
         const uint32_t red = __reduce_or_sync(peers, flag);
         const bool leader = live && (lane_id() == (uint32_t)(__ffs(peers) - 1));
@@ -359,6 +388,9 @@ __global__ void __launch_bounds__(256) k_band_live(uint32_t n_curves, const uint
     }
 }
 
+#ifndef SLPR_MONO_PREFETCH
+#define SLPR_MONO_PREFETCH 1
+#endif
 template <bool FMA>
 __global__ void __launch_bounds__(256) k_monotonize_count(const FrameParams *__restrict__ P, uint32_t n_curves,
                                                           const uint32_t *__restrict__ curve_type,
@@ -384,12 +416,31 @@ __global__ void __launch_bounds__(256) k_monotonize_count(const FrameParams *__r
     const uint32_t n_work = live.count(n_curves);
     const uint32_t ipb = lay.items_per_block(n_work);  // a contiguous run of work items per block (PieceLayout)
     const uint32_t w_end = min(n_work, (blockIdx.x + 1u) * ipb);
+#if SLPR_MONO_PREFETCH
+    // Two levels of loads instead of four: what depends on the curve index alone (type, first point, path) is
+    // fetched one trip ahead, and the path's visibility mask together with the points (it used to be asked for only
+    // after the band test, behind the points: ncu showed a third of the kernel's stalls on these chains).
+    uint32_t w = blockIdx.x * ipb + threadIdx.x;
+    uint32_t c_nx = 0, type_nx = 0, po_nx = 0, path_nx = 0;
+    if (w < w_end) { c_nx = live.curve(w); type_nx = curve_type[c_nx]; po_nx = curve_pos_map[c_nx]; path_nx = curve_path[c_nx]; }
+    for (; w < w_end; w += blockDim.x) {
+        const uint32_t c = c_nx, type = type_nx, cpath = path_nx;
+        CurvePts cp;
+        load_points(type, po_nx, tpos, cp);
+        const int pvis = path_visible[cpath];
+        if (w + blockDim.x < w_end) {
+            c_nx = live.curve(w + blockDim.x); type_nx = curve_type[c_nx]; po_nx = curve_pos_map[c_nx]; path_nx = curve_path[c_nx];
+        }
+        full.stash_weight(type, c, cp);
+#else
     for (uint32_t w = blockIdx.x * ipb + threadIdx.x; w < w_end; w += blockDim.x) {
         const uint32_t c = live.curve(w);
         const uint32_t type = curve_type[c];
         CurvePts cp;
         load_points(type, curve_pos_map[c], tpos, cp);
         full.stash_weight(type, c, cp);
+        const uint32_t cpath = curve_path[c];
+#endif
         uint32_t n_cuts = 0;
         bool culled = false;  // band mode: a curve whose control-point box misses the band is skipped like an invisible one
         // (only for curves that stay inside their control points' box: a type without a shader arm — and ARC without the
@@ -402,7 +453,11 @@ __global__ void __launch_bounds__(256) k_monotonize_count(const FrameParams *__r
                 if (i < np) { ymin = fminf(ymin, cp.y[i]); ymax = fmaxf(ymax, cp.y[i]); }
             culled = (ymax < band_lo) || (ymin >= band_hi);
         }
-        const bool visible = !culled && !path_invisible(path_visible[curve_path[c]]);  // MI0:260-261
+#if SLPR_MONO_PREFETCH
+        const bool visible = !culled && !path_invisible(pvis);  // MI0:260-261
+#else
+        const bool visible = !culled && !path_invisible(path_visible[cpath]);  // MI0:260-261
+#endif
         float tq[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
         float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
         if (visible) {
