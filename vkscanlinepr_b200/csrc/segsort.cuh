@@ -108,6 +108,41 @@ __device__ __forceinline__ void warp_bitonic(W (&e)[R], int lane) {
     }
 }
 
+// 96 words: paths of 65..96 fragments are the largest class of the 4K bench scene (40 % of its paths, half of its
+// fragments) and the 128-word network above does a third more work than they need. A bitonic network wants a power
+// of two, but only in the number of BLOCKS: with a sorted block of three words per lane, the 15 compare-exchange
+// stages of the 32-lane network become merge-splits — a lane takes its partner's block reversed (three shuffles),
+// keeps the element-wise minima or maxima (the lower or upper half of the two blocks' union, a bitonic triple) and
+// sorts its three words again (min3 / max3 and the middle by exclusive-or). 13 instructions per stage against the
+// 25 x 12 + 3 register stages of R = 4; the result is blocked (lane L: ranks 3L..3L+2) and goes through the warp's
+// shared-memory slice to the striped order (rank r * 32 + lane) everything around expects.
+__device__ __forceinline__ void sort3(uint32_t &a, uint32_t &b, uint32_t &c) {
+    const uint32_t mn = min(min(a, b), c), mx = max(max(a, b), c);
+    const uint32_t md = a ^ b ^ c ^ mn ^ mx;
+    a = mn; b = md; c = mx;
+}
+__device__ __forceinline__ void warp_mergesplit96(uint32_t (&e)[3], int lane, uint32_t *__restrict__ s_tmp) {
+    sort3(e[0], e[1], e[2]);
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const bool keep_min = ((lane & k) == 0) == ((lane & j) == 0);
+            const uint32_t b0 = __shfl_xor_sync(0xFFFFFFFFu, e[2], j), b1 = __shfl_xor_sync(0xFFFFFFFFu, e[1], j),
+                           b2 = __shfl_xor_sync(0xFFFFFFFFu, e[0], j);
+            e[0] = keep_min ? min(e[0], b0) : max(e[0], b0);
+            e[1] = keep_min ? min(e[1], b1) : max(e[1], b1);
+            e[2] = keep_min ? min(e[2], b2) : max(e[2], b2);
+            sort3(e[0], e[1], e[2]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) s_tmp[3 * lane + r] = e[r];  // (stride 3: no bank conflicts)
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 3; ++r) e[r] = s_tmp[r * 32 + lane];
+}
+
 template <int R>
 __device__ __forceinline__ void warp_sort_segment(const uint64_t *__restrict__ key_in, const uint32_t *__restrict__ val_in,
                                                   uint64_t *__restrict__ key_out, uint32_t *__restrict__ val_out, int b, int n,
@@ -134,7 +169,7 @@ __device__ __forceinline__ void warp_sort_segment(const uint64_t *__restrict__ k
 
 template <int R>
 struct SegIdxBits {
-    static constexpr int value = (R == 1) ? 5 : (R == 2) ? 6 : (R == 4) ? 7 : (R == 8) ? 8 : 9;
+    static constexpr int value = (R == 1) ? 5 : (R == 2) ? 6 : (R == 3 || R == 4) ? 7 : (R == 8) ? 8 : 9;
 };
 
 // Same, on 32-bit words: (row|x relative to the path's smallest row|x) above the fragment's position
@@ -160,7 +195,7 @@ __device__ __forceinline__ bool warp_sort_segment32(const uint64_t *__restrict__
                                                     uint64_t *__restrict__ key_out, uint32_t *__restrict__ val_out, int b, int n,
                                                     int yx_bits, int lane, uint32_t *__restrict__ s_val, SegGeo geo, int (&sums)[3]) {
     constexpr int IB = SegIdxBits<R>::value;
-    static_assert(R == 1 || R == 2 || R == 4 || R == 8 || R == 16, "R must be 1, 2, 4, 8 or 16");
+    static_assert(R == 1 || R == 2 || R == 3 || R == 4 || R == 8 || R == 16, "R must be 1, 2, 3, 4, 8 or 16");
     const uint64_t mask = (1ull << yx_bits) - 1;
     const uint32_t special_from = (uint32_t)(geo.ny - 1) << geo.bits_x;  // keys at or above this are invalid / row 0
     uint32_t e[R];
@@ -223,7 +258,8 @@ __device__ __forceinline__ bool warp_sort_segment32(const uint64_t *__restrict__
             e[r] = (j < n) ? ((rel << IB) | (uint32_t)j) : 0xFFFFFFFFu;
         }
     }
-    warp_bitonic<R, uint32_t>(e, lane);
+    if constexpr (R == 3) warp_mergesplit96(e, lane, s_val + 128);  // (the path's values take the first 96 words of the slice)
+    else warp_bitonic<R, uint32_t>(e, lane);
     __syncwarp();
     if (!special) {
 #pragma unroll
@@ -305,6 +341,9 @@ struct SegBand {
     SegGeo geo;
 };
 
+#ifndef SLPR_SEG_R3
+#define SLPR_SEG_R3 1 /* paths of 65..96 fragments on the 96-word merge-split network instead of the 128-word bitonic one */
+#endif
 #ifndef SLPR_SEG_BAND_BLOCKS
 #define SLPR_SEG_BAND_BLOCKS 4
 #endif
@@ -367,6 +406,9 @@ __global__ void __launch_bounds__(256, BAND ? SLPR_SEG_BAND_BLOCKS : 4) k_segsor
             bool fit = false, done = true;
             if (n <= 32) fit = warp_sort_segment32<1, BAND>(key_in, val_in, key_out, val_out, b, n, yx_bits, lane, s_val, band.geo, sums);
             else if (n <= 64) fit = warp_sort_segment32<2, BAND>(key_in, val_in, key_out, val_out, b, n, yx_bits, lane, s_val, band.geo, sums);
+#if SLPR_SEG_R3
+            else if (n <= 96) fit = warp_sort_segment32<3, BAND>(key_in, val_in, key_out, val_out, b, n, yx_bits, lane, s_val, band.geo, sums);
+#endif
             else if (n <= 128) fit = warp_sort_segment32<4, BAND>(key_in, val_in, key_out, val_out, b, n, yx_bits, lane, s_val, band.geo, sums);
             else if (n <= 256) fit = warp_sort_segment32<8, BAND>(key_in, val_in, key_out, val_out, b, n, yx_bits, lane, s_val, band.geo, sums);
             else if (n <= SEG_WARP_MAX) fit = warp_sort_segment32<16, BAND>(key_in, val_in, key_out, val_out, b, n, yx_bits, lane, s_val, band.geo, sums);
