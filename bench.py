@@ -132,7 +132,8 @@ def run_reference(args):
     t0, _ = cpu_frame(sc, rows, W, H)  # first frame doubles as warm-up and as the size probe
     budget_s = 150.0
     steps = max(1, min(args.steps, int(budget_s / max(t0, 1e-3))))
-    warm = 0 if t0 * (steps + 1) > budget_s else min(args.warmup, 1)
+    # the requested warm-up (the probe frame is its first frame) as far as the budget goes
+    warm = max(0, min(args.warmup - 1, int(budget_s / max(t0, 1e-3)) - steps))
     for _ in range(warm):
         cpu_frame(sc, rows, W, H)
     t = time.perf_counter()
