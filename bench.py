@@ -117,6 +117,21 @@ def cpu_frame(sc, rows, W, H, threads=None):
     return time.perf_counter() - t, r
 
 
+L2_NOTE = "per-frame working set (fragments x 44 B + 33 MB frame) exceeds the 126 MB L2; no flush needed"
+
+
+def workload_config(args, sc, W, H, world):
+    """The `config` object of BOTH arms' lines (the driver compares them): what is rendered and how it is spread over the
+    GPUs. What a run found out about the workload (fragment counts, the sort it chose, ...) goes under `run`."""
+    bands, anim = args.mode == "bands" and world > 1, args.mode == "anim"
+    par = ((("bands%d" % world) + ("+independent" if args.independent_bands else "+nccl-allgather-of-winding-sums")
+            + ("+no-gather" if args.no_gather else "+pipelined-nccl-gather")
+            + ("" if args.rank0_share == 1.0 else "+rank0-share-%.2f" % args.rank0_share)) if bands
+           else (("anim%d-frame-f-on-rank-f-mod-%d" % (args.anim_frames, world)) if anim else ("frames-dp%d" % world)))
+    return {"workload": args.workload, "width": W, "height": H, "curves": sc.n_curves, "paths": sc.n_paths, "points": sc.n_points,
+            "scene_sha256": sc.sha256()[:16], "parallelism": par, "l2": L2_NOTE}
+
+
 def run_reference(args):
     """Reference arm: the reference's algorithm (oracle port) on all host cores, full frames."""
     rank = int(os.environ.get("RANK", "0"))
@@ -146,8 +161,7 @@ def run_reference(args):
         "impl": "reference", "metric": "Mpixel/s", "value": mpix, "unit": "Mpixel/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warm + 1, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32+i32", "data": "synthetic",
-        "config": {"workload": args.workload, "width": W, "height": H, "curves": sc.n_curves, "paths": sc.n_paths,
-                   "scene_sha256": sc.sha256()[:16]},
+        "config": workload_config(args, sc, W, H, args.gpus),
         "cpu_baseline": {"value": mpix, "unit": "Mpixel/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": mpix, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -816,16 +830,10 @@ def main():
             "metric": "Mpixel/s", "value": mpix, "unit": "Mpixel/s", "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if bands else "weak",
             "vs_baseline": None, "dtype": "f32+i32", "data": "synthetic",
-            "config": {"workload": args.workload, "width": W, "height": H, "curves": sc.n_curves, "paths": sc.n_paths,
-                       "points": sc.n_points, "fragments": cnt["n_fragments"], "records": cnt["n_out_frag"] + cnt["n_span"],
-                       "scene_sha256": sc.sha256()[:16], "sort": sort_now, "fill": "fused into k_spans" if fused_now else "k_fill_cells", "long_piece_walk": long_now[0], "long_pieces": long_now[1], "sort_key_bits": info["key_bits"],
-                       "radix_passes_if_radix": info["passes"],
-                       "parallelism": (("bands%d" % world) + ("+independent" if args.independent_bands else "+nccl-allgather-of-winding-sums")
-                                        + ("+no-gather" if args.no_gather else "+pipelined-nccl-gather")
-                                        + ("" if args.rank0_share == 1.0 else "+rank0-share-%.2f" % args.rank0_share)) if bands
-                                       else (("anim%d-frame-f-on-rank-f-mod-%d" % (args.anim_frames, world)) if anim else ("frames-dp%d" % world)),
-                       "l2": "per-frame working set (fragments x 44 B + 33 MB frame) exceeds the 126 MB L2; no flush needed",
-                       "frame_replay": "cuda-graph"},
+            "config": workload_config(args, sc, W, H, world),
+            "run": {"fragments": cnt["n_fragments"], "records": cnt["n_out_frag"] + cnt["n_span"], "sort": sort_now,
+                    "fill": "fused into k_spans" if fused_now else "k_fill_cells", "long_piece_walk": long_now[0], "long_pieces": long_now[1],
+                    "sort_key_bits": info["key_bits"], "radix_passes_if_radix": info["passes"], "frame_replay": "cuda-graph"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
             "stage_ms": stage_avg, "frame_ms": frame_dist,
         }
