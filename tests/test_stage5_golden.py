@@ -127,6 +127,29 @@ def test_diamond_exit_on_sloped_segments():
     assert sorted(i.tolist()) == [3, 4, 5, 6] and set(j.tolist()) == {1}
 
 
+def test_all_eleven_shaders_end_to_end_at_the_native_viewport():
+    """tests/golden/e2e1200.npz: one small scene through ALL of the reference's shipped shaders at its native
+    1200x1024 viewport — the nine compute shaders along drawFrame's dispatch sequence, then scanlinepr.vert / .frag
+    over the records they produced (tools/make_stage5_golden.py end_to_end). The oracle reproduces every compute
+    buffer bit for bit and its frame equals the executed stage-5 shaders' lines under the fixed-function rules."""
+    from vkscanlinepr_b200 import scene as S
+    import test_spirv_golden as T
+    z = np.load(os.path.join(util.GOLDEN, "e2e1200.npz"))
+    assert int(z["width"]) == W and int(z["height"]) == H
+    sc = S.Scene(z["pos"], z["pos_path"], z["curve_pos_map"], z["curve_type"], z["curve_path"], z["fill_rule"], z["fill_info"], "e2e1200")
+    r = O.render(sc, z["rows"], W, H)
+    for k in ("n_fragments", "n_out_frag", "n_span"):
+        assert int(z[k]) == r[k], k
+    T.check_cut_cache(z["cut_cache"], r["cut_cache"])
+    for k in T.BUFFERS:
+        assert z[k].shape == r[k].shape and np.array_equal(T.bits(z[k]), T.bits(r[k])), f"buffer {k}"
+    pos = z["s5_position"].view(np.float32).reshape(-1, 4)
+    col = z["s5_color"].view(np.float32).reshape(-1, 4)
+    want = rasterize(z["records"], pos, col)
+    assert np.count_nonzero(want != 0xFFFFFFFF) > 1000
+    assert np.array_equal(r["rgba"].view(np.uint32).reshape(H, W), want)
+
+
 @pytest.mark.skipif(not os.path.isdir("/root/reference/workdir/shaders"), reason="reference shaders not present")
 def test_interpreter_still_reproduces_the_stage5_fixture():
     import sys

@@ -72,11 +72,27 @@ def run_records(rec, log=print):
     return dict(position=position, color=color, frag_pos=frag_pos, sample_mask=np.uint32(masks.pop()))
 
 
+def end_to_end():
+    """All eleven shipped shaders on one small scene at the reference's native 1200x1024 viewport: the nine compute
+    shaders along drawFrame's dispatch sequence (tools/make_spirv_golden.py run_frame), then the vertex / fragment pair
+    over the draw records they produced -> tests/golden/e2e1200.npz (every compute buffer + s5_* = the stage-5 outputs)."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import make_spirv_golden as G
+    from vkscanlinepr_b200 import scene as S
+    sc = S.synth_scene(16, 1200, 1024, 8.0, 30.0, seed=77)
+    r = G.run_frame(sc, S.identity_rows(), 1200, 1024, log=lambda *a: None)
+    print(f"e2e1200: {sc.n_curves} curves, {r['n_fragments']} fragments, {r['records'].shape[0]} records")
+    s5 = run_records(r["records"])
+    np.savez_compressed(os.path.join(GOLD, "e2e1200.npz"), **G.scene_arrays(sc), **r, **{"s5_" + k: v for k, v in s5.items()})
+
+
 def main():
     for tag in ("1", "3"):
         rec = np.load(os.path.join(GOLD, f"ref_records_{tag}.npz"))["records"]
         print(f"stage5_{tag}: {rec.shape[0]} records")
         np.savez_compressed(os.path.join(GOLD, f"stage5_{tag}.npz"), **run_records(rec))
+    end_to_end()
 
 
 if __name__ == "__main__":
